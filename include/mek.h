@@ -1,0 +1,156 @@
+/*
+ * mek.h -- C ABI of libmek, the batched B200 implementation of MPC-EKF4FastCharge's per-timestep
+ * control loop.  Plain pointers and sizes only; every array argument is a caller-owned HOST
+ * buffer unless stated otherwise.  All functions return 0 (MEK_OK) or a negative mek_status;
+ * mek_last_error() gives the message.  A trailing batch dimension B replaces the reference's
+ * single cell, so B = 1 reproduces the MATLAB shapes.
+ *
+ * Reference interfaces replaced (paths under /root/reference/src):
+ *   mek_bank_create / mek_bank_load  <- load(ROMfile,'ROM')             MPC-EKF4FastCharge/runMPC.m:4-5
+ *   mek_pop_init                     <- initKF(...)                     UTILITY/initKF.m:30
+ *                                       initMPC(...)                    MPC-EKF4FastCharge/initMPC.m:1
+ *                                       OB_step(0,TC,[],ROM,initCfg)    MPC-EKF4FastCharge/runMPC.m:72-74, OB_step.m:39-72
+ *   mek_run                          <- the k-loop of runMPC            MPC-EKF4FastCharge/runMPC.m:83-112
+ *   mek_pop_ob_step                  <- OB_step(Iapp,Tc,cellState,ROM)  MPC-EKF4FastCharge/OB_step.m:1
+ *   mek_pop_iter_ekf                 <- iterEKF(vk,ik,Tk,ekfData)       UTILITY/iterEKF.m:30
+ *                                       EKFmatsHandler(ekfData,Xind,zk,Tk)  MPC-EKF4FastCharge/EKFmatsHandler.m:1
+ *   mek_pop_iter_mpc                 <- iterMPC(xk,cellState,mpcData)   MPC-EKF4FastCharge/iterMPC.m:1
+ *   mek_pred_mat                     <- predMat(A,B,C,D,Np,Nc)          MPC-EKF4FastCharge/predMat.m:1
+ *   mek_constraints                  <- constraintsMPC(x_aug,cellState,mpcData)  MPC-EKF4FastCharge/constraintsMPC.m:1
+ *   mek_hildreth                     <- hildreth(E,F,M,gamma,lambda0,maxIter)    MPC-EKF4FastCharge/hildreth.m:1
+ *   mek_read_logs                    <- u_store, voltage_store, SOC_store, phise_store  runMPC.m:55-60,106-111
+ */
+#ifndef MEK_H
+#define MEK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MEK_OK = 0,
+  MEK_ERR_ARG = -1,        /* bad argument / shape (MATLAB error() at initKF.m:67, OB_step.m:41)             */
+  MEK_ERR_BANK = -2,       /* structural problem in the ROM bank (OB_step.m:140-157, iterEKF.m:692-733,      */
+                           /*   initKF.m:74-87)                                                              */
+  MEK_ERR_CUDA = -3,       /* CUDA runtime failure                                                           */
+  MEK_ERR_UNSUPPORTED = -4,/* configuration outside the built kernel instances                               */
+  MEK_ERR_STATE = -5       /* call order (e.g. run before init)                                              */
+} mek_status;
+
+/* per-cell status word bits (replaces NaN-latching, iterEKF.m:55-59) */
+#define MEK_ST_LOST 1u       /* EKF warnCount > 10: outputs NaN from that step on, the cell idles          */
+#define MEK_ST_Q18 2u        /* Thetae < 0 branch reached (iterEKF.m:384-389; the reference would throw)   */
+#define MEK_ST_NONFINITE 4u  /* the current command became NaN/Inf                                         */
+
+typedef struct mek_bank mek_bank;
+typedef struct mek_pop mek_pop;
+
+/* ROM struct surface.  Matrices are row-major with the model index
+ * m = iT*nZ + iZ slowest; A is the diagonal of ROMmdls(iT,iZ).A including the integrator (== 1). */
+typedef struct {
+  int n;                    /* transient states (5)                                   */
+  int nz;                   /* ROM outputs                                            */
+  int nT, nZ;               /* set-point grid                                         */
+  double Tsamp;             /* xraData.Tsamp                                          */
+  const double *Tpts_C;     /* [nT] xraData.T, deg C, ascending                       */
+  const double *Zpts_pct;   /* [nZ] xraData.SOC, percent, ascending                   */
+  const char *const *names; /* [nz] tfData.names                                      */
+  const double *xloc;       /* [nz] tfData.xLoc                                       */
+  const double *A;          /* [M][n+1]                                               */
+  const double *C;          /* [M][nz][n+1] (last column: integrator residue)         */
+  const double *D;          /* [M][nz]                                                */
+  const double *params;     /* cellData closed-form parameters (mek/bank.py P_*)      */
+  int nparams;
+} mek_bank_desc;
+
+typedef struct {
+  int Np, Nc;               /* runMPC.m:28-29 (clamped like initMPC.m:32-33)          */
+  int maxHild;              /* initMPC.m:47 (100)                                     */
+  int constraints[3];       /* [current voltage eta], runMPC.m:33                     */
+  int use_zmax;             /* SOC upper-bound rows, constraintsMPC.m:89 (1 in runMPC)*/
+  double ref;               /* mpcData.ref = targetSOC (95, percent! Q9)              */
+  double SigmaV, SigmaW;    /* runMPC.m:18-19                                         */
+  int force_jacobi;         /* 1: always run the eigen-decomposition PSD repair       */
+  int threads_per_block;    /* 0 = default                                            */
+  int blocks_per_sm;        /* 0 = from the occupancy calculator                      */
+} mek_config;
+
+/* ---- bank ---- */
+int mek_bank_create(const mek_bank_desc *desc, mek_bank **out);
+int mek_bank_load(const char *path, mek_bank **out);           /* MEKBANK1 file (mek/bank.py)  */
+void mek_bank_destroy(mek_bank *bank);
+int mek_bank_dims(const mek_bank *bank, int *n, int *nz, int *nT, int *nZ);
+double mek_bank_capacity_Ah(const mek_bank *bank);               /* cellData.function.const.Q()  */
+
+/* ---- population (one shard on one device) ---- */
+int mek_pop_create(const mek_bank *bank, const mek_config *cfg, int64_t B, int device, mek_pop **out);
+void mek_pop_destroy(mek_pop *pop);
+/* logs are kept for the first n_log_cells cells of the shard, for up to max_steps sample instants */
+int mek_pop_set_logging(mek_pop *pop, int64_t n_log_cells, int max_steps);
+/* initKF + initMPC + first OB_step call.  SOC0pct[B] (plant), ekfSOC0pct[B] or NULL (= SOC0pct),
+ * Tc[B] deg C, SigmaX0[36*B] (6x6 column-major per cell, symmetric), limits[7*B] =
+ * u_max,u_min,du_max,du_min,v_max,phise_min,z_max+z_tol per cell (runMPC.m:36-44, initMPC.m:66-67). */
+int mek_pop_init(mek_pop *pop, const double *SOC0pct, const double *ekfSOC0pct, const double *Tc, const double *SigmaX0,
+                 const double *limits);
+int mek_pop_reset(mek_pop *pop);    /* re-run the initialisation from the inputs already on the device */
+/* loop body of runMPC for sample instants k in [k0,k1) (0-based), asynchronously on the pop's stream */
+int mek_run(mek_pop *pop, int k0, int k1);
+int mek_run_timed(mek_pop *pop, int k0, int k1, float *ms);     /* mek_run + sync, CUDA-event time of the kernel */
+int mek_sync(mek_pop *pop);
+void *mek_pop_stream(mek_pop *pop);                              /* cudaStream_t                  */
+int64_t mek_pop_launches(const mek_pop *pop);                    /* kernels launched so far       */
+int mek_pop_ncon(const mek_pop *pop);                            /* constraint rows nC            */
+int mek_pop_state_len(const mek_pop *pop);                       /* doubles per cell in read/write_state */
+/* logs for instants [k0,k1) x first n_log_cells cells, [step][cell] row-major.  Any pointer may be NULL.
+ * u = command computed at k (applied at k+1, runMPC.m:106), V = voltage_store, soc = zk(end),
+ * phise = phise_store (runMPC.m:94-95); iT,iZ = MPC.iT/iZ (1-based); nexec = mpcData.nexec;
+ * active[step][cell][4] = bit i set <=> lambda_i > 0 on exit of hildreth. */
+int mek_read_logs(mek_pop *pop, int k0, int k1, double *u, double *V, double *soc, double *phise, int32_t *iT, int32_t *iZ,
+                  int32_t *nexec, uint32_t *active);
+/* full per-cell state, cell-major: [B][state_len] (layout: DESIGN.md "state block") */
+int mek_read_state(mek_pop *pop, double *state);
+int mek_write_state(mek_pop *pop, const double *state);
+/* population statistics reduced on the device: totals[MEK_NSTAT] */
+#define MEK_NSTAT 16
+enum {
+  MEK_STAT_CELLS = 0, MEK_STAT_CELLSTEPS, MEK_STAT_SUM_NEXEC, MEK_STAT_N_QP, MEK_STAT_N_CAP, MEK_STAT_N_REACHED,
+  MEK_STAT_SUM_T_REACH, MEK_STAT_MIN_PHISE, MEK_STAT_MAX_V, MEK_STAT_N_LOST, MEK_STAT_N_NONFINITE, MEK_STAT_SUM_SOC,
+  MEK_STAT_N_JACOBI, MEK_STAT_N_BUMP, MEK_STAT_N_WARN, MEK_STAT_N_Q18
+};
+int mek_summary(mek_pop *pop, double *totals);
+
+/* ---- function-level batched entry points on a population's state (one call = one line of the loop body) ---- */
+int mek_pop_ob_step(mek_pop *pop, const double *Iapp, double *Vcell);
+/* zk[(nz+2)*B] cell-major or NULL; mats[31*B] cell-major or NULL =
+ *   lost, iT, iZ, xhat(6), diag A(5), Cv(5), Dv, Cphi(5), Dphi, bv, bphi, vhat, SOC */
+#define MEK_NMATS 31
+int mek_pop_iter_ekf(mek_pop *pop, const double *vk, const double *ik, double *zk, double *mats);
+/* consumes mats (from mek_pop_iter_ekf) and the applied current; returns the new command and diagnostics */
+int mek_pop_iter_mpc(mek_pop *pop, const double *mats, const double *uk_applied, double *uk, double *phise, int32_t *nexec,
+                     uint32_t *active);
+
+/* ---- stateless batched entry points ---- */
+/* hildreth.m: E[Nc*Nc*B], F[Nc*B], M[nC*Nc*B] (row-major per problem), gamma[nC*B], lambda0[nC*B] or NULL */
+int mek_hildreth(int64_t B, int Nc, int nC, const double *E, const double *F, const double *M, const double *gamma,
+                 const double *lambda0, int maxIter, double *DU, double *lambda, int32_t *nexec, int device);
+/* predMat.m for one scalar output, diagonal A (a[6*B] incl. the integrator entry) and B = ones:
+ * c[6*B], d[B] -> Phi[Np*7*B] (row-major Np x 7 per problem), G[Np*Nc*B] */
+int mek_pred_mat(int64_t B, const double *a, const double *c, const double *d, int Np, int Nc, double *Phi, double *G, int device);
+
+/* constraintsMPC.m plus the pre-QP part of iterMPC.m.  x_aug[7*B] = [x_k(6); u_k-1]; mats[31*B] as produced by
+ * mek_pop_iter_ekf (diag A, Cv, Dv, Cphi, Dphi, bv, bphi are read); SOCk_1[B]; limits[7*B]; r = -Ts/(3600*Q)
+ * (EKFmatsHandler.m:43); ref = mpcData.ref.  Outputs M[nC*Nc*B], gamma[nC*B]; optional E[Nc*Nc*B], F[Nc*B],
+ * DU[Nc*B] (iterMPC.m:38-48). */
+int mek_constraints(int64_t B, int Np, int Nc, const int *constraints, int use_zmax, const double *x_aug, const double *mats,
+                    const double *SOCk_1, const double *limits, double *M, double *gamma, double r, double ref, double *E,
+                    double *F, double *DU, int device);
+
+const char *mek_last_error(void);
+int mek_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEK_H */

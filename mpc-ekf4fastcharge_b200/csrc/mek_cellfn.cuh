@@ -1,0 +1,64 @@
+// Closed forms behind ROM.cellData.function.* for the synthetic NMC30-like bank.
+//
+// In the reference these are MATLAB function handles stored in ROM_NMC30_HRA.mat (missing); call
+// sites: OB_step.m:205-217,231-232,313-314,329-330,337-340; iterEKF.m:282-283,362-363,392-393,
+// 404-407,439-442,463-464,495-500; EKFmatsHandler.m:57-69,84-85,96.  Here they are a parameter
+// vector (layout = mek/bank.py P_*) evaluated in a fixed operation order.
+#pragma once
+#include "mek_math.cuh"
+
+namespace mek {
+
+enum : int { P_F = 0, P_R, P_Q, P_RC, P_TREF, P_NEG = 5, P_POS = 16, P_UN = 27, P_UP = 33, P_UP_COEF = 36, N_PARAMS = 44 };
+enum : int { E_THETA0 = 0, E_THETA100, E_K0REF, E_K0SLOPE, E_EA_K0, E_RFREF, E_RFSLOPE, E_EA_RF, E_WDL, E_CDL, E_NDL };
+constexpr int UP_MAXCOEF = 8;
+
+// function.{neg,pos}.soc(z,T)
+MEK_HD double soc_e(const double* p, int base, double z) {
+  return p[base + E_THETA0] + z * (p[base + E_THETA100] - p[base + E_THETA0]);
+}
+// function.neg.Uocp / dUocp
+MEK_HD double uocp_n(const double* p, double th) {
+  const double* c = p + P_UN;
+  const double x = (th - c[4]) / c[5];
+  const double t = th + c[2];
+  return (c[0] + c[1] / (t * t)) + c[3] * (1.0 - x / sqrt(1.0 + x * x));
+}
+MEK_HD double duocp_n(const double* p, double th) {
+  const double* c = p + P_UN;
+  const double x = (th - c[4]) / c[5];
+  const double q = 1.0 + x * x;
+  const double t = th + c[2];
+  return (-2.0 * c[1]) / ((t * t) * t) - (c[3] / c[5]) / (q * sqrt(q));
+}
+// function.pos.Uocp / dUocp: Horner polynomial in x = (th - centre)/width
+MEK_HD double uocp_p(const double* p, double th) {
+  const double x = (th - p[P_UP]) / p[P_UP + 1];
+  const int nc = (int)p[P_UP + 2];
+  double acc = p[P_UP_COEF + nc - 1];
+  for (int i = nc - 2; i >= 0; --i) acc = acc * x + p[P_UP_COEF + i];
+  return acc;
+}
+MEK_HD double duocp_p(const double* p, double th) {
+  const double x = (th - p[P_UP]) / p[P_UP + 1];
+  const int nc = (int)p[P_UP + 2];
+  double acc = (double)(nc - 1) * p[P_UP_COEF + nc - 1];
+  for (int i = nc - 2; i >= 1; --i) acc = acc * x + (double)i * p[P_UP_COEF + i];
+  return acc / p[P_UP + 1];
+}
+// function.{neg,pos}.k0(theta,T), .Rf(theta,T): Arrhenius factor hoisted (T is constant per cell)
+MEK_HD double k0_e(const double* p, int base, double th, double arr) {
+  return (p[base + E_K0REF] * (1.0 + p[base + E_K0SLOPE] * (th - 0.5))) * arr;
+}
+MEK_HD double rf_e(const double* p, int base, double th, double arr) {
+  return (p[base + E_RFREF] * (1.0 + p[base + E_RFSLOPE] * th)) * arr;
+}
+MEK_HD double arrhenius(const double* p, double T, double Ea) {
+  return exp_d((Ea / p[P_R]) * (1.0 / p[P_TREF] - 1.0 / T));
+}
+// OB_step.m:218-219  Cdleff = Cdl^(2-nDL) * wDL^(nDL-1)
+MEK_HD double cdl_eff(const double* p, int base) {
+  return exp_d((2.0 - p[base + E_NDL]) * log_d(p[base + E_CDL])) * exp_d((p[base + E_NDL] - 1.0) * log_d(p[base + E_WDL]));
+}
+
+}  // namespace mek

@@ -1,0 +1,878 @@
+// Device functions of the fused MPC-EKF control loop: one thread per cell, state in a
+// structure-of-arrays block in HBM (cell index fastest => every warp access is one coalesced
+// 256-byte line), the hot rows of the ROM table bank in shared memory.
+//
+// Each function cites the reference lines it implements (paths under /root/reference/src).
+// Arithmetic order is fixed and FMA contraction is disabled (-fmad=false): see DESIGN.md
+// "numerics contract".
+#pragma once
+#include <cstdint>
+#include "mek_cellfn.cuh"
+
+namespace mek {
+
+// ---- per-cell state fields (SoA: value of field f for cell c lives at st[f*ld + c]) ----
+enum : int {
+  S_SOCN = 0, S_SOCP, S_SOC0N, S_SOC0P, S_CDLN, S_CDLP, S_TC, S_ARRK0N, S_ARRK0P, S_ARRRFN, S_ARRRFP,
+  S_X0, S_SIGX0, S_PRIORI, S_EKFSOC0, S_WARN, S_UK, S_LAMVALID, S_STATUS, S_PLANTWARN,
+  S_UMAX, S_UMIN, S_DUMAX, S_DUMIN, S_VMAX, S_PHIMIN, S_ZMAX, S_NJAC, S_NBUMP, S_SPARE,
+  S_SUM_NEXEC, S_N_QP, S_N_CAP, S_MIN_PHISE, S_MAX_V, S_T_REACH, S_STEPS, S_LAST_SOC, S_LAST_V, S_LAST_PHISE,
+  S_HDR = 40
+};
+constexpr unsigned ST_LOST = 1u, ST_Q18 = 2u, ST_NONFINITE = 4u;
+constexpr int N5 = 5, NSYM = 15;
+
+// ---- hot rows of the bank kept in shared memory (subset of ROMmdls(iT,iZ).C/.D the control path reads) ----
+enum : int { HR_IFDL0 = 0, HR_IFDL3, HR_IF0, HR_IF3, HR_TSS0, HR_TSS3, HR_THE0, HR_THE3, HR_PHIE, HR_PHI, HR_FIXED = 10 };
+constexpr int HR_MAX = 24;
+
+struct Dims {
+  int M, nT, nZ, nz;
+  int R;             // hot rows per model (HR_FIXED + extras)
+  int nx_negtss;     // extra negThetass rows (beyond Thetass0), then extra posThetass, then extra Thetae
+  int nx_postss;
+  int nx_thetae;
+  int mstride;       // doubles per model in the hot bank: 6 (diag A) + R*7 (C row 6 + D)
+  int nC;            // constraint rows
+  int Np, Nc, maxHild;
+  int useCurrent, useVoltage, useEta, useZmax;
+  int force_jacobi;
+  double Ts, ref, SigmaV, SigmaW, sigmin;
+  long long B, ld;   // cells in this shard, leading dimension of the SoA block
+  int f_lambda, f_bigx, f_xhat, f_sig, nfields;
+};
+
+struct BankSmem {
+  const double* Tpts;  // [nT] K
+  const double* Zpts;  // [nZ]
+  const double* mdl;   // [M][mstride]
+};
+
+struct Cell {
+  double* st;
+  long long ld;
+  __device__ __forceinline__ double& f(int field) const { return st[(long long)field * ld]; }
+};
+
+__device__ __forceinline__ int sym_idx(int i, int j) {
+  // upper triangle, row-major: (0,0..4)=0..4, (1,1..4)=5..8, (2,2..4)=9..11, (3,3..4)=12,13, (4,4)=14
+  const int a = i <= j ? i : j, b = i <= j ? j : i;
+  return a * 5 - (a * (a - 1)) / 2 + (b - a);
+}
+
+// first two entries of a stable ascending sort of |v - pts| (OB_step.m:251,261; iterEKF.m:221,234)
+__device__ __forceinline__ void two_nearest(double v, const double* pts, int n, int& i1, int& i2) {
+  int a = 0;
+  double best = fabs(v - pts[0]);
+  for (int i = 1; i < n; ++i) {
+    const double d = fabs(v - pts[i]);
+    if (d < best) { best = d; a = i; }
+  }
+  int b = -1;
+  double best2 = 0.0;
+  for (int i = 0; i < n; ++i) {
+    if (i == a) continue;
+    const double d = fabs(v - pts[i]);
+    if (b < 0 || d < best2) { best2 = d; b = i; }
+  }
+  i1 = a;
+  i2 = (b < 0) ? a : b;
+}
+
+struct Xind {          // iterEKF.m:249-254
+  double gamma[4];
+  int m[4];            // model column (iT*nZ+iZ) of the 4 neighbours
+  int iT[4], iZ[4];
+};
+
+// getXind (iterEKF.m:219-255): ordering by value with swap, alphas not clamped (Q14)
+__device__ __forceinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Xind& X) {
+  int z1, z2, t1, t2;
+  two_nearest(SOC, bk.Zpts, d.nZ, z1, z2);
+  int iZup = z1, iZlo = z1;
+  double Zup = bk.Zpts[z1], Zlo = bk.Zpts[z1];
+  if (d.nZ > 1) {
+    Zup = bk.Zpts[z1]; iZup = z1; Zlo = bk.Zpts[z2]; iZlo = z2;
+    if (Zup < Zlo) { Zup = bk.Zpts[z2]; iZup = z2; Zlo = bk.Zpts[z1]; iZlo = z1; }
+  }
+  two_nearest(Tk, bk.Tpts, d.nT, t1, t2);
+  int iTup = t1, iTlo = t1;
+  double Tup = bk.Tpts[t1], Tlo = bk.Tpts[t1];
+  if (d.nT > 1) {
+    Tup = bk.Tpts[t1]; iTup = t1; Tlo = bk.Tpts[t2]; iTlo = t2;
+    if (Tup < Tlo) { Tup = bk.Tpts[t2]; iTup = t2; Tlo = bk.Tpts[t1]; iTlo = t1; }
+  }
+  double aZ = 0.0, aT = 0.0;
+  if (d.nZ > 1) aZ = (SOC - Zlo) / (Zup - Zlo);
+  if (d.nT > 1) aT = (Tk - Tlo) / (Tup - Tlo);
+  X.gamma[0] = (1.0 - aT) * (1.0 - aZ);
+  X.gamma[1] = (1.0 - aT) * aZ;
+  X.gamma[2] = aT * (1.0 - aZ);
+  X.gamma[3] = aT * aZ;
+  X.iT[0] = iTlo; X.iT[1] = iTlo; X.iT[2] = iTup; X.iT[3] = iTup;
+  X.iZ[0] = iZlo; X.iZ[1] = iZup; X.iZ[2] = iZlo; X.iZ[3] = iZup;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) X.m[k] = X.iT[k] * d.nZ + X.iZ[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// plant: OB_step.m simStep (:188-357).  Returns Vcell.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
+                                             double Iapp) {
+  const double T = c.f(S_TC) + 273.15;                               // OB_step.m:75
+  const double th0n = p[P_NEG + E_THETA0], th100n = p[P_NEG + E_THETA100];
+  const double th0p = p[P_POS + E_THETA0], th100p = p[P_POS + E_THETA100];
+  const double Q = p[P_Q];
+  double SOCn = c.f(S_SOCN), SOCp = c.f(S_SOCP);
+  const double negSOC = SOCn, posSOC = SOCp;                         // :226-227 (Q16)
+  const double cellSOC = (SOCn - th0n) / (th100n - th0n);            // :228
+  const double dUn = duocp_n(p, SOCn), dUp = duocp_p(p, SOCp);       // :231-232
+  const double dQn = fabs(th100n - th0n), dQp = fabs(th100p - th0p);
+  const double res0n = -dQn / (3600.0 * Q - (c.f(S_CDLN) * dQn) * dUn);  // :235
+  const double res0p = dQp / (3600.0 * Q - (c.f(S_CDLP) * dQp) * dUp);   // :236
+  SOCn = SOCn + (res0n * Iapp) * d.Ts;                               // :239-240
+  SOCp = SOCp + (res0p * Iapp) * d.Ts;
+  int nw = 0;
+  if (SOCn < 0.0) { SOCn = 0.0; ++nw; }                              // :241-244
+  if (SOCn > 1.0) { SOCn = 1.0; ++nw; }
+  if (SOCp < 0.0) { SOCp = 0.0; ++nw; }
+  if (SOCp > 1.0) { SOCp = 1.0; ++nw; }
+  if (nw) c.f(S_PLANTWARN) += (double)nw;
+  int z1, z2, t1, t2;
+  two_nearest(cellSOC, bk.Zpts, d.nZ, z1, z2);                       // :251-259 (ordering by index, Q15)
+  const int iZup = z1 > z2 ? z1 : z2, iZlo = z1 < z2 ? z1 : z2;
+  two_nearest(T, bk.Tpts, d.nT, t1, t2);                             // :261-269
+  const int iTup = t1 > t2 ? t1 : t2, iTlo = t1 < t2 ? t1 : t2;
+  const double Zup = bk.Zpts[iZup], Zlo = bk.Zpts[iZlo], Tup = bk.Tpts[iTup], Tlo = bk.Tpts[iTlo];
+  const int mc[4] = {iTlo * d.nZ + iZlo, iTlo * d.nZ + iZup, iTup * d.nZ + iZlo, iTup * d.nZ + iZup};
+  double y[4][9];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                                      // :272-275 four corner outputs
+    const double* mm = bk.mdl + mc[k] * d.mstride + 6;
+    double x[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) x[j] = c.f(d.f_bigx + mc[k] * 6 + j);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const double* cr = mm + r * 7;
+      double acc = cr[0] * x[0];
+#pragma unroll
+      for (int j = 1; j < 6; ++j) acc = acc + cr[j] * x[j];
+      y[k][r] = acc + cr[6] * Iapp;
+    }
+  }
+  for (int m = 0; m < d.M; ++m) {                                    // :278 advance ALL models
+    const double* a = bk.mdl + m * d.mstride;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double& x = c.f(d.f_bigx + m * 6 + j);
+      x = a[j] * x + Iapp;
+    }
+  }
+  double aZ = 0.0, aT = 0.0;                                         // :281-283
+  if (Zup != Zlo) aZ = (cellSOC - Zlo) / (Zup - Zlo);
+  if (Tup != Tlo) aT = (T - Tlo) / (Tup - Tlo);
+  double yk[9];
+#pragma unroll
+  for (int r = 0; r < 9; ++r)                                        // :285
+    yk[r] = (1.0 - aT) * ((1.0 - aZ) * y[0][r] + aZ * y[1][r]) + aT * ((1.0 - aZ) * y[2][r] + aZ * y[3][r]);
+  double tss0 = yk[HR_TSS0] + c.f(S_SOC0N), tss3 = yk[HR_TSS3] + c.f(S_SOC0P);   // :304-305 (Q6)
+  tss0 = fmin(fmax(tss0, 1e-6), 1.0 - 1e-6);                         // :309-310
+  tss3 = fmin(fmax(tss3, 1e-6), 1.0 - 1e-6);
+  const double the0 = fmax(yk[HR_THE0] + 1.0, 1e-6), the3 = fmax(yk[HR_THE3] + 1.0, 1e-6);   // :325-326
+  const double k0n = k0_e(p, P_NEG, negSOC, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, posSOC, c.f(S_ARRK0P));
+  const double i0n = k0n * sqrt((the0 * (1.0 - tss0)) * tss0);       // :331-332
+  const double i0p = k0p * sqrt((the3 * (1.0 - tss3)) * tss3);
+  const double pref = ((2.0 * p[P_R]) * T) / p[P_F];
+  const double negEta0 = pref * asinh_d(yk[HR_IF0] / (2.0 * i0n));   // :333-334
+  const double posEta3 = pref * asinh_d(yk[HR_IF3] / (2.0 * i0p));
+  const double Un0 = uocp_n(p, tss0), Up3 = uocp_p(p, tss3);         // :337-340
+  const double Rfn = rf_e(p, P_NEG, negSOC, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, posSOC, c.f(S_ARRRFP));
+  double V = ((((posEta3 - negEta0) + yk[HR_PHIE]) + Up3) - Un0) + (Rfp * yk[HR_IFDL3] - Rfn * yk[HR_IFDL0]);   // :341-342
+  V = V - p[P_RC] * Iapp;                                            // :344
+  c.f(S_SOCN) = SOCn;
+  c.f(S_SOCP) = SOCp;
+  return V;
+}
+
+// ------------------------------------------------------------------------------------------
+// EKF pieces
+// ------------------------------------------------------------------------------------------
+struct HotZ {            // corrected outputs the control path consumes (subset of Z / zk)
+  double If0, If3, Ifdl0, Ifdl3, tss0, tss3, the0, the3, phie;
+};
+
+// one blended linear output row r (iterEKF.m:302-313): Z = [C1*x1+D1*i, ...]*gamma
+__device__ __forceinline__ double blend_row(const Dims& d, const BankSmem& bk, const Xind& X, const double (*xk)[N5], double ik, int r) {
+  double yc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double* cr = bk.mdl + X.m[k] * d.mstride + 6 + r * 7;
+    double acc = cr[0] * xk[k][0];
+#pragma unroll
+    for (int j = 1; j < N5; ++j) acc = acc + cr[j] * xk[k][j];
+    yc[k] = acc + cr[6] * ik;
+  }
+  return ((yc[0] * X.gamma[0] + yc[1] * X.gamma[1]) + yc[2] * X.gamma[2]) + yc[3] * X.gamma[3];
+}
+
+// getVariables (iterEKF.m:259-417) restricted to the rows that feed Vcell, the warnings and EKFmatsHandler
+__device__ __forceinline__ double get_variables(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
+                                                double ik, const Xind& X, double T, HotZ& z, int& nwarn, unsigned& status) {
+  double xk[4][N5];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < N5; ++j) xk[k][j] = c.f(d.f_xhat + X.m[k] * N5 + j);   // :267-270
+  const double rpa = d.Ts / (3600.0 * p[P_Q]);
+  const double xSOC = c.f(S_EKFSOC0) - c.f(S_X0) * rpa;              // :277
+  double SOCn = soc_e(p, P_NEG, xSOC), SOCp = soc_e(p, P_POS, xSOC); // :282-283
+  if (SOCn < 0.0) { ++nwarn; SOCn = 1e-6; }                          // :284-295 (Q17)
+  if (SOCn > 1.0) { ++nwarn; SOCn = 1.0 - 1e-6; }
+  if (SOCp < 0.0) { ++nwarn; SOCp = 1e-6; }
+  if (SOCp > 0.998) { ++nwarn; SOCp = 0.998; }
+  z.If0 = blend_row(d, bk, X, xk, ik, HR_IF0);                       // :324-325
+  z.If3 = blend_row(d, bk, X, xk, ik, HR_IF3);
+  z.Ifdl0 = blend_row(d, bk, X, xk, ik, HR_IFDL0);
+  z.Ifdl3 = blend_row(d, bk, X, xk, ik, HR_IFDL3);
+  // negThetass rows (:331-343): Thetass0 plus the extra rows, which only matter for the warnings
+  {
+    double v = blend_row(d, bk, X, xk, ik, HR_TSS0) + SOCn;
+    bool lo = v < 0.0;
+    if (lo) v = 1e-6;
+    bool hi = v > 1.0;
+    if (hi) v = 1.0 - 1e-6;
+    for (int e = 0; e < d.nx_negtss; ++e) {
+      double w = blend_row(d, bk, X, xk, ik, HR_FIXED + e) + SOCn;
+      if (w < 0.0) { lo = true; w = 1e-6; }
+      if (w > 1.0) hi = true;
+    }
+    nwarn += (int)lo + (int)hi;
+    z.tss0 = v;
+  }
+  {                                                                  // posThetass rows (:345-357)
+    double v = blend_row(d, bk, X, xk, ik, HR_TSS3) + SOCp;
+    bool lo = v < 0.0;
+    if (lo) v = 1e-6;
+    bool hi = v > 0.998;
+    if (hi) v = 0.998;
+    for (int e = 0; e < d.nx_postss; ++e) {
+      double w = blend_row(d, bk, X, xk, ik, HR_FIXED + d.nx_negtss + e) + SOCp;
+      if (w < 0.0) { lo = true; w = 1e-6; }
+      if (w > 0.998) hi = true;
+    }
+    nwarn += (int)lo + (int)hi;
+    z.tss3 = v;
+  }
+  z.phie = blend_row(d, bk, X, xk, ik, HR_PHIE);                     // :371 PhieTilde3 (before the Phise0 shift)
+  {                                                                  // Thetae rows (:383-389, Q18)
+    double v0 = blend_row(d, bk, X, xk, ik, HR_THE0) + 1.0;
+    double v3 = blend_row(d, bk, X, xk, ik, HR_THE3) + 1.0;
+    bool lo = false;
+    if (v0 < 0.0) { lo = true; v0 = 1e-6; }
+    if (v3 < 0.0) { lo = true; v3 = 1e-6; }
+    for (int e = 0; e < d.nx_thetae; ++e) {
+      const double w = blend_row(d, bk, X, xk, ik, HR_FIXED + d.nx_negtss + d.nx_postss + e) + 1.0;
+      if (w < 0.0) lo = true;
+    }
+    if (lo) { ++nwarn; status |= ST_Q18; }
+    z.the0 = v0;
+    z.the3 = v3;
+  }
+  const double k0n = k0_e(p, P_NEG, SOCn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, SOCp, c.f(S_ARRK0P));   // :392-393
+  const double i0n = k0n * sqrt((z.the0 * (1.0 - z.tss0)) * z.tss0); // :395-398
+  const double i0p = k0p * sqrt((z.the3 * (1.0 - z.tss3)) * z.tss3);
+  const double pref = ((2.0 * p[P_R]) * T) / p[P_F];
+  const double negEta0 = pref * asinh_d(z.If0 / (2.0 * i0n));        // :400-401
+  const double posEta3 = pref * asinh_d(z.If3 / (2.0 * i0p));
+  const double Un0 = uocp_n(p, z.tss0), Up3 = uocp_p(p, z.tss3);     // :404-407
+  const double Rfn = rf_e(p, P_NEG, SOCn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, SOCp, c.f(S_ARRRFP));
+  return ((((posEta3 - negEta0) + z.phie) + Up3) - Un0) + (Rfp * z.Ifdl3 - Rfn * z.Ifdl0);   // :409-410 (Q5: no Rc*i)
+}
+
+// PSD repair (iterEKF.m:143-145) on the symmetric 15-entry storage.  If an LDL^T sweep finds every
+// pivot > 0 the matrix is positive definite, V*S*V' equals SigmaX and line 145 is the identity;
+// otherwise a cyclic Jacobi eigen-decomposition gives HH = V|w|V'.  Returns 1 if the eigen path ran.
+__device__ __noinline__ int psd_repair_jacobi(double* S) {
+  double A[5][5], V[5][5];
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 5; ++j) { A[i][j] = S[sym_idx(i, j)]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < 5; ++i) {
+      dg = dg + A[i][i] * A[i][i];
+      for (int j = i + 1; j < 5; ++j) off = off + A[i][j] * A[i][j];
+    }
+    if (!(off > 1e-34 * dg)) break;
+    for (int pI = 0; pI < 4; ++pI)
+      for (int q = pI + 1; q < 5; ++q) {
+        const double apq = A[pI][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[pI][pI]) / (2.0 * apq);
+        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < 5; ++k) {
+          const double akp = A[k][pI], akq = A[k][q];
+          A[k][pI] = cs * akp - sn * akq;
+          A[k][q] = sn * akp + cs * akq;
+        }
+        for (int k = 0; k < 5; ++k) {
+          const double apk = A[pI][k], aqk = A[q][k];
+          A[pI][k] = cs * apk - sn * aqk;
+          A[q][k] = sn * apk + cs * aqk;
+        }
+        for (int k = 0; k < 5; ++k) {
+          const double vkp = V[k][pI], vkq = V[k][q];
+          V[k][pI] = cs * vkp - sn * vkq;
+          V[k][q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < 5; ++i)
+    for (int j = i; j < 5; ++j) {
+      double hh = 0.0;
+      for (int k = 0; k < 5; ++k) hh = hh + (V[i][k] * fabs(A[k][k])) * V[j][k];
+      const double s = S[sym_idx(i, j)];
+      S[sym_idx(i, j)] = (((s + s) + hh) + hh) / 4.0;                // :145
+    }
+  return 1;
+}
+
+__device__ __forceinline__ int psd_repair(double* S, int force) {
+  if (!force) {
+    double L[5][5], dd[5];
+    bool pd = true;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (pd) {
+        double dj = S[sym_idx(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) dj = dj - (L[j][k] * L[j][k]) * dd[k];
+        if (!(dj > 0.0)) {
+          pd = false;
+        } else {
+          dd[j] = dj;
+#pragma unroll
+          for (int i = j + 1; i < 5; ++i) {
+            double v = S[sym_idx(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v = v - (L[i][k] * L[j][k]) * dd[k];
+            L[i][j] = v / dj;
+          }
+        }
+      }
+    }
+    if (pd) return 0;
+  }
+  return psd_repair_jacobi(S);
+}
+
+struct EkfOut {          // what EKFmatsHandler hands to the MPC (EKFmatsHandler.m:101-114) + zk(end), vhat
+  double vhat, soc;
+  int iT, iZ, lost;
+  double Cv[N5], Dv, Cphi[N5], Dphi, bv, bphi, a[N5], xhat[6];
+};
+
+// iterEKF (OB mode, iterEKF.m:55-210) followed by EKFmatsHandler (EKFmatsHandler.m:26-114)
+__device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double vk,
+                                         double ik, EkfOut& o, HotZ& zout) {
+  o.lost = 0;
+  if (c.f(S_WARN) > 10.0) {                                          // iterEKF.m:55-59 (Q19)
+    c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_LOST);
+    o.lost = 1;
+    return;
+  }
+  const double Tk = c.f(S_TC) + 273.15;                              // :65
+  const double prior = c.f(S_PRIORI), Sw = d.SigmaW;
+  for (int m = 0; m < d.M; ++m) {                                    // :73-84 time update of ALL models
+    const double* a = bk.mdl + m * d.mstride;
+#pragma unroll
+    for (int j = 0; j < N5; ++j) {
+      double& x = c.f(d.f_xhat + m * N5 + j);
+      x = a[j] * x + prior;                                          // :77
+    }
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < N5; ++i)
+#pragma unroll
+      for (int j = i; j < N5; ++j, ++q) {
+        double& s = c.f(d.f_sig + m * NSYM + q);
+        s = (a[i] * s) * a[j] + Sw;                                  // :81 (Q12)
+      }
+  }
+  double x0 = c.f(S_X0) + prior;                                     // :85
+  double sx0 = c.f(S_SIGX0) + Sw;                                    // :86
+  c.f(S_X0) = x0;
+  const double rpa = d.Ts / (3600.0 * p[P_Q]);
+  double SOC = c.f(S_EKFSOC0) - x0 * rpa;                            // :89
+  Xind X;
+  get_xind(d, bk, Tk, SOC, X);                                       // :107
+  HotZ z;
+  int nwarn = 0;
+  unsigned status = 0;
+  double vhat = get_variables(d, bk, p, c, ik, X, Tk, z, nwarn, status);   // :108
+  // ---- getChatV (:421-519) ----
+  double Chat[4][N5], C0;
+  {
+    const double xSOC = c.f(S_EKFSOC0) - x0 * rpa;                   // :438
+    const double sn = soc_e(p, P_NEG, xSOC), sp = soc_e(p, P_POS, xSOC);
+    const double Rfn = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
+    const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
+    const double i0n = k0n * sqrt((z.the0 * (1.0 - z.tss0)) * z.tss0);
+    const double i0p = k0p * sqrt((z.the3 * (1.0 - z.tss3)) * z.tss3);
+    const double Rctn = (p[P_R] * Tk) / (p[P_F] * i0n), Rctp = (p[P_R] * Tk) / (p[P_F] * i0p);   // :467-468
+    const double dUn0 = duocp_n(p, z.tss0), dUp3 = duocp_p(p, z.tss3);   // :495-496
+    const double dsn = soc_e(p, P_NEG, 1.0) - soc_e(p, P_NEG, 0.0), dsp = soc_e(p, P_POS, 1.0) - soc_e(p, P_POS, 0.0);
+    const double res0n = (((-dUn0) * d.Ts) * dsn) / (3600.0 * p[P_Q]);   // :497-500
+    const double res0p = (((-dUp3) * d.Ts) * dsp) / (3600.0 * p[P_Q]);
+    C0 = res0p - res0n;                                              // :501
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double* mm = bk.mdl + X.m[k] * d.mstride + 6;
+      const double g = X.gamma[k];
+#pragma unroll
+      for (int j = 0; j < N5; ++j) {
+        double v = Rfp * (g * mm[HR_IFDL3 * 7 + j]) - Rfn * (g * mm[HR_IFDL0 * 7 + j]);    // :444
+        v = (v + Rctp * (g * mm[HR_IF3 * 7 + j])) - Rctn * (g * mm[HR_IF0 * 7 + j]);       // :471
+        v = v + g * mm[HR_PHIE * 7 + j];                                                    // :485
+        v = v + (dUp3 * (g * mm[HR_TSS3 * 7 + j]) - dUn0 * (g * mm[HR_TSS0 * 7 + j]));      // :504
+        Chat[k][j] = v;
+      }
+    }
+  }
+  // ---- gains from neighbour #1's SigmaX (:116-124, Q1) ----
+  double L[4][N5], svt[4];
+  {
+    double S1[NSYM];
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) S1[q] = c.f(d.f_sig + X.m[0] * NSYM + q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double v[N5];
+#pragma unroll
+      for (int i = 0; i < N5; ++i) {
+        double acc = S1[sym_idx(i, 0)] * Chat[k][0];
+#pragma unroll
+        for (int j = 1; j < N5; ++j) acc = acc + S1[sym_idx(i, j)] * Chat[k][j];
+        v[i] = acc;
+      }
+      double s = Chat[k][0] * v[0];
+#pragma unroll
+      for (int i = 1; i < N5; ++i) s = s + Chat[k][i] * v[i];
+      svt[k] = s + d.SigmaV;
+#pragma unroll
+      for (int i = 0; i < N5; ++i) L[k][i] = v[i] / svt[k];
+    }
+  }
+  const double svt0 = (C0 * sx0) * C0 + d.SigmaV;                    // :123
+  const double L0 = (sx0 * C0) / svt0;                               // :124
+  const double resid = vk - vhat;                                    // :133
+  int njac = 0, nbump = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                                      // :136-154 sequential (Q2)
+    double S[NSYM];
+    const int mo = X.m[k];
+#pragma unroll
+    for (int j = 0; j < N5; ++j) {
+      double& x = c.f(d.f_xhat + mo * N5 + j);
+      x = x + L[k][j] * resid;                                       // :138
+    }
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) S[q] = c.f(d.f_sig + mo * NSYM + q);
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < N5; ++i)
+#pragma unroll
+      for (int j = i; j < N5; ++j, ++q) S[q] = S[q] - (L[k][i] * svt[k]) * L[k][j];   // :142
+    njac += psd_repair(S, d.force_jacobi);                           // :143-145
+    if (resid * resid > 9.0 * svt[k]) {                              // :148-151 Q-bump
+#pragma unroll
+      for (int q2 = 0; q2 < NSYM; ++q2) S[q2] = S[q2] * 2.0;
+      ++nbump;
+    }
+#pragma unroll
+    for (int q2 = 0; q2 < NSYM; ++q2) c.f(d.f_sig + mo * NSYM + q2) = S[q2];
+  }
+  x0 = x0 + L0 * resid;                                              // :155
+  sx0 = sx0 - (L0 * svt0) * L0;                                      // :156
+  c.f(S_X0) = x0;
+  c.f(S_SIGX0) = sx0;
+  SOC = c.f(S_EKFSOC0) - x0 * rpa;                                   // :159
+  get_xind(d, bk, Tk, SOC, X);                                       // :181
+  vhat = get_variables(d, bk, p, c, ik, X, Tk, z, nwarn, status);    // :182
+  const double Zsoc = c.f(S_EKFSOC0) - x0 * rpa;                     // :416
+  c.f(S_PRIORI) = ik;                                                // :210
+  if (nwarn) c.f(S_WARN) += (double)nwarn;
+  if (njac) c.f(S_NJAC) += (double)njac;
+  if (nbump) c.f(S_NBUMP) += (double)nbump;
+  if (status) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | status);
+  o.vhat = vhat;
+  o.soc = Zsoc;
+  zout = z;
+  // ---- EKFmatsHandler ----
+  int imax = 0;                                                      // EKFmatsHandler.m:26 first max, NaN ignored
+  {
+    bool have = false;
+    double best = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double g = X.gamma[k];
+      if (g != g) continue;
+      if (!have || g > best) { best = g; imax = k; have = true; }
+    }
+  }
+  int mp = X.m[0];
+  o.iT = X.iT[0];
+  o.iZ = X.iZ[0];
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+    if (imax == k) { mp = X.m[k]; o.iT = X.iT[k]; o.iZ = X.iZ[k]; }
+  const double* am = bk.mdl + mp * d.mstride;
+#pragma unroll
+  for (int j = 0; j < N5; ++j) { o.xhat[j] = c.f(d.f_xhat + mp * N5 + j); o.a[j] = am[j]; }   // :33-35
+  o.xhat[5] = 0.0;                                                   // :33 (Q3)
+  {
+    const double TK = c.f(S_TC) + 273.15;                            // :53
+    const double sn = soc_e(p, P_NEG, Zsoc), sp = soc_e(p, P_POS, Zsoc);   // :56-58
+    const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
+    const double i0n = k0n * sqrt((z.the0 * (1.0 - z.tss0)) * z.tss0);   // :63-66
+    const double i0p = k0p * sqrt((z.the3 * (1.0 - z.tss3)) * z.tss3);
+    const double Rfn = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
+    const double* mm = am + 6;
+#pragma unroll
+    for (int j = 0; j < N5; ++j)                                     // :75-76
+      o.Cv[j] = (Rfp * mm[HR_IFDL3 * 7 + j] - Rfn * mm[HR_IFDL0 * 7 + j]) + mm[HR_PHIE * 7 + j];
+    o.Dv = (Rfp * mm[HR_IFDL3 * 7 + 6] - Rfn * mm[HR_IFDL0 * 7 + 6]) + mm[HR_PHIE * 7 + 6];   // :79-80
+    const double Upos = uocp_p(p, z.tss3), Uneg = uocp_n(p, z.tss0); // :84-85
+    const double pref = ((2.0 * p[P_R]) * TK) / p[P_F];
+    const double negEta0 = pref * asinh_d(z.If0 / (2.0 * i0n));      // :88-89
+    const double posEta3 = pref * asinh_d(z.If3 / (2.0 * i0p));
+    o.bv = ((Upos - Uneg) + (posEta3 - negEta0)) + 0.0;              // :92
+    o.bphi = uocp_n(p, sn);                                          // :96 (Q21)
+#pragma unroll
+    for (int j = 0; j < N5; ++j) o.Cphi[j] = mm[HR_PHI * 7 + j];     // :97
+    o.Dphi = mm[HR_PHI * 7 + 6];                                     // :98
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// predMat.m for one scalar output with diagonal A and B = 1 (EKFmatsHandler.m:35-36):
+//   h[k] = Cbar*Abar^k*Bbar (k = 0..Np; h[i] doubles as Phi(i,7)),  phix[i-1] = Phi(i,1:6)*x
+// ------------------------------------------------------------------------------------------
+template <int NPM>
+__device__ __forceinline__ void pred_row(const double* a, const double* c5, double c6, double dd, const double* x6, int Np,
+                                         double* h, double* phix) {
+  double pk[6], pw[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { pk[j] = 0.0; pw[j] = 1.0; }
+#pragma unroll
+  for (int k = 0; k <= NPM; ++k) {
+    if (k <= Np) {
+      double acc = c5[0] * pk[0];
+#pragma unroll
+      for (int j = 1; j < N5; ++j) acc = acc + c5[j] * pk[j];
+      acc = acc + c6 * pk[5];
+      h[k] = acc + dd;                                               // predMat.m:34
+#pragma unroll
+      for (int j = 0; j < N5; ++j) pk[j] = a[j] * pk[j] + 1.0;       // predMat.m:35
+      pk[5] = pk[5] + 1.0;
+    }
+  }
+#pragma unroll
+  for (int i = 1; i <= NPM; ++i) {
+    if (i <= Np) {
+#pragma unroll
+      for (int j = 0; j < N5; ++j) pw[j] = a[j] * pw[j];             // predMat.m:41
+      double acc = (c5[0] * pw[0]) * x6[0];
+#pragma unroll
+      for (int j = 1; j < N5; ++j) acc = acc + (c5[j] * pw[j]) * x6[j];
+      acc = acc + (c6 * pw[5]) * x6[5];
+      phix[i - 1] = acc;                                             // predMat.m:43 (first six columns)
+    }
+  }
+}
+
+// E x = b for the SPD Nc x Nc Hessian: Gaussian elimination without pivoting, factor reused
+template <int NCM>
+__device__ __forceinline__ void spd_factor(int Nc, const double* E, double* LU) {
+#pragma unroll
+  for (int i = 0; i < NCM * NCM; ++i) LU[i] = E[i];
+#pragma unroll
+  for (int k = 0; k < NCM; ++k)
+#pragma unroll
+    for (int i = k + 1; i < NCM; ++i)
+      if (i < Nc) {
+        const double l = LU[i * NCM + k] / LU[k * NCM + k];
+        LU[i * NCM + k] = l;
+#pragma unroll
+        for (int j = k + 1; j < NCM; ++j)
+          if (j < Nc) LU[i * NCM + j] = LU[i * NCM + j] - l * LU[k * NCM + j];
+      }
+}
+template <int NCM>
+__device__ __forceinline__ void spd_solve(int Nc, const double* LU, const double* b, double* x) {
+  double y[NCM];
+#pragma unroll
+  for (int i = 0; i < NCM; ++i)
+    if (i < Nc) {
+      double acc = b[i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) acc = acc - LU[i * NCM + k] * y[k];
+      y[i] = acc;
+    }
+#pragma unroll
+  for (int i = NCM - 1; i >= 0; --i)
+    if (i < Nc) {
+      double acc = y[i];
+#pragma unroll
+      for (int k = i + 1; k < NCM; ++k)
+        if (k < Nc) acc = acc - LU[i * NCM + k] * x[k];
+      x[i] = acc / LU[i * NCM + i];
+    }
+}
+
+// Hildreth dual coordinate ascent (hildreth.m:16-46) in rank-Nc form.
+// H(i,:)*lambda = M(i,:)*v with v = (E\M')*lambda kept incrementally.  A row with H_ii == 0 is an
+// all-zero M row (Q7): it never touches v, and while it holds +Inf every row product is NaN,
+// exactly what 0*Inf yields in the dense form ("poison").  E, M row-major with leading dim NCM.
+template <int NCM, int NCONM>
+__device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, const double* F, const double* Mm, const double* gam,
+                                             int maxIter, double* lam /* in: warm start, out */, double* DU) {
+  double P[NCONM * NCM], K[NCONM], Hd[NCONM], v[NCM], x[NCM];
+  spd_solve<NCM>(Nc, LU, F, x);                                      // E\F
+#pragma unroll
+  for (int j = 0; j < NCM; ++j) v[j] = 0.0;
+  int npoison = 0;
+  for (int i = 0; i < nC; ++i) {
+    spd_solve<NCM>(Nc, LU, Mm + i * NCM, P + i * NCM);               // column i of E\M'
+    double hd = Mm[i * NCM] * P[i * NCM], k = Mm[i * NCM] * x[0];
+#pragma unroll
+    for (int j = 1; j < NCM; ++j)
+      if (j < Nc) { hd = hd + Mm[i * NCM + j] * P[i * NCM + j]; k = k + Mm[i * NCM + j] * x[j]; }
+    Hd[i] = hd;                                                      // H(i,i)  hildreth.m:28
+    K[i] = k + gam[i];                                               // K(i)    hildreth.m:29
+  }
+  for (int i = 0; i < nC; ++i) {
+    if (Hd[i] == 0.0) { if (!is_finite(lam[i])) ++npoison; continue; }
+#pragma unroll
+    for (int j = 0; j < NCM; ++j)
+      if (j < Nc) v[j] = v[j] + P[i * NCM + j] * lam[i];
+  }
+  int k = 1;
+  for (; k <= maxIter; ++k) {                                        // hildreth.m:32
+    double maxd = 0.0;
+    bool nanflag = false;
+    for (int i = 0; i < nC; ++i) {                                   // hildreth.m:34-37
+      const double li = lam[i];
+      double w;
+      if (npoison > 0) {
+        w = NAN;
+      } else {
+        double hl = Mm[i * NCM] * v[0];
+#pragma unroll
+        for (int j = 1; j < NCM; ++j)
+          if (j < Nc) hl = hl + Mm[i * NCM + j] * v[j];
+        w = -((K[i] + hl) - Hd[i] * li) / Hd[i];
+      }
+      const double nl = fmax(0.0, w);                                // max(0,NaN) = 0
+      const double dl = nl - li;
+      if (Hd[i] == 0.0) {
+        npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li));
+      } else if (dl != 0.0) {
+#pragma unroll
+        for (int j = 0; j < NCM; ++j)
+          if (j < Nc) v[j] = v[j] + P[i * NCM + j] * dl;
+      }
+      lam[i] = nl;
+      const double ad = fabs(dl);
+      if (ad != ad) nanflag = true; else if (ad > maxd) maxd = ad;
+    }
+    if (!nanflag && maxd < 1e-6) break;                              // hildreth.m:39 (NaN-propagating norm)
+  }
+  if (k > maxIter) k = maxIter;
+  double rhs[NCM];
+#pragma unroll
+  for (int j = 0; j < NCM; ++j)
+    if (j < Nc) {                                                    // hildreth.m:46
+      double acc = Mm[j] * lam[0];
+      for (int i = 1; i < nC; ++i) acc = acc + Mm[i * NCM + j] * lam[i];
+      rhs[j] = F[j] + acc;
+    }
+  spd_solve<NCM>(Nc, LU, rhs, x);
+#pragma unroll
+  for (int j = 0; j < NCM; ++j)
+    if (j < Nc) DU[j] = -x[j];
+  return k;
+}
+
+// Everything iterMPC needs before the QP: F, E (factored), the unconstrained DU and the stacked
+// constraints M, gamma in the reference's row order.
+template <int NPM, int NCM>
+struct MpcProblem {
+  static constexpr int NCONM = 4 * NCM + 3 * NPM;
+  double F[NCM], E[NCM * NCM], LU[NCM * NCM], DU[NCM];
+  double Mm[NCONM * NCM], gam[NCONM];
+  int nC;
+};
+
+struct Limits {
+  double u_max, u_min, du_max, du_min, v_max, phise_min, z_max;
+};
+
+// iterMPC.m:17-48 and constraintsMPC.m:18-101
+template <int NPM, int NCM>
+__device__ __forceinline__ void mpc_setup(const Dims& d, double r /* Csoc(end), EKFmatsHandler.m:43 */, const Limits& lim, const EkfOut& e,
+                                          double uk_1, MpcProblem<NPM, NCM>& q) {
+  const int Np = d.Np, Nc = d.Nc;
+  const double zero5[N5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double hs[NPM + 1], pxs[NPM];
+  pred_row<NPM>(e.a, zero5, r, 0.0, e.xhat, Np, hs, pxs);            // iterMPC.m:33
+  double err[NPM], x[NCM];
+#pragma unroll
+  for (int i = 1; i <= NPM; ++i)
+    if (i <= Np) err[i - 1] = d.ref - (pxs[i - 1] + hs[i] * uk_1);   // Ref - Phi_soc*dx
+#pragma unroll
+  for (int j = 0; j < NCM; ++j)
+    if (j < Nc) {                                                    // F = -2*G'*(...)  iterMPC.m:38
+      double acc = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int i = 1; i <= NPM; ++i)
+        if (i <= Np) {
+          const double g = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0;
+          const double t = g * err[i - 1];
+          acc = first ? t : acc + t;
+          first = false;
+        }
+      q.F[j] = -2.0 * acc;
+    }
+  double nf = q.F[0] * q.F[0];
+#pragma unroll
+  for (int j = 1; j < NCM; ++j)
+    if (j < Nc) nf = nf + q.F[j] * q.F[j];
+  const double Ru = sqrt(nf) / ((2.0 * lim.du_max) * sqrt((double)Nc)) - d.sigmin;   // iterMPC.m:43 (Q10)
+#pragma unroll
+  for (int j = 0; j < NCM; ++j)
+#pragma unroll
+    for (int l = 0; l < NCM; ++l) {
+      double acc = 0.0;
+      if (j < Nc && l < Nc) {
+        bool first = true;
+#pragma unroll
+        for (int i = 1; i <= NPM; ++i)
+          if (i <= Np) {
+            const double gj = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0, gl = (i - 1 - l >= 0) ? hs[i - 1 - l] : 0.0;
+            const double t = gj * gl;
+            acc = first ? t : acc + t;
+            first = false;
+          }
+        acc = 2.0 * (acc + ((j == l) ? Ru : 0.0));                   // iterMPC.m:47
+      }
+      q.E[j * NCM + l] = acc;
+    }
+  spd_factor<NCM>(Nc, q.E, q.LU);
+  spd_solve<NCM>(Nc, q.LU, q.F, x);
+#pragma unroll
+  for (int j = 0; j < NCM; ++j) q.DU[j] = (j < Nc) ? -x[j] : 0.0;    // iterMPC.m:48
+  // ---- constraintsMPC.m: rows in the reference's order ----
+  double* Mm = q.Mm;
+  double* gam = q.gam;
+  int nC = 0;
+  if (d.useCurrent) {                                                // constraintsMPC.m:23-42
+    for (int s = 0; s < 2; ++s)
+      for (int i = 0; i < Nc; ++i, ++nC) {
+#pragma unroll
+        for (int j = 0; j < NCM; ++j) Mm[nC * NCM + j] = (j <= i && j < Nc) ? (s ? -1.0 : 1.0) : (s ? -0.0 : 0.0);
+        gam[nC] = s ? -(lim.u_min - uk_1) : (lim.u_max - uk_1);
+      }
+    for (int s = 0; s < 2; ++s)
+      for (int i = 0; i < Nc; ++i, ++nC) {
+#pragma unroll
+        for (int j = 0; j < NCM; ++j) Mm[nC * NCM + j] = (j == i) ? (s ? -1.0 : 1.0) : (s ? -0.0 : 0.0);
+        gam[nC] = s ? -lim.du_min : lim.du_max;
+      }
+  }
+  if (d.useVoltage) {                                                // constraintsMPC.m:45-63
+    double hv[NPM + 1], pxv[NPM];
+    pred_row<NPM>(e.a, e.Cv, 0.0, e.Dv, e.xhat, Np, hv, pxv);
+    for (int i = 1; i <= Np; ++i, ++nC) {
+#pragma unroll
+      for (int j = 0; j < NCM; ++j) Mm[nC * NCM + j] = (i - 1 - j >= 0 && j < Nc) ? hv[i - 1 - j] : 0.0;
+      gam[nC] = lim.v_max - ((pxv[i - 1] + hv[i] * uk_1) + e.bv);
+    }
+  }
+  if (d.useEta) {                                                    // constraintsMPC.m:66-85
+    double he[NPM + 1], pxe[NPM];
+    pred_row<NPM>(e.a, e.Cphi, 0.0, e.Dphi, e.xhat, Np, he, pxe);
+    for (int i = 1; i <= Np; ++i, ++nC) {
+#pragma unroll
+      for (int j = 0; j < NCM; ++j) Mm[nC * NCM + j] = (i - 1 - j >= 0 && j < Nc) ? -he[i - 1 - j] : -0.0;
+      gam[nC] = -lim.phise_min + ((pxe[i - 1] + he[i] * uk_1) + e.bphi);
+    }
+  }
+  if (d.useZmax) {                                                   // constraintsMPC.m:89-101
+    for (int i = 1; i <= Np; ++i, ++nC) {
+#pragma unroll
+      for (int j = 0; j < NCM; ++j) Mm[nC * NCM + j] = (i - 1 - j >= 0 && j < Nc) ? hs[i - 1 - j] : 0.0;
+      gam[nC] = lim.z_max - ((pxs[i - 1] + hs[i] * uk_1) + e.soc);
+    }
+  }
+  q.nC = nC;
+}
+
+struct MpcOut {
+  double u, phise;
+  int nexec;
+  unsigned active[4];
+};
+
+// iterMPC.m:17-95 with constraintsMPC.m and hildreth.m inlined; the dual warm start lives in the cell state
+template <int NPM, int NCM>
+__device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict__ p, const Cell& c, const EkfOut& e, double uk_applied,
+                                         MpcOut& o) {
+  constexpr int NCONM = 4 * NCM + 3 * NPM;
+  const int Nc = d.Nc;
+  const double uk_1 = c.f(S_UK);                                     // iterMPC.m:19
+  {                                                                  // runMPC.m:94-95 (Q24)
+    double acc = e.Cphi[0] * e.xhat[0];
+#pragma unroll
+    for (int j = 1; j < N5; ++j) acc = acc + e.Cphi[j] * e.xhat[j];
+    acc = acc + 0.0 * e.xhat[5];
+    o.phise = (acc + uk_applied * e.Dphi) + e.bphi;
+  }
+  Limits lim = {c.f(S_UMAX), c.f(S_UMIN), c.f(S_DUMAX), c.f(S_DUMIN), c.f(S_VMAX), c.f(S_PHIMIN), c.f(S_ZMAX)};
+  MpcProblem<NPM, NCM> q;
+  const double r = -d.Ts / (3600.0 * p[P_Q]);                        // EKFmatsHandler.m:43
+  mpc_setup<NPM, NCM>(d, r, lim, e, uk_1, q);
+  const int nC = q.nC;
+  bool viol = false;                                                 // iterMPC.m:66 (Q8)
+  for (int i = 0; i < nC; ++i) {
+    double acc = q.Mm[i * NCM] * q.DU[0];
+#pragma unroll
+    for (int j = 1; j < NCM; ++j)
+      if (j < Nc) acc = acc + q.Mm[i * NCM + j] * q.DU[j];
+    if (acc - q.gam[i] > 0.0) viol = true;
+  }
+  o.nexec = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) o.active[w] = 0u;
+  if (viol) {
+    double lam[NCONM];
+    const bool warm = c.f(S_LAMVALID) != 0.0;                        // Q11: [] -> zeros on first use
+    for (int i = 0; i < nC; ++i) lam[i] = warm ? c.f(d.f_lambda + i) : 0.0;
+    o.nexec = hildreth_core<NCM, NCONM>(Nc, nC, q.LU, q.F, q.Mm, q.gam, d.maxHild, lam, q.DU);   // iterMPC.m:67
+    for (int i = 0; i < nC; ++i) {
+      c.f(d.f_lambda + i) = lam[i];                                  // iterMPC.m:68
+      if (lam[i] > 0.0) o.active[i >> 5] |= (1u << (i & 31));
+    }
+    c.f(S_LAMVALID) = 1.0;
+  }
+  const double uk = q.DU[0] + uk_1;                                  // iterMPC.m:75-76
+  c.f(S_UK) = uk;                                                    // iterMPC.m:78
+  o.u = uk;
+  if (!is_finite(uk)) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_NONFINITE);
+}
+
+}  // namespace mek

@@ -1,0 +1,1210 @@
+// libmek: kernels and the C ABI (include/mek.h) of the batched MPC-EKF fast-charge control loop.
+//
+// Execution model: one thread per cell; a persistent grid walks the shard's cells and, for each
+// cell, runs every sample instant of the charge without leaving the kernel (runMPC.m:83-112).
+// The hot rows of the ROM table bank are staged once per CTA into shared memory with one TMA bulk
+// copy (cp.async.bulk + mbarrier); per-cell state, covariance and trajectory logs are
+// structure-of-arrays in HBM with the cell index fastest, so each warp access is coalesced.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mek.h"
+#include "mek_core.cuh"
+
+using namespace mek;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) return fail(MEK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// bank (host object) : resolves tfData names to rows, packs the hot rows for shared memory
+// ------------------------------------------------------------------------------------------
+struct mek_bank {
+  int n, nz, nT, nZ, M;
+  double Tsamp;
+  std::vector<double> Tpts_K, Zpts, A, C, D, params;
+  std::vector<std::string> names;
+  std::vector<double> xloc;
+  // resolved rows (0-based)
+  int r_ifdl0, r_ifdl3, r_if0, r_if3, r_tss0, r_tss3, r_the0, r_the3, r_phie_last, r_phise0, r_phi;
+  std::vector<int> negtss, postss, thetae, negphise, posphise, phie, posphis;
+  // hot bank blob: [Tpts nT][Zpts nZ][pad][M][mstride]
+  int R, nx_negtss, nx_postss, nx_thetae, mstride, off_mdl;
+  std::vector<double> blob;
+};
+
+static std::vector<int> find_rows(const mek_bank& b, const char* nm, double loc = -1.0, bool use_loc = false) {
+  std::vector<int> out;
+  for (int i = 0; i < b.nz; ++i)
+    if (b.names[i] == nm && (!use_loc || b.xloc[i] == loc)) out.push_back(i);
+  return out;
+}
+static void append(std::vector<int>& a, const std::vector<int>& b) { a.insert(a.end(), b.begin(), b.end()); }
+
+static int bank_finalize(mek_bank* b) {
+  // structural checks the reference performs at set-up
+  for (int m = 0; m < b->M; ++m)
+    if (b->A[(size_t)m * 6 + 5] != 1.0) return fail(MEK_ERR_BANK, "A does not have integrator state (initKF.m:74-77)");
+  for (int i = 1; i < b->nT; ++i)
+    if (!(b->Tpts_K[i] > b->Tpts_K[i - 1])) return fail(MEK_ERR_BANK, "temperature set-points must be ascending");
+  for (int i = 1; i < b->nZ; ++i)
+    if (!(b->Zpts[i] > b->Zpts[i - 1])) return fail(MEK_ERR_BANK, "SOC set-points must be ascending");
+  const double eps = 2.220446049250313e-16;
+  std::vector<int> negIfdl0 = find_rows(*b, "negIfdl", 0, true), posIfdl3 = find_rows(*b, "posIfdl", 3, true);
+  std::vector<int> negIf0 = find_rows(*b, "negIf", 0, true), posIf3 = find_rows(*b, "posIf", 3, true);
+  std::vector<int> negT0 = find_rows(*b, "negThetass", 0, true), posT3 = find_rows(*b, "posThetass", 3, true);
+  std::vector<int> negP0 = find_rows(*b, "negPhise", 0, true);
+  b->negtss = find_rows(*b, "negThetass");
+  b->postss = find_rows(*b, "posThetass");
+  b->negphise = find_rows(*b, "negPhise");
+  b->posphise = find_rows(*b, "posPhise");
+  b->posphis = find_rows(*b, "posPhis");
+  b->thetae = find_rows(*b, "negThetae");
+  append(b->thetae, find_rows(*b, "sepThetae"));
+  append(b->thetae, find_rows(*b, "posThetae"));
+  b->phie = find_rows(*b, "negPhie");
+  append(b->phie, find_rows(*b, "sepPhie"));
+  append(b->phie, find_rows(*b, "posPhie"));
+  if (negIfdl0.empty()) return fail(MEK_ERR_BANK, "Requires ifdl at negative collector (OB_step.m:140)");
+  if (posIfdl3.empty()) return fail(MEK_ERR_BANK, "Requires ifdl at positive collector (OB_step.m:141)");
+  if (negIf0.empty()) return fail(MEK_ERR_BANK, "Requires if at negative collector (OB_step.m:142)");
+  if (posIf3.empty()) return fail(MEK_ERR_BANK, "Requires if at positive collector (OB_step.m:143)");
+  if (b->thetae.empty() || b->xloc[b->thetae.front()] > 0) return fail(MEK_ERR_BANK, "Requires thetae at negative collector (OB_step.m:144)");
+  if (b->xloc[b->thetae.back()] > 3 + eps || b->xloc[b->thetae.back()] < 3 - eps)
+    return fail(MEK_ERR_BANK, "Requires thetae at positive collector (OB_step.m:145)");
+  if (negT0.empty()) return fail(MEK_ERR_BANK, "Requires thetass at negative collector (OB_step.m:148)");
+  if (posT3.empty()) return fail(MEK_ERR_BANK, "Requires thetass at positive collector (OB_step.m:149)");
+  if (negP0.empty()) return fail(MEK_ERR_BANK, "Requires phise at negative collector (OB_step.m:150)");
+  if (!b->phie.empty() && b->xloc[b->phie.front()] == 0) b->phie.erase(b->phie.begin());   // OB_step.m:151-155
+  if (b->phie.empty() || b->xloc[b->phie.back()] > 3 + eps || b->xloc[b->phie.back()] < 3 - eps)
+    return fail(MEK_ERR_BANK, "Requires phie at positive collector (OB_step.m:156)");
+  if (b->negphise.size() < 2) return fail(MEK_ERR_BANK, "EKFmatsHandler.m:97 needs ind.negPhise(2)");
+  b->r_ifdl0 = negIfdl0[0]; b->r_ifdl3 = posIfdl3[0]; b->r_if0 = negIf0[0]; b->r_if3 = posIf3[0];
+  b->r_tss0 = negT0[0]; b->r_tss3 = posT3[0];
+  b->r_the0 = b->thetae.front(); b->r_the3 = b->thetae.back();
+  b->r_phie_last = b->phie.back(); b->r_phise0 = negP0[0]; b->r_phi = b->negphise[1];
+  // hot rows: the ten fixed ones, then the rows that only feed the EKF's warning counters
+  std::vector<int> hot = {b->r_ifdl0, b->r_ifdl3, b->r_if0, b->r_if3, b->r_tss0, b->r_tss3, b->r_the0, b->r_the3, b->r_phie_last, b->r_phi};
+  b->nx_negtss = b->nx_postss = b->nx_thetae = 0;
+  for (int r : b->negtss) if (r != b->r_tss0) { hot.push_back(r); b->nx_negtss++; }
+  for (int r : b->postss) if (r != b->r_tss3) { hot.push_back(r); b->nx_postss++; }
+  for (int r : b->thetae) if (r != b->r_the0 && r != b->r_the3) { hot.push_back(r); b->nx_thetae++; }
+  b->R = (int)hot.size();
+  if (b->R > HR_MAX) return fail(MEK_ERR_UNSUPPORTED, "too many Thetass/Thetae rows for the shared-memory hot bank");
+  b->mstride = 6 + b->R * 7;
+  int head = b->nT + b->nZ;
+  if (head & 1) head++;                                      // keep the model block 16-byte aligned
+  b->off_mdl = head;
+  size_t total = (size_t)head + (size_t)b->M * b->mstride;
+  if (total & 1) total++;                                    // TMA bulk size must be a multiple of 16 bytes
+  b->blob.assign(total, 0.0);
+  for (int i = 0; i < b->nT; ++i) b->blob[i] = b->Tpts_K[i];
+  for (int i = 0; i < b->nZ; ++i) b->blob[b->nT + i] = b->Zpts[i];
+  for (int m = 0; m < b->M; ++m) {
+    double* dst = &b->blob[(size_t)b->off_mdl + (size_t)m * b->mstride];
+    for (int j = 0; j < 6; ++j) dst[j] = b->A[(size_t)m * 6 + j];
+    for (int r = 0; r < b->R; ++r) {
+      for (int j = 0; j < 6; ++j) dst[6 + r * 7 + j] = b->C[((size_t)m * b->nz + hot[r]) * 6 + j];
+      dst[6 + r * 7 + 6] = b->D[(size_t)m * b->nz + hot[r]];
+    }
+  }
+  return MEK_OK;
+}
+
+extern "C" int mek_bank_create(const mek_bank_desc* d, mek_bank** out) {
+  if (!d || !out) return fail(MEK_ERR_ARG, "null argument");
+  if (d->n != N5) return fail(MEK_ERR_UNSUPPORTED, "bank must have n = 5 transient states (runMPC.m:17)");
+  if (d->nparams != N_PARAMS) return fail(MEK_ERR_ARG, "parameter vector has wrong length");
+  if (d->nT < 1 || d->nZ < 1 || d->nz < 1 || d->nz > 64) return fail(MEK_ERR_ARG, "bad bank dimensions");
+  mek_bank* b = new mek_bank();
+  b->n = d->n; b->nz = d->nz; b->nT = d->nT; b->nZ = d->nZ; b->M = d->nT * d->nZ; b->Tsamp = d->Tsamp;
+  for (int i = 0; i < d->nT; ++i) b->Tpts_K.push_back(d->Tpts_C[i] + 273.15);     // OB_step.m:166
+  for (int i = 0; i < d->nZ; ++i) b->Zpts.push_back(d->Zpts_pct[i] / 100.0);      // OB_step.m:167
+  b->A.assign(d->A, d->A + (size_t)b->M * 6);
+  b->C.assign(d->C, d->C + (size_t)b->M * b->nz * 6);
+  b->D.assign(d->D, d->D + (size_t)b->M * b->nz);
+  b->params.assign(d->params, d->params + N_PARAMS);
+  for (int i = 0; i < d->nz; ++i) { b->names.push_back(d->names[i]); b->xloc.push_back(d->xloc[i]); }
+  int rc = bank_finalize(b);
+  if (rc != MEK_OK) { delete b; return rc; }
+  *out = b;
+  return MEK_OK;
+}
+
+extern "C" int mek_bank_load(const char* path, mek_bank** out) {
+  if (!path || !out) return fail(MEK_ERR_ARG, "null argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(MEK_ERR_ARG, std::string("cannot open ") + path);
+  std::vector<unsigned char> buf;
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  buf.resize(sz > 0 ? (size_t)sz : 0);
+  size_t got = fread(buf.data(), 1, buf.size(), f);
+  fclose(f);
+  if (got != buf.size() || buf.size() < 40 || memcmp(buf.data(), "MEKBANK1", 8) != 0) return fail(MEK_ERR_BANK, "not a MEKBANK1 file");
+  size_t off = 8;
+  int hdr[6];
+  memcpy(hdr, &buf[off], 24); off += 24;
+  const int n = hdr[1], nz = hdr[2], nT = hdr[3], nZ = hdr[4], npar = hdr[5];
+  if (hdr[0] != 1) return fail(MEK_ERR_BANK, "unsupported bank version");
+  const size_t M = (size_t)nT * nZ;
+  const size_t need = off + 8 + 8 * ((size_t)nT + nZ) + (size_t)nz * 24 + 8 * (2 * M + M * (n + 1) + M * nz * (n + 1) + M * nz + npar);
+  if (n < 1 || nz < 1 || nT < 1 || nZ < 1 || buf.size() < need) return fail(MEK_ERR_BANK, "truncated bank file");
+  double Tsamp;
+  memcpy(&Tsamp, &buf[off], 8); off += 8;
+  auto take = [&](size_t cnt) { std::vector<double> v(cnt); memcpy(v.data(), &buf[off], 8 * cnt); off += 8 * cnt; return v; };
+  std::vector<double> Tp = take(nT), Zp = take(nZ);
+  std::vector<std::string> names;
+  std::vector<const char*> cnames;
+  std::vector<double> xloc;
+  for (int i = 0; i < nz; ++i) {
+    char nm[17];
+    memcpy(nm, &buf[off], 16); nm[16] = 0; off += 16;
+    names.push_back(nm);
+    double x;
+    memcpy(&x, &buf[off], 8); off += 8;
+    xloc.push_back(x);
+  }
+  for (auto& s : names) cnames.push_back(s.c_str());
+  take(M); take(M);   // ROMmdls.T / .SOC per model (the grid vectors above are what the loop uses)
+  std::vector<double> A = take(M * (n + 1)), C = take(M * nz * (n + 1)), D = take(M * nz), par = take(npar);
+  mek_bank_desc d = {n, nz, nT, nZ, Tsamp, Tp.data(), Zp.data(), cnames.data(), xloc.data(), A.data(), C.data(), D.data(), par.data(), npar};
+  return mek_bank_create(&d, out);
+}
+
+extern "C" void mek_bank_destroy(mek_bank* b) { delete b; }
+extern "C" int mek_bank_dims(const mek_bank* b, int* n, int* nz, int* nT, int* nZ) {
+  if (!b) return fail(MEK_ERR_ARG, "null bank");
+  if (n) *n = b->n; if (nz) *nz = b->nz; if (nT) *nT = b->nT; if (nZ) *nZ = b->nZ;
+  return MEK_OK;
+}
+extern "C" double mek_bank_capacity_Ah(const mek_bank* b) { return b ? b->params[P_Q] : NAN; }
+
+// ------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------
+struct Params {
+  Dims d;
+  double cp[N_PARAMS];        // cellData closed-form parameters
+  double* st;                 // SoA state block [nfields][ld]
+  const double* bank_blob;    // hot bank in global memory (source of the TMA bulk copy)
+  int blob_doubles, off_mdl;
+  // full bank (function-level zk output only)
+  const double* Cfull;        // [M][nz][6]
+  const double* Dfull;        // [M][nz]
+  // inputs staged on the device (mek_pop_init / mek_pop_reset)
+  const double* in_soc0; const double* in_ekf; const double* in_T; const double* in_sigx0; const double* in_lim;
+  // trajectory logs [step][nlog]
+  long long nlog; int log_steps;
+  double* log_u; double* log_V; double* log_soc; double* log_phise;
+  unsigned char* log_iT; unsigned char* log_iZ; unsigned short* log_nexec; unsigned* log_active; int log_words;
+};
+
+// ---- TMA bulk copy of the hot bank into shared memory ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_bank(double* sm, const Params& P, BankSmem& bk) {
+  __shared__ __align__(8) unsigned long long mbar;
+  const unsigned bytes = (unsigned)P.blob_doubles * 8u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+    unsigned done = 0;
+    while (done < bytes) {                                   // chunks keep each bulk request modest
+      const unsigned chunk = (bytes - done) < 32768u ? (bytes - done) : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(reinterpret_cast<char*>(sm) + done)),
+                   "l"(reinterpret_cast<const char*>(P.bank_blob) + done), "r"(chunk), "r"(smem_u32(&mbar))
+                   : "memory");
+      done += chunk;
+    }
+  }
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(&mbar)), "r"(0u)
+        : "memory");
+  }
+  bk.Tpts = sm;
+  bk.Zpts = sm + P.d.nT;
+  bk.mdl = sm + P.off_mdl;
+}
+
+// ---- one pass of the loop body runMPC.m:83-112 for one cell ----
+struct StepLog {
+  double u, V, soc, phise;
+  int iT, iZ, nexec;
+  unsigned active[4];
+};
+
+template <int NPM, int NCM>
+__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg) {
+  const Dims& d = P.d;
+  lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) lg.active[w] = 0u;
+  if ((unsigned)c.f(S_STATUS) & ST_LOST) return;                     // Q19: a lost cell idles
+  const double uk = c.f(S_UK);
+  const double V = plant_step(d, bk, P.cp, c, uk);                   // runMPC.m:85
+  EkfOut e;
+  HotZ z;
+  ekf_step(d, bk, P.cp, c, V, uk, e, z);                             // runMPC.m:88,92
+  if (e.lost) return;
+  MpcOut o;
+  mpc_step<NPM, NCM>(d, P.cp, c, e, uk, o);                          // runMPC.m:94-103
+  lg.u = o.u; lg.V = V; lg.soc = e.soc; lg.phise = o.phise;          // runMPC.m:106-109
+  lg.iT = e.iT + 1; lg.iZ = e.iZ + 1; lg.nexec = o.nexec;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) lg.active[w] = o.active[w];
+}
+
+// ---- k_run_population: the fused persistent kernel ----
+template <int NPM, int NCM>
+__global__ void __launch_bounds__(128) k_run_population(const __grid_constant__ Params P, int k0, int k1) {
+  extern __shared__ __align__(16) double sm[];
+  BankSmem bk;
+  stage_bank(sm, P, bk);
+  const Dims& d = P.d;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
+    Cell c{P.st + cell, d.ld};
+    double sum_nexec = 0.0, n_qp = 0.0, n_cap = 0.0;
+    double min_phise = c.f(S_MIN_PHISE), max_V = c.f(S_MAX_V), t_reach = c.f(S_T_REACH);
+    const double ztarget = c.f(S_ZMAX) - 1e-3;
+    StepLog lg;
+    lg.soc = NAN; lg.V = NAN; lg.phise = NAN;
+    for (int k = k0; k < k1; ++k) {
+      cell_step<NPM, NCM>(P, bk, c, lg);
+      sum_nexec += (double)lg.nexec;
+      if (lg.nexec > 0) n_qp += 1.0;
+      if (lg.nexec >= d.maxHild) n_cap += 1.0;
+      min_phise = fmin(min_phise, lg.phise);
+      max_V = fmax(max_V, lg.V);
+      if (t_reach < 0.0 && lg.soc >= ztarget) t_reach = (double)k;
+      if (cell < P.nlog && k < P.log_steps) {
+        const long long o = (long long)k * P.nlog + cell;
+        P.log_u[o] = lg.u; P.log_V[o] = lg.V; P.log_soc[o] = lg.soc; P.log_phise[o] = lg.phise;
+        P.log_iT[o] = (unsigned char)lg.iT; P.log_iZ[o] = (unsigned char)lg.iZ; P.log_nexec[o] = (unsigned short)lg.nexec;
+        for (int w = 0; w < P.log_words; ++w) P.log_active[o * P.log_words + w] = lg.active[w];
+      }
+    }
+    c.f(S_SUM_NEXEC) += sum_nexec; c.f(S_N_QP) += n_qp; c.f(S_N_CAP) += n_cap;
+    c.f(S_MIN_PHISE) = min_phise; c.f(S_MAX_V) = max_V; c.f(S_T_REACH) = t_reach;
+    c.f(S_STEPS) += (double)(k1 - k0);
+    c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
+  }
+}
+
+// ---- initialisation: initKF.m:37-133, initMPC.m:32-72, OB_step.m:63-71 and the first I = 0 call (runMPC.m:72-74) ----
+__global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params P) {
+  extern __shared__ __align__(16) double sm[];
+  BankSmem bk;
+  stage_bank(sm, P, bk);
+  const Dims& d = P.d;
+  const double* p = P.cp;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
+    Cell c{P.st + cell, d.ld};
+    for (int f = 0; f < d.nfields; ++f) c.f(f) = 0.0;
+    const double Tc = P.in_T[cell], z0 = P.in_soc0[cell] / 100.0;
+    const double Tk1 = Tc + 273.15;
+    c.f(S_TC) = Tc;
+    c.f(S_SOC0N) = soc_e(p, P_NEG, z0);                              // OB_step.m:64-71
+    c.f(S_SOC0P) = soc_e(p, P_POS, z0);
+    c.f(S_SOCN) = c.f(S_SOC0N);
+    c.f(S_SOCP) = c.f(S_SOC0P);
+    c.f(S_CDLN) = cdl_eff(p, P_NEG);                                 // OB_step.m:212-219 (run constants)
+    c.f(S_CDLP) = cdl_eff(p, P_POS);
+    c.f(S_ARRK0N) = arrhenius(p, Tk1, p[P_NEG + E_EA_K0]);
+    c.f(S_ARRK0P) = arrhenius(p, Tk1, p[P_POS + E_EA_K0]);
+    c.f(S_ARRRFN) = arrhenius(p, Tk1, -p[P_NEG + E_EA_RF]);
+    c.f(S_ARRRFP) = arrhenius(p, Tk1, -p[P_POS + E_EA_RF]);
+    const double* sx = P.in_sigx0 + cell * 36;
+    c.f(S_SIGX0) = sx[5 * 6 + 5];                                    // initKF.m:99
+    c.f(S_EKFSOC0) = P.in_ekf[cell] / 100.0;                         // initKF.m:133
+    for (int m = 0; m < d.M; ++m) {                                  // initKF.m:70,94-95
+      int q = 0;
+      for (int i = 0; i < N5; ++i)
+        for (int j = i; j < N5; ++j, ++q) c.f(d.f_sig + m * NSYM + q) = sx[j * 6 + i];
+    }
+    for (int k = 0; k < 7; ++k) c.f(S_UMAX + k) = P.in_lim[cell * 7 + k];
+    c.f(S_MIN_PHISE) = INFINITY;
+    c.f(S_MAX_V) = -INFINITY;
+    c.f(S_T_REACH) = -1.0;
+    plant_step(d, bk, p, c, 0.0);                                    // runMPC.m:74 (Q20)
+  }
+}
+
+// ---- function-level kernels (each is one line of the loop body) ----
+__global__ void __launch_bounds__(128) k_ob_step(const __grid_constant__ Params P, const double* Iapp, double* V) {
+  extern __shared__ __align__(16) double sm[];
+  BankSmem bk;
+  stage_bank(sm, P, bk);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < P.d.B; cell += stride) {
+    Cell c{P.st + cell, P.d.ld};
+    V[cell] = plant_step(P.d, bk, P.cp, c, Iapp[cell]);
+  }
+}
+
+__device__ __forceinline__ void pack_mats(const EkfOut& e, double* m) {
+  int q = 0;
+  m[q++] = (double)e.lost; m[q++] = (double)(e.iT + 1); m[q++] = (double)(e.iZ + 1);
+  for (int j = 0; j < 6; ++j) m[q++] = e.xhat[j];
+  for (int j = 0; j < 5; ++j) m[q++] = e.a[j];
+  for (int j = 0; j < 5; ++j) m[q++] = e.Cv[j];
+  m[q++] = e.Dv;
+  for (int j = 0; j < 5; ++j) m[q++] = e.Cphi[j];
+  m[q++] = e.Dphi; m[q++] = e.bv; m[q++] = e.bphi; m[q++] = e.vhat; m[q++] = e.soc;
+}
+__device__ __forceinline__ void unpack_mats(const double* m, EkfOut& e) {
+  int q = 0;
+  e.lost = (int)m[q++]; e.iT = (int)m[q++] - 1; e.iZ = (int)m[q++] - 1;
+  for (int j = 0; j < 6; ++j) e.xhat[j] = m[q++];
+  for (int j = 0; j < 5; ++j) e.a[j] = m[q++];
+  for (int j = 0; j < 5; ++j) e.Cv[j] = m[q++];
+  e.Dv = m[q++];
+  for (int j = 0; j < 5; ++j) e.Cphi[j] = m[q++];
+  e.Dphi = m[q++]; e.bv = m[q++]; e.bphi = m[q++]; e.vhat = m[q++]; e.soc = m[q++];
+}
+
+// full zk = [Z; vhat; SOC] (iterEKF.m:183) for the function-level entry: all nz rows from the full bank
+__device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, double ik, const HotZ& hz, double vhat, double soc,
+                        double* zk) {
+  const Dims& d = P.d;
+  const double Tk = c.f(S_TC) + 273.15;
+  Xind X;
+  get_xind(d, bk, Tk, soc, X);                                       // iterEKF.m:181
+  double xk[4][N5];
+  for (int k = 0; k < 4; ++k)
+    for (int j = 0; j < N5; ++j) xk[k][j] = c.f(d.f_xhat + X.m[k] * N5 + j);
+  for (int r = 0; r < d.nz; ++r) {                                   // iterEKF.m:302-313
+    double yc[4];
+    for (int k = 0; k < 4; ++k) {
+      const double* cr = P.Cfull + ((size_t)X.m[k] * d.nz + r) * 6;
+      double acc = cr[0] * xk[k][0];
+      for (int j = 1; j < N5; ++j) acc = acc + cr[j] * xk[k][j];
+      yc[k] = acc + P.Dfull[(size_t)X.m[k] * d.nz + r] * ik;
+    }
+    zk[r] = ((yc[0] * X.gamma[0] + yc[1] * X.gamma[1]) + yc[2] * X.gamma[2]) + yc[3] * X.gamma[3];
+  }
+  (void)hz;
+  zk[d.nz] = vhat;
+  zk[d.nz + 1] = soc;       // the per-kind corrections (iterEKF.m:331-413) follow in k_iter_ekf
+}
+
+struct RowLists {            // output-row kinds for the full-zk corrections
+  int n_negtss, n_postss, n_thetae, n_negphise, n_posphise, n_phie, n_posphis, r_phise0;
+  int negtss[16], postss[16], thetae[16], negphise[16], posphise[16], phie[16], posphis[16];
+};
+
+__global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params P, const __grid_constant__ RowLists RL, const double* vk,
+                                                   const double* ik, double* zk, double* mats) {
+  extern __shared__ __align__(16) double sm[];
+  BankSmem bk;
+  stage_bank(sm, P, bk);
+  const Dims& d = P.d;
+  const double* p = P.cp;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
+    Cell c{P.st + cell, d.ld};
+    EkfOut e;
+    HotZ hz;
+    memset(&e, 0, sizeof(e));
+    ekf_step(d, bk, p, c, vk[cell], ik[cell], e, hz);
+    if (mats) pack_mats(e, mats + cell * MEK_NMATS);
+    if (zk) {
+      double* z = zk + cell * (d.nz + 2);
+      if (e.lost) {
+        for (int r = 0; r < d.nz + 2; ++r) z[r] = NAN;
+        continue;
+      }
+      full_zk(P, bk, c, ik[cell], hz, e.vhat, e.soc, z);
+      // nonlinear corrections of getVariables on the full vector (iterEKF.m:331-413)
+      const double rpa = d.Ts / (3600.0 * p[P_Q]);
+      const double xSOC = c.f(S_EKFSOC0) - c.f(S_X0) * rpa;
+      double SOCn = soc_e(p, P_NEG, xSOC), SOCp = soc_e(p, P_POS, xSOC);
+      if (SOCn < 0.0) SOCn = 1e-6;
+      if (SOCn > 1.0) SOCn = 1.0 - 1e-6;
+      if (SOCp < 0.0) SOCp = 1e-6;
+      if (SOCp > 0.998) SOCp = 0.998;
+      for (int k = 0; k < RL.n_negtss; ++k) {
+        double v = z[RL.negtss[k]] + SOCn;
+        if (v < 0.0) v = 1e-6;
+        if (v > 1.0) v = 1.0 - 1e-6;
+        z[RL.negtss[k]] = v;
+      }
+      for (int k = 0; k < RL.n_postss; ++k) {
+        double v = z[RL.postss[k]] + SOCp;
+        if (v < 0.0) v = 1e-6;
+        if (v > 0.998) v = 0.998;
+        z[RL.postss[k]] = v;
+      }
+      const double UnAvg = uocp_n(p, SOCn), UpAvg = uocp_p(p, SOCp);
+      for (int k = 0; k < RL.n_negphise; ++k) z[RL.negphise[k]] = z[RL.negphise[k]] + UnAvg;
+      for (int k = 0; k < RL.n_posphise; ++k) z[RL.posphise[k]] = z[RL.posphise[k]] + UpAvg;
+      const double Phise0 = z[RL.r_phise0];
+      for (int k = 0; k < RL.n_phie; ++k) z[RL.phie[k]] = z[RL.phie[k]] - Phise0;
+      for (int k = 0; k < RL.n_thetae; ++k) {
+        double v = z[RL.thetae[k]] + 1.0;
+        if (v < 0.0) v = 1e-6;
+        z[RL.thetae[k]] = v;
+      }
+      for (int k = 0; k < RL.n_posphis; ++k) z[RL.posphis[k]] = z[RL.posphis[k]] + e.vhat;
+    }
+  }
+}
+
+template <int NPM, int NCM>
+__global__ void __launch_bounds__(128) k_iter_mpc(const __grid_constant__ Params P, const double* mats, const double* uk_applied, double* uk,
+                                                   double* phise, int* nexec, unsigned* active) {
+  const Dims& d = P.d;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
+    Cell c{P.st + cell, d.ld};
+    EkfOut e;
+    unpack_mats(mats + cell * MEK_NMATS, e);
+    if (e.lost) {
+      uk[cell] = NAN; if (phise) phise[cell] = NAN; if (nexec) nexec[cell] = 0;
+      if (active) for (int w = 0; w < 4; ++w) active[cell * 4 + w] = 0u;
+      continue;
+    }
+    MpcOut o;
+    mpc_step<NPM, NCM>(d, P.cp, c, e, uk_applied[cell], o);
+    uk[cell] = o.u;
+    if (phise) phise[cell] = o.phise;
+    if (nexec) nexec[cell] = o.nexec;
+    if (active) for (int w = 0; w < 4; ++w) active[cell * 4 + w] = o.active[w];
+  }
+}
+
+// stateless hildreth.m: one thread per QP
+template <int NCM, int NCONM>
+__global__ void __launch_bounds__(128) k_hildreth(long long B, int Nc, int nC, const double* E, const double* F, const double* M,
+                                                   const double* gamma, const double* lambda0, int maxIter, double* DU, double* lam_out,
+                                                   int* nexec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < B; q += stride) {
+    double Ep[NCM * NCM], LU[NCM * NCM], Fp[NCM], Mp[NCONM * NCM], gp[NCONM], lam[NCONM], du[NCM];
+    for (int i = 0; i < NCM * NCM; ++i) Ep[i] = 0.0;
+    for (int i = 0; i < Nc; ++i) {
+      Fp[i] = F[q * Nc + i];
+      for (int j = 0; j < Nc; ++j) Ep[i * NCM + j] = E[q * Nc * Nc + i * Nc + j];
+    }
+    for (int i = 0; i < nC; ++i) {
+      for (int j = 0; j < NCM; ++j) Mp[i * NCM + j] = (j < Nc) ? M[(q * nC + i) * Nc + j] : 0.0;
+      gp[i] = gamma[q * nC + i];
+      lam[i] = lambda0 ? lambda0[q * nC + i] : 0.0;                  // hildreth.m:18-22
+    }
+    spd_factor<NCM>(Nc, Ep, LU);
+    const int k = hildreth_core<NCM, NCONM>(Nc, nC, LU, Fp, Mp, gp, maxIter, lam, du);
+    for (int i = 0; i < Nc; ++i) DU[q * Nc + i] = du[i];
+    for (int i = 0; i < nC; ++i) lam_out[q * nC + i] = lam[i];
+    nexec[q] = k;
+  }
+}
+
+
+// stateless constraintsMPC.m (+ the pre-QP part of iterMPC.m: F, E, unconstrained DU)
+template <int NPM, int NCM>
+__global__ void __launch_bounds__(128) k_constraints(long long B, const __grid_constant__ Dims d, double r, const double* x_aug,
+                                                      const double* mats, const double* SOCk_1, const double* limits, double* M, double* gamma,
+                                                      double* E, double* F, double* DU) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < B; q += stride) {
+    EkfOut e;
+    unpack_mats(mats + q * MEK_NMATS, e);
+    for (int j = 0; j < 6; ++j) e.xhat[j] = x_aug[q * 7 + j];       // x_aug_k = [x_k; u_k]  constraintsMPC.m:4
+    e.soc = SOCk_1[q];                                               // mpcData.SOCk_1 (runMPC.m:99)
+    const double* l = limits + q * 7;
+    Limits lim = {l[0], l[1], l[2], l[3], l[4], l[5], l[6]};
+    MpcProblem<NPM, NCM> pr;
+    mpc_setup<NPM, NCM>(d, r, lim, e, x_aug[q * 7 + 6], pr);
+    for (int i = 0; i < pr.nC; ++i) {
+      for (int j = 0; j < d.Nc; ++j) M[(q * d.nC + i) * d.Nc + j] = pr.Mm[i * NCM + j];
+      gamma[q * d.nC + i] = pr.gam[i];
+    }
+    for (int i = 0; i < d.Nc; ++i) {
+      if (F) F[q * d.Nc + i] = pr.F[i];
+      if (DU) DU[q * d.Nc + i] = pr.DU[i];
+      if (E) for (int j = 0; j < d.Nc; ++j) E[(q * d.Nc + i) * d.Nc + j] = pr.E[i * NCM + j];
+    }
+  }
+}
+
+// stateless predMat.m (scalar output, diagonal A, B = 1): Phi [Np][7], G [Np][Nc]
+__global__ void __launch_bounds__(128) k_pred_mat(long long B, const double* a, const double* cc, const double* dd, int Np, int Nc,
+                                                   double* Phi, double* G) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < B; q += stride) {
+    const double* aq = a + q * 6;
+    const double* cq = cc + q * 6;
+    double pk[6], pw[6], h[33];
+    for (int j = 0; j < 6; ++j) { pk[j] = 0.0; pw[j] = 1.0; }
+    for (int k = 0; k <= Np; ++k) {                                  // predMat.m:31-36 (one extra term: Phi(Np,7))
+      double acc = cq[0] * pk[0];
+      for (int j = 1; j < 6; ++j) acc = acc + cq[j] * pk[j];
+      h[k] = acc + dd[q];
+      for (int j = 0; j < 6; ++j) pk[j] = aq[j] * pk[j] + 1.0;
+    }
+    for (int i = 1; i <= Np; ++i) {                                  // predMat.m:39-50
+      double* ph = Phi + (q * Np + (i - 1)) * 7;
+      for (int j = 0; j < 6; ++j) { pw[j] = aq[j] * pw[j]; ph[j] = cq[j] * pw[j]; }
+      ph[6] = h[i];
+      for (int j = 0; j < Nc; ++j) G[(q * Np + (i - 1)) * Nc + j] = (i - 1 - j >= 0) ? h[i - 1 - j] : 0.0;
+    }
+  }
+}
+
+// population statistics: per-block partials in shared memory, then one atomic per block
+__global__ void __launch_bounds__(256) k_summary(const __grid_constant__ Params P, double* totals) {
+  __shared__ double sh[MEK_NSTAT][8];
+  const Dims& d = P.d;
+  double acc[MEK_NSTAT];
+  for (int i = 0; i < MEK_NSTAT; ++i) acc[i] = 0.0;
+  acc[MEK_STAT_MIN_PHISE] = INFINITY;
+  acc[MEK_STAT_MAX_V] = -INFINITY;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
+    Cell c{P.st + cell, d.ld};
+    const unsigned st = (unsigned)c.f(S_STATUS);
+    acc[MEK_STAT_CELLS] += 1.0;
+    acc[MEK_STAT_CELLSTEPS] += c.f(S_STEPS);
+    acc[MEK_STAT_SUM_NEXEC] += c.f(S_SUM_NEXEC);
+    acc[MEK_STAT_N_QP] += c.f(S_N_QP);
+    acc[MEK_STAT_N_CAP] += c.f(S_N_CAP);
+    const double tr = c.f(S_T_REACH);
+    if (tr >= 0.0) { acc[MEK_STAT_N_REACHED] += 1.0; acc[MEK_STAT_SUM_T_REACH] += tr; }
+    acc[MEK_STAT_MIN_PHISE] = fmin(acc[MEK_STAT_MIN_PHISE], c.f(S_MIN_PHISE));
+    acc[MEK_STAT_MAX_V] = fmax(acc[MEK_STAT_MAX_V], c.f(S_MAX_V));
+    if (st & ST_LOST) acc[MEK_STAT_N_LOST] += 1.0;
+    if (st & ST_NONFINITE) acc[MEK_STAT_N_NONFINITE] += 1.0;
+    if (st & ST_Q18) acc[MEK_STAT_N_Q18] += 1.0;
+    const double ls = c.f(S_LAST_SOC);
+    if (ls == ls) acc[MEK_STAT_SUM_SOC] += ls;
+    acc[MEK_STAT_N_JACOBI] += c.f(S_NJAC);
+    acc[MEK_STAT_N_BUMP] += c.f(S_NBUMP);
+    acc[MEK_STAT_N_WARN] += c.f(S_WARN);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = 0; i < MEK_NSTAT; ++i) {
+    double v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double w = __shfl_down_sync(0xffffffffu, v, o);
+      if (i == MEK_STAT_MIN_PHISE) v = fmin(v, w); else if (i == MEK_STAT_MAX_V) v = fmax(v, w); else v += w;
+    }
+    if (lane == 0) sh[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < MEK_NSTAT) {
+    const int i = threadIdx.x;
+    double v = sh[i][0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      if (i == MEK_STAT_MIN_PHISE) v = fmin(v, sh[i][w]); else if (i == MEK_STAT_MAX_V) v = fmax(v, sh[i][w]); else v += sh[i][w];
+    }
+    if (i == MEK_STAT_MIN_PHISE || i == MEK_STAT_MAX_V) {
+      unsigned long long* addr = reinterpret_cast<unsigned long long*>(totals + i);
+      unsigned long long old = *addr, assumed;
+      do {
+        assumed = old;
+        const double cur = __longlong_as_double((long long)assumed);
+        const double nv = (i == MEK_STAT_MIN_PHISE) ? fmin(cur, v) : fmax(cur, v);
+        old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(nv));
+      } while (assumed != old);
+    } else {
+      atomicAdd(totals + i, v);
+    }
+  }
+}
+
+// AoS <-> SoA transposition for mek_read_state / mek_write_state
+__global__ void k_state_gather(const __grid_constant__ Params P, double* aos, int to_aos) {
+  const Dims& d = P.d;
+  const long long total = d.B * (long long)d.nfields;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long f = i / d.B, cell = i % d.B;
+    if (to_aos) aos[cell * d.nfields + f] = P.st[f * d.ld + cell];
+    else P.st[f * d.ld + cell] = aos[cell * d.nfields + f];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// population (host object)
+// ------------------------------------------------------------------------------------------
+struct mek_pop {
+  const mek_bank* bank;
+  mek_config cfg;
+  int device, sms, threads, blocks;
+  size_t smem_bytes;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  Params P;
+  RowLists RL;
+  double *d_blob, *d_Cfull, *d_Dfull, *d_st, *d_in, *d_totals, *d_scratch;
+  size_t scratch_bytes;
+  void* d_logs;
+  bool inited;
+  int64_t launches;
+  int inst;     // kernel instance: 0 = <5,2>, 1 = <20,5>, 2 = <32,8>
+};
+
+static double sigma_min_gtg(int Np, int Nc, double r) {
+  // smallest singular value of G_soc'*G_soc (iterMPC.m:41-43), a run constant: G(i,j) = r*(i-j), cyclic Jacobi
+  double A[8][8];
+  for (int j = 0; j < Nc; ++j)
+    for (int l = 0; l < Nc; ++l) {
+      double acc = 0.0;
+      for (int i = 1; i <= Np; ++i) {
+        const double gj = (i - 1 - j >= 0) ? r * (double)(i - 1 - j) : 0.0;
+        const double gl = (i - 1 - l >= 0) ? r * (double)(i - 1 - l) : 0.0;
+        acc = acc + gj * gl;
+      }
+      A[j][l] = acc;
+    }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < Nc; ++i)
+      for (int j = i + 1; j < Nc; ++j) off += A[i][j] * A[i][j];
+    if (off == 0.0) break;
+    for (int pI = 0; pI < Nc - 1; ++pI)
+      for (int q = pI + 1; q < Nc; ++q) {
+        const double apq = A[pI][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[pI][pI]) / (2.0 * apq);
+        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < Nc; ++k) { const double akp = A[k][pI], akq = A[k][q]; A[k][pI] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+        for (int k = 0; k < Nc; ++k) { const double apk = A[pI][k], aqk = A[q][k]; A[pI][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+      }
+  }
+  double mn = fabs(A[0][0]);
+  for (int i = 1; i < Nc; ++i) if (fabs(A[i][i]) < mn) mn = fabs(A[i][i]);
+  return mn;
+}
+
+template <typename K>
+static int prep_kernel(K kern, size_t smem) {
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return MEK_OK;
+}
+
+static int grid_for(const mek_pop* p, long long B, int threads) {
+  long long blocks = (B + threads - 1) / threads;
+  const long long cap = (long long)p->blocks;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64_t B, int device, mek_pop** out) {
+  if (!bank || !cfg || !out || B < 1) return fail(MEK_ERR_ARG, "bad argument to mek_pop_create");
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev < 1)
+    return fail(MEK_ERR_CUDA, "no CUDA device: libmek has no CPU path (the oracle under oracle/ is test infrastructure only)");
+  if (device < 0 || device >= ndev) return fail(MEK_ERR_ARG, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  mek_pop* p = new mek_pop();
+  memset(&p->P, 0, sizeof(Params));
+  p->bank = bank;
+  p->cfg = *cfg;
+  p->device = device;
+  p->inited = false;
+  p->launches = 0;
+  p->d_logs = nullptr;
+  p->d_scratch = nullptr;
+  p->scratch_bytes = 0;
+  int Np = cfg->Np < 1 ? 1 : cfg->Np;                               // initMPC.m:32-33 (Q23)
+  int Nc = cfg->Nc < 1 ? 1 : (cfg->Nc > Np ? Np : cfg->Nc);
+  if (Np == 5 && Nc == 2) p->inst = 0;
+  else if (Np <= 20 && Nc <= 5) p->inst = 1;
+  else if (Np <= 32 && Nc <= 8) p->inst = 2;
+  else { delete p; return fail(MEK_ERR_UNSUPPORTED, "Np > 32 or Nc > 8 is outside the built kernel instances"); }
+  Dims& d = p->P.d;
+  d.M = bank->M; d.nT = bank->nT; d.nZ = bank->nZ; d.nz = bank->nz;
+  d.R = bank->R; d.nx_negtss = bank->nx_negtss; d.nx_postss = bank->nx_postss; d.nx_thetae = bank->nx_thetae;
+  d.mstride = bank->mstride;
+  d.Np = Np; d.Nc = Nc; d.maxHild = cfg->maxHild > 0 ? cfg->maxHild : 100;
+  d.useCurrent = cfg->constraints[0] == 1; d.useVoltage = cfg->constraints[1] == 1; d.useEta = cfg->constraints[2] == 1;
+  d.useZmax = cfg->use_zmax != 0;
+  d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax);
+  if (d.nC > 128) { delete p; return fail(MEK_ERR_UNSUPPORTED, "more than 128 constraint rows"); }
+  d.force_jacobi = cfg->force_jacobi;
+  d.Ts = bank->Tsamp; d.ref = cfg->ref; d.SigmaV = cfg->SigmaV; d.SigmaW = cfg->SigmaW;
+  d.sigmin = sigma_min_gtg(Np, Nc, -bank->Tsamp / (3600.0 * bank->params[P_Q]));
+  d.B = B;
+  d.ld = (B + 31) / 32 * 32;
+  d.f_lambda = S_HDR; d.f_bigx = d.f_lambda + d.nC; d.f_xhat = d.f_bigx + 6 * d.M; d.f_sig = d.f_xhat + N5 * d.M;
+  d.nfields = d.f_sig + NSYM * d.M;
+  memcpy(p->P.cp, bank->params.data(), sizeof(double) * N_PARAMS);
+  // row lists for the full-zk corrections
+  RowLists& RL = p->RL;
+  memset(&RL, 0, sizeof(RL));
+  auto fill = [](const std::vector<int>& v, int* dst, int& n) { n = (int)(v.size() > 16 ? 16 : v.size()); for (int i = 0; i < n; ++i) dst[i] = v[i]; };
+  fill(bank->negtss, RL.negtss, RL.n_negtss); fill(bank->postss, RL.postss, RL.n_postss); fill(bank->thetae, RL.thetae, RL.n_thetae);
+  fill(bank->negphise, RL.negphise, RL.n_negphise); fill(bank->posphise, RL.posphise, RL.n_posphise);
+  fill(bank->phie, RL.phie, RL.n_phie); fill(bank->posphis, RL.posphis, RL.n_posphis);
+  RL.r_phise0 = bank->r_phise0;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  p->sms = prop.multiProcessorCount;
+  p->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 128;
+  if (p->threads > 128 || (p->threads & 31)) { delete p; return fail(MEK_ERR_ARG, "threads_per_block must be a multiple of 32, at most 128"); }
+  p->smem_bytes = bank->blob.size() * sizeof(double);
+  if (p->smem_bytes > 200 * 1024) { delete p; return fail(MEK_ERR_UNSUPPORTED, "hot bank does not fit in shared memory"); }
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&p->ev0));
+  CUDA_TRY(cudaEventCreate(&p->ev1));
+  CUDA_TRY(cudaMalloc(&p->d_blob, p->smem_bytes));
+  CUDA_TRY(cudaMemcpy(p->d_blob, bank->blob.data(), p->smem_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&p->d_Cfull, bank->C.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(p->d_Cfull, bank->C.data(), bank->C.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&p->d_Dfull, bank->D.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(p->d_Dfull, bank->D.data(), bank->D.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&p->d_st, sizeof(double) * (size_t)d.nfields * (size_t)d.ld));
+  CUDA_TRY(cudaMemset(p->d_st, 0, sizeof(double) * (size_t)d.nfields * (size_t)d.ld));
+  CUDA_TRY(cudaMalloc(&p->d_in, sizeof(double) * (size_t)B * (3 + 36 + 7)));
+  CUDA_TRY(cudaMalloc(&p->d_totals, sizeof(double) * MEK_NSTAT));
+  p->P.st = p->d_st;
+  p->P.bank_blob = p->d_blob;
+  p->P.blob_doubles = (int)bank->blob.size();
+  p->P.off_mdl = bank->off_mdl;
+  p->P.Cfull = p->d_Cfull;
+  p->P.Dfull = p->d_Dfull;
+  p->P.in_soc0 = p->d_in;
+  p->P.in_ekf = p->d_in + B;
+  p->P.in_T = p->d_in + 2 * B;
+  p->P.in_sigx0 = p->d_in + 3 * B;
+  p->P.in_lim = p->d_in + 39 * B;
+  p->P.nlog = 0;
+  p->P.log_steps = 0;
+  p->P.log_words = (d.nC + 31) / 32;
+  // opt in to the dynamic shared memory each kernel needs and size the persistent grid
+  int rc = MEK_OK, occ = 0;
+  rc |= prep_kernel(k_pop_init, p->smem_bytes);
+  rc |= prep_kernel(k_ob_step, p->smem_bytes);
+  rc |= prep_kernel(k_iter_ekf, p->smem_bytes);
+  if (p->inst == 0) { rc |= prep_kernel(k_run_population<5, 2>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<5, 2>, p->threads, p->smem_bytes)); }
+  if (p->inst == 1) { rc |= prep_kernel(k_run_population<20, 5>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<20, 5>, p->threads, p->smem_bytes)); }
+  if (p->inst == 2) { rc |= prep_kernel(k_run_population<32, 8>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<32, 8>, p->threads, p->smem_bytes)); }
+  if (rc != MEK_OK) { return rc; }
+  if (occ < 1) occ = 1;
+  if (cfg->blocks_per_sm > 0 && cfg->blocks_per_sm < occ) occ = cfg->blocks_per_sm;
+  p->blocks = p->sms * occ;
+  *out = p;
+  return MEK_OK;
+}
+
+extern "C" void mek_pop_destroy(mek_pop* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaStreamSynchronize(p->stream);
+  cudaFree(p->d_blob); cudaFree(p->d_Cfull); cudaFree(p->d_Dfull); cudaFree(p->d_st); cudaFree(p->d_in); cudaFree(p->d_totals);
+  if (p->d_logs) cudaFree(p->d_logs);
+  if (p->d_scratch) cudaFree(p->d_scratch);
+  cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
+  cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+static int ensure_scratch(mek_pop* p, size_t bytes) {
+  if (bytes <= p->scratch_bytes) return MEK_OK;
+  if (p->d_scratch) CUDA_TRY(cudaFree(p->d_scratch));
+  p->d_scratch = nullptr;
+  p->scratch_bytes = 0;
+  CUDA_TRY(cudaMalloc(&p->d_scratch, bytes));
+  p->scratch_bytes = bytes;
+  return MEK_OK;
+}
+
+extern "C" int mek_pop_set_logging(mek_pop* p, int64_t n_log_cells, int max_steps) {
+  if (!p || n_log_cells < 0 || max_steps < 0) return fail(MEK_ERR_ARG, "bad argument to mek_pop_set_logging");
+  CUDA_TRY(cudaSetDevice(p->device));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  if (p->d_logs) { CUDA_TRY(cudaFree(p->d_logs)); p->d_logs = nullptr; }
+  if (n_log_cells > p->P.d.B) n_log_cells = p->P.d.B;
+  p->P.nlog = n_log_cells;
+  p->P.log_steps = max_steps;
+  const size_t n = (size_t)n_log_cells * (size_t)max_steps;
+  if (n == 0) { p->P.nlog = 0; p->P.log_steps = 0; return MEK_OK; }
+  const size_t bytes = n * (4 * 8 + 1 + 1 + 2 + 4 * (size_t)p->P.log_words) + 64;
+  CUDA_TRY(cudaMalloc(&p->d_logs, bytes));
+  CUDA_TRY(cudaMemset(p->d_logs, 0xFF, bytes));
+  char* base = reinterpret_cast<char*>(p->d_logs);
+  p->P.log_u = reinterpret_cast<double*>(base); base += n * 8;
+  p->P.log_V = reinterpret_cast<double*>(base); base += n * 8;
+  p->P.log_soc = reinterpret_cast<double*>(base); base += n * 8;
+  p->P.log_phise = reinterpret_cast<double*>(base); base += n * 8;
+  p->P.log_active = reinterpret_cast<unsigned*>(base); base += n * 4 * (size_t)p->P.log_words;
+  p->P.log_nexec = reinterpret_cast<unsigned short*>(base); base += n * 2;
+  p->P.log_iT = reinterpret_cast<unsigned char*>(base); base += n;
+  p->P.log_iZ = reinterpret_cast<unsigned char*>(base);
+  return MEK_OK;
+}
+
+extern "C" int mek_pop_reset(mek_pop* p) {
+  if (!p) return fail(MEK_ERR_ARG, "null pop");
+  CUDA_TRY(cudaSetDevice(p->device));
+  k_pop_init<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P);
+  CUDA_TRY(cudaGetLastError());
+  p->launches++;
+  p->inited = true;
+  return MEK_OK;
+}
+
+extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekfSOC0pct, const double* Tc, const double* SigmaX0,
+                            const double* limits) {
+  if (!p || !SOC0pct || !Tc || !SigmaX0 || !limits) return fail(MEK_ERR_ARG, "null argument to mek_pop_init");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const size_t B = (size_t)p->P.d.B;
+  double* in = p->d_in;
+  CUDA_TRY(cudaMemcpyAsync(in, SOC0pct, 8 * B, cudaMemcpyHostToDevice, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(in + B, ekfSOC0pct ? ekfSOC0pct : SOC0pct, 8 * B, cudaMemcpyHostToDevice, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(in + 2 * B, Tc, 8 * B, cudaMemcpyHostToDevice, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(in + 3 * B, SigmaX0, 8 * 36 * B, cudaMemcpyHostToDevice, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(in + 39 * B, limits, 8 * 7 * B, cudaMemcpyHostToDevice, p->stream));
+  return mek_pop_reset(p);
+}
+
+static int launch_run(mek_pop* p, int k0, int k1) {
+  const int g = grid_for(p, p->P.d.B, p->threads);
+  if (p->inst == 0) k_run_population<5, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  else if (p->inst == 1) k_run_population<20, 5><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  else k_run_population<32, 8><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  CUDA_TRY(cudaGetLastError());
+  p->launches++;
+  return MEK_OK;
+}
+
+extern "C" int mek_run(mek_pop* p, int k0, int k1) {
+  if (!p || k1 < k0 || k0 < 0) return fail(MEK_ERR_ARG, "bad argument to mek_run");
+  if (!p->inited) return fail(MEK_ERR_STATE, "mek_run before mek_pop_init");
+  CUDA_TRY(cudaSetDevice(p->device));
+  return launch_run(p, k0, k1);
+}
+
+extern "C" int mek_run_timed(mek_pop* p, int k0, int k1, float* ms) {
+  if (!p || k1 < k0 || k0 < 0) return fail(MEK_ERR_ARG, "bad argument to mek_run_timed");
+  if (!p->inited) return fail(MEK_ERR_STATE, "mek_run before mek_pop_init");
+  CUDA_TRY(cudaSetDevice(p->device));
+  CUDA_TRY(cudaEventRecord(p->ev0, p->stream));
+  int rc = launch_run(p, k0, k1);
+  if (rc != MEK_OK) return rc;
+  CUDA_TRY(cudaEventRecord(p->ev1, p->stream));
+  CUDA_TRY(cudaEventSynchronize(p->ev1));
+  if (ms) CUDA_TRY(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+  return MEK_OK;
+}
+
+extern "C" int mek_sync(mek_pop* p) {
+  if (!p) return fail(MEK_ERR_ARG, "null pop");
+  CUDA_TRY(cudaSetDevice(p->device));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MEK_OK;
+}
+extern "C" void* mek_pop_stream(mek_pop* p) { return p ? (void*)p->stream : nullptr; }
+extern "C" int64_t mek_pop_launches(const mek_pop* p) { return p ? p->launches : 0; }
+extern "C" int mek_pop_ncon(const mek_pop* p) { return p ? p->P.d.nC : 0; }
+extern "C" int mek_pop_state_len(const mek_pop* p) { return p ? p->P.d.nfields : 0; }
+
+extern "C" int mek_read_logs(mek_pop* p, int k0, int k1, double* u, double* V, double* soc, double* phise, int32_t* iT, int32_t* iZ,
+                             int32_t* nexec, uint32_t* active) {
+  if (!p || k0 < 0 || k1 < k0 || k1 > p->P.log_steps) return fail(MEK_ERR_ARG, "log range outside what mek_pop_set_logging reserved");
+  CUDA_TRY(cudaSetDevice(p->device));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  const size_t nl = (size_t)p->P.nlog, n = nl * (size_t)(k1 - k0), o = nl * (size_t)k0;
+  if (n == 0) return MEK_OK;
+  if (u) CUDA_TRY(cudaMemcpy(u, p->P.log_u + o, 8 * n, cudaMemcpyDeviceToHost));
+  if (V) CUDA_TRY(cudaMemcpy(V, p->P.log_V + o, 8 * n, cudaMemcpyDeviceToHost));
+  if (soc) CUDA_TRY(cudaMemcpy(soc, p->P.log_soc + o, 8 * n, cudaMemcpyDeviceToHost));
+  if (phise) CUDA_TRY(cudaMemcpy(phise, p->P.log_phise + o, 8 * n, cudaMemcpyDeviceToHost));
+  if (iT || iZ) {
+    std::vector<unsigned char> tmp(n);
+    if (iT) { CUDA_TRY(cudaMemcpy(tmp.data(), p->P.log_iT + o, n, cudaMemcpyDeviceToHost)); for (size_t i = 0; i < n; ++i) iT[i] = tmp[i]; }
+    if (iZ) { CUDA_TRY(cudaMemcpy(tmp.data(), p->P.log_iZ + o, n, cudaMemcpyDeviceToHost)); for (size_t i = 0; i < n; ++i) iZ[i] = tmp[i]; }
+  }
+  if (nexec) {
+    std::vector<unsigned short> tmp(n);
+    CUDA_TRY(cudaMemcpy(tmp.data(), p->P.log_nexec + o, 2 * n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) nexec[i] = tmp[i];
+  }
+  if (active) {
+    const int W = p->P.log_words;
+    std::vector<unsigned> tmp(n * W);
+    CUDA_TRY(cudaMemcpy(tmp.data(), p->P.log_active + o * W, 4 * n * W, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i)
+      for (int w = 0; w < 4; ++w) active[i * 4 + w] = (w < W) ? tmp[i * W + w] : 0u;
+  }
+  return MEK_OK;
+}
+
+static int state_xfer(mek_pop* p, double* host, int to_host) {
+  CUDA_TRY(cudaSetDevice(p->device));
+  const size_t bytes = sizeof(double) * (size_t)p->P.d.B * (size_t)p->P.d.nfields;
+  int rc = ensure_scratch(p, bytes);
+  if (rc != MEK_OK) return rc;
+  if (!to_host) CUDA_TRY(cudaMemcpyAsync(p->d_scratch, host, bytes, cudaMemcpyHostToDevice, p->stream));
+  k_state_gather<<<p->sms * 4, 256, 0, p->stream>>>(p->P, p->d_scratch, to_host);
+  CUDA_TRY(cudaGetLastError());
+  p->launches++;
+  if (to_host) CUDA_TRY(cudaMemcpyAsync(host, p->d_scratch, bytes, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MEK_OK;
+}
+extern "C" int mek_read_state(mek_pop* p, double* state) {
+  if (!p || !state) return fail(MEK_ERR_ARG, "null argument");
+  return state_xfer(p, state, 1);
+}
+extern "C" int mek_write_state(mek_pop* p, const double* state) {
+  if (!p || !state) return fail(MEK_ERR_ARG, "null argument");
+  int rc = state_xfer(p, const_cast<double*>(state), 0);
+  if (rc == MEK_OK) p->inited = true;
+  return rc;
+}
+
+extern "C" int mek_summary(mek_pop* p, double* totals) {
+  if (!p || !totals) return fail(MEK_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(p->device));
+  double init[MEK_NSTAT];
+  for (int i = 0; i < MEK_NSTAT; ++i) init[i] = 0.0;
+  init[MEK_STAT_MIN_PHISE] = INFINITY;
+  init[MEK_STAT_MAX_V] = -INFINITY;
+  CUDA_TRY(cudaMemcpyAsync(p->d_totals, init, sizeof(init), cudaMemcpyHostToDevice, p->stream));
+  k_summary<<<p->sms * 2, 256, 0, p->stream>>>(p->P, p->d_totals);
+  CUDA_TRY(cudaGetLastError());
+  p->launches++;
+  CUDA_TRY(cudaMemcpyAsync(totals, p->d_totals, sizeof(init), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MEK_OK;
+}
+
+// ---- function-level entry points ----
+extern "C" int mek_pop_ob_step(mek_pop* p, const double* Iapp, double* Vcell) {
+  if (!p || !Iapp || !Vcell) return fail(MEK_ERR_ARG, "null argument");
+  if (!p->inited) return fail(MEK_ERR_STATE, "First call requires mek_pop_init (OB_step.m:39-42)");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const size_t B = (size_t)p->P.d.B;
+  int rc = ensure_scratch(p, 16 * B);
+  if (rc != MEK_OK) return rc;
+  double* dI = p->d_scratch;
+  double* dV = p->d_scratch + B;
+  CUDA_TRY(cudaMemcpyAsync(dI, Iapp, 8 * B, cudaMemcpyHostToDevice, p->stream));
+  k_ob_step<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P, dI, dV);
+  CUDA_TRY(cudaGetLastError());
+  p->launches++;
+  CUDA_TRY(cudaMemcpyAsync(Vcell, dV, 8 * B, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MEK_OK;
+}
+
+extern "C" int mek_pop_iter_ekf(mek_pop* p, const double* vk, const double* ik, double* zk, double* mats) {
+  if (!p || !vk || !ik) return fail(MEK_ERR_ARG, "null argument");
+  if (!p->inited) return fail(MEK_ERR_STATE, "mek_pop_iter_ekf before mek_pop_init");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const size_t B = (size_t)p->P.d.B, nzk = (size_t)p->P.d.nz + 2;
+  int rc = ensure_scratch(p, 8 * B * (2 + nzk + MEK_NMATS));
+  if (rc != MEK_OK) return rc;
+  double* dv = p->d_scratch;
+  double* di = dv + B;
+  double* dz = di + B;
+  double* dm = dz + B * nzk;
+  CUDA_TRY(cudaMemcpyAsync(dv, vk, 8 * B, cudaMemcpyHostToDevice, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(di, ik, 8 * B, cudaMemcpyHostToDevice, p->stream));
+  k_iter_ekf<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, dv, di, zk ? dz : nullptr, dm);
+  CUDA_TRY(cudaGetLastError());
+  p->launches++;
+  if (zk) CUDA_TRY(cudaMemcpyAsync(zk, dz, 8 * B * nzk, cudaMemcpyDeviceToHost, p->stream));
+  if (mats) CUDA_TRY(cudaMemcpyAsync(mats, dm, 8 * B * MEK_NMATS, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MEK_OK;
+}
+
+extern "C" int mek_pop_iter_mpc(mek_pop* p, const double* mats, const double* uk_applied, double* uk, double* phise, int32_t* nexec,
+                                uint32_t* active) {
+  if (!p || !mats || !uk_applied || !uk) return fail(MEK_ERR_ARG, "null argument");
+  if (!p->inited) return fail(MEK_ERR_STATE, "mek_pop_iter_mpc before mek_pop_init");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const size_t B = (size_t)p->P.d.B;
+  int rc = ensure_scratch(p, 8 * B * (MEK_NMATS + 3) + 4 * B * 5);
+  if (rc != MEK_OK) return rc;
+  double* dm = p->d_scratch;
+  double* du_in = dm + B * MEK_NMATS;
+  double* du = du_in + B;
+  double* dph = du + B;
+  int* dn = reinterpret_cast<int*>(dph + B);
+  unsigned* da = reinterpret_cast<unsigned*>(dn + B);
+  CUDA_TRY(cudaMemcpyAsync(dm, mats, 8 * B * MEK_NMATS, cudaMemcpyHostToDevice, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(du_in, uk_applied, 8 * B, cudaMemcpyHostToDevice, p->stream));
+  const int g = grid_for(p, p->P.d.B, p->threads);
+  if (p->inst == 0) k_iter_mpc<5, 2><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da);
+  else if (p->inst == 1) k_iter_mpc<20, 5><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da);
+  else k_iter_mpc<32, 8><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da);
+  CUDA_TRY(cudaGetLastError());
+  p->launches++;
+  CUDA_TRY(cudaMemcpyAsync(uk, du, 8 * B, cudaMemcpyDeviceToHost, p->stream));
+  if (phise) CUDA_TRY(cudaMemcpyAsync(phise, dph, 8 * B, cudaMemcpyDeviceToHost, p->stream));
+  if (nexec) CUDA_TRY(cudaMemcpyAsync(nexec, dn, 4 * B, cudaMemcpyDeviceToHost, p->stream));
+  if (active) CUDA_TRY(cudaMemcpyAsync(active, da, 16 * B, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MEK_OK;
+}
+
+// ---- stateless entry points ----
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+static int use_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(MEK_ERR_CUDA, "no CUDA device: libmek has no CPU path (the oracle under oracle/ is test infrastructure only)");
+  if (device < 0 || device >= ndev) return fail(MEK_ERR_ARG, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  return MEK_OK;
+}
+
+extern "C" int mek_hildreth(int64_t B, int Nc, int nC, const double* E, const double* F, const double* M, const double* gamma,
+                            const double* lambda0, int maxIter, double* DU, double* lambda, int32_t* nexec, int device) {
+  if (B < 1 || Nc < 1 || nC < 1 || !E || !F || !M || !gamma || !DU || !lambda || !nexec) return fail(MEK_ERR_ARG, "bad argument to mek_hildreth");
+  if (Nc > 8 || nC > 128) return fail(MEK_ERR_UNSUPPORTED, "mek_hildreth supports Nc <= 8, nC <= 128");
+  int rc = use_device(device);
+  if (rc != MEK_OK) return rc;
+  const size_t b = (size_t)B;
+  const size_t nin = b * ((size_t)Nc * Nc + Nc + (size_t)nC * Nc + nC + (lambda0 ? nC : 0));
+  const size_t nout = b * ((size_t)Nc + nC);
+  DevBuf buf;
+  CUDA_TRY(cudaMalloc(&buf.p, 8 * (nin + nout) + 4 * b));
+  double* dE = reinterpret_cast<double*>(buf.p);
+  double* dF = dE + b * Nc * Nc;
+  double* dM = dF + b * Nc;
+  double* dg = dM + b * nC * Nc;
+  double* dl0 = dg + b * nC;
+  double* dDU = dl0 + (lambda0 ? b * nC : 0);
+  double* dlam = dDU + b * Nc;
+  int* dn = reinterpret_cast<int*>(dlam + b * nC);
+  CUDA_TRY(cudaMemcpy(dE, E, 8 * b * Nc * Nc, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dF, F, 8 * b * Nc, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dM, M, 8 * b * nC * Nc, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dg, gamma, 8 * b * nC, cudaMemcpyHostToDevice));
+  if (lambda0) CUDA_TRY(cudaMemcpy(dl0, lambda0, 8 * b * nC, cudaMemcpyHostToDevice));
+  const int threads = 128;
+  long long blocks = (B + threads - 1) / threads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (Nc <= 2 && nC <= 23) k_hildreth<2, 23><<<(int)blocks, threads>>>(B, Nc, nC, dE, dF, dM, dg, lambda0 ? dl0 : nullptr, maxIter, dDU, dlam, dn);
+  else if (Nc <= 5 && nC <= 80) k_hildreth<5, 80><<<(int)blocks, threads>>>(B, Nc, nC, dE, dF, dM, dg, lambda0 ? dl0 : nullptr, maxIter, dDU, dlam, dn);
+  else k_hildreth<8, 128><<<(int)blocks, threads>>>(B, Nc, nC, dE, dF, dM, dg, lambda0 ? dl0 : nullptr, maxIter, dDU, dlam, dn);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(DU, dDU, 8 * b * Nc, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(lambda, dlam, 8 * b * nC, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(nexec, dn, 4 * b, cudaMemcpyDeviceToHost));
+  return MEK_OK;
+}
+
+extern "C" int mek_pred_mat(int64_t B, const double* a, const double* c, const double* d, int Np, int Nc, double* Phi, double* G, int device) {
+  if (B < 1 || !a || !c || !d || !Phi || !G) return fail(MEK_ERR_ARG, "bad argument to mek_pred_mat");
+  Np = Np < 1 ? 1 : Np;                                             // predMat.m:15-16 (Q23)
+  Nc = Nc < 1 ? 1 : (Nc > Np ? Np : Nc);
+  if (Np > 32) return fail(MEK_ERR_UNSUPPORTED, "mek_pred_mat supports Np <= 32");
+  int rc = use_device(device);
+  if (rc != MEK_OK) return rc;
+  const size_t b = (size_t)B;
+  DevBuf buf;
+  CUDA_TRY(cudaMalloc(&buf.p, 8 * b * (6 + 6 + 1 + (size_t)Np * 7 + (size_t)Np * Nc)));
+  double* da = reinterpret_cast<double*>(buf.p);
+  double* dc = da + 6 * b;
+  double* dd = dc + 6 * b;
+  double* dPhi = dd + b;
+  double* dG = dPhi + b * Np * 7;
+  CUDA_TRY(cudaMemcpy(da, a, 8 * 6 * b, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dc, c, 8 * 6 * b, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dd, d, 8 * b, cudaMemcpyHostToDevice));
+  const int threads = 128;
+  long long blocks = (B + threads - 1) / threads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_pred_mat<<<(int)blocks, threads>>>(B, da, dc, dd, Np, Nc, dPhi, dG);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(Phi, dPhi, 8 * b * Np * 7, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(G, dG, 8 * b * Np * Nc, cudaMemcpyDeviceToHost));
+  return MEK_OK;
+}
+
+
+extern "C" int mek_constraints(int64_t B, int Np, int Nc, const int* constraints, int use_zmax, const double* x_aug, const double* mats,
+                               const double* SOCk_1, const double* limits, double* M, double* gamma, double r, double ref, double* E,
+                               double* F, double* DU, int device) {
+  if (B < 1 || !constraints || !x_aug || !mats || !SOCk_1 || !limits || !M || !gamma) return fail(MEK_ERR_ARG, "bad argument to mek_constraints");
+  Np = Np < 1 ? 1 : Np;
+  Nc = Nc < 1 ? 1 : (Nc > Np ? Np : Nc);
+  if (Np > 32 || Nc > 8) return fail(MEK_ERR_UNSUPPORTED, "mek_constraints supports Np <= 32, Nc <= 8");
+  int rc = use_device(device);
+  if (rc != MEK_OK) return rc;
+  Dims d;
+  memset(&d, 0, sizeof(d));
+  d.Np = Np; d.Nc = Nc; d.Ts = 1.0; d.ref = ref;
+  d.useCurrent = constraints[0] == 1; d.useVoltage = constraints[1] == 1; d.useEta = constraints[2] == 1; d.useZmax = use_zmax != 0;
+  d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax);
+  if (d.nC < 1 || d.nC > 128) return fail(MEK_ERR_UNSUPPORTED, "constraint row count outside 1..128");
+  d.sigmin = sigma_min_gtg(Np, Nc, r);
+  const size_t b = (size_t)B, nC = (size_t)d.nC;
+  DevBuf buf;
+  const size_t nin = b * (7 + MEK_NMATS + 1 + 7), nout = b * (nC * Nc + nC + (size_t)Nc * Nc + 2 * (size_t)Nc);
+  CUDA_TRY(cudaMalloc(&buf.p, 8 * (nin + nout)));
+  double* dx = reinterpret_cast<double*>(buf.p);
+  double* dm = dx + 7 * b;
+  double* ds = dm + MEK_NMATS * b;
+  double* dl = ds + b;
+  double* dM = dl + 7 * b;
+  double* dg = dM + b * nC * Nc;
+  double* dE = dg + b * nC;
+  double* dF = dE + b * Nc * Nc;
+  double* dDU = dF + b * Nc;
+  CUDA_TRY(cudaMemcpy(dx, x_aug, 8 * 7 * b, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dm, mats, 8 * MEK_NMATS * b, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(ds, SOCk_1, 8 * b, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dl, limits, 8 * 7 * b, cudaMemcpyHostToDevice));
+  const int threads = 128;
+  long long blocks = (B + threads - 1) / threads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (Np <= 5 && Nc <= 2) k_constraints<5, 2><<<(int)blocks, threads>>>(B, d, r, dx, dm, ds, dl, dM, dg, dE, dF, dDU);
+  else if (Np <= 20 && Nc <= 5) k_constraints<20, 5><<<(int)blocks, threads>>>(B, d, r, dx, dm, ds, dl, dM, dg, dE, dF, dDU);
+  else k_constraints<32, 8><<<(int)blocks, threads>>>(B, d, r, dx, dm, ds, dl, dM, dg, dE, dF, dDU);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(M, dM, 8 * b * nC * Nc, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(gamma, dg, 8 * b * nC, cudaMemcpyDeviceToHost));
+  if (E) CUDA_TRY(cudaMemcpy(E, dE, 8 * b * Nc * Nc, cudaMemcpyDeviceToHost));
+  if (F) CUDA_TRY(cudaMemcpy(F, dF, 8 * b * Nc, cudaMemcpyDeviceToHost));
+  if (DU) CUDA_TRY(cudaMemcpy(DU, dDU, 8 * b * Nc, cudaMemcpyDeviceToHost));
+  return MEK_OK;
+}
+
+extern "C" const char* mek_last_error(void) { return g_err.c_str(); }
+extern "C" int mek_version(void) { return 100; }

@@ -1,0 +1,90 @@
+"""GPU parity: the CUDA path (through the C ABI) against the C oracle on the same seeded inputs.
+The bar is bit-exact for every logged quantity (integers and doubles): both sides evaluate the same
+correctly rounded IEEE-754 operations in the same order (numerics contract)."""
+import numpy as np
+import pytest
+
+from conftest import SCALE, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(bank, coracle_mod, pop, N, Np=5, Nc=2, constraints=(1, 1, 1), force_jacobi=False, chunks=None):
+    from mek import api
+    rom = api.RomBank(bank)
+    cb = api.CellBatch(rom, len(pop), Np=Np, Nc=Nc, constraints=constraints, force_jacobi=force_jacobi)
+    cb.set_logging(len(pop), N)
+    cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    if chunks is None:
+        cb.run(0, N)
+    else:
+        for k0, k1 in chunks:
+            cb.run(k0, k1)
+    g = cb.logs(0, N)
+    co = coracle_mod.COracle(bank, Np=Np, Nc=Nc, constraints=constraints, force_jacobi=force_jacobi)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    c = co.run(0, N, nthreads=8)
+    return cb, g, co, c
+
+
+def _assert_bit_exact(g, c):
+    for k in ("iT", "iZ", "nexec"):
+        assert np.array_equal(g[k], c[k]), k
+    assert np.array_equal(g["active"], c["active"])
+    for k in ("u", "V", "SOC", "phise"):
+        same = (g[k] == c[k]) | (np.isnan(g[k]) & np.isnan(c[k]))
+        assert same.all(), "%s differs in %d entries, max rel %.3e" % (k, (~same).sum(), rel_err(g[k], c[k], SCALE[k]))
+
+
+def test_c1_single_cell_full_charge(bank, coracle_mod):
+    from mek import population as P
+    pop = P.single_cell(bank.params[2])
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 3001)
+    _assert_bit_exact(g, c)
+    assert g["SOC"][-1, 0] > 0.949
+
+
+def test_c2_population_full_charge(bank, coracle_mod):
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 256, seed=1)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 3001)
+    _assert_bit_exact(g, c)
+    s = cb.summary()
+    assert s["cells"] == 256 and s["cellsteps"] == 256 * 3001
+    assert s["sum_nexec"] == c["nexec"].sum()
+
+
+def test_c5_heterogeneous(bank, coracle_mod):
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 192, seed=4, heterogeneous=True, ekf_soc_error=5.0)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 1500)
+    _assert_bit_exact(g, c)
+
+
+def test_c3_without_phise_constraint(bank, coracle_mod):
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 128, seed=2)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 2200, constraints=(1, 1, 0))
+    _assert_bit_exact(g, c)
+
+
+def test_c4_long_horizon(bank, coracle_mod):
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 64, seed=3)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 1200, Np=20, Nc=5)
+    _assert_bit_exact(g, c)
+
+
+def test_force_jacobi_path(bank, coracle_mod):
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 64, seed=5)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 400, force_jacobi=True)
+    _assert_bit_exact(g, c)
+    assert cb.summary()["n_jacobi"] == 64 * 400 * 4
+
+
+def test_resume_in_chunks_matches_single_launch(bank, coracle_mod):
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 96, seed=6)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 900, chunks=[(0, 1), (1, 300), (300, 900)])
+    _assert_bit_exact(g, c)
