@@ -988,6 +988,9 @@ int mko_run(const mko_bank *bk, const mko_config *cf, int B, double *state, int 
 }
 
 /* function-level entries used by tests */
+int mko_test_psd(double *S15, int force) { return psd_repair(S15, force); }
+void mko_test_two_nearest(double v, const double *pts, int n, int *i1, int *i2) { two_nearest(v, pts, n, i1, i2); }
+
 double mko_ob_step(const mko_bank *bk, double *st, double Iapp) { return plant_step(bk, st, Iapp); }
 
 /* iterEKF + EKFmatsHandler; mats = [lost,iT,iZ, xhat(6), a(5), Cv(5), Dv, Cphi(5), Dphi, bv, bphi, vhat, soc] (31) */

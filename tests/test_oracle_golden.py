@@ -1,0 +1,101 @@
+"""CPU tests: the C oracle against the committed golden trajectories (made by the literal NumPy
+oracle, tests/golden/make_golden.py) and the literal oracle re-run live on short horizons.
+
+Tolerance (north_star: 1e-9 relative in FP64): |a-b| <= 1e-9 * max(|a|, scale) with the signal
+scales in conftest.SCALE; discrete outcomes (local-ROM indices iT/iZ, Hildreth sweep counts,
+active-set masks) must be identical."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SCALE, rel_err
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+TOL = 1e-9
+
+
+def _run_c(bank, coracle_mod, g, N=None):
+    N = int(g["N"]) if N is None else N
+    co = coracle_mod.COracle(bank, Np=int(g["Np"]), Nc=int(g["Nc"]), constraints=tuple(int(c) for c in g["constraints"]))
+    co.init(g["SOC0"], g["T"], g["SigmaX0"], g["limits"], g["ekf_SOC0"])
+    return co, co.run(0, N, nthreads=4)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_c_oracle_matches_golden(bank, coracle_mod, path):
+    g = np.load(path)
+    co, c = _run_c(bank, coracle_mod, g)
+    for k in ("iT", "iZ", "nexec"):
+        assert np.array_equal(c[k], g[k]), "%s: %d mismatches" % (k, (c[k] != g[k]).sum())
+    assert np.array_equal(c["active"], g["active"])
+    for k in ("u", "V", "SOC", "phise"):
+        assert rel_err(c[k], g[k], SCALE[k]) <= TOL, k
+
+
+def test_golden_has_the_qualitative_pins():
+    """CC at u_min from the second sample, phi_se rides 0.08 V, V <= 4.1 V, SOC holds 0.95."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_111.npz"))
+    u, V, soc, ph = (g[k][:, 0] for k in ("u", "V", "SOC", "phise"))
+    assert abs(u[0] + 50) < 10 and abs(u[5] + 59.72) < 1e-3 and np.all(np.abs(u[5:600] + 59.72) < 1e-3)
+    assert ph[1000:2400].min() > 0.079 and np.median(np.abs(ph[1000:2400] - 0.08)) < 1e-4
+    assert V.max() < 4.105 and abs(soc[-1] - 0.95) < 1e-4 and soc.max() < 0.9502
+    g2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_110.npz"))
+    t95 = lambda s: int(np.argmax(s >= 0.9495))
+    assert t95(g2["SOC"][:, 0]) < t95(soc)          # no plating constraint => faster charge (README.md:85)
+
+
+def test_literal_live_matches_golden_prefix(bank):
+    """Guards oracle/literal.py against edits: re-run 150 steps and compare with the stored run."""
+    from oracle import literal as L
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c2_seed1.npz"))
+    Q = bank.params[2]
+    lim = g["limits"][1]
+    o = L.run_mpc(bank, SOC0=g["SOC0"][1], TC=g["T"][1], N=150, Crate=-lim[1] / Q,
+                  limits=dict(u_max=lim[0], du_max=lim[2], du_min=lim[3], v_max=lim[4], phise_min=lim[5], z_max=lim[6]),
+                  SigmaX0=g["SigmaX0"][1], ekf_SOC0=g["ekf_SOC0"][1])
+    for k in ("u", "V", "SOC", "phise"):
+        assert np.array_equal(o[k], g[k][:150, 1]), k
+    assert np.array_equal(o["nexec"], g["nexec"][:150, 1])
+
+
+def test_fast_psd_path_equals_always_jacobi(bank, coracle_mod):
+    """The LDL^T fast path (skip the eigen-decomposition when SigmaX is PD) must not move trajectories."""
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 6, seed=9, heterogeneous=True, ekf_soc_error=5.0)
+    outs = []
+    for fj in (False, True):
+        co = coracle_mod.COracle(bank, force_jacobi=fj)
+        co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        outs.append(co.run(0, 1200, nthreads=4))
+    for k in ("iT", "iZ", "nexec"):
+        assert np.array_equal(outs[0][k], outs[1][k])
+    for k in ("u", "V", "SOC", "phise"):
+        assert rel_err(outs[0][k], outs[1][k], SCALE[k]) <= TOL
+
+
+def test_function_level_c_vs_literal(bank, coracle_mod):
+    """OB_step / iterEKF / EKFmatsHandler one call at a time: C restatement vs literal, incl. the full zk vector."""
+    from oracle import literal as L
+    ROM = L.build_rom(bank)
+    SigmaX0 = np.diag([1.0] * 5 + [2e6])
+    kf = L.initKF(22.0, 30.0, SigmaX0, 1e-3, 1e2, "OutB", ROM)
+    V, obs, cs = L.OB_step(0.0, 30.0, None, ROM, dict(SOC0=22.0, warnOff=True))
+    co = coracle_mod.COracle(bank)
+    co.init([22.0], 30.0, SigmaX0, coracle_mod.default_limits(bank))
+    rng = np.random.default_rng(0)
+    for k in range(40):
+        I = float(rng.uniform(-60, 5))
+        V, obs, cs = L.OB_step(I, 30.0, cs, ROM)
+        Vc = co.ob_step(0, I)
+        assert abs(V - Vc) <= 1e-12 * 4
+        zk, zb, kf, X = L.iterEKF(V, I, 30.0, kf)
+        MPC, xhat = L.EKFmatsHandler(kf, X, zk, 30.0)
+        zkc, mats = co.iter_ekf(0, Vc, I)
+        assert np.allclose(zk, zkc, rtol=1e-10, atol=1e-12)
+        assert mats[1] == MPC.iT and mats[2] == MPC.iZ
+        assert np.allclose(mats[3:9], xhat, rtol=1e-9, atol=1e-9)
+        assert np.allclose(mats[14:19], MPC.Cv[:5], rtol=1e-10) and np.isclose(mats[19], MPC.Dv, rtol=1e-10)
+        assert np.allclose(mats[20:25], MPC.Cphi[:5], rtol=1e-12) and mats[25] == MPC.Dphi
+        assert np.isclose(mats[26], MPC.bv, rtol=1e-10) and np.isclose(mats[27], MPC.bphi, rtol=1e-12)
