@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py -- cell-steps/s of the fused ROM+EKF+MPC loop (BASELINE.json metric).
+
+One "step" = one full charge (N_SIM sample instants, runMPC.m:83-112) of every cell of the
+population: a device-side re-initialisation (initKF+initMPC+first OB_step) followed by ONE launch of
+the persistent kernel.  Workload at any N: C3 of SURVEY.md 8(d) -- `--cells` cells PER GPU (weak
+scaling, cells are independent), C2 distributions, constraints [1 1 1], Np=5, Nc=2.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N>1: launched under torchrun by the driver)
+  python bench.py --impl reference ...                     the CPU restatement on the host cores
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "mpc-ekf4fastcharge_b200"))
+
+import numpy as np  # noqa: E402
+
+N_SIM = 3001            # runMPC.m:10-12
+METRIC = "cell-steps/sec (ROM+EKF+MPC)"
+UNIT = "cell-steps/s"
+SEED = 2                # C3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mek", choices=["mek", "reference"])
+    ap.add_argument("--cells", type=int, default=1 << 20, help="cells per GPU")
+    ap.add_argument("--nsim", type=int, default=N_SIM)
+    ap.add_argument("--log-cells", type=int, default=4096, help="cells per GPU whose full trajectory is logged and read back in the e2e leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-cells-per-core", type=int, default=96)
+    return ap.parse_args()
+
+
+def workload_name(cells, nsim):
+    return ("C3: %d NMC30 cells per GPU x %d sample instants (10..30%% -> 95%% SOC), limits 2C/4.1V/80mV, "
+            "constraints [1 1 1], Np=5, Nc=2, seed %d" % (cells, nsim, SEED))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sampled during the timed region through NVML
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.sm_max = [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._loop, daemon=True)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, attr in names.items():
+                    if r & getattr(nv, attr, 0):
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        if self.nv:
+            self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.nv and self.t.is_alive():
+            self.t.join(1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement on the host cores (the only CPU implementation that exists:
+# the reference is MATLAB and cannot run here)
+# ------------------------------------------------------------------------------------------------
+def cpu_run(bank, cells, nsim, nthreads, first_cell=0):
+    from mek import population as P
+    from oracle import coracle
+    pop = P.make_population(bank.params[2], cells, SEED, first_cell=first_cell)
+    warm = coracle.COracle(bank)                                   # spin the OpenMP team up outside the timed region
+    warm.init(pop.SOC0[:nthreads], pop.T[:nthreads], pop.SigmaX0[:nthreads], pop.limits[:nthreads])
+    warm.run(0, 20, logs=False, nthreads=nthreads)
+    co = coracle.COracle(bank)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    t0 = time.perf_counter()
+    co.run(0, nsim, logs=False, nthreads=nthreads)
+    return cells * nsim / (time.perf_counter() - t0)
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mek import bank as Bk
+    bank = Bk.Bank.load(Bk.default_bank_path())
+    cores = os.cpu_count() or 1
+    cells = max(cores * a.cpu_cells_per_core // 4, cores)
+    vals = []
+    for i in range(a.warmup + a.steps):
+        v = cpu_run(bank, cells, a.nsim, cores)
+        if i >= a.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    sample = "%d cells x %d instants per step (first cells of the same population), C restatement oracle/mek_oracle.c, OpenMP over cells" % (cells, a.nsim)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": 1e3 * cells * a.nsim / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": workload_name(a.cells, a.nsim)},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "the reference is MATLAB (no MATLAB/Octave here, ROM .mat missing): this arm times the plain-C restatement of its loop"}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main_mek(a):
+    import torch
+    import torch.distributed as dist
+    from mek import api, bank as Bk, dist as D, population as P
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl mek needs a CUDA device: libmek has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    bank = Bk.Bank.load(Bk.default_bank_path())
+    rom = api.RomBank(bank)
+    B = a.cells
+    pop = P.make_population(bank.params[2], B, SEED, first_cell=rank * B)       # weak scaling: B cells on every rank
+    # pinned host inputs (what a user hands to the ABI)
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    h_soc, h_ekf, h_T = pin(pop.SOC0), pin(pop.ekf_SOC0), pin(pop.T)
+    h_sx, h_lim = pin(np.swapaxes(pop.SigmaX0, 1, 2)), pin(pop.limits)
+    h2d = sum(t.numel() * 8 for t in (h_soc, h_ekf, h_T, h_sx, h_lim))
+    cb = api.CellBatch(rom, B, device=local)
+    nlog = min(a.log_cells, B)
+    cb.set_logging(nlog, a.nsim)
+    cb.init_raw(h_soc.data_ptr(), h_ekf.data_ptr(), h_T.data_ptr(), h_sx.data_ptr(), h_lim.data_ptr())
+    cb.sync()
+
+    def step():
+        cb.reset()
+        return cb.run_timed(0, a.nsim)
+
+    for _ in range(a.warmup):
+        step()
+    # ---- timed region: K steps, device time (CUDA events on the library's stream), max over ranks ----
+    sampler = ClockSampler(local)
+    ext = torch.cuda.ExternalStream(cb.stream, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = cb.launches
+    barrier()
+    sampler.start()
+    ev0.record(ext)
+    kern_ms = [step() for _ in range(a.steps)]
+    ev1.record(ext)
+    ev1.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = cb.launches - l0
+    total_ms = D.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
+    summ = D.reduce_summaries(cb.summary(), device=dev)           # the only collective: ~16 scalars (NCCL all-reduce)
+    cellsteps = float(B) * a.nsim * world
+    value = cellsteps * a.steps / (total_ms * 1e-3)
+    kern_avg_ms = D.max_over_ranks(float(np.mean(kern_ms)), device=dev)
+
+    # ---- e2e: the public API with HOST buffers, H2D of the inputs and D2H of the results inside the timed region ----
+    d2h = 16 * 8 + nlog * a.nsim * (4 * 8 + 3 * 4 + 16)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cb.init_raw(h_soc.data_ptr(), h_ekf.data_ptr(), h_T.data_ptr(), h_sx.data_ptr(), h_lim.data_ptr())
+        cb.run(0, a.nsim, sync=False)
+        s_e2e = cb.summary()
+        lg = cb.logs(0, a.nsim)
+    barrier()
+    e2e_s = D.max_over_ranks(time.perf_counter() - t0, device=dev)
+    e2e_value = cellsteps * a.steps / e2e_s
+    assert s_e2e["cellsteps"] == B * a.nsim and np.isfinite(lg["u"]).all()
+
+    if rank == 0:
+        nC = cb.nC
+        M = bank.M
+        state_bytes = 8 * (26 * M + 40 + nC)                       # SoA state block per cell
+        bytes_per_cellstep = 2 * state_bytes + 40                  # state streamed once in, once out, + log record
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_per_cellstep * float(B) * a.nsim / (kern_avg_ms * 1e-3) / 1e9
+        fp64_tf = api.fp64_peak_tflops(local)
+        qps = summ["n_qp"] / summ["cellsteps"]
+        sweeps = summ["sum_nexec"] / summ["cellsteps"]
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": workload_name(B, a.nsim), "cells_total": B * world, "nsim": a.nsim,
+                          "l2": "inputs larger than L2: per-GPU state block %.2f GB streamed every sample instant" % (state_bytes * B / 1e9)},
+               "clocks": clocks,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "what": "mek_pop_init (pinned host inputs) + mek_run + mek_summary + mek_read_logs of %d cells' trajectories" % nlog},
+               "gpu_launches": launches,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                            "traffic": None, "kernel": "k_run_population<5,2>", "peak_source": "measured" if peaks else "fallback",
+                            "bytes_per_cellstep": bytes_per_cellstep, "kernel_ms": kern_avg_ms},
+               "fp64": {"peak_tflops_measured": fp64_tf},
+               "qp_solves_per_s": value * qps, "hildreth_sweeps_per_s": value * sweeps, "mean_sweeps_per_step": sweeps,
+               "summary": {k: summ[k] for k in ("n_reached", "n_cap", "n_lost", "n_nonfinite", "min_phise", "max_V")}}
+        if not a.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cells = cores * a.cpu_cells_per_core
+            v = cpu_run(bank, cells, a.nsim, cores)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "first %d cells of the same population x %d instants, oracle/mek_oracle.c with OpenMP over cells" % (cells, a.nsim)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_mek(args)

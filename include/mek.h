@@ -147,6 +147,9 @@ int mek_constraints(int64_t B, int Np, int Nc, const int *constraints, int use_z
                     const double *SOCk_1, const double *limits, double *M, double *gamma, double r, double ref, double *E,
                     double *F, double *DU, int device);
 
+/* measured FP64 FMA throughput of the device (2 flops per DFMA), the FP64-pipe roofline denominator */
+int mek_fp64_peak(int device, double *tflops);
+
 const char *mek_last_error(void);
 int mek_version(void);
 

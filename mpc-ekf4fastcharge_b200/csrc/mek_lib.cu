@@ -1206,5 +1206,47 @@ extern "C" int mek_constraints(int64_t B, int Np, int Nc, const int* constraints
   return MEK_OK;
 }
 
+
+// ---- FP64 FMA microbenchmark: the measured denominator of the FP64-pipe roofline ----
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3,
+         a7 = a0 + 7e-3;
+  const double m = 0.999999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int mek_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(MEK_ERR_ARG, "null argument");
+  int rc = use_device(device);
+  if (rc != MEK_OK) return rc;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  DevBuf buf;
+  CUDA_TRY(cudaMalloc(&buf.p, sizeof(double) * (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, threads>>>(reinterpret_cast<double*>(buf.p), iters);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * (double)iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return MEK_OK;
+}
+
 extern "C" const char* mek_last_error(void) { return g_err.c_str(); }
 extern "C" int mek_version(void) { return 100; }

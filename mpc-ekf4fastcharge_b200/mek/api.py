@@ -227,3 +227,10 @@ def constraints_batch(x_aug, mats, SOCk_1, limits, Np, Nc, constraints, r, ref=9
     check(_lib.lib().mek_constraints(B, Np, Nc, cons, int(bool(use_zmax)), _p(x_aug), _p(mats), _p(SOCk_1), _p(limits), _p(M), _p(g),
                                      float(r), float(ref), _p(E), _p(F), _p(DU), int(device)))
     return M, g, E, F, DU
+
+
+def fp64_peak_tflops(device=0):
+    """Measured DFMA throughput (TFLOP/s, 2 flops per FMA) -- denominator of the FP64-pipe roofline."""
+    t = C.c_double(0.0)
+    check(_lib.lib().mek_fp64_peak(int(device), C.byref(t)))
+    return t.value
