@@ -115,9 +115,87 @@ __device__ __forceinline__ void get_xind(const Dims& d, const BankSmem& bk, doub
   for (int k = 0; k < 4; ++k) X.m[k] = X.iT[k] * d.nZ + X.iZ[k];
 }
 
+
+// ------------------------------------------------------------------------------------------
+// One pass over all M local models: plant state advance bigX = bigA.*bigX + Iapp (OB_step.m:278)
+// and EKF time update xhat = A.*xhat + priorI, SigmaX = diag(A)*SigmaX*diag(A) + SigmaW
+// (iterEKF.m:73-84).  This is the HBM stream of the kernel: 26 doubles per model in and out.
+// Loads of two models are issued back to back before any store (the compiler may not move a load
+// across a store to the same array), with evict-first hints so the stream does not flush the
+// header fields and local arrays out of L1.
+// ------------------------------------------------------------------------------------------
+template <bool PLANT, bool EKF>
+struct ModelRegs {
+  double bx[PLANT ? 6 : 1], x[EKF ? N5 : 1], s[EKF ? NSYM : 1];
+};
+
+template <bool PLANT, bool EKF>
+__device__ __forceinline__ void model_load(const Dims& d, const Cell& c, int m, ModelRegs<PLANT, EKF>& r) {
+  if (PLANT) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) r.bx[j] = __ldcs(&c.f(d.f_bigx + m * 6 + j));
+  }
+  if (EKF) {
+#pragma unroll
+    for (int j = 0; j < N5; ++j) r.x[j] = __ldcs(&c.f(d.f_xhat + m * N5 + j));
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) r.s[q] = __ldcs(&c.f(d.f_sig + m * NSYM + q));
+  }
+}
+template <bool PLANT, bool EKF>
+__device__ __forceinline__ void model_update(const double* a, double Iapp, double prior, double Sw, ModelRegs<PLANT, EKF>& r) {
+  if (PLANT) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) r.bx[j] = a[j] * r.bx[j] + Iapp;                  // OB_step.m:278
+  }
+  if (EKF) {
+#pragma unroll
+    for (int j = 0; j < N5; ++j) r.x[j] = a[j] * r.x[j] + prior;                 // iterEKF.m:77
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < N5; ++i)
+#pragma unroll
+      for (int j = i; j < N5; ++j, ++q) r.s[q] = (a[i] * r.s[q]) * a[j] + Sw;    // iterEKF.m:81 (Q12)
+  }
+}
+template <bool PLANT, bool EKF>
+__device__ __forceinline__ void model_store(const Dims& d, const Cell& c, int m, const ModelRegs<PLANT, EKF>& r) {
+  if (PLANT) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) __stcs(&c.f(d.f_bigx + m * 6 + j), r.bx[j]);
+  }
+  if (EKF) {
+#pragma unroll
+    for (int j = 0; j < N5; ++j) __stcs(&c.f(d.f_xhat + m * N5 + j), r.x[j]);
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) __stcs(&c.f(d.f_sig + m * NSYM + q), r.s[q]);
+  }
+}
+template <bool PLANT, bool EKF>
+__device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk, const Cell& c, double Iapp, double prior) {
+  const double Sw = d.SigmaW;
+  int m = 0;
+  for (; m + 1 < d.M; m += 2) {
+    ModelRegs<PLANT, EKF> r0, r1;
+    model_load<PLANT, EKF>(d, c, m, r0);
+    model_load<PLANT, EKF>(d, c, m + 1, r1);
+    model_update<PLANT, EKF>(bk.mdl + m * d.mstride, Iapp, prior, Sw, r0);
+    model_update<PLANT, EKF>(bk.mdl + (m + 1) * d.mstride, Iapp, prior, Sw, r1);
+    model_store<PLANT, EKF>(d, c, m, r0);
+    model_store<PLANT, EKF>(d, c, m + 1, r1);
+  }
+  if (m < d.M) {
+    ModelRegs<PLANT, EKF> r0;
+    model_load<PLANT, EKF>(d, c, m, r0);
+    model_update<PLANT, EKF>(bk.mdl + m * d.mstride, Iapp, prior, Sw, r0);
+    model_store<PLANT, EKF>(d, c, m, r0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // plant: OB_step.m simStep (:188-357).  Returns Vcell.
 // ------------------------------------------------------------------------------------------
+template <bool ADVANCE>   // ADVANCE=false: the caller runs stream_models<true,...> right after (fused pass)
 __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
                                              double Iapp) {
   const double T = c.f(S_TC) + 273.15;                               // OB_step.m:75
@@ -162,14 +240,7 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
       y[k][r] = acc + cr[6] * Iapp;
     }
   }
-  for (int m = 0; m < d.M; ++m) {                                    // :278 advance ALL models
-    const double* a = bk.mdl + m * d.mstride;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      double& x = c.f(d.f_bigx + m * 6 + j);
-      x = a[j] * x + Iapp;
-    }
-  }
+  if (ADVANCE) stream_models<true, false>(d, bk, c, Iapp, 0.0);         // :278 advance ALL models
   double aZ = 0.0, aT = 0.0;                                         // :281-283
   if (Zup != Zlo) aZ = (cellSOC - Zlo) / (Zup - Zlo);
   if (Tup != Tlo) aT = (T - Tlo) / (Tup - Tlo);
@@ -376,6 +447,7 @@ struct EkfOut {          // what EKFmatsHandler hands to the MPC (EKFmatsHandler
 };
 
 // iterEKF (OB mode, iterEKF.m:55-210) followed by EKFmatsHandler (EKFmatsHandler.m:26-114)
+template <bool TIME_UPDATE>   // TIME_UPDATE=false: the caller already ran stream_models<...,true> with priorI
 __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double vk,
                                          double ik, EkfOut& o, HotZ& zout) {
   o.lost = 0;
@@ -386,22 +458,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   }
   const double Tk = c.f(S_TC) + 273.15;                              // :65
   const double prior = c.f(S_PRIORI), Sw = d.SigmaW;
-  for (int m = 0; m < d.M; ++m) {                                    // :73-84 time update of ALL models
-    const double* a = bk.mdl + m * d.mstride;
-#pragma unroll
-    for (int j = 0; j < N5; ++j) {
-      double& x = c.f(d.f_xhat + m * N5 + j);
-      x = a[j] * x + prior;                                          // :77
-    }
-    int q = 0;
-#pragma unroll
-    for (int i = 0; i < N5; ++i)
-#pragma unroll
-      for (int j = i; j < N5; ++j, ++q) {
-        double& s = c.f(d.f_sig + m * NSYM + q);
-        s = (a[i] * s) * a[j] + Sw;                                  // :81 (Q12)
-      }
-  }
+  if (TIME_UPDATE) stream_models<false, true>(d, bk, c, 0.0, prior); // :73-84 time update of ALL models
   double x0 = c.f(S_X0) + prior;                                     // :85
   double sx0 = c.f(S_SIGX0) + Sw;                                    // :86
   c.f(S_X0) = x0;

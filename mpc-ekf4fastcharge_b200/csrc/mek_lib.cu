@@ -271,10 +271,12 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   for (int w = 0; w < 4; ++w) lg.active[w] = 0u;
   if ((unsigned)c.f(S_STATUS) & ST_LOST) return;                     // Q19: a lost cell idles
   const double uk = c.f(S_UK);
-  const double V = plant_step(d, bk, P.cp, c, uk);                   // runMPC.m:85
+  const double V = plant_step<false>(d, bk, P.cp, c, uk);            // runMPC.m:85 (outputs; the state advance is fused below)
+  // one HBM pass over the M local models: OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}
+  stream_models<true, true>(d, bk, c, uk, c.f(S_PRIORI));
   EkfOut e;
   HotZ z;
-  ekf_step(d, bk, P.cp, c, V, uk, e, z);                             // runMPC.m:88,92
+  ekf_step<false>(d, bk, P.cp, c, V, uk, e, z);                      // runMPC.m:88,92
   if (e.lost) return;
   MpcOut o;
   mpc_step<NPM, NCM>(d, P.cp, c, e, uk, o);                          // runMPC.m:94-103
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params
     c.f(S_MIN_PHISE) = INFINITY;
     c.f(S_MAX_V) = -INFINITY;
     c.f(S_T_REACH) = -1.0;
-    plant_step(d, bk, p, c, 0.0);                                    // runMPC.m:74 (Q20)
+    plant_step<true>(d, bk, p, c, 0.0);                              // runMPC.m:74 (Q20)
   }
 }
 
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(128) k_ob_step(const __grid_constant__ Params 
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < P.d.B; cell += stride) {
     Cell c{P.st + cell, P.d.ld};
-    V[cell] = plant_step(P.d, bk, P.cp, c, Iapp[cell]);
+    V[cell] = plant_step<true>(P.d, bk, P.cp, c, Iapp[cell]);
   }
 }
 
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
     EkfOut e;
     HotZ hz;
     memset(&e, 0, sizeof(e));
-    ekf_step(d, bk, p, c, vk[cell], ik[cell], e, hz);
+    ekf_step<true>(d, bk, p, c, vk[cell], ik[cell], e, hz);
     if (mats) pack_mats(e, mats + cell * MEK_NMATS);
     if (zk) {
       double* z = zk + cell * (d.nz + 2);

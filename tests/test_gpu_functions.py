@@ -1,0 +1,151 @@
+"""GPU parity of the function-level C-ABI entry points (one line of runMPC's loop body per call) and of
+the stateless batched hildreth / predMat / constraintsMPC, against the oracles."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(bank, B, seed=11, **kw):
+    from mek import api, population as P
+    pop = P.make_population(bank.params[2], B, seed=seed, heterogeneous=True)
+    rom = api.RomBank(bank)
+    cb = api.CellBatch(rom, B, **kw)
+    cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    return pop, cb
+
+
+def test_stepwise_calls_reproduce_fused_run(bank):
+    """OB_step -> iterEKF/EKFmatsHandler -> iterMPC called one at a time == k_run_population."""
+    N, B = 120, 64
+    pop, cb = _mk(bank, B)
+    cb.set_logging(B, N)
+    cb.run(0, N)
+    ref = cb.logs(0, N)
+    pop, cb2 = _mk(bank, B)
+    uk = np.zeros(B)
+    for k in range(N):
+        V = cb2.ob_step(uk)
+        zk, mats = cb2.iter_ekf(V, uk)
+        unew, ph, nx, act = cb2.iter_mpc(mats, uk)
+        assert np.array_equal(V, ref["V"][k]) and np.array_equal(unew, ref["u"][k])
+        assert np.array_equal(ph, ref["phise"][k]) and np.array_equal(nx, ref["nexec"][k])
+        assert np.array_equal(zk[:, -1], ref["SOC"][k]) and np.array_equal(act, ref["active"][k])
+        assert np.array_equal(mats[:, 1].astype(np.int32), ref["iT"][k]) and np.array_equal(mats[:, 2].astype(np.int32), ref["iZ"][k])
+        uk = unew
+
+
+def test_function_level_vs_c_oracle_and_full_zk(bank, coracle_mod):
+    B = 32
+    pop, cb = _mk(bank, B)
+    co = coracle_mod.COracle(bank)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    rng = np.random.default_rng(0)
+    for k in range(25):
+        I = rng.uniform(-60, 5, B)
+        V = cb.ob_step(I)
+        Vc = np.array([co.ob_step(c, I[c]) for c in range(B)])
+        assert np.array_equal(V, Vc)
+        zk, mats = cb.iter_ekf(V, I)
+        for c in range(B):
+            zkc, matsc = co.iter_ekf(c, Vc[c], I[c])
+            assert np.array_equal(zk[c], zkc), (k, c)
+            assert np.array_equal(mats[c], matsc), (k, c)
+    st = cb.read_state()
+    # state block round trip (checkpoint / resume): write it back into a fresh batch and continue identically
+    pop2, cb2 = _mk(bank, B)
+    cb2.write_state(st)
+    assert np.array_equal(cb2.read_state(), st)
+    I = rng.uniform(-60, 5, B)
+    assert np.array_equal(cb.ob_step(I), cb2.ob_step(I))
+
+
+def test_hildreth_batch_vs_oracles(bank, coracle_mod):
+    from mek import api
+    from oracle import literal as L
+    co = coracle_mod.COracle(bank)
+    rng = np.random.default_rng(3)
+    for Nc, nC in ((2, 23), (2, 18), (5, 80), (3, 11), (1, 4), (8, 100)):
+        Bq = 64
+        E = np.empty((Bq, Nc, Nc)); F = np.empty((Bq, Nc)); M = np.empty((Bq, nC, Nc)); g = np.empty((Bq, nC)); l0 = np.abs(rng.normal(size=(Bq, nC)))
+        for q in range(Bq):
+            A = rng.normal(size=(Nc, Nc)); E[q] = A @ A.T + Nc * np.eye(Nc)
+            F[q] = rng.normal(size=Nc) * 3
+            M[q] = rng.normal(size=(nC, Nc)) * np.exp(rng.uniform(-3, 1, size=(nC, 1)))
+            if q % 4 == 0:
+                M[q, rng.integers(nC)] = 0.0                        # Q7 zero row
+            g[q] = np.abs(rng.normal(size=nC)) * 0.5 + M[q] @ (-np.linalg.solve(E[q], F[q])) * rng.uniform(0.2, 0.9)
+            if q % 8 == 0:
+                g[q, np.all(M[q] == 0, axis=1)] = -0.1
+        for warm in (None, l0):
+            DU, lam, nexec = api.hildreth_batch(E, F, M, g, warm, 100)
+            for q in range(Bq):
+                DUc, lc, nc = co.hildreth(E[q], F[q], M[q], g[q], None if warm is None else warm[q], 100)
+                assert nexec[q] == nc
+                assert np.array_equal(DU[q], DUc, equal_nan=True) and np.array_equal(lam[q], lc, equal_nan=True)
+            q = 1
+            DUl, ll, nl = L.hildreth(E[q], F[q], M[q], g[q], None if warm is None else warm[q], 100)
+            assert nl == nexec[q] and np.allclose(DUl, DU[q], rtol=1e-9, atol=1e-11)
+
+
+def test_pred_mat_batch_vs_literal(bank):
+    from mek import api
+    from oracle import literal as L
+    rng = np.random.default_rng(4)
+    Bq = 40
+    a = np.concatenate([rng.uniform(0.1, 0.9999, (Bq, 5)), np.ones((Bq, 1))], axis=1)
+    c = rng.normal(size=(Bq, 6)); d = rng.normal(size=Bq)
+    for Np, Nc in ((5, 2), (20, 5), (1, 1), (7, 9)):
+        Phi, G = api.pred_mat_batch(a, c, d, Np, Nc)
+        for q in range(0, Bq, 7):
+            Pl, Gl, _ = L.predMat(np.diag(a[q]), np.ones((6, 1)), c[q][None], np.array([[d[q]]]), Np, Nc)
+            assert Phi[q].shape == Pl.shape and G[q].shape == Gl.shape
+            assert np.allclose(Phi[q], Pl, rtol=1e-12, atol=1e-14) and np.allclose(G[q], Gl, rtol=1e-12, atol=1e-14)
+
+
+def test_constraints_batch_vs_literal(bank):
+    """constraintsMPC + the pre-QP part of iterMPC from the same linearisation, vs the literal restatement."""
+    from types import SimpleNamespace as NS
+    from mek import api
+    from oracle import literal as L
+    B = 16
+    pop, cb = _mk(bank, B)
+    V = cb.ob_step(np.full(B, -30.0))
+    zk, mats = cb.iter_ekf(V, np.full(B, -30.0))
+    Q = bank.params[2]; r = -1.0 / (3600 * Q)
+    x_aug = np.concatenate([mats[:, 3:9], np.full((B, 1), -30.0)], axis=1)
+    for cons in ((1, 1, 1), (1, 1, 0), (0, 1, 1)):
+        M, g, E, F, DU = api.constraints_batch(x_aug, mats, zk[:, -1], pop.limits, 5, 2, cons, r)
+        for q in range(B):
+            m = mats[q]; lim = pop.limits[q]
+            MPC = NS(A=np.diag(np.concatenate([m[9:14], [1.0]])), B=np.ones((6, 1)), Csoc=np.array([0, 0, 0, 0, 0, r]), Dsoc=0.0,
+                     Cv=np.concatenate([m[14:19], [0.0]]), Dv=m[19], Cphi=np.concatenate([m[20:25], [0.0]]), Dphi=m[25], bv=m[26], bphi=m[27])
+            md = NS(Np=5, Nc=2, uk_1=-30.0, ref=95.0, SOCk_1=zk[q, -1], maxHild=100, lambda_=None, Ts=1, k=1,
+                    const=NS(constraints=np.array(cons), u_max=lim[0], u_min=lim[1], du_max=lim[2], du_min=lim[3], v_max=lim[4],
+                             phise_min=lim[5], z_max=lim[6], z_tol=0.0))
+            cs = NS(MPC=MPC)
+            L.iterMPC(m[3:9], cs, md, diagnostics=False)
+            assert M[q].shape == md.M_last.shape
+            assert np.allclose(M[q], md.M_last, rtol=1e-11, atol=1e-16) and np.allclose(g[q], md.gamma_last, rtol=1e-10, atol=1e-12)
+            assert np.allclose(E[q], 2 * (md.G_soc.T @ md.G_soc + md.Ru), rtol=1e-10)
+
+
+def test_summary_matches_logs(bank):
+    N, B = 200, 96
+    pop, cb = _mk(bank, B)
+    cb.set_logging(B, N)
+    cb.run(0, N)
+    lg = cb.logs()
+    s = cb.summary()
+    assert s["cells"] == B and s["cellsteps"] == B * N
+    assert s["sum_nexec"] == lg["nexec"].sum() and s["n_qp"] == (lg["nexec"] > 0).sum() and s["n_cap"] == (lg["nexec"] >= 100).sum()
+    assert s["min_phise"] == lg["phise"].min() and s["max_V"] == lg["V"].max()
+    assert abs(s["sum_soc"] - lg["SOC"][-1].sum()) < 1e-9
+    assert cb.launches >= 3
+    assert api_fp64_ok()
+
+
+def api_fp64_ok():
+    from mek import api
+    tf = api.fp64_peak_tflops(0)
+    return 5.0 < tf < 100.0

@@ -89,3 +89,14 @@ def test_shard_ranges_cover_population():
             assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in rs]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_mex_gateway_sources_compile_against_stub():
+    """No MATLAB here: the MEX gateway is syntax-checked against matlab/mex_stub.h with the real include/mek.h."""
+    import subprocess
+    d = os.path.join(ROOT, "mpc-ekf4fastcharge_b200", "matlab")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-DMEK_MEX_STUB", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(d, "mek_mex.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for shim in ("runMPC", "initKF", "iterEKF", "iterMPC", "hildreth", "OB_step", "EKFmatsHandler", "predMat", "initMPC"):
+        assert os.path.exists(os.path.join(d, shim + ".m"))
