@@ -11,7 +11,7 @@
 
 namespace mek {
 
-// ---- per-cell state fields (SoA: value of field f for cell c lives at st[f*ld + c]) ----
+// ---- per-cell state fields (value of field f for cell c lives at st[c/32][f][c%32]) ----
 enum : int {
   S_SOCN = 0, S_SOCP, S_SOC0N, S_SOC0P, S_CDLN, S_CDLP, S_TC, S_ARRK0N, S_ARRK0P, S_ARRRFN, S_ARRRFP,
   S_X0, S_SIGX0, S_PRIORI, S_EKFSOC0, S_WARN, S_UK, S_LAMVALID, S_STATUS, S_PLANTWARN,
@@ -38,7 +38,7 @@ struct Dims {
   int useCurrent, useVoltage, useEta, useZmax;
   int force_jacobi;
   double Ts, ref, SigmaV, SigmaW, sigmin;
-  long long B, ld;   // cells in this shard, leading dimension of the SoA block
+  long long B, ld;   // cells in this shard, cells rounded up to whole 32-cell tiles
   int f_lambda, f_bigx, f_xhat, f_sig, nfields;
 };
 
@@ -48,11 +48,16 @@ struct BankSmem {
   const double* mdl;   // [M][mstride]
 };
 
+// State block layout: tiles of 32 cells, st[tile][field][lane] (AoSoA).  A warp owns one tile, so every
+// field access is one coalesced 256-byte request and a static field index is an immediate offset.
+constexpr int TILE = 32;
 struct Cell {
-  double* st;
-  long long ld;
-  __device__ __forceinline__ double& f(int field) const { return st[(long long)field * ld]; }
+  double* base;          // &st[tile][0][lane]
+  __device__ __forceinline__ double& f(int field) const { return base[field * TILE]; }
 };
+__device__ __forceinline__ Cell cell_ref(double* st, int nfields, long long cell) {
+  return Cell{st + (cell >> 5) * ((long long)nfields * TILE) + (cell & 31)};
+}
 
 __device__ __forceinline__ int sym_idx(int i, int j) {
   // upper triangle, row-major: (0,0..4)=0..4, (1,1..4)=5..8, (2,2..4)=9..11, (3,3..4)=12,13, (4,4)=14
@@ -425,12 +430,13 @@ __device__ __forceinline__ int psd_repair(double* S, int force) {
           pd = false;
         } else {
           dd[j] = dj;
+          const double idj = 1.0 / dj;
 #pragma unroll
           for (int i = j + 1; i < 5; ++i) {
             double v = S[sym_idx(i, j)];
 #pragma unroll
             for (int k = 0; k < j; ++k) v = v - (L[i][k] * L[j][k]) * dd[k];
-            L[i][j] = v / dj;
+            L[i][j] = v * idj;
           }
         }
       }
@@ -519,8 +525,9 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
 #pragma unroll
       for (int i = 1; i < N5; ++i) s = s + Chat[k][i] * v[i];
       svt[k] = s + d.SigmaV;
+      const double isv = 1.0 / svt[k];
 #pragma unroll
-      for (int i = 0; i < N5; ++i) L[k][i] = v[i] / svt[k];
+      for (int i = 0; i < N5; ++i) L[k][i] = v[i] * isv;
     }
   }
   const double svt0 = (C0 * sx0) * C0 + d.SigmaV;                    // :123
@@ -651,22 +658,27 @@ __device__ __forceinline__ void pred_row(const double* a, const double* c5, doub
   }
 }
 
-// E x = b for the SPD Nc x Nc Hessian: Gaussian elimination without pivoting, factor reused
+// E x = b for the SPD Nc x Nc Hessian: Gaussian elimination without pivoting.  The factor keeps the
+// RECIPROCAL of each pivot on the diagonal so the many solves against it need no division.
 template <int NCM>
 __device__ __forceinline__ void spd_factor(int Nc, const double* E, double* LU) {
 #pragma unroll
   for (int i = 0; i < NCM * NCM; ++i) LU[i] = E[i];
 #pragma unroll
   for (int k = 0; k < NCM; ++k)
+    if (k < Nc) {
+      const double ip = 1.0 / LU[k * NCM + k];
+      LU[k * NCM + k] = ip;
 #pragma unroll
-    for (int i = k + 1; i < NCM; ++i)
-      if (i < Nc) {
-        const double l = LU[i * NCM + k] / LU[k * NCM + k];
-        LU[i * NCM + k] = l;
+      for (int i = k + 1; i < NCM; ++i)
+        if (i < Nc) {
+          const double l = LU[i * NCM + k] * ip;
+          LU[i * NCM + k] = l;
 #pragma unroll
-        for (int j = k + 1; j < NCM; ++j)
-          if (j < Nc) LU[i * NCM + j] = LU[i * NCM + j] - l * LU[k * NCM + j];
-      }
+          for (int j = k + 1; j < NCM; ++j)
+            if (j < Nc) LU[i * NCM + j] = LU[i * NCM + j] - l * LU[k * NCM + j];
+        }
+    }
 }
 template <int NCM>
 __device__ __forceinline__ void spd_solve(int Nc, const double* LU, const double* b, double* x) {
@@ -686,7 +698,7 @@ __device__ __forceinline__ void spd_solve(int Nc, const double* LU, const double
 #pragma unroll
       for (int k = i + 1; k < NCM; ++k)
         if (k < Nc) acc = acc - LU[i * NCM + k] * x[k];
-      x[i] = acc / LU[i * NCM + i];
+      x[i] = acc * LU[i * NCM + i];
     }
 }
 
@@ -697,66 +709,87 @@ __device__ __forceinline__ void spd_solve(int Nc, const double* LU, const double
 template <int NCM, int NCONM>
 __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, const double* F, const double* Mm, const double* gam,
                                              int maxIter, double* lam /* in: warm start, out */, double* DU) {
-  double P[NCONM * NCM], K[NCONM], Hd[NCONM], v[NCM], x[NCM];
+  // small duals are fully unrolled so that lambda and all row indices are static
+  constexpr int UNR = (NCONM <= 32) ? NCONM : 4;
+  const int nrows = (NCONM <= 32) ? NCONM : nC;
+  double P[NCONM * NCM], K[NCONM], Hd[NCONM], rH[NCONM], v[NCM], x[NCM];
+  unsigned long long zrow[(NCONM + 63) / 64];                        // rows with H_ii == 0
+#pragma unroll
+  for (int w = 0; w < (NCONM + 63) / 64; ++w) zrow[w] = 0ull;
   spd_solve<NCM>(Nc, LU, F, x);                                      // E\F
 #pragma unroll
   for (int j = 0; j < NCM; ++j) v[j] = 0.0;
   int npoison = 0;
-  for (int i = 0; i < nC; ++i) {
-    spd_solve<NCM>(Nc, LU, Mm + i * NCM, P + i * NCM);               // column i of E\M'
-    double hd = Mm[i * NCM] * P[i * NCM], k = Mm[i * NCM] * x[0];
+#pragma unroll UNR
+  for (int i = 0; i < nrows; ++i)
+    if (i < nC) {
+      spd_solve<NCM>(Nc, LU, Mm + i * NCM, P + i * NCM);             // column i of E\M'
+      double hd = Mm[i * NCM] * P[i * NCM], k = Mm[i * NCM] * x[0];
 #pragma unroll
-    for (int j = 1; j < NCM; ++j)
-      if (j < Nc) { hd = hd + Mm[i * NCM + j] * P[i * NCM + j]; k = k + Mm[i * NCM + j] * x[j]; }
-    Hd[i] = hd;                                                      // H(i,i)  hildreth.m:28
-    K[i] = k + gam[i];                                               // K(i)    hildreth.m:29
-  }
-  for (int i = 0; i < nC; ++i) {
-    if (Hd[i] == 0.0) { if (!is_finite(lam[i])) ++npoison; continue; }
-#pragma unroll
-    for (int j = 0; j < NCM; ++j)
-      if (j < Nc) v[j] = v[j] + P[i * NCM + j] * lam[i];
-  }
-  int k = 1;
-  for (; k <= maxIter; ++k) {                                        // hildreth.m:32
-    double maxd = 0.0;
-    bool nanflag = false;
-    for (int i = 0; i < nC; ++i) {                                   // hildreth.m:34-37
-      const double li = lam[i];
-      double w;
-      if (npoison > 0) {
-        w = NAN;
+      for (int j = 1; j < NCM; ++j)
+        if (j < Nc) { hd = hd + Mm[i * NCM + j] * P[i * NCM + j]; k = k + Mm[i * NCM + j] * x[j]; }
+      Hd[i] = hd;                                                    // H(i,i)  hildreth.m:28
+      rH[i] = 1.0 / hd;                                              // the sweep multiplies by 1/H(i,i) (+Inf on a zero row)
+      K[i] = k + gam[i];                                             // K(i)    hildreth.m:29
+      if (hd == 0.0) {
+        zrow[i >> 6] |= 1ull << (i & 63);
+        if (!is_finite(lam[i])) ++npoison;
       } else {
-        double hl = Mm[i * NCM] * v[0];
-#pragma unroll
-        for (int j = 1; j < NCM; ++j)
-          if (j < Nc) hl = hl + Mm[i * NCM + j] * v[j];
-        w = -((K[i] + hl) - Hd[i] * li) / Hd[i];
-      }
-      const double nl = fmax(0.0, w);                                // max(0,NaN) = 0
-      const double dl = nl - li;
-      if (Hd[i] == 0.0) {
-        npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li));
-      } else if (dl != 0.0) {
 #pragma unroll
         for (int j = 0; j < NCM; ++j)
-          if (j < Nc) v[j] = v[j] + P[i * NCM + j] * dl;
+          if (j < Nc) v[j] = v[j] + P[i * NCM + j] * lam[i];
       }
-      lam[i] = nl;
-      const double ad = fabs(dl);
-      if (ad != ad) nanflag = true; else if (ad > maxd) maxd = ad;
     }
-    if (!nanflag && maxd < 1e-6) break;                              // hildreth.m:39 (NaN-propagating norm)
+  int k = 1;
+  for (; k <= maxIter; ++k) {                                        // hildreth.m:32
+    bool notconv = false;
+#pragma unroll UNR
+    for (int i = 0; i < nrows; ++i)                                  // hildreth.m:34-37
+      if (i < nC) {
+        const double li = lam[i];
+        double w;
+        if (npoison > 0) {
+          w = NAN;
+        } else {
+          double hl = Mm[i * NCM] * v[0];
+#pragma unroll
+          for (int j = 1; j < NCM; ++j)
+            if (j < Nc) hl = hl + Mm[i * NCM + j] * v[j];
+          w = -(((K[i] + hl) - Hd[i] * li) * rH[i]);
+        }
+        const double nl = fmax(0.0, w);                              // max(0,NaN) = 0
+        const double dl = nl - li;
+        if ((zrow[i >> 6] >> (i & 63)) & 1ull) {
+          npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li));
+        } else {
+#pragma unroll
+          for (int j = 0; j < NCM; ++j)
+            if (j < Nc) v[j] = v[j] + P[i * NCM + j] * dl;
+        }
+        lam[i] = nl;
+        if (!(fabs(dl) < 1e-6)) notconv = true;                      // hildreth.m:39 norm(.,Inf) < 1e-6, NaN-propagating
+      }
+    if (!notconv) break;
   }
   if (k > maxIter) k = maxIter;
   double rhs[NCM];
 #pragma unroll
-  for (int j = 0; j < NCM; ++j)
-    if (j < Nc) {                                                    // hildreth.m:46
-      double acc = Mm[j] * lam[0];
-      for (int i = 1; i < nC; ++i) acc = acc + Mm[i * NCM + j] * lam[i];
-      rhs[j] = F[j] + acc;
+  for (int j = 0; j < NCM; ++j) rhs[j] = 0.0;
+  bool first = true;
+#pragma unroll UNR
+  for (int i = 0; i < nrows; ++i)
+    if (i < nC) {                                                    // hildreth.m:46  M'*lambda, rows in order
+#pragma unroll
+      for (int j = 0; j < NCM; ++j)
+        if (j < Nc) {
+          const double t = Mm[i * NCM + j] * lam[i];
+          rhs[j] = first ? t : rhs[j] + t;
+        }
+      first = false;
     }
+#pragma unroll
+  for (int j = 0; j < NCM; ++j)
+    if (j < Nc) rhs[j] = F[j] + rhs[j];
   spd_solve<NCM>(Nc, LU, rhs, x);
 #pragma unroll
   for (int j = 0; j < NCM; ++j)
@@ -916,14 +949,20 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
 #pragma unroll
   for (int w = 0; w < 4; ++w) o.active[w] = 0u;
   if (viol) {
+    constexpr int UNR = (NCONM <= 32) ? NCONM : 4;
+    const int nrows = (NCONM <= 32) ? NCONM : nC;
     double lam[NCONM];
     const bool warm = c.f(S_LAMVALID) != 0.0;                        // Q11: [] -> zeros on first use
-    for (int i = 0; i < nC; ++i) lam[i] = warm ? c.f(d.f_lambda + i) : 0.0;
+#pragma unroll UNR
+    for (int i = 0; i < nrows; ++i)
+      if (i < nC) lam[i] = warm ? c.f(d.f_lambda + i) : 0.0;
     o.nexec = hildreth_core<NCM, NCONM>(Nc, nC, q.LU, q.F, q.Mm, q.gam, d.maxHild, lam, q.DU);   // iterMPC.m:67
-    for (int i = 0; i < nC; ++i) {
-      c.f(d.f_lambda + i) = lam[i];                                  // iterMPC.m:68
-      if (lam[i] > 0.0) o.active[i >> 5] |= (1u << (i & 31));
-    }
+#pragma unroll UNR
+    for (int i = 0; i < nrows; ++i)
+      if (i < nC) {
+        c.f(d.f_lambda + i) = lam[i];                                // iterMPC.m:68
+        if (lam[i] > 0.0) o.active[i >> 5] |= (1u << (i & 31));
+      }
     c.f(S_LAMVALID) = 1.0;
   }
   const double uk = q.DU[0] + uk_1;                                  // iterMPC.m:75-76

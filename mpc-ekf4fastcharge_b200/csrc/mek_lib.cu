@@ -287,15 +287,15 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
 }
 
 // ---- k_run_population: the fused persistent kernel ----
-template <int NPM, int NCM>
-__global__ void __launch_bounds__(128) k_run_population(const __grid_constant__ Params P, int k0, int k1) {
+template <int NPM, int NCM, int MINB>   // MINB = resident CTAs per SM the register allocation is capped for
+__global__ void __launch_bounds__(128, MINB) k_run_population(const __grid_constant__ Params P, int k0, int k1) {
   extern __shared__ __align__(16) double sm[];
   BankSmem bk;
   stage_bank(sm, P, bk);
   const Dims& d = P.d;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c{P.st + cell, d.ld};
+    Cell c = cell_ref(P.st, d.nfields, cell);
     double sum_nexec = 0.0, n_qp = 0.0, n_cap = 0.0;
     double min_phise = c.f(S_MIN_PHISE), max_V = c.f(S_MAX_V), t_reach = c.f(S_T_REACH);
     const double ztarget = c.f(S_ZMAX) - 1e-3;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params
   const double* p = P.cp;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c{P.st + cell, d.ld};
+    Cell c = cell_ref(P.st, d.nfields, cell);
     for (int f = 0; f < d.nfields; ++f) c.f(f) = 0.0;
     const double Tc = P.in_T[cell], z0 = P.in_soc0[cell] / 100.0;
     const double Tk1 = Tc + 273.15;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(128) k_ob_step(const __grid_constant__ Params 
   stage_bank(sm, P, bk);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < P.d.B; cell += stride) {
-    Cell c{P.st + cell, P.d.ld};
+    Cell c = cell_ref(P.st, P.d.nfields, cell);
     V[cell] = plant_step<true>(P.d, bk, P.cp, c, Iapp[cell]);
   }
 }
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
   const double* p = P.cp;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c{P.st + cell, d.ld};
+    Cell c = cell_ref(P.st, d.nfields, cell);
     EkfOut e;
     HotZ hz;
     memset(&e, 0, sizeof(e));
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(128) k_iter_mpc(const __grid_constant__ Params
   const Dims& d = P.d;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c{P.st + cell, d.ld};
+    Cell c = cell_ref(P.st, d.nfields, cell);
     EkfOut e;
     unpack_mats(mats + cell * MEK_NMATS, e);
     if (e.lost) {
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(256) k_summary(const __grid_constant__ Params 
   acc[MEK_STAT_MAX_V] = -INFINITY;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c{P.st + cell, d.ld};
+    Cell c = cell_ref(P.st, d.nfields, cell);
     const unsigned st = (unsigned)c.f(S_STATUS);
     acc[MEK_STAT_CELLS] += 1.0;
     acc[MEK_STAT_CELLSTEPS] += c.f(S_STEPS);
@@ -652,8 +652,9 @@ __global__ void k_state_gather(const __grid_constant__ Params P, double* aos, in
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long f = i / d.B, cell = i % d.B;
-    if (to_aos) aos[cell * d.nfields + f] = P.st[f * d.ld + cell];
-    else P.st[f * d.ld + cell] = aos[cell * d.nfields + f];
+    double* slot = P.st + (cell >> 5) * ((long long)d.nfields * TILE) + f * TILE + (cell & 31);
+    if (to_aos) aos[cell * d.nfields + f] = *slot;
+    else *slot = aos[cell * d.nfields + f];
   }
 }
 
@@ -675,6 +676,7 @@ struct mek_pop {
   bool inited;
   int64_t launches;
   int inst;     // kernel instance: 0 = <5,2>, 1 = <20,5>, 2 = <32,8>
+  int minb;     // register cap variant of the <5,2> instance (CTAs per SM)
 };
 
 static double sigma_min_gtg(int Np, int Nc, double r) {
@@ -814,12 +816,16 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   rc |= prep_kernel(k_pop_init, p->smem_bytes);
   rc |= prep_kernel(k_ob_step, p->smem_bytes);
   rc |= prep_kernel(k_iter_ekf, p->smem_bytes);
-  if (p->inst == 0) { rc |= prep_kernel(k_run_population<5, 2>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<5, 2>, p->threads, p->smem_bytes)); }
-  if (p->inst == 1) { rc |= prep_kernel(k_run_population<20, 5>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<20, 5>, p->threads, p->smem_bytes)); }
-  if (p->inst == 2) { rc |= prep_kernel(k_run_population<32, 8>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<32, 8>, p->threads, p->smem_bytes)); }
+  p->minb = (cfg->blocks_per_sm >= 2 && cfg->blocks_per_sm <= 4) ? cfg->blocks_per_sm : 2;
+  if (p->inst != 0) p->minb = 2;
+  if (p->inst == 0 && p->minb == 2) { rc |= prep_kernel(k_run_population<5, 2, 2>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<5, 2, 2>, p->threads, p->smem_bytes)); }
+  if (p->inst == 0 && p->minb == 3) { rc |= prep_kernel(k_run_population<5, 2, 3>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<5, 2, 3>, p->threads, p->smem_bytes)); }
+  if (p->inst == 0 && p->minb == 4) { rc |= prep_kernel(k_run_population<5, 2, 4>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<5, 2, 4>, p->threads, p->smem_bytes)); }
+  if (p->inst == 1) { rc |= prep_kernel(k_run_population<20, 5, 2>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<20, 5, 2>, p->threads, p->smem_bytes)); }
+  if (p->inst == 2) { rc |= prep_kernel(k_run_population<32, 8, 2>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<32, 8, 2>, p->threads, p->smem_bytes)); }
   if (rc != MEK_OK) { return rc; }
   if (occ < 1) occ = 1;
-  if (cfg->blocks_per_sm > 0 && cfg->blocks_per_sm < occ) occ = cfg->blocks_per_sm;
+  if (cfg->blocks_per_sm == 1) occ = 1;
   p->blocks = p->sms * occ;
   *out = p;
   return MEK_OK;
@@ -898,9 +904,11 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 
 static int launch_run(mek_pop* p, int k0, int k1) {
   const int g = grid_for(p, p->P.d.B, p->threads);
-  if (p->inst == 0) k_run_population<5, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
-  else if (p->inst == 1) k_run_population<20, 5><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
-  else k_run_population<32, 8><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  if (p->inst == 0 && p->minb == 2) k_run_population<5, 2, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  else if (p->inst == 0 && p->minb == 3) k_run_population<5, 2, 3><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  else if (p->inst == 0) k_run_population<5, 2, 4><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  else if (p->inst == 1) k_run_population<20, 5, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  else k_run_population<32, 8, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
   CUDA_TRY(cudaGetLastError());
   p->launches++;
   return MEK_OK;

@@ -419,10 +419,11 @@ static int psd_repair(double *S, int force) {
       for (int k = 0; k < j; ++k) dj = dj - (L[j][k] * L[j][k]) * d[k];
       if (!(dj > 0.0)) { pd = 0; break; }
       d[j] = dj;
+      const double idj = 1.0 / dj;
       for (int i = j + 1; i < 5; ++i) {
         double v = S[sym_idx(i, j)];
         for (int k = 0; k < j; ++k) v = v - (L[i][k] * L[j][k]) * d[k];
-        L[i][j] = v / dj;
+        L[i][j] = v * idj;
       }
     }
     if (pd) return 0;
@@ -555,7 +556,8 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
       double s = Chat[c][0] * v[0];
       for (int i = 1; i < N5; ++i) s = s + Chat[c][i] * v[i];
       svt[c] = s + cf->SigmaV;
-      for (int i = 0; i < N5; ++i) L[c][i] = v[i] / svt[c];
+      const double isv = 1.0 / svt[c];
+      for (int i = 0; i < N5; ++i) L[c][i] = v[i] * isv;
     }
   }
   const double svt0 = (C0 * st[S_SIGX0]) * C0 + cf->SigmaV;        /* :123 */
@@ -661,13 +663,18 @@ static void pred_row(const double *a, const double *c5, double c6, double d, con
 
 /* solve E x = b, E SPD Nc x Nc, Gaussian elimination without pivoting (factor held in LU) */
 static void spd_factor(int Nc, const double *E, double *LU) {
+  /* LU holds the unit-lower multipliers below the diagonal, U on and above it, and the RECIPROCAL of
+     each pivot on the diagonal, so that the many solves against one factor need no division */
   for (int i = 0; i < Nc * Nc; ++i) LU[i] = E[i];
-  for (int k = 0; k < Nc; ++k)
+  for (int k = 0; k < Nc; ++k) {
+    const double ip = 1.0 / LU[k * Nc + k];
+    LU[k * Nc + k] = ip;
     for (int i = k + 1; i < Nc; ++i) {
-      double l = LU[i * Nc + k] / LU[k * Nc + k];
+      double l = LU[i * Nc + k] * ip;
       LU[i * Nc + k] = l;
       for (int j = k + 1; j < Nc; ++j) LU[i * Nc + j] = LU[i * Nc + j] - l * LU[k * Nc + j];
     }
+  }
 }
 static void spd_solve(int Nc, const double *LU, const double *b, double *x) {
   double y[NC_MAX];
@@ -679,7 +686,7 @@ static void spd_solve(int Nc, const double *LU, const double *b, double *x) {
   for (int i = Nc - 1; i >= 0; --i) {
     double acc = y[i];
     for (int k = i + 1; k < Nc; ++k) acc = acc - LU[i * Nc + k] * x[k];
-    x[i] = acc / LU[i * Nc + i];
+    x[i] = acc * LU[i * Nc + i];
   }
 }
 
@@ -688,7 +695,7 @@ static void spd_solve(int Nc, const double *LU, const double *b, double *x) {
    row product is NaN exactly as 0*Inf makes it in the dense form ("poison").              */
 int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double *Mm, const double *gam,
                  const double *lam0, int maxIter, double *DU, double *lam, int *nexec) {
-  double LU[NC_MAX * NC_MAX], P[NCON_MAX][NC_MAX], K[NCON_MAX], Hd[NCON_MAX], v[NC_MAX], x[NC_MAX];
+  double LU[NC_MAX * NC_MAX], P[NCON_MAX][NC_MAX], K[NCON_MAX], Hd[NCON_MAX], rH[NCON_MAX], v[NC_MAX], x[NC_MAX];
   if (Nc > NC_MAX || nC > NCON_MAX) return -1;
   spd_factor(Nc, E, LU);
   spd_solve(Nc, LU, F, x);                                         /* E\F */
@@ -697,6 +704,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
     double hd = Mm[i * Nc] * P[i][0], k = Mm[i * Nc] * x[0];
     for (int j = 1; j < Nc; ++j) { hd = hd + Mm[i * Nc + j] * P[i][j]; k = k + Mm[i * Nc + j] * x[j]; }
     Hd[i] = hd;                                                    /* H(i,i)  (:28) */
+    rH[i] = 1.0 / hd;                                              /* the sweep multiplies by 1/H(i,i) (+Inf on a zero row) */
     K[i] = k + gam[i];                                             /* K(i)    (:29) */
     lam[i] = lam0 ? lam0[i] : 0.0;                                 /* :18-22 */
   }
@@ -708,8 +716,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
   }
   int k = 0;
   for (k = 1; k <= maxIter; ++k) {                                 /* :32 */
-    double maxd = 0.0;
-    int nanflag = 0;
+    int notconv = 0;
     for (int i = 0; i < nC; ++i) {                                 /* :34-37 */
       const double li = lam[i];
       double w;
@@ -718,21 +725,20 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
       } else {
         double hl = Mm[i * Nc] * v[0];
         for (int j = 1; j < Nc; ++j) hl = hl + Mm[i * Nc + j] * v[j];
-        w = -((K[i] + hl) - Hd[i] * li) / Hd[i];
+        w = -(((K[i] + hl) - Hd[i] * li) * rH[i]);
       }
       const double nl = fmax(0.0, w);                              /* max(0,NaN) = 0 */
       const double dl = nl - li;
       if (Hd[i] == 0.0) {
         const int was = !(fabs(li) <= 1.79769313486231570815e308), is = !(fabs(nl) <= 1.79769313486231570815e308);
         npoison += is - was;
-      } else if (dl != 0.0) {
+      } else {
         for (int j = 0; j < Nc; ++j) v[j] = v[j] + P[i][j] * dl;
       }
       lam[i] = nl;
-      const double ad = fabs(dl);
-      if (ad != ad) nanflag = 1; else if (ad > maxd) maxd = ad;
+      if (!(fabs(dl) < 1e-6)) notconv = 1;                         /* :39: norm(.,Inf) < 1e-6, NaN-propagating */
     }
-    if (!nanflag && maxd < 1e-6) break;                            /* :39 norm(.,Inf) is NaN-propagating */
+    if (!notconv) break;
   }
   if (k > maxIter) k = maxIter;
   *nexec = k;                                                      /* :43 */

@@ -6,11 +6,13 @@ from mek import api, bank as B, population as P
 cells = int(sys.argv[1]); nsim = int(sys.argv[2])
 Np = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 Nc = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+bps = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+tpb = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 bk = B.Bank.load(B.default_bank_path())
 rom = api.RomBank(bk)
 pop = P.make_population(bk.params[2], cells, seed=2)
-cb = api.CellBatch(rom, cells, Np=Np, Nc=Nc)
+cb = api.CellBatch(rom, cells, Np=Np, Nc=Nc, blocks_per_sm=bps, threads_per_block=tpb)
 cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits)
 ms = cb.run_timed(0, nsim)
 s = cb.summary()
-print("cells %d nsim %d: %.1f ms  %.2f M cell-steps/s  mean sweeps %.2f" % (cells, nsim, ms, cells * nsim / ms / 1e3, s["sum_nexec"] / s["cellsteps"]))
+print("bps %d tpb %d" % (bps, tpb), "cells %d nsim %d: %.1f ms  %.2f M cell-steps/s  mean sweeps %.2f" % (cells, nsim, ms, cells * nsim / ms / 1e3, s["sum_nexec"] / s["cellsteps"]))
