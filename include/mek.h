@@ -74,7 +74,8 @@ typedef struct {
   double SigmaV, SigmaW;    /* runMPC.m:18-19                                         */
   int force_jacobi;         /* 1: always run the eigen-decomposition PSD repair       */
   int threads_per_block;    /* 0 = default                                            */
-  int blocks_per_sm;        /* 0 = from the occupancy calculator                      */
+  int blocks_per_sm;        /* 0 = from the occupancy calculator, 1 = one CTA per SM  */
+  int generic_path;         /* 1: never use the static-shape fast instances           */
 } mek_config;
 
 /* ---- bank ---- */
@@ -124,7 +125,7 @@ int mek_summary(mek_pop *pop, double *totals);
 /* ---- function-level batched entry points on a population's state (one call = one line of the loop body) ---- */
 int mek_pop_ob_step(mek_pop *pop, const double *Iapp, double *Vcell);
 /* zk[(nz+2)*B] cell-major or NULL; mats[31*B] cell-major or NULL =
- *   lost, iT, iZ, xhat(6), diag A(5), Cv(5), Dv, Cphi(5), Dphi, bv, bphi, vhat, SOC */
+ *   lost, iT, iZ, xhat(6), diag A(5), Cv(5), Dv, Cphi(5), Dphi, bv, bphi, vhat, SOC, reserved(0) */
 #define MEK_NMATS 31
 int mek_pop_iter_ekf(mek_pop *pop, const double *vk, const double *ik, double *zk, double *mats);
 /* consumes mats (from mek_pop_iter_ekf) and the applied current; returns the new command and diagnostics */

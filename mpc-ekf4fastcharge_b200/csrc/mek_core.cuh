@@ -755,7 +755,7 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
 #pragma unroll
           for (int j = 1; j < NCM; ++j)
             if (j < Nc) hl = hl + Mm[i * NCM + j] * v[j];
-          w = -(((K[i] + hl) - Hd[i] * li) * rH[i]);
+          w = li - (K[i] + hl) * rH[i];                               // == -(K + H(i,:)*lam - H_ii*lam_i)/H_ii
         }
         const double nl = fmax(0.0, w);                              // max(0,NaN) = 0
         const double dl = nl - li;
@@ -967,6 +967,222 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
   }
   const double uk = q.DU[0] + uk_1;                                  // iterMPC.m:75-76
   c.f(S_UK) = uk;                                                    // iterMPC.m:78
+  o.u = uk;
+  if (!is_finite(uk)) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_NONFINITE);
+}
+
+// ------------------------------------------------------------------------------------------
+// Static-shape fast path of iterMPC: Np == NP, Nc == NC and the constraint switches CONS
+// (bit0 current, bit1 voltage, bit2 eta, bit3 z_max) are compile-time, so every row index is static:
+// M, gamma and lambda live in registers and the per-row sweep data (K_i, 1/H_ii, column i of E\M')
+// in this thread's column of shared memory ([slot][thread] layout: conflict-free, no local memory).
+// Same arithmetic, in the same order, as mpc_step / hildreth_core.
+// ------------------------------------------------------------------------------------------
+template <int NP, int NC, int CONS>
+struct FastShape {
+  static constexpr bool UC = (CONS & 1) != 0, UV = (CONS & 2) != 0, UE = (CONS & 4) != 0, UZ = (CONS & 8) != 0;
+  static constexpr int O_V = UC ? 4 * NC : 0;
+  static constexpr int O_E = O_V + (UV ? NP : 0);
+  static constexpr int O_Z = O_E + (UE ? NP : 0);
+  static constexpr int nC = O_Z + (UZ ? NP : 0);
+  static constexpr int SLOTS = nC * (2 + NC);                        // doubles of shared memory per thread
+};
+
+template <int NP, int NC, int CONS>
+__device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __restrict__ p, const Cell& c, const EkfOut& e, double uk_applied,
+                                              MpcOut& o, double* smt, int sms) {
+  using FS = FastShape<NP, NC, CONS>;
+  constexpr int nC = FS::nC;
+  static_assert(nC <= 32, "fast path keeps the zero-row mask in one word");
+  const double uk_1 = c.f(S_UK);                                     // iterMPC.m:19
+  {                                                                  // runMPC.m:94-95 (Q24)
+    double acc = e.Cphi[0] * e.xhat[0];
+#pragma unroll
+    for (int j = 1; j < N5; ++j) acc = acc + e.Cphi[j] * e.xhat[j];
+    acc = acc + 0.0 * e.xhat[5];
+    o.phise = (acc + uk_applied * e.Dphi) + e.bphi;
+  }
+  const double r = -d.Ts / (3600.0 * p[P_Q]);                        // EKFmatsHandler.m:43
+  const double zero5[N5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double hs[NP + 1], pxs[NP];
+  pred_row<NP>(e.a, zero5, r, 0.0, e.xhat, NP, hs, pxs);             // iterMPC.m:33
+  double err[NP], F[NC], E[NC * NC], LU[NC * NC], DU[NC], x[NC];
+#pragma unroll
+  for (int i = 1; i <= NP; ++i) err[i - 1] = d.ref - (pxs[i - 1] + hs[i] * uk_1);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {                                     // iterMPC.m:38
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 1; i <= NP; ++i) {
+      const double g = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0;
+      const double t = g * err[i - 1];
+      acc = (i == 1) ? t : acc + t;
+    }
+    F[j] = -2.0 * acc;
+  }
+  double nf = F[0] * F[0];
+#pragma unroll
+  for (int j = 1; j < NC; ++j) nf = nf + F[j] * F[j];
+  const double Ru = sqrt(nf) / ((2.0 * c.f(S_DUMAX)) * sqrt((double)NC)) - d.sigmin;   // iterMPC.m:43 (Q10)
+#pragma unroll
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int l = 0; l < NC; ++l) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 1; i <= NP; ++i) {
+        const double gj = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0, gl = (i - 1 - l >= 0) ? hs[i - 1 - l] : 0.0;
+        const double t = gj * gl;
+        acc = (i == 1) ? t : acc + t;
+      }
+      E[j * NC + l] = 2.0 * (acc + ((j == l) ? Ru : 0.0));           // iterMPC.m:47
+    }
+  spd_factor<NC>(NC, E, LU);
+  spd_solve<NC>(NC, LU, F, x);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) DU[j] = -x[j];                        // iterMPC.m:48
+  // ---- constraintsMPC.m rows, static indices ----
+  double Mm[nC][NC], gam[nC];
+  if (FS::UC) {                                                      // constraintsMPC.m:23-42
+    const double umax = c.f(S_UMAX), umin = c.f(S_UMIN), dumax = c.f(S_DUMAX), dumin = c.f(S_DUMIN);
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) Mm[s * NC + i][j] = (j <= i) ? (s ? -1.0 : 1.0) : (s ? -0.0 : 0.0);
+        gam[s * NC + i] = s ? -(umin - uk_1) : (umax - uk_1);
+      }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) Mm[2 * NC + s * NC + i][j] = (j == i) ? (s ? -1.0 : 1.0) : (s ? -0.0 : 0.0);
+        gam[2 * NC + s * NC + i] = s ? -dumin : dumax;
+      }
+  }
+  if (FS::UV) {                                                      // constraintsMPC.m:45-63
+    double hv[NP + 1], pxv[NP];
+    pred_row<NP>(e.a, e.Cv, 0.0, e.Dv, e.xhat, NP, hv, pxv);
+    const double vmax = c.f(S_VMAX);
+#pragma unroll
+    for (int i = 1; i <= NP; ++i) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) Mm[FS::O_V + i - 1][j] = (i - 1 - j >= 0) ? hv[i - 1 - j] : 0.0;
+      gam[FS::O_V + i - 1] = vmax - ((pxv[i - 1] + hv[i] * uk_1) + e.bv);
+    }
+  }
+  if (FS::UE) {                                                      // constraintsMPC.m:66-85
+    double he[NP + 1], pxe[NP];
+    pred_row<NP>(e.a, e.Cphi, 0.0, e.Dphi, e.xhat, NP, he, pxe);
+    const double pmin = c.f(S_PHIMIN);
+#pragma unroll
+    for (int i = 1; i <= NP; ++i) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) Mm[FS::O_E + i - 1][j] = (i - 1 - j >= 0) ? -he[i - 1 - j] : -0.0;
+      gam[FS::O_E + i - 1] = -pmin + ((pxe[i - 1] + he[i] * uk_1) + e.bphi);
+    }
+  }
+  if (FS::UZ) {                                                      // constraintsMPC.m:89-101
+    const double zmax = c.f(S_ZMAX);
+#pragma unroll
+    for (int i = 1; i <= NP; ++i) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) Mm[FS::O_Z + i - 1][j] = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0;
+      gam[FS::O_Z + i - 1] = zmax - ((pxs[i - 1] + hs[i] * uk_1) + e.soc);
+    }
+  }
+  bool viol = false;                                                 // iterMPC.m:66 (Q8)
+#pragma unroll
+  for (int i = 0; i < nC; ++i) {
+    double acc = Mm[i][0] * DU[0];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) acc = acc + Mm[i][j] * DU[j];
+    if (acc - gam[i] > 0.0) viol = true;
+  }
+  o.nexec = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) o.active[w] = 0u;
+  if (viol) {                                                        // hildreth.m:16-46 (see hildreth_core)
+    double lam[nC], v[NC];
+    const bool warm = c.f(S_LAMVALID) != 0.0;                        // Q11
+#pragma unroll
+    for (int i = 0; i < nC; ++i) lam[i] = warm ? c.f(d.f_lambda + i) : 0.0;
+    spd_solve<NC>(NC, LU, F, x);                                     // E\F
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = 0.0;
+    unsigned zmask = 0u;
+    int npoison = 0;
+#pragma unroll
+    for (int i = 0; i < nC; ++i) {
+      double P[NC];
+      spd_solve<NC>(NC, LU, Mm[i], P);                               // column i of E\M'
+      double hd = Mm[i][0] * P[0], k = Mm[i][0] * x[0];
+#pragma unroll
+      for (int j = 1; j < NC; ++j) { hd = hd + Mm[i][j] * P[j]; k = k + Mm[i][j] * x[j]; }
+      smt[(i * (2 + NC) + 0) * sms] = k + gam[i];                    // K(i)
+      smt[(i * (2 + NC) + 1) * sms] = 1.0 / hd;                      // 1/H(i,i)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) smt[(i * (2 + NC) + 2 + j) * sms] = P[j];
+      if (hd == 0.0) {
+        zmask |= 1u << i;
+        if (!is_finite(lam[i])) ++npoison;
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] = v[j] + P[j] * lam[i];
+      }
+    }
+    int k = 1;
+    for (; k <= d.maxHild; ++k) {                                    // hildreth.m:32
+      bool notconv = false;
+#pragma unroll
+      for (int i = 0; i < nC; ++i) {                                 // hildreth.m:34-37
+        const double li = lam[i];
+        double w;
+        if (npoison > 0) {
+          w = NAN;
+        } else {
+          double hl = Mm[i][0] * v[0];
+#pragma unroll
+          for (int j = 1; j < NC; ++j) hl = hl + Mm[i][j] * v[j];
+          w = li - (smt[(i * (2 + NC) + 0) * sms] + hl) * smt[(i * (2 + NC) + 1) * sms];
+        }
+        const double nl = fmax(0.0, w);
+        const double dl = nl - li;
+        if ((zmask >> i) & 1u) {
+          npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li));
+        } else {
+#pragma unroll
+          for (int j = 0; j < NC; ++j) v[j] = v[j] + smt[(i * (2 + NC) + 2 + j) * sms] * dl;
+        }
+        lam[i] = nl;
+        if (!(fabs(dl) < 1e-6)) notconv = true;
+      }
+      if (!notconv) break;
+    }
+    if (k > d.maxHild) k = d.maxHild;
+    double rhs[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {                                   // hildreth.m:46
+      double acc = Mm[0][j] * lam[0];
+#pragma unroll
+      for (int i = 1; i < nC; ++i) acc = acc + Mm[i][j] * lam[i];
+      rhs[j] = F[j] + acc;
+    }
+    spd_solve<NC>(NC, LU, rhs, x);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) DU[j] = -x[j];
+    o.nexec = k;                                                     // iterMPC.m:67-69
+#pragma unroll
+    for (int i = 0; i < nC; ++i) {
+      c.f(d.f_lambda + i) = lam[i];
+      if (lam[i] > 0.0) o.active[i >> 5] |= (1u << (i & 31));
+    }
+    c.f(S_LAMVALID) = 1.0;
+  }
+  const double uk = DU[0] + uk_1;                                    // iterMPC.m:75-76
+  c.f(S_UK) = uk;
   o.u = uk;
   if (!is_finite(uk)) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_NONFINITE);
 }

@@ -263,8 +263,8 @@ struct StepLog {
   unsigned active[4];
 };
 
-template <int NPM, int NCM>
-__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg) {
+template <int NPM, int NCM, int CONS>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
+__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, int sms) {
   const Dims& d = P.d;
   lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
 #pragma unroll
@@ -279,7 +279,8 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   ekf_step<false>(d, bk, P.cp, c, V, uk, e, z);                      // runMPC.m:88,92
   if (e.lost) return;
   MpcOut o;
-  mpc_step<NPM, NCM>(d, P.cp, c, e, uk, o);                          // runMPC.m:94-103
+  if constexpr (CONS >= 0) mpc_step_fast<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, smt, sms);   // runMPC.m:94-103
+  else mpc_step<NPM, NCM>(d, P.cp, c, e, uk, o);
   lg.u = o.u; lg.V = V; lg.soc = e.soc; lg.phise = o.phise;          // runMPC.m:106-109
   lg.iT = e.iT + 1; lg.iZ = e.iZ + 1; lg.nexec = o.nexec;
 #pragma unroll
@@ -287,11 +288,13 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
 }
 
 // ---- k_run_population: the fused persistent kernel ----
-template <int NPM, int NCM, int MINB>   // MINB = resident CTAs per SM the register allocation is capped for
-__global__ void __launch_bounds__(128, MINB) k_run_population(const __grid_constant__ Params P, int k0, int k1) {
+template <int NPM, int NCM, int CONS, int THREADS, int MINB>   // THREADS/MINB: launch bounds (register cap)
+__global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_constant__ Params P, int k0, int k1) {
   extern __shared__ __align__(16) double sm[];
   BankSmem bk;
   stage_bank(sm, P, bk);
+  double* smt = sm + P.blob_doubles + threadIdx.x;   // this thread's column of the per-thread shared arrays (fast path)
+  const int sms = blockDim.x;
   const Dims& d = P.d;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(128, MINB) k_run_population(const __grid_const
     StepLog lg;
     lg.soc = NAN; lg.V = NAN; lg.phise = NAN;
     for (int k = k0; k < k1; ++k) {
-      cell_step<NPM, NCM>(P, bk, c, lg);
+      cell_step<NPM, NCM, CONS>(P, bk, c, lg, smt, sms);
       sum_nexec += (double)lg.nexec;
       if (lg.nexec > 0) n_qp += 1.0;
       if (lg.nexec >= d.maxHild) n_cap += 1.0;
@@ -384,6 +387,7 @@ __device__ __forceinline__ void pack_mats(const EkfOut& e, double* m) {
   m[q++] = e.Dv;
   for (int j = 0; j < 5; ++j) m[q++] = e.Cphi[j];
   m[q++] = e.Dphi; m[q++] = e.bv; m[q++] = e.bphi; m[q++] = e.vhat; m[q++] = e.soc;
+  m[q++] = 0.0;   // reserved
 }
 __device__ __forceinline__ void unpack_mats(const double* m, EkfOut& e) {
   int q = 0;
@@ -677,6 +681,8 @@ struct mek_pop {
   int64_t launches;
   int inst;     // kernel instance: 0 = <5,2>, 1 = <20,5>, 2 = <32,8>
   int minb;     // register cap variant of the <5,2> instance (CTAs per SM)
+  int cons;     // >= 0: static-shape fast instance with these constraint switches
+  size_t run_smem; int run_threads;
 };
 
 static double sigma_min_gtg(int Np, int Nc, double r) {
@@ -816,13 +822,31 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   rc |= prep_kernel(k_pop_init, p->smem_bytes);
   rc |= prep_kernel(k_ob_step, p->smem_bytes);
   rc |= prep_kernel(k_iter_ekf, p->smem_bytes);
-  p->minb = (cfg->blocks_per_sm >= 2 && cfg->blocks_per_sm <= 4) ? cfg->blocks_per_sm : 2;
-  if (p->inst != 0) p->minb = 2;
-  if (p->inst == 0 && p->minb == 2) { rc |= prep_kernel(k_run_population<5, 2, 2>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<5, 2, 2>, p->threads, p->smem_bytes)); }
-  if (p->inst == 0 && p->minb == 3) { rc |= prep_kernel(k_run_population<5, 2, 3>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<5, 2, 3>, p->threads, p->smem_bytes)); }
-  if (p->inst == 0 && p->minb == 4) { rc |= prep_kernel(k_run_population<5, 2, 4>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<5, 2, 4>, p->threads, p->smem_bytes)); }
-  if (p->inst == 1) { rc |= prep_kernel(k_run_population<20, 5, 2>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<20, 5, 2>, p->threads, p->smem_bytes)); }
-  if (p->inst == 2) { rc |= prep_kernel(k_run_population<32, 8, 2>, p->smem_bytes); CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_population<32, 8, 2>, p->threads, p->smem_bytes)); }
+  p->minb = 1;
+  p->cons = -1;
+  p->run_threads = p->threads;
+  p->run_smem = p->smem_bytes;
+  {
+    const int mask = (d.useCurrent ? 1 : 0) | (d.useVoltage ? 2 : 0) | (d.useEta ? 4 : 0) | (d.useZmax ? 8 : 0);
+    if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path) {
+      p->cons = mask;
+      p->run_threads = 256;
+      const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
+      p->run_smem = p->smem_bytes + sizeof(double) * (size_t)slots * 256;
+      if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
+    }
+  }
+#define MEK_PREP(KERN)                                                                                          \
+  do {                                                                                                          \
+    rc |= prep_kernel(KERN, p->run_smem);                                                                       \
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, p->run_threads, p->run_smem));           \
+  } while (0)
+  if (p->cons == 15) MEK_PREP((k_run_population<5, 2, 15, 256, 1>));
+  else if (p->cons == 11) MEK_PREP((k_run_population<5, 2, 11, 256, 1>));
+  else if (p->inst == 0) MEK_PREP((k_run_population<5, 2, -1, 128, 2>));
+  else if (p->inst == 1) MEK_PREP((k_run_population<20, 5, -1, 128, 2>));
+  else MEK_PREP((k_run_population<32, 8, -1, 128, 2>));
+#undef MEK_PREP
   if (rc != MEK_OK) { return rc; }
   if (occ < 1) occ = 1;
   if (cfg->blocks_per_sm == 1) occ = 1;
@@ -903,12 +927,12 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 }
 
 static int launch_run(mek_pop* p, int k0, int k1) {
-  const int g = grid_for(p, p->P.d.B, p->threads);
-  if (p->inst == 0 && p->minb == 2) k_run_population<5, 2, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
-  else if (p->inst == 0 && p->minb == 3) k_run_population<5, 2, 3><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
-  else if (p->inst == 0) k_run_population<5, 2, 4><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
-  else if (p->inst == 1) k_run_population<20, 5, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
-  else k_run_population<32, 8, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, k0, k1);
+  const int g = grid_for(p, p->P.d.B, p->run_threads);
+  if (p->cons == 15) k_run_population<5, 2, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->cons == 11) k_run_population<5, 2, 11, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->inst == 0) k_run_population<5, 2, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->inst == 1) k_run_population<20, 5, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else k_run_population<32, 8, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   CUDA_TRY(cudaGetLastError());
   p->launches++;
   return MEK_OK;

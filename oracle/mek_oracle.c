@@ -725,7 +725,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
       } else {
         double hl = Mm[i * Nc] * v[0];
         for (int j = 1; j < Nc; ++j) hl = hl + Mm[i * Nc + j] * v[j];
-        w = -(((K[i] + hl) - Hd[i] * li) * rH[i]);
+        w = li - (K[i] + hl) * rH[i];                       /* == -(K + H(i,:)*lam - H_ii*lam_i)/H_ii */
       }
       const double nl = fmax(0.0, w);                              /* max(0,NaN) = 0 */
       const double dl = nl - li;
@@ -1012,6 +1012,7 @@ void mko_iter_ekf(const mko_bank *bk, const mko_config *cf, double *st, double v
   mats[q++] = e.Dv;
   for (int j = 0; j < 5; ++j) mats[q++] = e.Cphi[j];
   mats[q++] = e.Dphi; mats[q++] = e.bv; mats[q++] = e.bphi; mats[q++] = e.vhat; mats[q++] = e.soc;
+  mats[q++] = 0.0; /* reserved */
 }
 
 /* predMat for a scalar output (returns h[0..Np], Phi*x part) */

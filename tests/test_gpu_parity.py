@@ -9,10 +9,10 @@ from conftest import SCALE, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _run_both(bank, coracle_mod, pop, N, Np=5, Nc=2, constraints=(1, 1, 1), force_jacobi=False, chunks=None):
+def _run_both(bank, coracle_mod, pop, N, Np=5, Nc=2, constraints=(1, 1, 1), force_jacobi=False, chunks=None, generic_path=False):
     from mek import api
     rom = api.RomBank(bank)
-    cb = api.CellBatch(rom, len(pop), Np=Np, Nc=Nc, constraints=constraints, force_jacobi=force_jacobi)
+    cb = api.CellBatch(rom, len(pop), Np=Np, Nc=Nc, constraints=constraints, force_jacobi=force_jacobi, generic_path=generic_path)
     cb.set_logging(len(pop), N)
     cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
     if chunks is None:
@@ -87,4 +87,16 @@ def test_resume_in_chunks_matches_single_launch(bank, coracle_mod):
     from mek import population as P
     pop = P.make_population(bank.params[2], 96, seed=6)
     cb, g, co, c = _run_both(bank, coracle_mod, pop, 900, chunks=[(0, 1), (1, 300), (300, 900)])
+    _assert_bit_exact(g, c)
+
+
+def test_generic_instance_matches_too(bank, coracle_mod):
+    """The generic (runtime-shape, local-memory) instance of the fused kernel, and constraint sets without a fast instance."""
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 96, seed=8)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 1000, generic_path=True)
+    _assert_bit_exact(g, c)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 600, constraints=(0, 1, 1))
+    _assert_bit_exact(g, c)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 600, Np=7, Nc=3)
     _assert_bit_exact(g, c)

@@ -11,7 +11,7 @@ rom = api.RomBank(bank); cb = api.CellBatch(rom, Bn)
 cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
 co = coracle.COracle(bank); co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
 rng = np.random.default_rng(0)
-names = ['lost','iT','iZ'] + ['xhat%d'%i for i in range(6)] + ['a%d'%i for i in range(5)] + ['Cv%d'%i for i in range(5)] + ['Dv'] + ['Cphi%d'%i for i in range(5)] + ['Dphi','bv','bphi','vhat','soc']
+names = ['lost','iT','iZ'] + ['xhat%d'%i for i in range(6)] + ['a%d'%i for i in range(5)] + ['Cv%d'%i for i in range(5)] + ['Dv'] + ['Cphi%d'%i for i in range(5)] + ['Dphi','bv','bphi','vhat','soc','rsvd']
 nbad = 0
 for k in range(25):
     I = rng.uniform(-60, 5, Bn)
