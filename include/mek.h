@@ -73,9 +73,10 @@ typedef struct {
   double ref;               /* mpcData.ref = targetSOC (95, percent! Q9)              */
   double SigmaV, SigmaW;    /* runMPC.m:18-19                                         */
   int force_jacobi;         /* 1: always run the eigen-decomposition PSD repair       */
-  int threads_per_block;    /* 0 = default                                            */
+  int threads_per_block;    /* reserved (the fused kernels use a fixed CTA size)      */
   int blocks_per_sm;        /* 0 = from the occupancy calculator, 1 = one CTA per SM  */
   int generic_path;         /* 1: never use the static-shape fast instances           */
+  int sync_steps;           /* 1: CTA-wide barrier before every sample instant        */
 } mek_config;
 
 /* ---- bank ---- */

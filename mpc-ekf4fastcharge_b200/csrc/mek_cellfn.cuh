@@ -18,13 +18,13 @@ MEK_HD double soc_e(const double* p, int base, double z) {
   return p[base + E_THETA0] + z * (p[base + E_THETA100] - p[base + E_THETA0]);
 }
 // function.neg.Uocp / dUocp
-MEK_HD double uocp_n(const double* p, double th) {
+MEK_HDN double uocp_n(const double* p, double th) {
   const double* c = p + P_UN;
   const double x = (th - c[4]) / c[5];
   const double t = th + c[2];
   return (c[0] + c[1] / (t * t)) + c[3] * (1.0 - x / sqrt(1.0 + x * x));
 }
-MEK_HD double duocp_n(const double* p, double th) {
+MEK_HDN double duocp_n(const double* p, double th) {
   const double* c = p + P_UN;
   const double x = (th - c[4]) / c[5];
   const double q = 1.0 + x * x;
@@ -32,14 +32,14 @@ MEK_HD double duocp_n(const double* p, double th) {
   return (-2.0 * c[1]) / ((t * t) * t) - (c[3] / c[5]) / (q * sqrt(q));
 }
 // function.pos.Uocp / dUocp: Horner polynomial in x = (th - centre)/width
-MEK_HD double uocp_p(const double* p, double th) {
+MEK_HDN double uocp_p(const double* p, double th) {
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
   double acc = p[P_UP_COEF + nc - 1];
   for (int i = nc - 2; i >= 0; --i) acc = acc * x + p[P_UP_COEF + i];
   return acc;
 }
-MEK_HD double duocp_p(const double* p, double th) {
+MEK_HDN double duocp_p(const double* p, double th) {
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
   double acc = (double)(nc - 1) * p[P_UP_COEF + nc - 1];

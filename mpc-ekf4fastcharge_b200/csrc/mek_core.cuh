@@ -53,11 +53,27 @@ struct BankSmem {
 constexpr int TILE = 32;
 struct Cell {
   double* base;          // &st[tile][0][lane]
+  double *bx, *xh, *sg, *lm;   // first bigX / xhat / SigmaX / lambda field of this cell
   __device__ __forceinline__ double& f(int field) const { return base[field * TILE]; }
+  __device__ __forceinline__ double& bigx(int m, int j) const { return bx[(m * 6 + j) * TILE]; }
+  __device__ __forceinline__ double& xhat(int m, int j) const { return xh[(m * N5 + j) * TILE]; }
+  __device__ __forceinline__ double& sig(int m, int q) const { return sg[(m * NSYM + q) * TILE]; }
+  __device__ __forceinline__ double& lam(int i) const { return lm[i * TILE]; }
 };
-__device__ __forceinline__ Cell cell_ref(double* st, int nfields, long long cell) {
-  return Cell{st + (cell >> 5) * ((long long)nfields * TILE) + (cell & 31)};
+__device__ __forceinline__ Cell cell_ref(double* st, const Dims& d, long long cell) {
+  double* b = st + (cell >> 5) * ((long long)d.nfields * TILE) + (cell & 31);
+  return Cell{b, b + d.f_bigx * TILE, b + d.f_xhat * TILE, b + d.f_sig * TILE, b + d.f_lambda * TILE};
 }
+
+// Per-thread scratch column in shared memory ([slot][thread]: conflict-free).  Small arrays that are
+// indexed by a loop variable live here instead of in local memory, so the code can stay rolled
+// (the kernel must fit the instruction cache) without paying L1/L2 round trips.
+struct Scratch {
+  double* p;
+  int s;
+  __device__ __forceinline__ double& operator[](int i) const { return p[i * s]; }
+};
+enum : int { SC_GAMMA = 0, SC_M = 4, SC_IT = 8, SC_IZ = 12, SC_Z = 16, SC_TOTAL = SC_Z + HR_MAX };
 
 __device__ __forceinline__ int sym_idx(int i, int j) {
   // upper triangle, row-major: (0,0..4)=0..4, (1,1..4)=5..8, (2,2..4)=9..11, (3,3..4)=12,13, (4,4)=14
@@ -65,42 +81,37 @@ __device__ __forceinline__ int sym_idx(int i, int j) {
   return a * 5 - (a * (a - 1)) / 2 + (b - a);
 }
 
-// first two entries of a stable ascending sort of |v - pts| (OB_step.m:251,261; iterEKF.m:221,234)
-__device__ __forceinline__ void two_nearest(double v, const double* pts, int n, int& i1, int& i2) {
+// first two entries of a stable ascending sort of |v - pts| (OB_step.m:251,261; iterEKF.m:221,234); returns i1 | i2 << 16
+__device__ __noinline__ int two_nearest(double v, const double* pts, int n) {
   int a = 0;
   double best = fabs(v - pts[0]);
+#pragma unroll 1
   for (int i = 1; i < n; ++i) {
     const double d = fabs(v - pts[i]);
     if (d < best) { best = d; a = i; }
   }
   int b = -1;
   double best2 = 0.0;
+#pragma unroll 1
   for (int i = 0; i < n; ++i) {
     if (i == a) continue;
     const double d = fabs(v - pts[i]);
     if (b < 0 || d < best2) { best2 = d; b = i; }
   }
-  i1 = a;
-  i2 = (b < 0) ? a : b;
+  return a | (((b < 0) ? a : b) << 16);
 }
 
-struct Xind {          // iterEKF.m:249-254
-  double gamma[4];
-  int m[4];            // model column (iT*nZ+iZ) of the 4 neighbours
-  int iT[4], iZ[4];
-};
-
-// getXind (iterEKF.m:219-255): ordering by value with swap, alphas not clamped (Q14)
-__device__ __forceinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Xind& X) {
-  int z1, z2, t1, t2;
-  two_nearest(SOC, bk.Zpts, d.nZ, z1, z2);
+// getXind (iterEKF.m:219-255): ordering by value with swap, alphas not clamped (Q14).
+// Writes gamma[4], model column m[4] = iT*nZ+iZ, iT[4], iZ[4] into the scratch column.
+__device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc) {
+  const int zz = two_nearest(SOC, bk.Zpts, d.nZ), z1 = zz & 0xffff, z2 = zz >> 16;
   int iZup = z1, iZlo = z1;
   double Zup = bk.Zpts[z1], Zlo = bk.Zpts[z1];
   if (d.nZ > 1) {
     Zup = bk.Zpts[z1]; iZup = z1; Zlo = bk.Zpts[z2]; iZlo = z2;
     if (Zup < Zlo) { Zup = bk.Zpts[z2]; iZup = z2; Zlo = bk.Zpts[z1]; iZlo = z1; }
   }
-  two_nearest(Tk, bk.Tpts, d.nT, t1, t2);
+  const int tt = two_nearest(Tk, bk.Tpts, d.nT), t1 = tt & 0xffff, t2 = tt >> 16;
   int iTup = t1, iTlo = t1;
   double Tup = bk.Tpts[t1], Tlo = bk.Tpts[t1];
   if (d.nT > 1) {
@@ -110,16 +121,15 @@ __device__ __forceinline__ void get_xind(const Dims& d, const BankSmem& bk, doub
   double aZ = 0.0, aT = 0.0;
   if (d.nZ > 1) aZ = (SOC - Zlo) / (Zup - Zlo);
   if (d.nT > 1) aT = (Tk - Tlo) / (Tup - Tlo);
-  X.gamma[0] = (1.0 - aT) * (1.0 - aZ);
-  X.gamma[1] = (1.0 - aT) * aZ;
-  X.gamma[2] = aT * (1.0 - aZ);
-  X.gamma[3] = aT * aZ;
-  X.iT[0] = iTlo; X.iT[1] = iTlo; X.iT[2] = iTup; X.iT[3] = iTup;
-  X.iZ[0] = iZlo; X.iZ[1] = iZup; X.iZ[2] = iZlo; X.iZ[3] = iZup;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) X.m[k] = X.iT[k] * d.nZ + X.iZ[k];
+  sc[SC_GAMMA + 0] = (1.0 - aT) * (1.0 - aZ);
+  sc[SC_GAMMA + 1] = (1.0 - aT) * aZ;
+  sc[SC_GAMMA + 2] = aT * (1.0 - aZ);
+  sc[SC_GAMMA + 3] = aT * aZ;
+  sc[SC_IT + 0] = (double)iTlo; sc[SC_IT + 1] = (double)iTlo; sc[SC_IT + 2] = (double)iTup; sc[SC_IT + 3] = (double)iTup;
+  sc[SC_IZ + 0] = (double)iZlo; sc[SC_IZ + 1] = (double)iZup; sc[SC_IZ + 2] = (double)iZlo; sc[SC_IZ + 3] = (double)iZup;
+  sc[SC_M + 0] = (double)(iTlo * d.nZ + iZlo); sc[SC_M + 1] = (double)(iTlo * d.nZ + iZup);
+  sc[SC_M + 2] = (double)(iTup * d.nZ + iZlo); sc[SC_M + 3] = (double)(iTup * d.nZ + iZup);
 }
-
 
 // ------------------------------------------------------------------------------------------
 // One pass over all M local models: plant state advance bigX = bigA.*bigX + Iapp (OB_step.m:278)
@@ -127,7 +137,7 @@ __device__ __forceinline__ void get_xind(const Dims& d, const BankSmem& bk, doub
 // (iterEKF.m:73-84).  This is the HBM stream of the kernel: 26 doubles per model in and out.
 // Loads of two models are issued back to back before any store (the compiler may not move a load
 // across a store to the same array), with evict-first hints so the stream does not flush the
-// header fields and local arrays out of L1.
+// header fields out of L1.
 // ------------------------------------------------------------------------------------------
 template <bool PLANT, bool EKF>
 struct ModelRegs {
@@ -135,16 +145,19 @@ struct ModelRegs {
 };
 
 template <bool PLANT, bool EKF>
-__device__ __forceinline__ void model_load(const Dims& d, const Cell& c, int m, ModelRegs<PLANT, EKF>& r) {
+__device__ __forceinline__ void model_load(const Cell& c, int m, ModelRegs<PLANT, EKF>& r) {
   if (PLANT) {
+    const double* q = &c.bigx(m, 0);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) r.bx[j] = __ldcs(&c.f(d.f_bigx + m * 6 + j));
+    for (int j = 0; j < 6; ++j) r.bx[j] = __ldcs(q + j * TILE);
   }
   if (EKF) {
+    const double* q = &c.xhat(m, 0);
 #pragma unroll
-    for (int j = 0; j < N5; ++j) r.x[j] = __ldcs(&c.f(d.f_xhat + m * N5 + j));
+    for (int j = 0; j < N5; ++j) r.x[j] = __ldcs(q + j * TILE);
+    const double* w = &c.sig(m, 0);
 #pragma unroll
-    for (int q = 0; q < NSYM; ++q) r.s[q] = __ldcs(&c.f(d.f_sig + m * NSYM + q));
+    for (int k = 0; k < NSYM; ++k) r.s[k] = __ldcs(w + k * TILE);
   }
 }
 template <bool PLANT, bool EKF>
@@ -164,36 +177,40 @@ __device__ __forceinline__ void model_update(const double* a, double Iapp, doubl
   }
 }
 template <bool PLANT, bool EKF>
-__device__ __forceinline__ void model_store(const Dims& d, const Cell& c, int m, const ModelRegs<PLANT, EKF>& r) {
+__device__ __forceinline__ void model_store(const Cell& c, int m, const ModelRegs<PLANT, EKF>& r) {
   if (PLANT) {
+    double* q = &c.bigx(m, 0);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) __stcs(&c.f(d.f_bigx + m * 6 + j), r.bx[j]);
+    for (int j = 0; j < 6; ++j) __stcs(q + j * TILE, r.bx[j]);
   }
   if (EKF) {
+    double* q = &c.xhat(m, 0);
 #pragma unroll
-    for (int j = 0; j < N5; ++j) __stcs(&c.f(d.f_xhat + m * N5 + j), r.x[j]);
+    for (int j = 0; j < N5; ++j) __stcs(q + j * TILE, r.x[j]);
+    double* w = &c.sig(m, 0);
 #pragma unroll
-    for (int q = 0; q < NSYM; ++q) __stcs(&c.f(d.f_sig + m * NSYM + q), r.s[q]);
+    for (int k = 0; k < NSYM; ++k) __stcs(w + k * TILE, r.s[k]);
   }
 }
 template <bool PLANT, bool EKF>
 __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk, const Cell& c, double Iapp, double prior) {
   const double Sw = d.SigmaW;
   int m = 0;
+#pragma unroll 1
   for (; m + 1 < d.M; m += 2) {
     ModelRegs<PLANT, EKF> r0, r1;
-    model_load<PLANT, EKF>(d, c, m, r0);
-    model_load<PLANT, EKF>(d, c, m + 1, r1);
+    model_load<PLANT, EKF>(c, m, r0);
+    model_load<PLANT, EKF>(c, m + 1, r1);
     model_update<PLANT, EKF>(bk.mdl + m * d.mstride, Iapp, prior, Sw, r0);
     model_update<PLANT, EKF>(bk.mdl + (m + 1) * d.mstride, Iapp, prior, Sw, r1);
-    model_store<PLANT, EKF>(d, c, m, r0);
-    model_store<PLANT, EKF>(d, c, m + 1, r1);
+    model_store<PLANT, EKF>(c, m, r0);
+    model_store<PLANT, EKF>(c, m + 1, r1);
   }
   if (m < d.M) {
     ModelRegs<PLANT, EKF> r0;
-    model_load<PLANT, EKF>(d, c, m, r0);
+    model_load<PLANT, EKF>(c, m, r0);
     model_update<PLANT, EKF>(bk.mdl + m * d.mstride, Iapp, prior, Sw, r0);
-    model_store<PLANT, EKF>(d, c, m, r0);
+    model_store<PLANT, EKF>(c, m, r0);
   }
 }
 
@@ -222,37 +239,42 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   if (SOCp < 0.0) { SOCp = 0.0; ++nw; }
   if (SOCp > 1.0) { SOCp = 1.0; ++nw; }
   if (nw) c.f(S_PLANTWARN) += (double)nw;
-  int z1, z2, t1, t2;
-  two_nearest(cellSOC, bk.Zpts, d.nZ, z1, z2);                       // :251-259 (ordering by index, Q15)
+  const int zz = two_nearest(cellSOC, bk.Zpts, d.nZ), z1 = zz & 0xffff, z2 = zz >> 16;   // :251-259 (ordering by index, Q15)
   const int iZup = z1 > z2 ? z1 : z2, iZlo = z1 < z2 ? z1 : z2;
-  two_nearest(T, bk.Tpts, d.nT, t1, t2);                             // :261-269
+  const int tt = two_nearest(T, bk.Tpts, d.nT), t1 = tt & 0xffff, t2 = tt >> 16;         // :261-269
   const int iTup = t1 > t2 ? t1 : t2, iTlo = t1 < t2 ? t1 : t2;
   const double Zup = bk.Zpts[iZup], Zlo = bk.Zpts[iZlo], Tup = bk.Tpts[iTup], Tlo = bk.Tpts[iTlo];
-  const int mc[4] = {iTlo * d.nZ + iZlo, iTlo * d.nZ + iZup, iTup * d.nZ + iZlo, iTup * d.nZ + iZup};
-  double y[4][9];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {                                      // :272-275 four corner outputs
-    const double* mm = bk.mdl + mc[k] * d.mstride + 6;
-    double x[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) x[j] = c.f(d.f_bigx + mc[k] * 6 + j);
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      const double* cr = mm + r * 7;
-      double acc = cr[0] * x[0];
-#pragma unroll
-      for (int j = 1; j < 6; ++j) acc = acc + cr[j] * x[j];
-      y[k][r] = acc + cr[6] * Iapp;
-    }
-  }
-  if (ADVANCE) stream_models<true, false>(d, bk, c, Iapp, 0.0);         // :278 advance ALL models
   double aZ = 0.0, aT = 0.0;                                         // :281-283
   if (Zup != Zlo) aZ = (cellSOC - Zlo) / (Zup - Zlo);
   if (Tup != Tlo) aT = (T - Tlo) / (Tup - Tlo);
+  // four corner outputs (:272-275) blended as (1-aT)*((1-aZ)*y1 + aZ*y2) + aT*((1-aZ)*y3 + aZ*y4) (:285):
+  // one rolled pass per temperature set-point computes the inner SOC blend of its two corners
+  double tlo[9], tcur[9];
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int iT = h ? iTup : iTlo;
+    const int ma = iT * d.nZ + iZlo, mb = iT * d.nZ + iZup;
+    const double* ra = bk.mdl + ma * d.mstride + 6;
+    const double* rb = bk.mdl + mb * d.mstride + 6;
+    double xa[6], xb[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { xa[j] = c.bigx(ma, j); xb[j] = c.bigx(mb, j); }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const double* ca = ra + r * 7;
+      const double* cb = rb + r * 7;
+      double ya = ca[0] * xa[0], yb = cb[0] * xb[0];
+#pragma unroll
+      for (int j = 1; j < 6; ++j) { ya = ya + ca[j] * xa[j]; yb = yb + cb[j] * xb[j]; }
+      ya = ya + ca[6] * Iapp;
+      yb = yb + cb[6] * Iapp;
+      if (h == 0) tlo[r] = (1.0 - aZ) * ya + aZ * yb; else tcur[r] = (1.0 - aZ) * ya + aZ * yb;
+    }
+  }
+  if (ADVANCE) stream_models<true, false>(d, bk, c, Iapp, 0.0);         // :278 advance ALL models
   double yk[9];
 #pragma unroll
-  for (int r = 0; r < 9; ++r)                                        // :285
-    yk[r] = (1.0 - aT) * ((1.0 - aZ) * y[0][r] + aZ * y[1][r]) + aT * ((1.0 - aZ) * y[2][r] + aZ * y[3][r]);
+  for (int r = 0; r < 9; ++r) yk[r] = (1.0 - aT) * tlo[r] + aT * tcur[r];   // :285
   double tss0 = yk[HR_TSS0] + c.f(S_SOC0N), tss3 = yk[HR_TSS3] + c.f(S_SOC0P);   // :304-305 (Q6)
   tss0 = fmin(fmax(tss0, 1e-6), 1.0 - 1e-6);                         // :309-310
   tss3 = fmin(fmax(tss3, 1e-6), 1.0 - 1e-6);
@@ -275,96 +297,104 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
 // ------------------------------------------------------------------------------------------
 // EKF pieces
 // ------------------------------------------------------------------------------------------
-struct HotZ {            // corrected outputs the control path consumes (subset of Z / zk)
-  double If0, If3, Ifdl0, Ifdl3, tss0, tss3, the0, the3, phie;
-};
-
-// one blended linear output row r (iterEKF.m:302-313): Z = [C1*x1+D1*i, ...]*gamma
-__device__ __forceinline__ double blend_row(const Dims& d, const BankSmem& bk, const Xind& X, const double (*xk)[N5], double ik, int r) {
-  double yc[4];
+// getVariables (iterEKF.m:259-417) restricted to the rows that feed Vcell, the warnings and
+// EKFmatsHandler.  Reads the neighbour set from the scratch column (get_xind), leaves the corrected
+// outputs in sc[SC_Z + HR_*] and returns Vcell.  Warnings go straight to the cell's counters.
+__device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double ik,
+                                             double T, Scratch sc) {
+  double xk[4][N5], g[4];
+  const double* mm[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const double* cr = bk.mdl + X.m[k] * d.mstride + 6 + r * 7;
-    double acc = cr[0] * xk[k][0];
+    const int m = (int)sc[SC_M + k];
+    g[k] = sc[SC_GAMMA + k];
+    mm[k] = bk.mdl + m * d.mstride + 6;
 #pragma unroll
-    for (int j = 1; j < N5; ++j) acc = acc + cr[j] * xk[k][j];
-    yc[k] = acc + cr[6] * ik;
+    for (int j = 0; j < N5; ++j) xk[k][j] = c.xhat(m, j);            // :267-270
   }
-  return ((yc[0] * X.gamma[0] + yc[1] * X.gamma[1]) + yc[2] * X.gamma[2]) + yc[3] * X.gamma[3];
-}
-
-// getVariables (iterEKF.m:259-417) restricted to the rows that feed Vcell, the warnings and EKFmatsHandler
-__device__ __forceinline__ double get_variables(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
-                                                double ik, const Xind& X, double T, HotZ& z, int& nwarn, unsigned& status) {
-  double xk[4][N5];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int j = 0; j < N5; ++j) xk[k][j] = c.f(d.f_xhat + X.m[k] * N5 + j);   // :267-270
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
   const double xSOC = c.f(S_EKFSOC0) - c.f(S_X0) * rpa;              // :277
   double SOCn = soc_e(p, P_NEG, xSOC), SOCp = soc_e(p, P_POS, xSOC); // :282-283
+  int nwarn = 0;
+  unsigned status = 0u;
   if (SOCn < 0.0) { ++nwarn; SOCn = 1e-6; }                          // :284-295 (Q17)
   if (SOCn > 1.0) { ++nwarn; SOCn = 1.0 - 1e-6; }
   if (SOCp < 0.0) { ++nwarn; SOCp = 1e-6; }
   if (SOCp > 0.998) { ++nwarn; SOCp = 0.998; }
-  z.If0 = blend_row(d, bk, X, xk, ik, HR_IF0);                       // :324-325
-  z.If3 = blend_row(d, bk, X, xk, ik, HR_IF3);
-  z.Ifdl0 = blend_row(d, bk, X, xk, ik, HR_IFDL0);
-  z.Ifdl3 = blend_row(d, bk, X, xk, ik, HR_IFDL3);
+#pragma unroll 1
+  for (int r = 0; r < d.R; ++r) {                                    // :302-313  Z = [C1*x1+D1*i, ...]*gamma, hot rows only
+    if (r == HR_PHI) continue;
+    double yc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double* cr = mm[k] + r * 7;
+      double acc = cr[0] * xk[k][0];
+#pragma unroll
+      for (int j = 1; j < N5; ++j) acc = acc + cr[j] * xk[k][j];
+      yc[k] = acc + cr[6] * ik;
+    }
+    sc[SC_Z + r] = ((yc[0] * g[0] + yc[1] * g[1]) + yc[2] * g[2]) + yc[3] * g[3];
+  }
   // negThetass rows (:331-343): Thetass0 plus the extra rows, which only matter for the warnings
+  double tss0, tss3, the0, the3;
   {
-    double v = blend_row(d, bk, X, xk, ik, HR_TSS0) + SOCn;
+    double v = sc[SC_Z + HR_TSS0] + SOCn;
     bool lo = v < 0.0;
     if (lo) v = 1e-6;
     bool hi = v > 1.0;
     if (hi) v = 1.0 - 1e-6;
+#pragma unroll 1
     for (int e = 0; e < d.nx_negtss; ++e) {
-      double w = blend_row(d, bk, X, xk, ik, HR_FIXED + e) + SOCn;
+      double w = sc[SC_Z + HR_FIXED + e] + SOCn;
       if (w < 0.0) { lo = true; w = 1e-6; }
       if (w > 1.0) hi = true;
     }
     nwarn += (int)lo + (int)hi;
-    z.tss0 = v;
+    tss0 = v;
   }
   {                                                                  // posThetass rows (:345-357)
-    double v = blend_row(d, bk, X, xk, ik, HR_TSS3) + SOCp;
+    double v = sc[SC_Z + HR_TSS3] + SOCp;
     bool lo = v < 0.0;
     if (lo) v = 1e-6;
     bool hi = v > 0.998;
     if (hi) v = 0.998;
+#pragma unroll 1
     for (int e = 0; e < d.nx_postss; ++e) {
-      double w = blend_row(d, bk, X, xk, ik, HR_FIXED + d.nx_negtss + e) + SOCp;
+      double w = sc[SC_Z + HR_FIXED + d.nx_negtss + e] + SOCp;
       if (w < 0.0) { lo = true; w = 1e-6; }
       if (w > 0.998) hi = true;
     }
     nwarn += (int)lo + (int)hi;
-    z.tss3 = v;
+    tss3 = v;
   }
-  z.phie = blend_row(d, bk, X, xk, ik, HR_PHIE);                     // :371 PhieTilde3 (before the Phise0 shift)
   {                                                                  // Thetae rows (:383-389, Q18)
-    double v0 = blend_row(d, bk, X, xk, ik, HR_THE0) + 1.0;
-    double v3 = blend_row(d, bk, X, xk, ik, HR_THE3) + 1.0;
+    double v0 = sc[SC_Z + HR_THE0] + 1.0;
+    double v3 = sc[SC_Z + HR_THE3] + 1.0;
     bool lo = false;
     if (v0 < 0.0) { lo = true; v0 = 1e-6; }
     if (v3 < 0.0) { lo = true; v3 = 1e-6; }
+#pragma unroll 1
     for (int e = 0; e < d.nx_thetae; ++e) {
-      const double w = blend_row(d, bk, X, xk, ik, HR_FIXED + d.nx_negtss + d.nx_postss + e) + 1.0;
+      const double w = sc[SC_Z + HR_FIXED + d.nx_negtss + d.nx_postss + e] + 1.0;
       if (w < 0.0) lo = true;
     }
     if (lo) { ++nwarn; status |= ST_Q18; }
-    z.the0 = v0;
-    z.the3 = v3;
+    the0 = v0;
+    the3 = v3;
   }
+  sc[SC_Z + HR_TSS0] = tss0; sc[SC_Z + HR_TSS3] = tss3; sc[SC_Z + HR_THE0] = the0; sc[SC_Z + HR_THE3] = the3;
+  const double If0 = sc[SC_Z + HR_IF0], If3 = sc[SC_Z + HR_IF3];     // :324-325
   const double k0n = k0_e(p, P_NEG, SOCn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, SOCp, c.f(S_ARRK0P));   // :392-393
-  const double i0n = k0n * sqrt((z.the0 * (1.0 - z.tss0)) * z.tss0); // :395-398
-  const double i0p = k0p * sqrt((z.the3 * (1.0 - z.tss3)) * z.tss3);
+  const double i0n = k0n * sqrt((the0 * (1.0 - tss0)) * tss0);       // :395-398
+  const double i0p = k0p * sqrt((the3 * (1.0 - tss3)) * tss3);
   const double pref = ((2.0 * p[P_R]) * T) / p[P_F];
-  const double negEta0 = pref * asinh_d(z.If0 / (2.0 * i0n));        // :400-401
-  const double posEta3 = pref * asinh_d(z.If3 / (2.0 * i0p));
-  const double Un0 = uocp_n(p, z.tss0), Up3 = uocp_p(p, z.tss3);     // :404-407
+  const double negEta0 = pref * asinh_d(If0 / (2.0 * i0n));          // :400-401
+  const double posEta3 = pref * asinh_d(If3 / (2.0 * i0p));
+  const double Un0 = uocp_n(p, tss0), Up3 = uocp_p(p, tss3);         // :404-407
   const double Rfn = rf_e(p, P_NEG, SOCn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, SOCp, c.f(S_ARRRFP));
-  return ((((posEta3 - negEta0) + z.phie) + Up3) - Un0) + (Rfp * z.Ifdl3 - Rfn * z.Ifdl0);   // :409-410 (Q5: no Rc*i)
+  if (nwarn) c.f(S_WARN) += (double)nwarn;                           // shortWarn -> warnCount (:749)
+  if (status) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | status);
+  return ((((posEta3 - negEta0) + sc[SC_Z + HR_PHIE]) + Up3) - Un0) + (Rfp * sc[SC_Z + HR_IFDL3] - Rfn * sc[SC_Z + HR_IFDL0]);   // :409-410 (Q5)
 }
 
 // PSD repair (iterEKF.m:143-145) on the symmetric 15-entry storage.  If an LDL^T sweep finds every
@@ -430,7 +460,7 @@ __device__ __forceinline__ int psd_repair(double* S, int force) {
           pd = false;
         } else {
           dd[j] = dj;
-          const double idj = 1.0 / dj;
+          const double idj = rcp_d(dj);
 #pragma unroll
           for (int i = j + 1; i < 5; ++i) {
             double v = S[sym_idx(i, j)];
@@ -455,7 +485,7 @@ struct EkfOut {          // what EKFmatsHandler hands to the MPC (EKFmatsHandler
 // iterEKF (OB mode, iterEKF.m:55-210) followed by EKFmatsHandler (EKFmatsHandler.m:26-114)
 template <bool TIME_UPDATE>   // TIME_UPDATE=false: the caller already ran stream_models<...,true> with priorI
 __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double vk,
-                                         double ik, EkfOut& o, HotZ& zout) {
+                                         double ik, EkfOut& o, Scratch sc) {
   o.lost = 0;
   if (c.f(S_WARN) > 10.0) {                                          // iterEKF.m:55-59 (Q19)
     c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_LOST);
@@ -470,111 +500,98 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   c.f(S_X0) = x0;
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
   double SOC = c.f(S_EKFSOC0) - x0 * rpa;                            // :89
-  Xind X;
-  get_xind(d, bk, Tk, SOC, X);                                       // :107
-  HotZ z;
-  int nwarn = 0;
-  unsigned status = 0;
-  double vhat = get_variables(d, bk, p, c, ik, X, Tk, z, nwarn, status);   // :108
-  // ---- getChatV (:421-519) ----
-  double Chat[4][N5], C0;
+  get_xind(d, bk, Tk, SOC, sc);                                      // :107
+  double vhat = get_variables(d, bk, p, c, ik, Tk, sc);              // :108
+  // ---- getChatV scalars (:421-519) ----
+  const double tss0 = sc[SC_Z + HR_TSS0], tss3 = sc[SC_Z + HR_TSS3];
+  double Rfn, Rfp, Rctn, Rctp, dUn0, dUp3, C0;
   {
     const double xSOC = c.f(S_EKFSOC0) - x0 * rpa;                   // :438
     const double sn = soc_e(p, P_NEG, xSOC), sp = soc_e(p, P_POS, xSOC);
-    const double Rfn = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
+    Rfn = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)); Rfp = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
     const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
-    const double i0n = k0n * sqrt((z.the0 * (1.0 - z.tss0)) * z.tss0);
-    const double i0p = k0p * sqrt((z.the3 * (1.0 - z.tss3)) * z.tss3);
-    const double Rctn = (p[P_R] * Tk) / (p[P_F] * i0n), Rctp = (p[P_R] * Tk) / (p[P_F] * i0p);   // :467-468
-    const double dUn0 = duocp_n(p, z.tss0), dUp3 = duocp_p(p, z.tss3);   // :495-496
+    const double i0n = k0n * sqrt((sc[SC_Z + HR_THE0] * (1.0 - tss0)) * tss0);
+    const double i0p = k0p * sqrt((sc[SC_Z + HR_THE3] * (1.0 - tss3)) * tss3);
+    Rctn = (p[P_R] * Tk) / (p[P_F] * i0n); Rctp = (p[P_R] * Tk) / (p[P_F] * i0p);   // :467-468
+    dUn0 = duocp_n(p, tss0); dUp3 = duocp_p(p, tss3);                // :495-496
     const double dsn = soc_e(p, P_NEG, 1.0) - soc_e(p, P_NEG, 0.0), dsp = soc_e(p, P_POS, 1.0) - soc_e(p, P_POS, 0.0);
     const double res0n = (((-dUn0) * d.Ts) * dsn) / (3600.0 * p[P_Q]);   // :497-500
     const double res0p = (((-dUp3) * d.Ts) * dsp) / (3600.0 * p[P_Q]);
     C0 = res0p - res0n;                                              // :501
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double* mm = bk.mdl + X.m[k] * d.mstride + 6;
-      const double g = X.gamma[k];
-#pragma unroll
-      for (int j = 0; j < N5; ++j) {
-        double v = Rfp * (g * mm[HR_IFDL3 * 7 + j]) - Rfn * (g * mm[HR_IFDL0 * 7 + j]);    // :444
-        v = (v + Rctp * (g * mm[HR_IF3 * 7 + j])) - Rctn * (g * mm[HR_IF0 * 7 + j]);       // :471
-        v = v + g * mm[HR_PHIE * 7 + j];                                                    // :485
-        v = v + (dUp3 * (g * mm[HR_TSS3 * 7 + j]) - dUn0 * (g * mm[HR_TSS0 * 7 + j]));      // :504
-        Chat[k][j] = v;
-      }
-    }
-  }
-  // ---- gains from neighbour #1's SigmaX (:116-124, Q1) ----
-  double L[4][N5], svt[4];
-  {
-    double S1[NSYM];
-#pragma unroll
-    for (int q = 0; q < NSYM; ++q) S1[q] = c.f(d.f_sig + X.m[0] * NSYM + q);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      double v[N5];
-#pragma unroll
-      for (int i = 0; i < N5; ++i) {
-        double acc = S1[sym_idx(i, 0)] * Chat[k][0];
-#pragma unroll
-        for (int j = 1; j < N5; ++j) acc = acc + S1[sym_idx(i, j)] * Chat[k][j];
-        v[i] = acc;
-      }
-      double s = Chat[k][0] * v[0];
-#pragma unroll
-      for (int i = 1; i < N5; ++i) s = s + Chat[k][i] * v[i];
-      svt[k] = s + d.SigmaV;
-      const double isv = 1.0 / svt[k];
-#pragma unroll
-      for (int i = 0; i < N5; ++i) L[k][i] = v[i] * isv;
-    }
   }
   const double svt0 = (C0 * sx0) * C0 + d.SigmaV;                    // :123
   const double L0 = (sx0 * C0) / svt0;                               // :124
   const double resid = vk - vhat;                                    // :133
+  // SigmaX of neighbour #1 *before* any update: every gain uses it (:117, Q1)
+  double S1[NSYM];
+  {
+    const int m0 = (int)sc[SC_M + 0];
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) S1[q] = c.sig(m0, q);
+  }
   int njac = 0, nbump = 0;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {                                      // :116-121 gain, :136-154 update; sequential (Q2)
+    const int mo = (int)sc[SC_M + k];
+    const double g = sc[SC_GAMMA + k];
+    const double* mm = bk.mdl + mo * d.mstride + 6;
+    double Chat[N5], v[N5], L[N5], S[NSYM];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {                                      // :136-154 sequential (Q2)
-    double S[NSYM];
-    const int mo = X.m[k];
-#pragma unroll
-    for (int j = 0; j < N5; ++j) {
-      double& x = c.f(d.f_xhat + mo * N5 + j);
-      x = x + L[k][j] * resid;                                       // :138
+    for (int j = 0; j < N5; ++j) {                                   // getChatV for this neighbour
+      double t = Rfp * (g * mm[HR_IFDL3 * 7 + j]) - Rfn * (g * mm[HR_IFDL0 * 7 + j]);    // :444
+      t = (t + Rctp * (g * mm[HR_IF3 * 7 + j])) - Rctn * (g * mm[HR_IF0 * 7 + j]);       // :471
+      t = t + g * mm[HR_PHIE * 7 + j];                                                    // :485
+      t = t + (dUp3 * (g * mm[HR_TSS3 * 7 + j]) - dUn0 * (g * mm[HR_TSS0 * 7 + j]));      // :504
+      Chat[j] = t;
     }
 #pragma unroll
-    for (int q = 0; q < NSYM; ++q) S[q] = c.f(d.f_sig + mo * NSYM + q);
+    for (int i = 0; i < N5; ++i) {
+      double acc = S1[sym_idx(i, 0)] * Chat[0];
+#pragma unroll
+      for (int j = 1; j < N5; ++j) acc = acc + S1[sym_idx(i, j)] * Chat[j];
+      v[i] = acc;
+    }
+    double s = Chat[0] * v[0];
+#pragma unroll
+    for (int i = 1; i < N5; ++i) s = s + Chat[i] * v[i];
+    const double svt = s + d.SigmaV;                                 // :118
+    const double isv = rcp_d(svt);
+#pragma unroll
+    for (int i = 0; i < N5; ++i) L[i] = v[i] * isv;                  // :120
+#pragma unroll
+    for (int j = 0; j < N5; ++j) {
+      double& x = c.xhat(mo, j);
+      x = x + L[j] * resid;                                          // :138
+    }
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) S[q] = c.sig(mo, q);
     int q = 0;
 #pragma unroll
     for (int i = 0; i < N5; ++i)
 #pragma unroll
-      for (int j = i; j < N5; ++j, ++q) S[q] = S[q] - (L[k][i] * svt[k]) * L[k][j];   // :142
+      for (int j = i; j < N5; ++j, ++q) S[q] = S[q] - (L[i] * svt) * L[j];   // :142
     njac += psd_repair(S, d.force_jacobi);                           // :143-145
-    if (resid * resid > 9.0 * svt[k]) {                              // :148-151 Q-bump
+    if (resid * resid > 9.0 * svt) {                                 // :148-151 Q-bump
 #pragma unroll
       for (int q2 = 0; q2 < NSYM; ++q2) S[q2] = S[q2] * 2.0;
       ++nbump;
     }
 #pragma unroll
-    for (int q2 = 0; q2 < NSYM; ++q2) c.f(d.f_sig + mo * NSYM + q2) = S[q2];
+    for (int q2 = 0; q2 < NSYM; ++q2) c.sig(mo, q2) = S[q2];
   }
   x0 = x0 + L0 * resid;                                              // :155
   sx0 = sx0 - (L0 * svt0) * L0;                                      // :156
   c.f(S_X0) = x0;
   c.f(S_SIGX0) = sx0;
   SOC = c.f(S_EKFSOC0) - x0 * rpa;                                   // :159
-  get_xind(d, bk, Tk, SOC, X);                                       // :181
-  vhat = get_variables(d, bk, p, c, ik, X, Tk, z, nwarn, status);    // :182
+  get_xind(d, bk, Tk, SOC, sc);                                      // :181
+  vhat = get_variables(d, bk, p, c, ik, Tk, sc);                     // :182
   const double Zsoc = c.f(S_EKFSOC0) - x0 * rpa;                     // :416
   c.f(S_PRIORI) = ik;                                                // :210
-  if (nwarn) c.f(S_WARN) += (double)nwarn;
   if (njac) c.f(S_NJAC) += (double)njac;
   if (nbump) c.f(S_NBUMP) += (double)nbump;
-  if (status) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | status);
   o.vhat = vhat;
   o.soc = Zsoc;
-  zout = z;
   // ---- EKFmatsHandler ----
   int imax = 0;                                                      // EKFmatsHandler.m:26 first max, NaN ignored
   {
@@ -582,37 +599,35 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     double best = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const double g = X.gamma[k];
+      const double g = sc[SC_GAMMA + k];
       if (g != g) continue;
       if (!have || g > best) { best = g; imax = k; have = true; }
     }
   }
-  int mp = X.m[0];
-  o.iT = X.iT[0];
-  o.iZ = X.iZ[0];
-#pragma unroll
-  for (int k = 1; k < 4; ++k)
-    if (imax == k) { mp = X.m[k]; o.iT = X.iT[k]; o.iZ = X.iZ[k]; }
+  const int mp = (int)sc[SC_M + imax];
+  o.iT = (int)sc[SC_IT + imax];
+  o.iZ = (int)sc[SC_IZ + imax];
   const double* am = bk.mdl + mp * d.mstride;
 #pragma unroll
-  for (int j = 0; j < N5; ++j) { o.xhat[j] = c.f(d.f_xhat + mp * N5 + j); o.a[j] = am[j]; }   // :33-35
+  for (int j = 0; j < N5; ++j) { o.xhat[j] = c.xhat(mp, j); o.a[j] = am[j]; }   // :33-35
   o.xhat[5] = 0.0;                                                   // :33 (Q3)
   {
+    const double ztss0 = sc[SC_Z + HR_TSS0], ztss3 = sc[SC_Z + HR_TSS3];
     const double TK = c.f(S_TC) + 273.15;                            // :53
     const double sn = soc_e(p, P_NEG, Zsoc), sp = soc_e(p, P_POS, Zsoc);   // :56-58
     const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
-    const double i0n = k0n * sqrt((z.the0 * (1.0 - z.tss0)) * z.tss0);   // :63-66
-    const double i0p = k0p * sqrt((z.the3 * (1.0 - z.tss3)) * z.tss3);
-    const double Rfn = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
+    const double i0n = k0n * sqrt((sc[SC_Z + HR_THE0] * (1.0 - ztss0)) * ztss0);   // :63-66
+    const double i0p = k0p * sqrt((sc[SC_Z + HR_THE3] * (1.0 - ztss3)) * ztss3);
+    const double Rfn2 = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)), Rfp2 = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
     const double* mm = am + 6;
 #pragma unroll
     for (int j = 0; j < N5; ++j)                                     // :75-76
-      o.Cv[j] = (Rfp * mm[HR_IFDL3 * 7 + j] - Rfn * mm[HR_IFDL0 * 7 + j]) + mm[HR_PHIE * 7 + j];
-    o.Dv = (Rfp * mm[HR_IFDL3 * 7 + 6] - Rfn * mm[HR_IFDL0 * 7 + 6]) + mm[HR_PHIE * 7 + 6];   // :79-80
-    const double Upos = uocp_p(p, z.tss3), Uneg = uocp_n(p, z.tss0); // :84-85
+      o.Cv[j] = (Rfp2 * mm[HR_IFDL3 * 7 + j] - Rfn2 * mm[HR_IFDL0 * 7 + j]) + mm[HR_PHIE * 7 + j];
+    o.Dv = (Rfp2 * mm[HR_IFDL3 * 7 + 6] - Rfn2 * mm[HR_IFDL0 * 7 + 6]) + mm[HR_PHIE * 7 + 6];   // :79-80
+    const double Upos = uocp_p(p, ztss3), Uneg = uocp_n(p, ztss0);   // :84-85
     const double pref = ((2.0 * p[P_R]) * TK) / p[P_F];
-    const double negEta0 = pref * asinh_d(z.If0 / (2.0 * i0n));      // :88-89
-    const double posEta3 = pref * asinh_d(z.If3 / (2.0 * i0p));
+    const double negEta0 = pref * asinh_d(sc[SC_Z + HR_IF0] / (2.0 * i0n));   // :88-89
+    const double posEta3 = pref * asinh_d(sc[SC_Z + HR_IF3] / (2.0 * i0p));
     o.bv = ((Upos - Uneg) + (posEta3 - negEta0)) + 0.0;              // :92
     o.bphi = uocp_n(p, sn);                                          // :96 (Q21)
 #pragma unroll
@@ -667,7 +682,7 @@ __device__ __forceinline__ void spd_factor(int Nc, const double* E, double* LU) 
 #pragma unroll
   for (int k = 0; k < NCM; ++k)
     if (k < Nc) {
-      const double ip = 1.0 / LU[k * NCM + k];
+      const double ip = rcp_d(LU[k * NCM + k]);
       LU[k * NCM + k] = ip;
 #pragma unroll
       for (int i = k + 1; i < NCM; ++i)
@@ -729,7 +744,7 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
       for (int j = 1; j < NCM; ++j)
         if (j < Nc) { hd = hd + Mm[i * NCM + j] * P[i * NCM + j]; k = k + Mm[i * NCM + j] * x[j]; }
       Hd[i] = hd;                                                    // H(i,i)  hildreth.m:28
-      rH[i] = 1.0 / hd;                                              // the sweep multiplies by 1/H(i,i) (+Inf on a zero row)
+      rH[i] = rcp_d(hd);                                             // the sweep multiplies by 1/H(i,i) (+Inf on a zero row)
       K[i] = k + gam[i];                                             // K(i)    hildreth.m:29
       if (hd == 0.0) {
         zrow[i >> 6] |= 1ull << (i & 63);
@@ -955,12 +970,12 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
     const bool warm = c.f(S_LAMVALID) != 0.0;                        // Q11: [] -> zeros on first use
 #pragma unroll UNR
     for (int i = 0; i < nrows; ++i)
-      if (i < nC) lam[i] = warm ? c.f(d.f_lambda + i) : 0.0;
+      if (i < nC) lam[i] = warm ? c.lam(i) : 0.0;
     o.nexec = hildreth_core<NCM, NCONM>(Nc, nC, q.LU, q.F, q.Mm, q.gam, d.maxHild, lam, q.DU);   // iterMPC.m:67
 #pragma unroll UNR
     for (int i = 0; i < nrows; ++i)
       if (i < nC) {
-        c.f(d.f_lambda + i) = lam[i];                                // iterMPC.m:68
+        c.lam(i) = lam[i];                                // iterMPC.m:68
         if (lam[i] > 0.0) o.active[i >> 5] |= (1u << (i & 31));
       }
     c.f(S_LAMVALID) = 1.0;
@@ -1108,7 +1123,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     double lam[nC], v[NC];
     const bool warm = c.f(S_LAMVALID) != 0.0;                        // Q11
 #pragma unroll
-    for (int i = 0; i < nC; ++i) lam[i] = warm ? c.f(d.f_lambda + i) : 0.0;
+    for (int i = 0; i < nC; ++i) lam[i] = warm ? c.lam(i) : 0.0;
     spd_solve<NC>(NC, LU, F, x);                                     // E\F
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
@@ -1122,7 +1137,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 #pragma unroll
       for (int j = 1; j < NC; ++j) { hd = hd + Mm[i][j] * P[j]; k = k + Mm[i][j] * x[j]; }
       smt[(i * (2 + NC) + 0) * sms] = k + gam[i];                    // K(i)
-      smt[(i * (2 + NC) + 1) * sms] = 1.0 / hd;                      // 1/H(i,i)
+      smt[(i * (2 + NC) + 1) * sms] = rcp_d(hd);                    // 1/H(i,i)
 #pragma unroll
       for (int j = 0; j < NC; ++j) smt[(i * (2 + NC) + 2 + j) * sms] = P[j];
       if (hd == 0.0) {
@@ -1176,7 +1191,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     o.nexec = k;                                                     // iterMPC.m:67-69
 #pragma unroll
     for (int i = 0; i < nC; ++i) {
-      c.f(d.f_lambda + i) = lam[i];
+      c.lam(i) = lam[i];
       if (lam[i] > 0.0) o.active[i >> 5] |= (1u << (i & 31));
     }
     c.f(S_LAMVALID) = 1.0;

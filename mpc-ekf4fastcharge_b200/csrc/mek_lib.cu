@@ -216,6 +216,7 @@ struct Params {
   long long nlog; int log_steps;
   double* log_u; double* log_V; double* log_soc; double* log_phise;
   unsigned char* log_iT; unsigned char* log_iZ; unsigned short* log_nexec; unsigned* log_active; int log_words;
+  int sync_steps;             // 1: CTA-wide barrier before every sample instant
 };
 
 // ---- TMA bulk copy of the hot bank into shared memory ----
@@ -264,7 +265,7 @@ struct StepLog {
 };
 
 template <int NPM, int NCM, int CONS>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
-__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, int sms) {
+__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms) {
   const Dims& d = P.d;
   lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
 #pragma unroll
@@ -275,8 +276,7 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   // one HBM pass over the M local models: OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}
   stream_models<true, true>(d, bk, c, uk, c.f(S_PRIORI));
   EkfOut e;
-  HotZ z;
-  ekf_step<false>(d, bk, P.cp, c, V, uk, e, z);                      // runMPC.m:88,92
+  ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms});      // runMPC.m:88,92
   if (e.lost) return;
   MpcOut o;
   if constexpr (CONS >= 0) mpc_step_fast<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, smt, sms);   // runMPC.m:94-103
@@ -293,18 +293,25 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
   extern __shared__ __align__(16) double sm[];
   BankSmem bk;
   stage_bank(sm, P, bk);
-  double* smt = sm + P.blob_doubles + threadIdx.x;   // this thread's column of the per-thread shared arrays (fast path)
-  const int sms = blockDim.x;
+  double* smt = sm + P.blob_doubles + threadIdx.x;   // this thread's column of the per-thread shared arrays
+  constexpr int sms = THREADS;                       // launched with exactly THREADS threads per CTA
   const Dims& d = P.d;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c = cell_ref(P.st, d.nfields, cell);
+  const long long stride = (long long)gridDim.x * THREADS;
+  const long long first = (long long)blockIdx.x * THREADS;
+  // every thread of the CTA walks the same number of rounds so that the optional per-instant barrier is legal
+  for (long long base = first; base < d.B; base += stride) {
+    const long long cell = base + threadIdx.x;
+    const bool active = cell < d.B;
+    Cell c = cell_ref(P.st, d, active ? cell : 0);
     double sum_nexec = 0.0, n_qp = 0.0, n_cap = 0.0;
-    double min_phise = c.f(S_MIN_PHISE), max_V = c.f(S_MAX_V), t_reach = c.f(S_T_REACH);
-    const double ztarget = c.f(S_ZMAX) - 1e-3;
+    double min_phise = INFINITY, max_V = -INFINITY, t_reach = -1.0, ztarget = 0.0;
+    if (active) { min_phise = c.f(S_MIN_PHISE); max_V = c.f(S_MAX_V); t_reach = c.f(S_T_REACH); ztarget = c.f(S_ZMAX) - 1e-3; }
     StepLog lg;
     lg.soc = NAN; lg.V = NAN; lg.phise = NAN;
+#pragma unroll 1
     for (int k = k0; k < k1; ++k) {
+      if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
+      if (!active) continue;
       cell_step<NPM, NCM, CONS>(P, bk, c, lg, smt, sms);
       sum_nexec += (double)lg.nexec;
       if (lg.nexec > 0) n_qp += 1.0;
@@ -319,10 +326,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
         for (int w = 0; w < P.log_words; ++w) P.log_active[o * P.log_words + w] = lg.active[w];
       }
     }
-    c.f(S_SUM_NEXEC) += sum_nexec; c.f(S_N_QP) += n_qp; c.f(S_N_CAP) += n_cap;
-    c.f(S_MIN_PHISE) = min_phise; c.f(S_MAX_V) = max_V; c.f(S_T_REACH) = t_reach;
-    c.f(S_STEPS) += (double)(k1 - k0);
-    c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
+    if (active) {
+      c.f(S_SUM_NEXEC) += sum_nexec; c.f(S_N_QP) += n_qp; c.f(S_N_CAP) += n_cap;
+      c.f(S_MIN_PHISE) = min_phise; c.f(S_MAX_V) = max_V; c.f(S_T_REACH) = t_reach;
+      c.f(S_STEPS) += (double)(k1 - k0);
+      c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
+    }
   }
 }
 
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params
   const double* p = P.cp;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c = cell_ref(P.st, d.nfields, cell);
+    Cell c = cell_ref(P.st, d, cell);
     for (int f = 0; f < d.nfields; ++f) c.f(f) = 0.0;
     const double Tc = P.in_T[cell], z0 = P.in_soc0[cell] / 100.0;
     const double Tk1 = Tc + 273.15;
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(128) k_ob_step(const __grid_constant__ Params 
   stage_bank(sm, P, bk);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < P.d.B; cell += stride) {
-    Cell c = cell_ref(P.st, P.d.nfields, cell);
+    Cell c = cell_ref(P.st, P.d, cell);
     V[cell] = plant_step<true>(P.d, bk, P.cp, c, Iapp[cell]);
   }
 }
@@ -401,26 +410,28 @@ __device__ __forceinline__ void unpack_mats(const double* m, EkfOut& e) {
 }
 
 // full zk = [Z; vhat; SOC] (iterEKF.m:183) for the function-level entry: all nz rows from the full bank
-__device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, double ik, const HotZ& hz, double vhat, double soc,
-                        double* zk) {
+__device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, double ik, double vhat, double soc, double* zk) {
   const Dims& d = P.d;
   const double Tk = c.f(S_TC) + 273.15;
-  Xind X;
-  get_xind(d, bk, Tk, soc, X);                                       // iterEKF.m:181
-  double xk[4][N5];
-  for (int k = 0; k < 4; ++k)
-    for (int j = 0; j < N5; ++j) xk[k][j] = c.f(d.f_xhat + X.m[k] * N5 + j);
+  Scratch sc{const_cast<double*>(bk.Tpts) + P.blob_doubles + threadIdx.x, (int)blockDim.x};
+  get_xind(d, bk, Tk, soc, sc);                                      // iterEKF.m:181
+  double xk[4][N5], gam4[4];
+  int mk[4];
+  for (int k = 0; k < 4; ++k) {
+    mk[k] = (int)sc[SC_M + k];
+    gam4[k] = sc[SC_GAMMA + k];
+    for (int j = 0; j < N5; ++j) xk[k][j] = c.xhat(mk[k], j);
+  }
   for (int r = 0; r < d.nz; ++r) {                                   // iterEKF.m:302-313
     double yc[4];
     for (int k = 0; k < 4; ++k) {
-      const double* cr = P.Cfull + ((size_t)X.m[k] * d.nz + r) * 6;
+      const double* cr = P.Cfull + ((size_t)mk[k] * d.nz + r) * 6;
       double acc = cr[0] * xk[k][0];
       for (int j = 1; j < N5; ++j) acc = acc + cr[j] * xk[k][j];
-      yc[k] = acc + P.Dfull[(size_t)X.m[k] * d.nz + r] * ik;
+      yc[k] = acc + P.Dfull[(size_t)mk[k] * d.nz + r] * ik;
     }
-    zk[r] = ((yc[0] * X.gamma[0] + yc[1] * X.gamma[1]) + yc[2] * X.gamma[2]) + yc[3] * X.gamma[3];
+    zk[r] = ((yc[0] * gam4[0] + yc[1] * gam4[1]) + yc[2] * gam4[2]) + yc[3] * gam4[3];
   }
-  (void)hz;
   zk[d.nz] = vhat;
   zk[d.nz + 1] = soc;       // the per-kind corrections (iterEKF.m:331-413) follow in k_iter_ekf
 }
@@ -439,11 +450,10 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
   const double* p = P.cp;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c = cell_ref(P.st, d.nfields, cell);
+    Cell c = cell_ref(P.st, d, cell);
     EkfOut e;
-    HotZ hz;
     memset(&e, 0, sizeof(e));
-    ekf_step<true>(d, bk, p, c, vk[cell], ik[cell], e, hz);
+    ekf_step<true>(d, bk, p, c, vk[cell], ik[cell], e, Scratch{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x});
     if (mats) pack_mats(e, mats + cell * MEK_NMATS);
     if (zk) {
       double* z = zk + cell * (d.nz + 2);
@@ -451,7 +461,7 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
         for (int r = 0; r < d.nz + 2; ++r) z[r] = NAN;
         continue;
       }
-      full_zk(P, bk, c, ik[cell], hz, e.vhat, e.soc, z);
+      full_zk(P, bk, c, ik[cell], e.vhat, e.soc, z);
       // nonlinear corrections of getVariables on the full vector (iterEKF.m:331-413)
       const double rpa = d.Ts / (3600.0 * p[P_Q]);
       const double xSOC = c.f(S_EKFSOC0) - c.f(S_X0) * rpa;
@@ -493,7 +503,7 @@ __global__ void __launch_bounds__(128) k_iter_mpc(const __grid_constant__ Params
   const Dims& d = P.d;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c = cell_ref(P.st, d.nfields, cell);
+    Cell c = cell_ref(P.st, d, cell);
     EkfOut e;
     unpack_mats(mats + cell * MEK_NMATS, e);
     if (e.lost) {
@@ -598,7 +608,7 @@ __global__ void __launch_bounds__(256) k_summary(const __grid_constant__ Params 
   acc[MEK_STAT_MAX_V] = -INFINITY;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
-    Cell c = cell_ref(P.st, d.nfields, cell);
+    Cell c = cell_ref(P.st, d, cell);
     const unsigned st = (unsigned)c.f(S_STATUS);
     acc[MEK_STAT_CELLS] += 1.0;
     acc[MEK_STAT_CELLSTEPS] += c.f(S_STEPS);
@@ -669,7 +679,7 @@ struct mek_pop {
   const mek_bank* bank;
   mek_config cfg;
   int device, sms, threads, blocks;
-  size_t smem_bytes;
+  size_t smem_bytes, blob_bytes;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
   Params P;
@@ -786,15 +796,15 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   p->sms = prop.multiProcessorCount;
-  p->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 128;
-  if (p->threads > 128 || (p->threads & 31)) { delete p; return fail(MEK_ERR_ARG, "threads_per_block must be a multiple of 32, at most 128"); }
-  p->smem_bytes = bank->blob.size() * sizeof(double);
+  p->threads = 128;   // the fused kernels are compiled for a fixed CTA size (their shared-memory columns use it as a constant stride)
+  p->blob_bytes = bank->blob.size() * sizeof(double);
+  p->smem_bytes = p->blob_bytes + sizeof(double) * (size_t)SC_TOTAL * (size_t)p->threads;   // hot bank + per-thread scratch columns
   if (p->smem_bytes > 200 * 1024) { delete p; return fail(MEK_ERR_UNSUPPORTED, "hot bank does not fit in shared memory"); }
   CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&p->ev0));
   CUDA_TRY(cudaEventCreate(&p->ev1));
-  CUDA_TRY(cudaMalloc(&p->d_blob, p->smem_bytes));
-  CUDA_TRY(cudaMemcpy(p->d_blob, bank->blob.data(), p->smem_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&p->d_blob, p->blob_bytes));
+  CUDA_TRY(cudaMemcpy(p->d_blob, bank->blob.data(), p->blob_bytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&p->d_Cfull, bank->C.size() * sizeof(double)));
   CUDA_TRY(cudaMemcpy(p->d_Cfull, bank->C.data(), bank->C.size() * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&p->d_Dfull, bank->D.size() * sizeof(double)));
@@ -817,6 +827,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   p->P.nlog = 0;
   p->P.log_steps = 0;
   p->P.log_words = (d.nC + 31) / 32;
+  p->P.sync_steps = cfg->sync_steps;
   // opt in to the dynamic shared memory each kernel needs and size the persistent grid
   int rc = MEK_OK, occ = 0;
   rc |= prep_kernel(k_pop_init, p->smem_bytes);
@@ -832,7 +843,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
       p->cons = mask;
       p->run_threads = 256;
       const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
-      p->run_smem = p->smem_bytes + sizeof(double) * (size_t)slots * 256;
+      p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * 256;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
     }
   }
