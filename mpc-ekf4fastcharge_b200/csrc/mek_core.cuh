@@ -83,27 +83,22 @@ __device__ __forceinline__ int sym_idx(int i, int j) {
 
 // first two entries of a stable ascending sort of |v - pts| (OB_step.m:251,261; iterEKF.m:221,234); returns i1 | i2 << 16
 __device__ __noinline__ int two_nearest(double v, const double* pts, int n) {
-  int a = 0;
-  double best = fabs(v - pts[0]);
-#pragma unroll 1
-  for (int i = 1; i < n; ++i) {
-    const double d = fabs(v - pts[i]);
-    if (d < best) { best = d; a = i; }
-  }
-  int b = -1;
-  double best2 = 0.0;
+  int a = -1, b = -1;
+  double b1 = INFINITY, b2 = INFINITY;
 #pragma unroll 1
   for (int i = 0; i < n; ++i) {
-    if (i == a) continue;
     const double d = fabs(v - pts[i]);
-    if (b < 0 || d < best2) { best2 = d; b = i; }
+    if (d < b1) { b2 = b1; b = a; b1 = d; a = i; }
+    else if (d < b2) { b2 = d; b = i; }
   }
-  return a | (((b < 0) ? a : b) << 16);
+  if (a < 0) { a = 0; b = (n > 1) ? 1 : 0; }       // all distances NaN/Inf: the sort keeps the original order
+  if (b < 0) b = a;
+  return a | (b << 16);
 }
 
 // getXind (iterEKF.m:219-255): ordering by value with swap, alphas not clamped (Q14).
 // Writes gamma[4], model column m[4] = iT*nZ+iZ, iT[4], iZ[4] into the scratch column.
-__device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc) {
+__device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc, int tt_cached) {
   const int zz = two_nearest(SOC, bk.Zpts, d.nZ), z1 = zz & 0xffff, z2 = zz >> 16;
   int iZup = z1, iZlo = z1;
   double Zup = bk.Zpts[z1], Zlo = bk.Zpts[z1];
@@ -111,7 +106,7 @@ __device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double 
     Zup = bk.Zpts[z1]; iZup = z1; Zlo = bk.Zpts[z2]; iZlo = z2;
     if (Zup < Zlo) { Zup = bk.Zpts[z2]; iZup = z2; Zlo = bk.Zpts[z1]; iZlo = z1; }
   }
-  const int tt = two_nearest(Tk, bk.Tpts, d.nT), t1 = tt & 0xffff, t2 = tt >> 16;
+  const int tt = (tt_cached >= 0) ? tt_cached : two_nearest(Tk, bk.Tpts, d.nT), t1 = tt & 0xffff, t2 = tt >> 16;   // T is constant per cell
   int iTup = t1, iTlo = t1;
   double Tup = bk.Tpts[t1], Tlo = bk.Tpts[t1];
   if (d.nT > 1) {
@@ -219,7 +214,7 @@ __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk,
 // ------------------------------------------------------------------------------------------
 template <bool ADVANCE>   // ADVANCE=false: the caller runs stream_models<true,...> right after (fused pass)
 __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
-                                             double Iapp) {
+                                             double Iapp, int tt_cached) {
   const double T = c.f(S_TC) + 273.15;                               // OB_step.m:75
   const double th0n = p[P_NEG + E_THETA0], th100n = p[P_NEG + E_THETA100];
   const double th0p = p[P_POS + E_THETA0], th100p = p[P_POS + E_THETA100];
@@ -241,7 +236,7 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   if (nw) c.f(S_PLANTWARN) += (double)nw;
   const int zz = two_nearest(cellSOC, bk.Zpts, d.nZ), z1 = zz & 0xffff, z2 = zz >> 16;   // :251-259 (ordering by index, Q15)
   const int iZup = z1 > z2 ? z1 : z2, iZlo = z1 < z2 ? z1 : z2;
-  const int tt = two_nearest(T, bk.Tpts, d.nT), t1 = tt & 0xffff, t2 = tt >> 16;         // :261-269
+  const int tt = (tt_cached >= 0) ? tt_cached : two_nearest(T, bk.Tpts, d.nT), t1 = tt & 0xffff, t2 = tt >> 16;   // :261-269
   const int iTup = t1 > t2 ? t1 : t2, iTlo = t1 < t2 ? t1 : t2;
   const double Zup = bk.Zpts[iZup], Zlo = bk.Zpts[iZlo], Tup = bk.Tpts[iTup], Tlo = bk.Tpts[iTlo];
   double aZ = 0.0, aT = 0.0;                                         // :281-283
@@ -485,7 +480,7 @@ struct EkfOut {          // what EKFmatsHandler hands to the MPC (EKFmatsHandler
 // iterEKF (OB mode, iterEKF.m:55-210) followed by EKFmatsHandler (EKFmatsHandler.m:26-114)
 template <bool TIME_UPDATE>   // TIME_UPDATE=false: the caller already ran stream_models<...,true> with priorI
 __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double vk,
-                                         double ik, EkfOut& o, Scratch sc) {
+                                         double ik, EkfOut& o, Scratch sc, int tt_cached) {
   o.lost = 0;
   if (c.f(S_WARN) > 10.0) {                                          // iterEKF.m:55-59 (Q19)
     c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_LOST);
@@ -500,7 +495,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   c.f(S_X0) = x0;
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
   double SOC = c.f(S_EKFSOC0) - x0 * rpa;                            // :89
-  get_xind(d, bk, Tk, SOC, sc);                                      // :107
+  get_xind(d, bk, Tk, SOC, sc, tt_cached);                           // :107
   double vhat = get_variables(d, bk, p, c, ik, Tk, sc);              // :108
   // ---- getChatV scalars (:421-519) ----
   const double tss0 = sc[SC_Z + HR_TSS0], tss3 = sc[SC_Z + HR_TSS3];
@@ -584,7 +579,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   c.f(S_X0) = x0;
   c.f(S_SIGX0) = sx0;
   SOC = c.f(S_EKFSOC0) - x0 * rpa;                                   // :159
-  get_xind(d, bk, Tk, SOC, sc);                                      // :181
+  get_xind(d, bk, Tk, SOC, sc, tt_cached);                           // :181
   vhat = get_variables(d, bk, p, c, ik, Tk, sc);                     // :182
   const double Zsoc = c.f(S_EKFSOC0) - x0 * rpa;                     // :416
   c.f(S_PRIORI) = ik;                                                // :210
@@ -772,7 +767,7 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
             if (j < Nc) hl = hl + Mm[i * NCM + j] * v[j];
           w = li - (K[i] + hl) * rH[i];                               // == -(K + H(i,:)*lam - H_ii*lam_i)/H_ii
         }
-        const double nl = fmax(0.0, w);                              // max(0,NaN) = 0
+        const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
         const double dl = nl - li;
         if ((zrow[i >> 6] >> (i & 63)) & 1ull) {
           npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li));
@@ -1128,7 +1123,6 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
     unsigned zmask = 0u;
-    int npoison = 0;
 #pragma unroll
     for (int i = 0; i < nC; ++i) {
       double P[NC];
@@ -1142,37 +1136,36 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
       for (int j = 0; j < NC; ++j) smt[(i * (2 + NC) + 2 + j) * sms] = P[j];
       if (hd == 0.0) {
         zmask |= 1u << i;
-        if (!is_finite(lam[i])) ++npoison;
       } else {
 #pragma unroll
         for (int j = 0; j < NC; ++j) v[j] = v[j] + P[j] * lam[i];
       }
     }
+    // rows whose lambda is non-finite (only all-zero rows can get there): while any is set every row product is NaN
+    unsigned pmask = 0u;
+#pragma unroll
+    for (int i = 0; i < nC; ++i)
+      if (((zmask >> i) & 1u) && !is_finite(lam[i])) pmask |= 1u << i;
     int k = 1;
     for (; k <= d.maxHild; ++k) {                                    // hildreth.m:32
       bool notconv = false;
 #pragma unroll
-      for (int i = 0; i < nC; ++i) {                                 // hildreth.m:34-37
+      for (int i = 0; i < nC; ++i) {                                 // hildreth.m:34-37, branch-free
         const double li = lam[i];
-        double w;
-        if (npoison > 0) {
-          w = NAN;
-        } else {
-          double hl = Mm[i][0] * v[0];
+        double hl = Mm[i][0] * v[0];
 #pragma unroll
-          for (int j = 1; j < NC; ++j) hl = hl + Mm[i][j] * v[j];
-          w = li - (smt[(i * (2 + NC) + 0) * sms] + hl) * smt[(i * (2 + NC) + 1) * sms];
-        }
-        const double nl = fmax(0.0, w);
+        for (int j = 1; j < NC; ++j) hl = hl + Mm[i][j] * v[j];
+        double w = li - (smt[(i * (2 + NC) + 0) * sms] + hl) * smt[(i * (2 + NC) + 1) * sms];
+        w = (pmask != 0u) ? NAN : w;
+        const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
         const double dl = nl - li;
-        if ((zmask >> i) & 1u) {
-          npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li));
-        } else {
+        const bool zr = ((zmask >> i) & 1u) != 0u;
+        const double pd = zr ? 0.0 : dl;                             // an all-zero row never touches v
 #pragma unroll
-          for (int j = 0; j < NC; ++j) v[j] = v[j] + smt[(i * (2 + NC) + 2 + j) * sms] * dl;
-        }
+        for (int j = 0; j < NC; ++j) v[j] = v[j] + smt[(i * (2 + NC) + 2 + j) * sms] * pd;
+        pmask = (zr && !(nl <= kDblMax)) ? (pmask | (1u << i)) : (pmask & ~(1u << i));
         lam[i] = nl;
-        if (!(fabs(dl) < 1e-6)) notconv = true;
+        if (!(fabs(dl) < 1e-6)) notconv = true;                      // hildreth.m:39 norm(.,Inf) < 1e-6, NaN-propagating
       }
       if (!notconv) break;
     }

@@ -265,18 +265,18 @@ struct StepLog {
 };
 
 template <int NPM, int NCM, int CONS>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
-__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms) {
+__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms, int tt) {
   const Dims& d = P.d;
   lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) lg.active[w] = 0u;
   if ((unsigned)c.f(S_STATUS) & ST_LOST) return;                     // Q19: a lost cell idles
   const double uk = c.f(S_UK);
-  const double V = plant_step<false>(d, bk, P.cp, c, uk);            // runMPC.m:85 (outputs; the state advance is fused below)
+  const double V = plant_step<false>(d, bk, P.cp, c, uk, tt);        // runMPC.m:85 (outputs; the state advance is fused below)
   // one HBM pass over the M local models: OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}
   stream_models<true, true>(d, bk, c, uk, c.f(S_PRIORI));
   EkfOut e;
-  ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms});      // runMPC.m:88,92
+  ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms}, tt);  // runMPC.m:88,92
   if (e.lost) return;
   MpcOut o;
   if constexpr (CONS >= 0) mpc_step_fast<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, smt, sms);   // runMPC.m:94-103
@@ -308,11 +308,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
     if (active) { min_phise = c.f(S_MIN_PHISE); max_V = c.f(S_MAX_V); t_reach = c.f(S_T_REACH); ztarget = c.f(S_ZMAX) - 1e-3; }
     StepLog lg;
     lg.soc = NAN; lg.V = NAN; lg.phise = NAN;
+    // the cell temperature is constant over a run: its two nearest set-points are looked up once (same rule as every step)
+    const int tt = active ? two_nearest(c.f(S_TC) + 273.15, bk.Tpts, d.nT) : 0;
 #pragma unroll 1
     for (int k = k0; k < k1; ++k) {
       if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
       if (!active) continue;
-      cell_step<NPM, NCM, CONS>(P, bk, c, lg, smt, sms);
+      cell_step<NPM, NCM, CONS>(P, bk, c, lg, smt, sms, tt);
       sum_nexec += (double)lg.nexec;
       if (lg.nexec > 0) n_qp += 1.0;
       if (lg.nexec >= d.maxHild) n_cap += 1.0;
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params
     c.f(S_MIN_PHISE) = INFINITY;
     c.f(S_MAX_V) = -INFINITY;
     c.f(S_T_REACH) = -1.0;
-    plant_step<true>(d, bk, p, c, 0.0);                              // runMPC.m:74 (Q20)
+    plant_step<true>(d, bk, p, c, 0.0, -1);                          // runMPC.m:74 (Q20)
   }
 }
 
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(128) k_ob_step(const __grid_constant__ Params 
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < P.d.B; cell += stride) {
     Cell c = cell_ref(P.st, P.d, cell);
-    V[cell] = plant_step<true>(P.d, bk, P.cp, c, Iapp[cell]);
+    V[cell] = plant_step<true>(P.d, bk, P.cp, c, Iapp[cell], -1);
   }
 }
 
@@ -414,7 +416,7 @@ __device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, doub
   const Dims& d = P.d;
   const double Tk = c.f(S_TC) + 273.15;
   Scratch sc{const_cast<double*>(bk.Tpts) + P.blob_doubles + threadIdx.x, (int)blockDim.x};
-  get_xind(d, bk, Tk, soc, sc);                                      // iterEKF.m:181
+  get_xind(d, bk, Tk, soc, sc, -1);                                  // iterEKF.m:181
   double xk[4][N5], gam4[4];
   int mk[4];
   for (int k = 0; k < 4; ++k) {
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
     Cell c = cell_ref(P.st, d, cell);
     EkfOut e;
     memset(&e, 0, sizeof(e));
-    ekf_step<true>(d, bk, p, c, vk[cell], ik[cell], e, Scratch{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x});
+    ekf_step<true>(d, bk, p, c, vk[cell], ik[cell], e, Scratch{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x}, -1);
     if (mats) pack_mats(e, mats + cell * MEK_NMATS);
     if (zk) {
       double* z = zk + cell * (d.nz + 2);

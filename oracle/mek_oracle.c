@@ -212,22 +212,18 @@ static double arrhenius(const double *p, double T, double Ea) {
 /* index helpers                                                                              */
 /* ------------------------------------------------------------------------------------------ */
 static void two_nearest(double v, const double *pts, int n, int *i1, int *i2) {
-  /* first two entries of a stable ascending sort of |v - pts| (OB_step.m:251, iterEKF.m:221) */
-  int a = 0;
-  double best = fabs(v - pts[0]);
-  for (int i = 1; i < n; ++i) {
-    double d = fabs(v - pts[i]);
-    if (d < best) { best = d; a = i; }
-  }
-  int b = -1;
-  double best2 = 0.0;
+  /* first two entries of a stable ascending sort of |v - pts| (OB_step.m:251, iterEKF.m:221), one pass */
+  int a = -1, b = -1;
+  double b1 = INFINITY, b2 = INFINITY;
   for (int i = 0; i < n; ++i) {
-    if (i == a) continue;
-    double d = fabs(v - pts[i]);
-    if (b < 0 || d < best2) { best2 = d; b = i; }
+    const double d = fabs(v - pts[i]);
+    if (d < b1) { b2 = b1; b = a; b1 = d; a = i; }
+    else if (d < b2) { b2 = d; b = i; }
   }
+  if (a < 0) { a = 0; b = (n > 1) ? 1 : 0; }   /* all distances NaN: sort keeps the original order */
+  if (b < 0) b = a;
   *i1 = a;
-  *i2 = (b < 0) ? a : b;
+  *i2 = b;
 }
 
 static int sym_idx(int i, int j) { /* upper triangle, row-major, i <= j */
@@ -727,7 +723,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
         for (int j = 1; j < Nc; ++j) hl = hl + Mm[i * Nc + j] * v[j];
         w = li - (K[i] + hl) * rH[i];                       /* == -(K + H(i,:)*lam - H_ii*lam_i)/H_ii */
       }
-      const double nl = fmax(0.0, w);                              /* max(0,NaN) = 0 */
+      const double nl = (w > 0.0) ? w : 0.0;                       /* max(0,w); max(0,NaN) = 0 */
       const double dl = nl - li;
       if (Hd[i] == 0.0) {
         const int was = !(fabs(li) <= 1.79769313486231570815e308), is = !(fabs(nl) <= 1.79769313486231570815e308);
