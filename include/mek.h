@@ -76,7 +76,7 @@ typedef struct {
   int threads_per_block;    /* reserved (the fused kernels use a fixed CTA size)      */
   int blocks_per_sm;        /* 0 = from the occupancy calculator, 1 = one CTA per SM  */
   int generic_path;         /* 1: never use the static-shape fast instances           */
-  int sync_steps;           /* 1: CTA-wide barrier before every sample instant        */
+  int sync_steps;           /* CTA-wide barrier before every sample instant: 0/1 = on (default), -1 = off */
 } mek_config;
 
 /* ---- bank ---- */

@@ -187,12 +187,26 @@ __device__ __forceinline__ void model_store(const Cell& c, int m, const ModelReg
     for (int k = 0; k < NSYM; ++k) __stcs(w + k * TILE, r.s[k]);
   }
 }
+// L2 prefetch of the state rows of models [m, m+cnt) of this warp's tile: in the AoSoA layout each of the three
+// arrays is one contiguous run of 256-byte rows, so a single lane issues three bulk prefetches per request.
+__device__ __forceinline__ void prefetch_models(const Dims& d, const Cell& c, int m, int cnt, bool plant, bool ekf) {
+  if ((threadIdx.x & 31) != 0 || m >= d.M) return;
+  if (m + cnt > d.M) cnt = d.M - m;
+  if (plant) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(&c.bigx(m, 0)), "r"(cnt * 6 * TILE * 8) : "memory");
+  if (ekf) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(&c.xhat(m, 0)), "r"(cnt * N5 * TILE * 8) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(&c.sig(m, 0)), "r"(cnt * NSYM * TILE * 8) : "memory");
+  }
+}
+
 template <bool PLANT, bool EKF>
 __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk, const Cell& c, double Iapp, double prior) {
   const double Sw = d.SigmaW;
+  constexpr int PD = 6;                                               // prefetch distance in models
   int m = 0;
 #pragma unroll 1
   for (; m + 1 < d.M; m += 2) {
+    prefetch_models(d, c, m + PD, 2, PLANT, EKF);
     ModelRegs<PLANT, EKF> r0, r1;
     model_load<PLANT, EKF>(c, m, r0);
     model_load<PLANT, EKF>(c, m + 1, r1);

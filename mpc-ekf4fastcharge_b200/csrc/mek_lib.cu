@@ -272,6 +272,7 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   for (int w = 0; w < 4; ++w) lg.active[w] = 0u;
   if ((unsigned)c.f(S_STATUS) & ST_LOST) return;                     // Q19: a lost cell idles
   const double uk = c.f(S_UK);
+  prefetch_models(d, c, 0, 6, true, true);                           // first rows of this instant's HBM stream -> L2 while the plant outputs are computed
   const double V = plant_step<false>(d, bk, P.cp, c, uk, tt);        // runMPC.m:85 (outputs; the state advance is fused below)
   // one HBM pass over the M local models: OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}
   stream_models<true, true>(d, bk, c, uk, c.f(S_PRIORI));
@@ -829,7 +830,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   p->P.nlog = 0;
   p->P.log_steps = 0;
   p->P.log_words = (d.nC + 31) / 32;
-  p->P.sync_steps = cfg->sync_steps;
+  p->P.sync_steps = cfg->sync_steps >= 0 ? 1 : 0;   // default on: the barrier keeps a CTA's warps on the same code (I-cache sharing)
   // opt in to the dynamic shared memory each kernel needs and size the persistent grid
   int rc = MEK_OK, occ = 0;
   rc |= prep_kernel(k_pop_init, p->smem_bytes);
