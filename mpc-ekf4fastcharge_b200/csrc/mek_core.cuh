@@ -741,13 +741,33 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
 #pragma unroll
   for (int w = 0; w < (NCONM + 63) / 64; ++w) zrow[w] = 0ull;
   spd_solve<NCM>(Nc, LU, F, x);                                      // E\F
+  double Ei[NCM * NCM];                                              // inv(E), column by column: E\M' = inv(E)*M'
+#pragma unroll
+  for (int l = 0; l < NCM; ++l)
+    if (l < Nc) {
+      double el[NCM], col[NCM];
+#pragma unroll
+      for (int j = 0; j < NCM; ++j) el[j] = (j == l) ? 1.0 : 0.0;
+      spd_solve<NCM>(Nc, LU, el, col);
+#pragma unroll
+      for (int j = 0; j < NCM; ++j)
+        if (j < Nc) Ei[j * NCM + l] = col[j];
+    }
 #pragma unroll
   for (int j = 0; j < NCM; ++j) v[j] = 0.0;
   int npoison = 0;
 #pragma unroll UNR
   for (int i = 0; i < nrows; ++i)
     if (i < nC) {
-      spd_solve<NCM>(Nc, LU, Mm + i * NCM, P + i * NCM);             // column i of E\M'
+#pragma unroll
+      for (int j = 0; j < NCM; ++j)
+        if (j < Nc) {                                                // column i of E\M'
+          double acc = Ei[j * NCM] * Mm[i * NCM];
+#pragma unroll
+          for (int l = 1; l < NCM; ++l)
+            if (l < Nc) acc = acc + Ei[j * NCM + l] * Mm[i * NCM + l];
+          P[i * NCM + j] = acc;
+        }
       double hd = Mm[i * NCM] * P[i * NCM], k = Mm[i * NCM] * x[0];
 #pragma unroll
       for (int j = 1; j < NCM; ++j)
@@ -1009,7 +1029,7 @@ struct FastShape {
   static constexpr int O_E = O_V + (UV ? NP : 0);
   static constexpr int O_Z = O_E + (UE ? NP : 0);
   static constexpr int nC = O_Z + (UZ ? NP : 0);
-  static constexpr int SLOTS = nC * (2 + NC);                        // doubles of shared memory per thread
+  static constexpr int SLOTS = nC * 2;                               // doubles of shared memory per thread: K_i, 1/H_ii
 };
 
 template <int NP, int NC, int CONS>
@@ -1134,20 +1154,35 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 #pragma unroll
     for (int i = 0; i < nC; ++i) lam[i] = warm ? c.lam(i) : 0.0;
     spd_solve<NC>(NC, LU, F, x);                                     // E\F
+    double Ei[NC][NC];                                               // inv(E): column i of E\M' is recomputed as inv(E)*M(i,:)'
+#pragma unroll
+    for (int l = 0; l < NC; ++l) {
+      double el[NC], col[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) el[j] = (j == l) ? 1.0 : 0.0;
+      spd_solve<NC>(NC, LU, el, col);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) Ei[j][l] = col[j];
+    }
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
     unsigned zmask = 0u;
+    volatile double* vs = smt;                                       // re-read K, 1/H from shared memory (keeps them out of registers)
 #pragma unroll
     for (int i = 0; i < nC; ++i) {
       double P[NC];
-      spd_solve<NC>(NC, LU, Mm[i], P);                               // column i of E\M'
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        double acc = Ei[j][0] * Mm[i][0];
+#pragma unroll
+        for (int l = 1; l < NC; ++l) acc = acc + Ei[j][l] * Mm[i][l];
+        P[j] = acc;
+      }
       double hd = Mm[i][0] * P[0], k = Mm[i][0] * x[0];
 #pragma unroll
       for (int j = 1; j < NC; ++j) { hd = hd + Mm[i][j] * P[j]; k = k + Mm[i][j] * x[j]; }
-      smt[(i * (2 + NC) + 0) * sms] = k + gam[i];                    // K(i)
-      smt[(i * (2 + NC) + 1) * sms] = rcp_d(hd);                    // 1/H(i,i)
-#pragma unroll
-      for (int j = 0; j < NC; ++j) smt[(i * (2 + NC) + 2 + j) * sms] = P[j];
+      vs[(i * 2 + 0) * sms] = k + gam[i];                            // K(i)
+      vs[(i * 2 + 1) * sms] = rcp_d(hd);                             // 1/H(i,i)
       if (hd == 0.0) {
         zmask |= 1u << i;
       } else {
@@ -1169,14 +1204,19 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
         double hl = Mm[i][0] * v[0];
 #pragma unroll
         for (int j = 1; j < NC; ++j) hl = hl + Mm[i][j] * v[j];
-        double w = li - (smt[(i * (2 + NC) + 0) * sms] + hl) * smt[(i * (2 + NC) + 1) * sms];
+        double w = li - (vs[(i * 2 + 0) * sms] + hl) * vs[(i * 2 + 1) * sms];
         w = (pmask != 0u) ? NAN : w;
         const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
         const double dl = nl - li;
         const bool zr = ((zmask >> i) & 1u) != 0u;
         const double pd = zr ? 0.0 : dl;                             // an all-zero row never touches v
 #pragma unroll
-        for (int j = 0; j < NC; ++j) v[j] = v[j] + smt[(i * (2 + NC) + 2 + j) * sms] * pd;
+        for (int j = 0; j < NC; ++j) {
+          double acc = Ei[j][0] * Mm[i][0];
+#pragma unroll
+          for (int l = 1; l < NC; ++l) acc = acc + Ei[j][l] * Mm[i][l];
+          v[j] = v[j] + acc * pd;
+        }
         pmask = (zr && !(nl <= kDblMax)) ? (pmask | (1u << i)) : (pmask & ~(1u << i));
         lam[i] = nl;
         if (!(fabs(dl) < 1e-6)) notconv = true;                      // hildreth.m:39 norm(.,Inf) < 1e-6, NaN-propagating

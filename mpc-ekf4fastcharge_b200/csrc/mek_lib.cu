@@ -844,9 +844,9 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     const int mask = (d.useCurrent ? 1 : 0) | (d.useVoltage ? 2 : 0) | (d.useEta ? 4 : 0) | (d.useZmax ? 8 : 0);
     if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path) {
       p->cons = mask;
-      p->run_threads = 256;
+      p->run_threads = (cfg->threads_per_block == 512) ? 512 : 256;
       const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
-      p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * 256;
+      p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
     }
   }
@@ -855,7 +855,9 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     rc |= prep_kernel(KERN, p->run_smem);                                                                       \
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, p->run_threads, p->run_smem));           \
   } while (0)
-  if (p->cons == 15) MEK_PREP((k_run_population<5, 2, 15, 256, 1>));
+  if (p->cons == 15 && p->run_threads == 512) MEK_PREP((k_run_population<5, 2, 15, 512, 1>));
+  else if (p->cons == 11 && p->run_threads == 512) MEK_PREP((k_run_population<5, 2, 11, 512, 1>));
+  else if (p->cons == 15) MEK_PREP((k_run_population<5, 2, 15, 256, 1>));
   else if (p->cons == 11) MEK_PREP((k_run_population<5, 2, 11, 256, 1>));
   else if (p->inst == 0) MEK_PREP((k_run_population<5, 2, -1, 128, 2>));
   else if (p->inst == 1) MEK_PREP((k_run_population<20, 5, -1, 128, 2>));
@@ -942,7 +944,9 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 
 static int launch_run(mek_pop* p, int k0, int k1) {
   const int g = grid_for(p, p->P.d.B, p->run_threads);
-  if (p->cons == 15) k_run_population<5, 2, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  if (p->cons == 15 && p->run_threads == 512) k_run_population<5, 2, 15, 512, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->cons == 11 && p->run_threads == 512) k_run_population<5, 2, 11, 512, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->cons == 15) k_run_population<5, 2, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->cons == 11) k_run_population<5, 2, 11, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->inst == 0) k_run_population<5, 2, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->inst == 1) k_run_population<20, 5, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);

@@ -691,12 +691,22 @@ static void spd_solve(int Nc, const double *LU, const double *b, double *x) {
    row product is NaN exactly as 0*Inf makes it in the dense form ("poison").              */
 int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double *Mm, const double *gam,
                  const double *lam0, int maxIter, double *DU, double *lam, int *nexec) {
-  double LU[NC_MAX * NC_MAX], P[NCON_MAX][NC_MAX], K[NCON_MAX], Hd[NCON_MAX], rH[NCON_MAX], v[NC_MAX], x[NC_MAX];
+  double LU[NC_MAX * NC_MAX], Ei[NC_MAX][NC_MAX], P[NCON_MAX][NC_MAX], K[NCON_MAX], Hd[NCON_MAX], rH[NCON_MAX], v[NC_MAX], x[NC_MAX];
   if (Nc > NC_MAX || nC > NCON_MAX) return -1;
   spd_factor(Nc, E, LU);
   spd_solve(Nc, LU, F, x);                                         /* E\F */
+  for (int l = 0; l < Nc; ++l) {                                   /* inv(E), column by column: E\M' = inv(E)*M' */
+    double el[NC_MAX], col[NC_MAX];
+    for (int j = 0; j < Nc; ++j) el[j] = (j == l) ? 1.0 : 0.0;
+    spd_solve(Nc, LU, el, col);
+    for (int j = 0; j < Nc; ++j) Ei[j][l] = col[j];
+  }
   for (int i = 0; i < nC; ++i) {
-    spd_solve(Nc, LU, Mm + i * Nc, P[i]);                          /* column i of E\M' */
+    for (int j = 0; j < Nc; ++j) {                                 /* column i of E\M' */
+      double acc = Ei[j][0] * Mm[i * Nc];
+      for (int l = 1; l < Nc; ++l) acc = acc + Ei[j][l] * Mm[i * Nc + l];
+      P[i][j] = acc;
+    }
     double hd = Mm[i * Nc] * P[i][0], k = Mm[i * Nc] * x[0];
     for (int j = 1; j < Nc; ++j) { hd = hd + Mm[i * Nc + j] * P[i][j]; k = k + Mm[i * Nc + j] * x[j]; }
     Hd[i] = hd;                                                    /* H(i,i)  (:28) */
