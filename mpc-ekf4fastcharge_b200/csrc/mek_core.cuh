@@ -199,13 +199,13 @@ __device__ __forceinline__ void prefetch_models(const Dims& d, const Cell& c, in
   }
 }
 
-template <bool PLANT, bool EKF>
+template <bool PLANT, bool EKF, int BATCH = 2>   // BATCH models' loads in flight per thread before the first store
 __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk, const Cell& c, double Iapp, double prior) {
   const double Sw = d.SigmaW;
   constexpr int PD = 6;                                               // prefetch distance in models
   int m = 0;
 #pragma unroll 1
-  for (; m + 1 < d.M; m += 2) {
+  for (; BATCH == 2 && m + 1 < d.M; m += 2) {
     prefetch_models(d, c, m + PD, 2, PLANT, EKF);
     ModelRegs<PLANT, EKF> r0, r1;
     model_load<PLANT, EKF>(c, m, r0);
@@ -215,7 +215,9 @@ __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk,
     model_store<PLANT, EKF>(c, m, r0);
     model_store<PLANT, EKF>(c, m + 1, r1);
   }
-  if (m < d.M) {
+#pragma unroll 1
+  for (; m < d.M; ++m) {
+    if (BATCH == 1) prefetch_models(d, c, m + PD, 1, PLANT, EKF);
     ModelRegs<PLANT, EKF> r0;
     model_load<PLANT, EKF>(c, m, r0);
     model_update<PLANT, EKF>(bk.mdl + m * d.mstride, Iapp, prior, Sw, r0);

@@ -264,7 +264,7 @@ struct StepLog {
   unsigned active[4];
 };
 
-template <int NPM, int NCM, int CONS>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
+template <int NPM, int NCM, int CONS, int BATCH>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
 __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms, int tt) {
   const Dims& d = P.d;
   lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
@@ -275,7 +275,7 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   prefetch_models(d, c, 0, 6, true, true);                           // first rows of this instant's HBM stream -> L2 while the plant outputs are computed
   const double V = plant_step<false>(d, bk, P.cp, c, uk, tt);        // runMPC.m:85 (outputs; the state advance is fused below)
   // one HBM pass over the M local models: OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}
-  stream_models<true, true>(d, bk, c, uk, c.f(S_PRIORI));
+  stream_models<true, true, BATCH>(d, bk, c, uk, c.f(S_PRIORI));
   EkfOut e;
   ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms}, tt);  // runMPC.m:88,92
   if (e.lost) return;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
     for (int k = k0; k < k1; ++k) {
       if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
       if (!active) continue;
-      cell_step<NPM, NCM, CONS>(P, bk, c, lg, smt, sms, tt);
+      cell_step<NPM, NCM, CONS, 2>(P, bk, c, lg, smt, sms, tt);
       sum_nexec += (double)lg.nexec;
       if (lg.nexec > 0) n_qp += 1.0;
       if (lg.nexec >= d.maxHild) n_cap += 1.0;
@@ -844,7 +844,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     const int mask = (d.useCurrent ? 1 : 0) | (d.useVoltage ? 2 : 0) | (d.useEta ? 4 : 0) | (d.useZmax ? 8 : 0);
     if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path) {
       p->cons = mask;
-      p->run_threads = (cfg->threads_per_block == 512) ? 512 : 256;
+      p->run_threads = (cfg->threads_per_block == 256) ? 256 : 384;
       const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
       p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
@@ -855,8 +855,8 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     rc |= prep_kernel(KERN, p->run_smem);                                                                       \
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, p->run_threads, p->run_smem));           \
   } while (0)
-  if (p->cons == 15 && p->run_threads == 512) MEK_PREP((k_run_population<5, 2, 15, 512, 1>));
-  else if (p->cons == 11 && p->run_threads == 512) MEK_PREP((k_run_population<5, 2, 11, 512, 1>));
+  if (p->cons == 15 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 15, 384, 1>));
+  else if (p->cons == 11 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 11, 384, 1>));
   else if (p->cons == 15) MEK_PREP((k_run_population<5, 2, 15, 256, 1>));
   else if (p->cons == 11) MEK_PREP((k_run_population<5, 2, 11, 256, 1>));
   else if (p->inst == 0) MEK_PREP((k_run_population<5, 2, -1, 128, 2>));
@@ -944,8 +944,8 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 
 static int launch_run(mek_pop* p, int k0, int k1) {
   const int g = grid_for(p, p->P.d.B, p->run_threads);
-  if (p->cons == 15 && p->run_threads == 512) k_run_population<5, 2, 15, 512, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->cons == 11 && p->run_threads == 512) k_run_population<5, 2, 11, 512, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  if (p->cons == 15 && p->run_threads == 384) k_run_population<5, 2, 15, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->cons == 11 && p->run_threads == 384) k_run_population<5, 2, 11, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->cons == 15) k_run_population<5, 2, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->cons == 11) k_run_population<5, 2, 11, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->inst == 0) k_run_population<5, 2, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
