@@ -36,14 +36,14 @@ MEK_HDN double uocp_p(const double* p, double th) {
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
   double acc = p[P_UP_COEF + nc - 1];
-  for (int i = nc - 2; i >= 0; --i) acc = acc * x + p[P_UP_COEF + i];
+  for (int i = nc - 2; i >= 0; --i) acc = fma(acc, x, p[P_UP_COEF + i]);
   return acc;
 }
 MEK_HDN double duocp_p(const double* p, double th) {
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
   double acc = (double)(nc - 1) * p[P_UP_COEF + nc - 1];
-  for (int i = nc - 2; i >= 1; --i) acc = acc * x + (double)i * p[P_UP_COEF + i];
+  for (int i = nc - 2; i >= 1; --i) acc = fma(acc, x, (double)i * p[P_UP_COEF + i]);
   return acc / p[P_UP + 1];
 }
 // function.{neg,pos}.k0(theta,T), .Rf(theta,T): Arrhenius factor hoisted (T is constant per cell)

@@ -159,16 +159,16 @@ template <bool PLANT, bool EKF>
 __device__ __forceinline__ void model_update(const double* a, double Iapp, double prior, double Sw, ModelRegs<PLANT, EKF>& r) {
   if (PLANT) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) r.bx[j] = a[j] * r.bx[j] + Iapp;                  // OB_step.m:278
+    for (int j = 0; j < 6; ++j) r.bx[j] = fma(a[j], r.bx[j], Iapp);               // OB_step.m:278
   }
   if (EKF) {
 #pragma unroll
-    for (int j = 0; j < N5; ++j) r.x[j] = a[j] * r.x[j] + prior;                 // iterEKF.m:77
+    for (int j = 0; j < N5; ++j) r.x[j] = fma(a[j], r.x[j], prior);              // iterEKF.m:77
     int q = 0;
 #pragma unroll
     for (int i = 0; i < N5; ++i)
 #pragma unroll
-      for (int j = i; j < N5; ++j, ++q) r.s[q] = (a[i] * r.s[q]) * a[j] + Sw;    // iterEKF.m:81 (Q12)
+      for (int j = i; j < N5; ++j, ++q) r.s[q] = fma(a[i] * r.s[q], a[j], Sw);   // iterEKF.m:81 (Q12)
   }
 }
 template <bool PLANT, bool EKF>
@@ -276,9 +276,9 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
       const double* cb = rb + r * 7;
       double ya = ca[0] * xa[0], yb = cb[0] * xb[0];
 #pragma unroll
-      for (int j = 1; j < 6; ++j) { ya = ya + ca[j] * xa[j]; yb = yb + cb[j] * xb[j]; }
-      ya = ya + ca[6] * Iapp;
-      yb = yb + cb[6] * Iapp;
+      for (int j = 1; j < 6; ++j) { ya = fma(ca[j], xa[j], ya); yb = fma(cb[j], xb[j], yb); }
+      ya = fma(ca[6], Iapp, ya);
+      yb = fma(cb[6], Iapp, yb);
       if (h == 0) tlo[r] = (1.0 - aZ) * ya + aZ * yb; else tcur[r] = (1.0 - aZ) * ya + aZ * yb;
     }
   }
@@ -341,10 +341,10 @@ __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, 
       const double* cr = mm[k] + r * 7;
       double acc = cr[0] * xk[k][0];
 #pragma unroll
-      for (int j = 1; j < N5; ++j) acc = acc + cr[j] * xk[k][j];
-      yc[k] = acc + cr[6] * ik;
+      for (int j = 1; j < N5; ++j) acc = fma(cr[j], xk[k][j], acc);
+      yc[k] = fma(cr[6], ik, acc);
     }
-    sc[SC_Z + r] = ((yc[0] * g[0] + yc[1] * g[1]) + yc[2] * g[2]) + yc[3] * g[3];
+    sc[SC_Z + r] = fma(yc[3], g[3], fma(yc[2], g[2], fma(yc[1], g[1], yc[0] * g[0])));
   }
   // negThetass rows (:331-343): Thetass0 plus the extra rows, which only matter for the warnings
   double tss0, tss3, the0, the3;
@@ -466,7 +466,7 @@ __device__ __forceinline__ int psd_repair(double* S, int force) {
       if (pd) {
         double dj = S[sym_idx(j, j)];
 #pragma unroll
-        for (int k = 0; k < j; ++k) dj = dj - (L[j][k] * L[j][k]) * dd[k];
+        for (int k = 0; k < j; ++k) dj = fma(-(L[j][k] * L[j][k]), dd[k], dj);
         if (!(dj > 0.0)) {
           pd = false;
         } else {
@@ -476,7 +476,7 @@ __device__ __forceinline__ int psd_repair(double* S, int force) {
           for (int i = j + 1; i < 5; ++i) {
             double v = S[sym_idx(i, j)];
 #pragma unroll
-            for (int k = 0; k < j; ++k) v = v - (L[i][k] * L[j][k]) * dd[k];
+            for (int k = 0; k < j; ++k) v = fma(-(L[i][k] * L[j][k]), dd[k], v);
             L[i][j] = v * idj;
           }
         }
@@ -559,12 +559,12 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     for (int i = 0; i < N5; ++i) {
       double acc = S1[sym_idx(i, 0)] * Chat[0];
 #pragma unroll
-      for (int j = 1; j < N5; ++j) acc = acc + S1[sym_idx(i, j)] * Chat[j];
+      for (int j = 1; j < N5; ++j) acc = fma(S1[sym_idx(i, j)], Chat[j], acc);
       v[i] = acc;
     }
     double s = Chat[0] * v[0];
 #pragma unroll
-    for (int i = 1; i < N5; ++i) s = s + Chat[i] * v[i];
+    for (int i = 1; i < N5; ++i) s = fma(Chat[i], v[i], s);
     const double svt = s + d.SigmaV;                                 // :118
     const double isv = rcp_d(svt);
 #pragma unroll
@@ -572,7 +572,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
 #pragma unroll
     for (int j = 0; j < N5; ++j) {
       double& x = c.xhat(mo, j);
-      x = x + L[j] * resid;                                          // :138
+      x = fma(L[j], resid, x);                                       // :138
     }
 #pragma unroll
     for (int q = 0; q < NSYM; ++q) S[q] = c.sig(mo, q);
@@ -580,7 +580,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
 #pragma unroll
     for (int i = 0; i < N5; ++i)
 #pragma unroll
-      for (int j = i; j < N5; ++j, ++q) S[q] = S[q] - (L[i] * svt) * L[j];   // :142
+      for (int j = i; j < N5; ++j, ++q) S[q] = fma(-(L[i] * svt), L[j], S[q]);   // :142
     njac += psd_repair(S, d.force_jacobi);                           // :143-145
     if (resid * resid > 9.0 * svt) {                                 // :148-151 Q-bump
 #pragma unroll
@@ -662,11 +662,11 @@ __device__ __forceinline__ void pred_row(const double* a, const double* c5, doub
     if (k <= Np) {
       double acc = c5[0] * pk[0];
 #pragma unroll
-      for (int j = 1; j < N5; ++j) acc = acc + c5[j] * pk[j];
-      acc = acc + c6 * pk[5];
+      for (int j = 1; j < N5; ++j) acc = fma(c5[j], pk[j], acc);
+      acc = fma(c6, pk[5], acc);
       h[k] = acc + dd;                                               // predMat.m:34
 #pragma unroll
-      for (int j = 0; j < N5; ++j) pk[j] = a[j] * pk[j] + 1.0;       // predMat.m:35
+      for (int j = 0; j < N5; ++j) pk[j] = fma(a[j], pk[j], 1.0);    // predMat.m:35
       pk[5] = pk[5] + 1.0;
     }
   }
@@ -677,8 +677,8 @@ __device__ __forceinline__ void pred_row(const double* a, const double* c5, doub
       for (int j = 0; j < N5; ++j) pw[j] = a[j] * pw[j];             // predMat.m:41
       double acc = (c5[0] * pw[0]) * x6[0];
 #pragma unroll
-      for (int j = 1; j < N5; ++j) acc = acc + (c5[j] * pw[j]) * x6[j];
-      acc = acc + (c6 * pw[5]) * x6[5];
+      for (int j = 1; j < N5; ++j) acc = fma(c5[j] * pw[j], x6[j], acc);
+      acc = fma(c6 * pw[5], x6[5], acc);
       phix[i - 1] = acc;                                             // predMat.m:43 (first six columns)
     }
   }
@@ -702,7 +702,7 @@ __device__ __forceinline__ void spd_factor(int Nc, const double* E, double* LU) 
           LU[i * NCM + k] = l;
 #pragma unroll
           for (int j = k + 1; j < NCM; ++j)
-            if (j < Nc) LU[i * NCM + j] = LU[i * NCM + j] - l * LU[k * NCM + j];
+            if (j < Nc) LU[i * NCM + j] = fma(-l, LU[k * NCM + j], LU[i * NCM + j]);
         }
     }
 }
@@ -714,7 +714,7 @@ __device__ __forceinline__ void spd_solve(int Nc, const double* LU, const double
     if (i < Nc) {
       double acc = b[i];
 #pragma unroll
-      for (int k = 0; k < i; ++k) acc = acc - LU[i * NCM + k] * y[k];
+      for (int k = 0; k < i; ++k) acc = fma(-LU[i * NCM + k], y[k], acc);
       y[i] = acc;
     }
 #pragma unroll
@@ -723,7 +723,7 @@ __device__ __forceinline__ void spd_solve(int Nc, const double* LU, const double
       double acc = y[i];
 #pragma unroll
       for (int k = i + 1; k < NCM; ++k)
-        if (k < Nc) acc = acc - LU[i * NCM + k] * x[k];
+        if (k < Nc) acc = fma(-LU[i * NCM + k], x[k], acc);
       x[i] = acc * LU[i * NCM + i];
     }
 }
@@ -767,13 +767,13 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
           double acc = Ei[j * NCM] * Mm[i * NCM];
 #pragma unroll
           for (int l = 1; l < NCM; ++l)
-            if (l < Nc) acc = acc + Ei[j * NCM + l] * Mm[i * NCM + l];
+            if (l < Nc) acc = fma(Ei[j * NCM + l], Mm[i * NCM + l], acc);
           P[i * NCM + j] = acc;
         }
       double hd = Mm[i * NCM] * P[i * NCM], k = Mm[i * NCM] * x[0];
 #pragma unroll
       for (int j = 1; j < NCM; ++j)
-        if (j < Nc) { hd = hd + Mm[i * NCM + j] * P[i * NCM + j]; k = k + Mm[i * NCM + j] * x[j]; }
+        if (j < Nc) { hd = fma(Mm[i * NCM + j], P[i * NCM + j], hd); k = fma(Mm[i * NCM + j], x[j], k); }
       Hd[i] = hd;                                                    // H(i,i)  hildreth.m:28
       rH[i] = rcp_d(hd);                                             // the sweep multiplies by 1/H(i,i) (+Inf on a zero row)
       K[i] = k + gam[i];                                             // K(i)    hildreth.m:29
@@ -783,7 +783,7 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
       } else {
 #pragma unroll
         for (int j = 0; j < NCM; ++j)
-          if (j < Nc) v[j] = v[j] + P[i * NCM + j] * lam[i];
+          if (j < Nc) v[j] = fma(P[i * NCM + j], lam[i], v[j]);
       }
     }
   int k = 1;
@@ -800,8 +800,8 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
           double hl = Mm[i * NCM] * v[0];
 #pragma unroll
           for (int j = 1; j < NCM; ++j)
-            if (j < Nc) hl = hl + Mm[i * NCM + j] * v[j];
-          w = li - (K[i] + hl) * rH[i];                               // == -(K + H(i,:)*lam - H_ii*lam_i)/H_ii
+            if (j < Nc) hl = fma(Mm[i * NCM + j], v[j], hl);
+          w = fma(-(K[i] + hl), rH[i], li);                           // == -(K + H(i,:)*lam - H_ii*lam_i)/H_ii
         }
         const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
         const double dl = nl - li;
@@ -810,7 +810,7 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
         } else {
 #pragma unroll
           for (int j = 0; j < NCM; ++j)
-            if (j < Nc) v[j] = v[j] + P[i * NCM + j] * dl;
+            if (j < Nc) v[j] = fma(P[i * NCM + j], dl, v[j]);
         }
         lam[i] = nl;
         if (!(fabs(dl) < 1e-6)) notconv = true;                      // hildreth.m:39 norm(.,Inf) < 1e-6, NaN-propagating
@@ -828,8 +828,7 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
 #pragma unroll
       for (int j = 0; j < NCM; ++j)
         if (j < Nc) {
-          const double t = Mm[i * NCM + j] * lam[i];
-          rhs[j] = first ? t : rhs[j] + t;
+          rhs[j] = first ? Mm[i * NCM + j] * lam[i] : fma(Mm[i * NCM + j], lam[i], rhs[j]);
         }
       first = false;
     }
@@ -974,7 +973,7 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
   {                                                                  // runMPC.m:94-95 (Q24)
     double acc = e.Cphi[0] * e.xhat[0];
 #pragma unroll
-    for (int j = 1; j < N5; ++j) acc = acc + e.Cphi[j] * e.xhat[j];
+    for (int j = 1; j < N5; ++j) acc = fma(e.Cphi[j], e.xhat[j], acc);
     acc = acc + 0.0 * e.xhat[5];
     o.phise = (acc + uk_applied * e.Dphi) + e.bphi;
   }
@@ -988,7 +987,7 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
     double acc = q.Mm[i * NCM] * q.DU[0];
 #pragma unroll
     for (int j = 1; j < NCM; ++j)
-      if (j < Nc) acc = acc + q.Mm[i * NCM + j] * q.DU[j];
+      if (j < Nc) acc = fma(q.Mm[i * NCM + j], q.DU[j], acc);
     if (acc - q.gam[i] > 0.0) viol = true;
   }
   o.nexec = 0;
@@ -1044,7 +1043,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
   {                                                                  // runMPC.m:94-95 (Q24)
     double acc = e.Cphi[0] * e.xhat[0];
 #pragma unroll
-    for (int j = 1; j < N5; ++j) acc = acc + e.Cphi[j] * e.xhat[j];
+    for (int j = 1; j < N5; ++j) acc = fma(e.Cphi[j], e.xhat[j], acc);
     acc = acc + 0.0 * e.xhat[5];
     o.phise = (acc + uk_applied * e.Dphi) + e.bphi;
   }
@@ -1144,7 +1143,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
   for (int i = 0; i < nC; ++i) {
     double acc = Mm[i][0] * DU[0];
 #pragma unroll
-    for (int j = 1; j < NC; ++j) acc = acc + Mm[i][j] * DU[j];
+    for (int j = 1; j < NC; ++j) acc = fma(Mm[i][j], DU[j], acc);
     if (acc - gam[i] > 0.0) viol = true;
   }
   o.nexec = 0;
@@ -1177,19 +1176,19 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
       for (int j = 0; j < NC; ++j) {
         double acc = Ei[j][0] * Mm[i][0];
 #pragma unroll
-        for (int l = 1; l < NC; ++l) acc = acc + Ei[j][l] * Mm[i][l];
+        for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
         P[j] = acc;
       }
       double hd = Mm[i][0] * P[0], k = Mm[i][0] * x[0];
 #pragma unroll
-      for (int j = 1; j < NC; ++j) { hd = hd + Mm[i][j] * P[j]; k = k + Mm[i][j] * x[j]; }
+      for (int j = 1; j < NC; ++j) { hd = fma(Mm[i][j], P[j], hd); k = fma(Mm[i][j], x[j], k); }
       vs[(i * 2 + 0) * sms] = k + gam[i];                            // K(i)
       vs[(i * 2 + 1) * sms] = rcp_d(hd);                             // 1/H(i,i)
       if (hd == 0.0) {
         zmask |= 1u << i;
       } else {
 #pragma unroll
-        for (int j = 0; j < NC; ++j) v[j] = v[j] + P[j] * lam[i];
+        for (int j = 0; j < NC; ++j) v[j] = fma(P[j], lam[i], v[j]);
       }
     }
     // rows whose lambda is non-finite (only all-zero rows can get there): while any is set every row product is NaN
@@ -1205,8 +1204,8 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
         const double li = lam[i];
         double hl = Mm[i][0] * v[0];
 #pragma unroll
-        for (int j = 1; j < NC; ++j) hl = hl + Mm[i][j] * v[j];
-        double w = li - (vs[(i * 2 + 0) * sms] + hl) * vs[(i * 2 + 1) * sms];
+        for (int j = 1; j < NC; ++j) hl = fma(Mm[i][j], v[j], hl);
+        double w = fma(-(vs[(i * 2 + 0) * sms] + hl), vs[(i * 2 + 1) * sms], li);
         w = (pmask != 0u) ? NAN : w;
         const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
         const double dl = nl - li;
@@ -1216,8 +1215,8 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
         for (int j = 0; j < NC; ++j) {
           double acc = Ei[j][0] * Mm[i][0];
 #pragma unroll
-          for (int l = 1; l < NC; ++l) acc = acc + Ei[j][l] * Mm[i][l];
-          v[j] = v[j] + acc * pd;
+          for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
+          v[j] = fma(acc, pd, v[j]);
         }
         pmask = (zr && !(nl <= kDblMax)) ? (pmask | (1u << i)) : (pmask & ~(1u << i));
         lam[i] = nl;
@@ -1231,7 +1230,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     for (int j = 0; j < NC; ++j) {                                   // hildreth.m:46
       double acc = Mm[0][j] * lam[0];
 #pragma unroll
-      for (int i = 1; i < nC; ++i) acc = acc + Mm[i][j] * lam[i];
+      for (int i = 1; i < nC; ++i) acc = fma(Mm[i][j], lam[i], acc);
       rhs[j] = F[j] + acc;
     }
     spd_solve<NC>(NC, LU, rhs, x);

@@ -304,24 +304,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
     const long long cell = base + threadIdx.x;
     const bool active = cell < d.B;
     Cell c = cell_ref(P.st, d, active ? cell : 0);
-    double sum_nexec = 0.0, n_qp = 0.0, n_cap = 0.0;
-    double min_phise = INFINITY, max_V = -INFINITY, t_reach = -1.0, ztarget = 0.0;
-    if (active) { min_phise = c.f(S_MIN_PHISE); max_V = c.f(S_MAX_V); t_reach = c.f(S_T_REACH); ztarget = c.f(S_ZMAX) - 1e-3; }
-    StepLog lg;
-    lg.soc = NAN; lg.V = NAN; lg.phise = NAN;
     // the cell temperature is constant over a run: its two nearest set-points are looked up once (same rule as every step)
     const int tt = active ? two_nearest(c.f(S_TC) + 273.15, bk.Tpts, d.nT) : 0;
 #pragma unroll 1
     for (int k = k0; k < k1; ++k) {
       if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
       if (!active) continue;
+      StepLog lg;
       cell_step<NPM, NCM, CONS, 2>(P, bk, c, lg, smt, sms, tt);
-      sum_nexec += (double)lg.nexec;
-      if (lg.nexec > 0) n_qp += 1.0;
-      if (lg.nexec >= d.maxHild) n_cap += 1.0;
-      min_phise = fmin(min_phise, lg.phise);
-      max_V = fmax(max_V, lg.V);
-      if (t_reach < 0.0 && lg.soc >= ztarget) t_reach = (double)k;
+      // per-cell summary, kept in the state header (not in registers: they are the scarce resource of this kernel)
+      if (lg.nexec > 0) {
+        c.f(S_SUM_NEXEC) += (double)lg.nexec;
+        c.f(S_N_QP) += 1.0;
+        if (lg.nexec >= d.maxHild) c.f(S_N_CAP) += 1.0;
+      }
+      c.f(S_MIN_PHISE) = fmin(c.f(S_MIN_PHISE), lg.phise);
+      c.f(S_MAX_V) = fmax(c.f(S_MAX_V), lg.V);
+      if (c.f(S_T_REACH) < 0.0 && lg.soc >= c.f(S_ZMAX) - 1e-3) c.f(S_T_REACH) = (double)k;
+      c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
       if (cell < P.nlog && k < P.log_steps) {
         const long long o = (long long)k * P.nlog + cell;
         P.log_u[o] = lg.u; P.log_V[o] = lg.V; P.log_soc[o] = lg.soc; P.log_phise[o] = lg.phise;
@@ -329,12 +329,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
         for (int w = 0; w < P.log_words; ++w) P.log_active[o * P.log_words + w] = lg.active[w];
       }
     }
-    if (active) {
-      c.f(S_SUM_NEXEC) += sum_nexec; c.f(S_N_QP) += n_qp; c.f(S_N_CAP) += n_cap;
-      c.f(S_MIN_PHISE) = min_phise; c.f(S_MAX_V) = max_V; c.f(S_T_REACH) = t_reach;
-      c.f(S_STEPS) += (double)(k1 - k0);
-      c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
-    }
+    if (active) c.f(S_STEPS) += (double)(k1 - k0);
   }
 }
 
@@ -430,10 +425,10 @@ __device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, doub
     for (int k = 0; k < 4; ++k) {
       const double* cr = P.Cfull + ((size_t)mk[k] * d.nz + r) * 6;
       double acc = cr[0] * xk[k][0];
-      for (int j = 1; j < N5; ++j) acc = acc + cr[j] * xk[k][j];
-      yc[k] = acc + P.Dfull[(size_t)mk[k] * d.nz + r] * ik;
+      for (int j = 1; j < N5; ++j) acc = fma(cr[j], xk[k][j], acc);
+      yc[k] = fma(P.Dfull[(size_t)mk[k] * d.nz + r], ik, acc);
     }
-    zk[r] = ((yc[0] * gam4[0] + yc[1] * gam4[1]) + yc[2] * gam4[2]) + yc[3] * gam4[3];
+    zk[r] = fma(yc[3], gam4[3], fma(yc[2], gam4[2], fma(yc[1], gam4[1], yc[0] * gam4[0])));
   }
   zk[d.nz] = vhat;
   zk[d.nz + 1] = soc;       // the per-kind corrections (iterEKF.m:331-413) follow in k_iter_ekf

@@ -14,7 +14,18 @@ import numpy as np
 from . import literal
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_build", "libmek_oracle.so")
+def _has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " fma " in line + " "
+    except OSError:
+        pass
+    return False
+
+
+_SO = os.path.join(_HERE, "_build", "libmek_oracle_fma.so" if _has_fma() else "libmek_oracle.so")
 MAXROWS = 16
 
 # state-vector field offsets (enum in mek_oracle.c)

@@ -88,17 +88,17 @@ static const double INV_LN2 = 1.44269504088896338700e+00, LN2 = 6.93147180559945
 static double atanh_series(double s) { /* 2*atanh(s) for |s| <= 0.1716 */
   double z = s * s;
   double p = 1.0 / 23.0;
-  p = p * z + 1.0 / 21.0;
-  p = p * z + 1.0 / 19.0;
-  p = p * z + 1.0 / 17.0;
-  p = p * z + 1.0 / 15.0;
-  p = p * z + 1.0 / 13.0;
-  p = p * z + 1.0 / 11.0;
-  p = p * z + 1.0 / 9.0;
-  p = p * z + 1.0 / 7.0;
-  p = p * z + 1.0 / 5.0;
-  p = p * z + 1.0 / 3.0;
-  p = p * z + 1.0;
+  p = fma(p, z, 1.0 / 21.0);
+  p = fma(p, z, 1.0 / 19.0);
+  p = fma(p, z, 1.0 / 17.0);
+  p = fma(p, z, 1.0 / 15.0);
+  p = fma(p, z, 1.0 / 13.0);
+  p = fma(p, z, 1.0 / 11.0);
+  p = fma(p, z, 1.0 / 9.0);
+  p = fma(p, z, 1.0 / 7.0);
+  p = fma(p, z, 1.0 / 5.0);
+  p = fma(p, z, 1.0 / 3.0);
+  p = fma(p, z, 1.0);
   return (2.0 * s) * p;
 }
 
@@ -125,19 +125,19 @@ static double mko_exp(double x) {
   double kf = floor(x * INV_LN2 + 0.5);
   double r = (x - kf * LN2_HI) - kf * LN2_LO;
   double p = 1.0 / 6227020800.0;
-  p = p * r + 1.0 / 479001600.0;
-  p = p * r + 1.0 / 39916800.0;
-  p = p * r + 1.0 / 3628800.0;
-  p = p * r + 1.0 / 362880.0;
-  p = p * r + 1.0 / 40320.0;
-  p = p * r + 1.0 / 5040.0;
-  p = p * r + 1.0 / 720.0;
-  p = p * r + 1.0 / 120.0;
-  p = p * r + 1.0 / 24.0;
-  p = p * r + 1.0 / 6.0;
-  p = p * r + 0.5;
-  p = p * r + 1.0;
-  p = p * r + 1.0;
+  p = fma(p, r, 1.0 / 479001600.0);
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
   uint64_t b = (uint64_t)((int64_t)kf + 1023) << 52;
   double sc;
   memcpy(&sc, &b, 8);
@@ -188,14 +188,14 @@ static double uocp_p(const double *p, double th) {
   double x = (th - p[P_UP]) / p[P_UP + 1];
   int nc = (int)p[P_UP + 2];
   double acc = p[P_UP_COEF + nc - 1];
-  for (int i = nc - 2; i >= 0; --i) acc = acc * x + p[P_UP_COEF + i];
+  for (int i = nc - 2; i >= 0; --i) acc = fma(acc, x, p[P_UP_COEF + i]);
   return acc;
 }
 static double duocp_p(const double *p, double th) {
   double x = (th - p[P_UP]) / p[P_UP + 1];
   int nc = (int)p[P_UP + 2];
   double acc = (double)(nc - 1) * p[P_UP_COEF + nc - 1];
-  for (int i = nc - 2; i >= 1; --i) acc = acc * x + (double)i * p[P_UP_COEF + i];
+  for (int i = nc - 2; i >= 1; --i) acc = fma(acc, x, (double)i * p[P_UP_COEF + i]);
   return acc / p[P_UP + 1];
 }
 static double k0_e(const double *p, int base, double th, double arr) {
@@ -271,12 +271,12 @@ static double plant_step(const mko_bank *bk, double *st, double Iapp) {
     for (int r = 0; r < 9; ++r) {
       const double *cr = Cm + rows[r] * 6;
       double acc = cr[0] * x[0];
-      for (int j = 1; j < 6; ++j) acc = acc + cr[j] * x[j];   /* no Phise row is consumed, so :178-181 is moot here */
-      y[c][r] = acc + Dm[rows[r]] * Iapp;
+      for (int j = 1; j < 6; ++j) acc = fma(cr[j], x[j], acc);   /* no Phise row is consumed, so :178-181 is moot here */
+      y[c][r] = fma(Dm[rows[r]], Iapp, acc);
     }
   }
   for (int m = 0; m < M; ++m)                                      /* :278 */
-    for (int j = 0; j < 6; ++j) bigX[6 * m + j] = bk->A[6 * m + j] * bigX[6 * m + j] + Iapp;
+    for (int j = 0; j < 6; ++j) bigX[6 * m + j] = fma(bk->A[6 * m + j], bigX[6 * m + j], Iapp);
   double aZ = 0.0, aT = 0.0;                                       /* :281-283 */
   if (Zup != Zlo) aZ = (cellSOC - Zlo) / (Zup - Zlo);
   if (Tup != Tlo) aT = (T - Tlo) / (Tup - Tlo);
@@ -359,10 +359,10 @@ static double get_variables(const mko_bank *bk, double *st, double ik, const xin
       const double *cr = bk->C + ((size_t)X->m[c] * nz + r) * 6;
       const double *x = xhat + N5 * X->m[c];
       double acc = cr[0] * x[0];
-      for (int j = 1; j < N5; ++j) acc = acc + cr[j] * x[j];
-      yc[c] = acc + bk->D[(size_t)X->m[c] * nz + r] * ik;
+      for (int j = 1; j < N5; ++j) acc = fma(cr[j], x[j], acc);
+      yc[c] = fma(bk->D[(size_t)X->m[c] * nz + r], ik, acc);
     }
-    Z[r] = ((yc[0] * X->gamma[0] + yc[1] * X->gamma[1]) + yc[2] * X->gamma[2]) + yc[3] * X->gamma[3];
+    Z[r] = fma(yc[3], X->gamma[3], fma(yc[2], X->gamma[2], fma(yc[1], X->gamma[1], yc[0] * X->gamma[0])));
   }
   const double If0 = Z[bk->r_if0], If3 = Z[bk->r_if3];             /* :324-325 */
   int any;
@@ -412,13 +412,13 @@ static int psd_repair(double *S, int force) {
     int pd = 1;
     for (int j = 0; j < 5 && pd; ++j) {
       double dj = S[sym_idx(j, j)];
-      for (int k = 0; k < j; ++k) dj = dj - (L[j][k] * L[j][k]) * d[k];
+      for (int k = 0; k < j; ++k) dj = fma(-(L[j][k] * L[j][k]), d[k], dj);
       if (!(dj > 0.0)) { pd = 0; break; }
       d[j] = dj;
       const double idj = 1.0 / dj;
       for (int i = j + 1; i < 5; ++i) {
         double v = S[sym_idx(i, j)];
-        for (int k = 0; k < j; ++k) v = v - (L[i][k] * L[j][k]) * d[k];
+        for (int k = 0; k < j; ++k) v = fma(-(L[i][k] * L[j][k]), d[k], v);
         L[i][j] = v * idj;
       }
     }
@@ -497,10 +497,10 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
   for (int m = 0; m < M; ++m) {                                    /* :73-84 */
     const double *a = bk->A + 6 * m;
     double *x = xhat + N5 * m, *S = Sig + NSYM * m;
-    for (int j = 0; j < N5; ++j) x[j] = a[j] * x[j] + prior;       /* :77 */
+    for (int j = 0; j < N5; ++j) x[j] = fma(a[j], x[j], prior);    /* :77 */
     int q = 0;
     for (int i = 0; i < N5; ++i)
-      for (int j = i; j < N5; ++j, ++q) S[q] = (a[i] * S[q]) * a[j] + Sw; /* :81 (Q12) */
+      for (int j = i; j < N5; ++j, ++q) S[q] = fma(a[i] * S[q], a[j], Sw); /* :81 (Q12) */
   }
   st[S_X0] = st[S_X0] + prior;                                     /* :85 */
   st[S_SIGX0] = st[S_SIGX0] + Sw;                                  /* :86 */
@@ -546,11 +546,11 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
       double v[N5];
       for (int i = 0; i < N5; ++i) {
         double acc = S1[sym_idx(i, 0)] * Chat[c][0];
-        for (int j = 1; j < N5; ++j) acc = acc + S1[sym_idx(i, j)] * Chat[c][j];
+        for (int j = 1; j < N5; ++j) acc = fma(S1[sym_idx(i, j)], Chat[c][j], acc);
         v[i] = acc;
       }
       double s = Chat[c][0] * v[0];
-      for (int i = 1; i < N5; ++i) s = s + Chat[c][i] * v[i];
+      for (int i = 1; i < N5; ++i) s = fma(Chat[c][i], v[i], s);
       svt[c] = s + cf->SigmaV;
       const double isv = 1.0 / svt[c];
       for (int i = 0; i < N5; ++i) L[c][i] = v[i] * isv;
@@ -561,10 +561,10 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
   const double resid = vk - vhat;                                  /* :133 */
   for (int c = 0; c < 4; ++c) {                                    /* :136-154 (Q2: sequential, duplicates re-processed) */
     double *x = xhat + N5 * X.m[c], *S = Sig + NSYM * X.m[c];
-    for (int j = 0; j < N5; ++j) x[j] = x[j] + L[c][j] * resid;    /* :138 */
+    for (int j = 0; j < N5; ++j) x[j] = fma(L[c][j], resid, x[j]);    /* :138 */
     int q = 0;
     for (int i = 0; i < N5; ++i)
-      for (int j = i; j < N5; ++j, ++q) S[q] = S[q] - (L[c][i] * svt[c]) * L[c][j]; /* :142 */
+      for (int j = i; j < N5; ++j, ++q) S[q] = fma(-(L[c][i] * svt[c]), L[c][j], S[q]); /* :142 */
     if (psd_repair(S, cf->force_jacobi)) st[S_NJAC] += 1.0;        /* :143-145 */
     if (resid * resid > 9.0 * svt[c]) {                            /* :148-151 */
       for (int k = 0; k < NSYM; ++k) S[k] = S[k] * 2.0;
@@ -642,17 +642,17 @@ static void pred_row(const double *a, const double *c5, double c6, double d, con
   for (int j = 0; j < 6; ++j) { pk[j] = 0.0; pw[j] = 1.0; }
   for (int k = 0; k <= Np; ++k) {
     double acc = c5[0] * pk[0];
-    for (int j = 1; j < N5; ++j) acc = acc + c5[j] * pk[j];
-    acc = acc + c6 * pk[5];
+    for (int j = 1; j < N5; ++j) acc = fma(c5[j], pk[j], acc);
+    acc = fma(c6, pk[5], acc);
     h[k] = acc + d;                                                /* Cbar*X, X = [p;1] */
-    for (int j = 0; j < N5; ++j) pk[j] = a[j] * pk[j] + 1.0;       /* X = Abar*X */
+    for (int j = 0; j < N5; ++j) pk[j] = fma(a[j], pk[j], 1.0);    /* X = Abar*X */
     pk[5] = pk[5] + 1.0;
   }
   for (int i = 1; i <= Np; ++i) {
     for (int j = 0; j < N5; ++j) pw[j] = a[j] * pw[j];             /* Ap = Abar*Ap */
     double acc = (c5[0] * pw[0]) * x6[0];
-    for (int j = 1; j < N5; ++j) acc = acc + (c5[j] * pw[j]) * x6[j];
-    acc = acc + (c6 * pw[5]) * x6[5];
+    for (int j = 1; j < N5; ++j) acc = fma(c5[j] * pw[j], x6[j], acc);
+    acc = fma(c6 * pw[5], x6[5], acc);
     phix[i - 1] = acc;
   }
 }
@@ -668,7 +668,7 @@ static void spd_factor(int Nc, const double *E, double *LU) {
     for (int i = k + 1; i < Nc; ++i) {
       double l = LU[i * Nc + k] * ip;
       LU[i * Nc + k] = l;
-      for (int j = k + 1; j < Nc; ++j) LU[i * Nc + j] = LU[i * Nc + j] - l * LU[k * Nc + j];
+      for (int j = k + 1; j < Nc; ++j) LU[i * Nc + j] = fma(-l, LU[k * Nc + j], LU[i * Nc + j]);
     }
   }
 }
@@ -676,12 +676,12 @@ static void spd_solve(int Nc, const double *LU, const double *b, double *x) {
   double y[NC_MAX];
   for (int i = 0; i < Nc; ++i) {
     double acc = b[i];
-    for (int k = 0; k < i; ++k) acc = acc - LU[i * Nc + k] * y[k];
+    for (int k = 0; k < i; ++k) acc = fma(-LU[i * Nc + k], y[k], acc);
     y[i] = acc;
   }
   for (int i = Nc - 1; i >= 0; --i) {
     double acc = y[i];
-    for (int k = i + 1; k < Nc; ++k) acc = acc - LU[i * Nc + k] * x[k];
+    for (int k = i + 1; k < Nc; ++k) acc = fma(-LU[i * Nc + k], x[k], acc);
     x[i] = acc * LU[i * Nc + i];
   }
 }
@@ -704,11 +704,11 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
   for (int i = 0; i < nC; ++i) {
     for (int j = 0; j < Nc; ++j) {                                 /* column i of E\M' */
       double acc = Ei[j][0] * Mm[i * Nc];
-      for (int l = 1; l < Nc; ++l) acc = acc + Ei[j][l] * Mm[i * Nc + l];
+      for (int l = 1; l < Nc; ++l) acc = fma(Ei[j][l], Mm[i * Nc + l], acc);
       P[i][j] = acc;
     }
     double hd = Mm[i * Nc] * P[i][0], k = Mm[i * Nc] * x[0];
-    for (int j = 1; j < Nc; ++j) { hd = hd + Mm[i * Nc + j] * P[i][j]; k = k + Mm[i * Nc + j] * x[j]; }
+    for (int j = 1; j < Nc; ++j) { hd = fma(Mm[i * Nc + j], P[i][j], hd); k = fma(Mm[i * Nc + j], x[j], k); }
     Hd[i] = hd;                                                    /* H(i,i)  (:28) */
     rH[i] = 1.0 / hd;                                              /* the sweep multiplies by 1/H(i,i) (+Inf on a zero row) */
     K[i] = k + gam[i];                                             /* K(i)    (:29) */
@@ -718,7 +718,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
   for (int j = 0; j < Nc; ++j) v[j] = 0.0;
   for (int i = 0; i < nC; ++i) {
     if (Hd[i] == 0.0) { if (!(fabs(lam[i]) <= 1.79769313486231570815e308)) npoison++; continue; }
-    for (int j = 0; j < Nc; ++j) v[j] = v[j] + P[i][j] * lam[i];
+    for (int j = 0; j < Nc; ++j) v[j] = fma(P[i][j], lam[i], v[j]);
   }
   int k = 0;
   for (k = 1; k <= maxIter; ++k) {                                 /* :32 */
@@ -730,8 +730,8 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
         w = NAN;
       } else {
         double hl = Mm[i * Nc] * v[0];
-        for (int j = 1; j < Nc; ++j) hl = hl + Mm[i * Nc + j] * v[j];
-        w = li - (K[i] + hl) * rH[i];                       /* == -(K + H(i,:)*lam - H_ii*lam_i)/H_ii */
+        for (int j = 1; j < Nc; ++j) hl = fma(Mm[i * Nc + j], v[j], hl);
+        w = fma(-(K[i] + hl), rH[i], li);                       /* == -(K + H(i,:)*lam - H_ii*lam_i)/H_ii */
       }
       const double nl = (w > 0.0) ? w : 0.0;                       /* max(0,w); max(0,NaN) = 0 */
       const double dl = nl - li;
@@ -739,7 +739,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
         const int was = !(fabs(li) <= 1.79769313486231570815e308), is = !(fabs(nl) <= 1.79769313486231570815e308);
         npoison += is - was;
       } else {
-        for (int j = 0; j < Nc; ++j) v[j] = v[j] + P[i][j] * dl;
+        for (int j = 0; j < Nc; ++j) v[j] = fma(P[i][j], dl, v[j]);
       }
       lam[i] = nl;
       if (!(fabs(dl) < 1e-6)) notconv = 1;                         /* :39: norm(.,Inf) < 1e-6, NaN-propagating */
@@ -751,7 +751,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
   double rhs[NC_MAX];
   for (int j = 0; j < Nc; ++j) {                                   /* :46 */
     double acc = Mm[j] * lam[0];
-    for (int i = 1; i < nC; ++i) acc = acc + Mm[i * Nc + j] * lam[i];
+    for (int i = 1; i < nC; ++i) acc = fma(Mm[i * Nc + j], lam[i], acc);
     rhs[j] = F[j] + acc;
   }
   spd_solve(Nc, LU, rhs, x);
@@ -811,7 +811,7 @@ static void mpc_step(const mko_bank *bk, const mko_config *cf, double sigmin, do
   /* runMPC.m:94-95 (Q24): logged phise uses the applied uk */
   {
     double acc = e->Cphi[0] * e->xhat[0];
-    for (int j = 1; j < N5; ++j) acc = acc + e->Cphi[j] * e->xhat[j];
+    for (int j = 1; j < N5; ++j) acc = fma(e->Cphi[j], e->xhat[j], acc);
     acc = acc + 0.0 * e->xhat[5];
     o->phise = (acc + uk_applied * e->Dphi) + e->bphi;
   }
@@ -889,7 +889,7 @@ static void mpc_step(const mko_bank *bk, const mko_config *cf, double sigmin, do
   int viol = 0;                                                    /* iterMPC.m:66 (Q8) */
   for (int i = 0; i < nC; ++i) {
     double acc = Mm[i * Nc] * DU[0];
-    for (int j = 1; j < Nc; ++j) acc = acc + Mm[i * Nc + j] * DU[j];
+    for (int j = 1; j < Nc; ++j) acc = fma(Mm[i * Nc + j], DU[j], acc);
     if (acc - gam[i] > 0.0) viol = 1;
   }
   o->nexec = 0;

@@ -265,3 +265,24 @@ def test_quirks_q3_q9_q20(bank):
     assert np.all(cs.bigX == 0) and cs.SOCnAvg == cs.SOC0n
     # u ramps at du_min per sample down to u_min = -Q*Crate (runMPC.m:36-38, initMPC.m:66-67)
     assert abs(o["u"][5] + 2 * 29.86) < 1e-3 and abs(o["u"][0] + 50) > 1.0
+
+
+def test_portable_and_fma_builds_of_the_c_oracle_agree_bitwise(bank, coracle_mod):
+    """oracle/Makefile builds mek_oracle.c twice (libm fma vs -mfma); fma is correctly rounded either way."""
+    import ctypes as C
+    import os
+    from mek import population as P
+    d = os.path.join(os.path.dirname(coracle_mod.__file__), "_build")
+    coracle_mod.build()
+    if not coracle_mod._has_fma():
+        pytest.skip("no hardware FMA on this host")
+    pop = P.make_population(bank.params[2], 3, seed=12, heterogeneous=True)
+    outs = []
+    for so in ("libmek_oracle.so", "libmek_oracle_fma.so"):
+        co = coracle_mod.COracle(bank)
+        co.L = C.CDLL(os.path.join(d, so))
+        co.L.mko_state_len.restype = C.c_int
+        co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        outs.append(co.run(0, 900))
+    for k in ("u", "V", "SOC", "phise", "nexec", "iT", "iZ", "active"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
