@@ -226,6 +226,15 @@ def main_mek(a):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_per_cellstep * float(B) * a.nsim / (kern_avg_ms * 1e-3) / 1e9
+        # DRAM bytes per cell-step measured by `ncu --set full` on this kernel (profiles/r01_final_ncu_summary.csv),
+        # scaled to the units one launch of this run processes
+        traffic = None
+        try:
+            for line in open(os.path.join(ROOT, "profiles", "r01_final_ncu_summary.csv")):
+                if line.startswith("# DRAM traffic per cell-step"):
+                    traffic = float(line.split("=")[1].split("B")[0].replace(" ", "")) * float(B) * a.nsim
+        except Exception:
+            pass
         fp64_tf = api.fp64_peak_tflops(local)
         qps = summ["n_qp"] / summ["cellsteps"]
         sweeps = summ["sum_nexec"] / summ["cellsteps"]
@@ -239,7 +248,7 @@ def main_mek(a):
                        "what": "mek_pop_init (pinned host inputs) + mek_run + mek_summary + mek_read_logs of %d cells' trajectories" % nlog},
                "gpu_launches": launches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                            "traffic": None, "kernel": "k_run_population<5,2>", "peak_source": "measured" if peaks else "fallback",
+                            "traffic": traffic, "kernel": "k_run_population<5,2,15,384,1>", "peak_source": "measured" if peaks else "fallback",
                             "bytes_per_cellstep": bytes_per_cellstep, "kernel_ms": kern_avg_ms},
                "fp64": {"peak_tflops_measured": fp64_tf},
                "qp_solves_per_s": value * qps, "hildreth_sweeps_per_s": value * sweeps, "mean_sweeps_per_step": sweeps,
