@@ -77,6 +77,7 @@ typedef struct {
   int blocks_per_sm;        /* 0 = from the occupancy calculator, 1 = one CTA per SM  */
   int generic_path;         /* 1: never use the static-shape fast instances           */
   int sync_steps;           /* CTA-wide barrier before every sample instant: 0/1 = on (default), -1 = off */
+  int keep_cell_order;      /* 1: do not reorder cells by (T, SOC0) inside the state block             */
 } mek_config;
 
 /* ---- bank ---- */

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -217,7 +218,10 @@ struct Params {
   double* log_u; double* log_V; double* log_soc; double* log_phise;
   unsigned char* log_iT; unsigned char* log_iZ; unsigned short* log_nexec; unsigned* log_active; int log_words;
   int sync_steps;             // 1: CTA-wide barrier before every sample instant
+  const int* slot2cell;       // state slot -> caller's cell index (cells are ordered by initial SOC inside the block), or null
 };
+
+__device__ __forceinline__ long long cell_id(const Params& P, long long slot) { return P.slot2cell ? (long long)P.slot2cell[slot] : slot; }
 
 // ---- TMA bulk copy of the hot bank into shared memory ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -306,6 +310,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
     Cell c = cell_ref(P.st, d, active ? cell : 0);
     // the cell temperature is constant over a run: its two nearest set-points are looked up once (same rule as every step)
     const int tt = active ? two_nearest(c.f(S_TC) + 273.15, bk.Tpts, d.nT) : 0;
+    const long long id = active ? cell_id(P, cell) : 0;   // the caller's index of this cell (logs are addressed by it)
 #pragma unroll 1
     for (int k = k0; k < k1; ++k) {
       if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
@@ -322,8 +327,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
       c.f(S_MAX_V) = fmax(c.f(S_MAX_V), lg.V);
       if (c.f(S_T_REACH) < 0.0 && lg.soc >= c.f(S_ZMAX) - 1e-3) c.f(S_T_REACH) = (double)k;
       c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
-      if (cell < P.nlog && k < P.log_steps) {
-        const long long o = (long long)k * P.nlog + cell;
+      if (id < P.nlog && k < P.log_steps) {
+        const long long o = (long long)k * P.nlog + id;
         P.log_u[o] = lg.u; P.log_V[o] = lg.V; P.log_soc[o] = lg.soc; P.log_phise[o] = lg.phise;
         P.log_iT[o] = (unsigned char)lg.iT; P.log_iZ[o] = (unsigned char)lg.iZ; P.log_nexec[o] = (unsigned short)lg.nexec;
         for (int w = 0; w < P.log_words; ++w) P.log_active[o * P.log_words + w] = lg.active[w];
@@ -344,7 +349,8 @@ __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
     Cell c = cell_ref(P.st, d, cell);
     for (int f = 0; f < d.nfields; ++f) c.f(f) = 0.0;
-    const double Tc = P.in_T[cell], z0 = P.in_soc0[cell] / 100.0;
+    const long long id = cell_id(P, cell);
+    const double Tc = P.in_T[id], z0 = P.in_soc0[id] / 100.0;
     const double Tk1 = Tc + 273.15;
     c.f(S_TC) = Tc;
     c.f(S_SOC0N) = soc_e(p, P_NEG, z0);                              // OB_step.m:64-71
@@ -357,15 +363,15 @@ __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params
     c.f(S_ARRK0P) = arrhenius(p, Tk1, p[P_POS + E_EA_K0]);
     c.f(S_ARRRFN) = arrhenius(p, Tk1, -p[P_NEG + E_EA_RF]);
     c.f(S_ARRRFP) = arrhenius(p, Tk1, -p[P_POS + E_EA_RF]);
-    const double* sx = P.in_sigx0 + cell * 36;
+    const double* sx = P.in_sigx0 + id * 36;
     c.f(S_SIGX0) = sx[5 * 6 + 5];                                    // initKF.m:99
-    c.f(S_EKFSOC0) = P.in_ekf[cell] / 100.0;                         // initKF.m:133
+    c.f(S_EKFSOC0) = P.in_ekf[id] / 100.0;                           // initKF.m:133
     for (int m = 0; m < d.M; ++m) {                                  // initKF.m:70,94-95
       int q = 0;
       for (int i = 0; i < N5; ++i)
         for (int j = i; j < N5; ++j, ++q) c.f(d.f_sig + m * NSYM + q) = sx[j * 6 + i];
     }
-    for (int k = 0; k < 7; ++k) c.f(S_UMAX + k) = P.in_lim[cell * 7 + k];
+    for (int k = 0; k < 7; ++k) c.f(S_UMAX + k) = P.in_lim[id * 7 + k];
     c.f(S_MIN_PHISE) = INFINITY;
     c.f(S_MAX_V) = -INFINITY;
     c.f(S_T_REACH) = -1.0;
@@ -381,7 +387,8 @@ __global__ void __launch_bounds__(128) k_ob_step(const __grid_constant__ Params 
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < P.d.B; cell += stride) {
     Cell c = cell_ref(P.st, P.d, cell);
-    V[cell] = plant_step<true>(P.d, bk, P.cp, c, Iapp[cell], -1);
+    const long long id = cell_id(P, cell);
+    V[id] = plant_step<true>(P.d, bk, P.cp, c, Iapp[id], -1);
   }
 }
 
@@ -451,15 +458,16 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
     Cell c = cell_ref(P.st, d, cell);
     EkfOut e;
     memset(&e, 0, sizeof(e));
-    ekf_step<true>(d, bk, p, c, vk[cell], ik[cell], e, Scratch{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x}, -1);
-    if (mats) pack_mats(e, mats + cell * MEK_NMATS);
+    const long long id = cell_id(P, cell);
+    ekf_step<true>(d, bk, p, c, vk[id], ik[id], e, Scratch{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x}, -1);
+    if (mats) pack_mats(e, mats + id * MEK_NMATS);
     if (zk) {
-      double* z = zk + cell * (d.nz + 2);
+      double* z = zk + id * (d.nz + 2);
       if (e.lost) {
         for (int r = 0; r < d.nz + 2; ++r) z[r] = NAN;
         continue;
       }
-      full_zk(P, bk, c, ik[cell], e.vhat, e.soc, z);
+      full_zk(P, bk, c, ik[id], e.vhat, e.soc, z);
       // nonlinear corrections of getVariables on the full vector (iterEKF.m:331-413)
       const double rpa = d.Ts / (3600.0 * p[P_Q]);
       const double xSOC = c.f(S_EKFSOC0) - c.f(S_X0) * rpa;
@@ -503,18 +511,19 @@ __global__ void __launch_bounds__(128) k_iter_mpc(const __grid_constant__ Params
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
     Cell c = cell_ref(P.st, d, cell);
     EkfOut e;
-    unpack_mats(mats + cell * MEK_NMATS, e);
+    const long long id = cell_id(P, cell);
+    unpack_mats(mats + id * MEK_NMATS, e);
     if (e.lost) {
-      uk[cell] = NAN; if (phise) phise[cell] = NAN; if (nexec) nexec[cell] = 0;
-      if (active) for (int w = 0; w < 4; ++w) active[cell * 4 + w] = 0u;
+      uk[id] = NAN; if (phise) phise[id] = NAN; if (nexec) nexec[id] = 0;
+      if (active) for (int w = 0; w < 4; ++w) active[id * 4 + w] = 0u;
       continue;
     }
     MpcOut o;
-    mpc_step<NPM, NCM>(d, P.cp, c, e, uk_applied[cell], o);
-    uk[cell] = o.u;
-    if (phise) phise[cell] = o.phise;
-    if (nexec) nexec[cell] = o.nexec;
-    if (active) for (int w = 0; w < 4; ++w) active[cell * 4 + w] = o.active[w];
+    mpc_step<NPM, NCM>(d, P.cp, c, e, uk_applied[id], o);
+    uk[id] = o.u;
+    if (phise) phise[id] = o.phise;
+    if (nexec) nexec[id] = o.nexec;
+    if (active) for (int w = 0; w < 4; ++w) active[id * 4 + w] = o.active[w];
   }
 }
 
@@ -663,10 +672,10 @@ __global__ void k_state_gather(const __grid_constant__ Params P, double* aos, in
   const long long total = d.B * (long long)d.nfields;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long f = i / d.B, cell = i % d.B;
+    const long long f = i / d.B, cell = i % d.B, id = cell_id(P, cell);
     double* slot = P.st + (cell >> 5) * ((long long)d.nfields * TILE) + f * TILE + (cell & 31);
-    if (to_aos) aos[cell * d.nfields + f] = *slot;
-    else *slot = aos[cell * d.nfields + f];
+    if (to_aos) aos[id * d.nfields + f] = *slot;
+    else *slot = aos[id * d.nfields + f];
   }
 }
 
@@ -683,6 +692,7 @@ struct mek_pop {
   Params P;
   RowLists RL;
   double *d_blob, *d_Cfull, *d_Dfull, *d_st, *d_in, *d_totals, *d_scratch;
+  int* d_slot2cell;           // cell order inside the state block (sorted by initial SOC at mek_pop_init)
   size_t scratch_bytes;
   void* d_logs;
   bool inited;
@@ -758,6 +768,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   p->inited = false;
   p->launches = 0;
   p->d_logs = nullptr;
+  p->d_slot2cell = nullptr;
   p->d_scratch = nullptr;
   p->scratch_bytes = 0;
   int Np = cfg->Np < 1 ? 1 : cfg->Np;                               // initMPC.m:32-33 (Q23)
@@ -870,6 +881,7 @@ extern "C" void mek_pop_destroy(mek_pop* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->stream);
+  if (p->d_slot2cell) cudaFree(p->d_slot2cell);
   cudaFree(p->d_blob); cudaFree(p->d_Cfull); cudaFree(p->d_Dfull); cudaFree(p->d_st); cudaFree(p->d_in); cudaFree(p->d_totals);
   if (p->d_logs) cudaFree(p->d_logs);
   if (p->d_scratch) cudaFree(p->d_scratch);
@@ -934,6 +946,21 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
   CUDA_TRY(cudaMemcpyAsync(in + 2 * B, Tc, 8 * B, cudaMemcpyHostToDevice, p->stream));
   CUDA_TRY(cudaMemcpyAsync(in + 3 * B, SigmaX0, 8 * 36 * B, cudaMemcpyHostToDevice, p->stream));
   CUDA_TRY(cudaMemcpyAsync(in + 39 * B, limits, 8 * 7 * B, cudaMemcpyHostToDevice, p->stream));
+  // Order the cells inside the state block by initial SOC: the 32 cells of a warp are then in the same phase of the
+  // charge (same local models, similar Hildreth sweep counts), which removes most of the warp divergence.  Pure
+  // scheduling: every per-cell input/output of the ABI keeps the caller's index (slot2cell).
+  if (!p->cfg.keep_cell_order) {
+    std::vector<int> order(B);
+    for (size_t i = 0; i < B; ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (Tc[a] != Tc[b]) return Tc[a] < Tc[b];
+      return SOC0pct[a] < SOC0pct[b];
+    });
+    if (!p->d_slot2cell) CUDA_TRY(cudaMalloc(&p->d_slot2cell, sizeof(int) * B));
+    CUDA_TRY(cudaMemcpyAsync(p->d_slot2cell, order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));        // `order` is a pageable temporary
+    p->P.slot2cell = p->d_slot2cell;
+  }
   return mek_pop_reset(p);
 }
 

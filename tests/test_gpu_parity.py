@@ -100,3 +100,22 @@ def test_generic_instance_matches_too(bank, coracle_mod):
     _assert_bit_exact(g, c)
     cb, g, co, c = _run_both(bank, coracle_mod, pop, 600, Np=7, Nc=3)
     _assert_bit_exact(g, c)
+
+
+def test_cell_ordering_is_invisible_to_the_caller(bank):
+    """mek_pop_init orders cells by (T, SOC0) inside the state block; logs, state read-back and summaries keep the caller's indices."""
+    from mek import api, population as P
+    pop = P.make_population(bank.params[2], 200, seed=13, heterogeneous=True)
+    rom = api.RomBank(bank)
+    outs = []
+    for keep in (False, True):
+        cb = api.CellBatch(rom, 200, keep_cell_order=keep)
+        cb.set_logging(150, 500)
+        cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        cb.run(0, 500)
+        outs.append((cb.logs(), cb.read_state(), cb.summary()))
+    for k in ("u", "V", "SOC", "phise", "iT", "iZ", "nexec", "active"):
+        assert np.array_equal(outs[0][0][k], outs[1][0][k]), k
+    assert outs[0][0]["u"].shape == (500, 150)
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2]["sum_nexec"] == outs[1][2]["sum_nexec"] and outs[0][2]["min_phise"] == outs[1][2]["min_phise"]
