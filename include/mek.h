@@ -73,7 +73,7 @@ typedef struct {
   double ref;               /* mpcData.ref = targetSOC (95, percent! Q9)              */
   double SigmaV, SigmaW;    /* runMPC.m:18-19                                         */
   int force_jacobi;         /* 1: always run the eigen-decomposition PSD repair       */
-  int threads_per_block;    /* reserved (the fused kernels use a fixed CTA size)      */
+  int threads_per_block;    /* fast instances: 0/256 = 256 threads x 255 regs (default), 384 = 384 x 168 */
   int blocks_per_sm;        /* 0 = from the occupancy calculator, 1 = one CTA per SM  */
   int generic_path;         /* 1: never use the static-shape fast instances           */
   int sync_steps;           /* CTA-wide barrier before every sample instant: 0/1 = on (default), -1 = off */
@@ -126,10 +126,11 @@ int mek_summary(mek_pop *pop, double *totals);
 
 /* ---- function-level batched entry points on a population's state (one call = one line of the loop body) ---- */
 int mek_pop_ob_step(mek_pop *pop, const double *Iapp, double *Vcell);
-/* zk[(nz+2)*B] cell-major or NULL; mats[31*B] cell-major or NULL =
+/* zk[(nz+2)*B] cell-major or NULL; boundzk[(nz+2)*B] = 3-sigma bounds (iterEKF.m:185-205) or NULL (needs zk);
+ * mats[31*B] cell-major or NULL =
  *   lost, iT, iZ, xhat(6), diag A(5), Cv(5), Dv, Cphi(5), Dphi, bv, bphi, vhat, SOC, reserved(0) */
 #define MEK_NMATS 31
-int mek_pop_iter_ekf(mek_pop *pop, const double *vk, const double *ik, double *zk, double *mats);
+int mek_pop_iter_ekf(mek_pop *pop, const double *vk, const double *ik, double *zk, double *boundzk, double *mats);
 /* consumes mats (from mek_pop_iter_ekf) and the applied current; returns the new command and diagnostics */
 int mek_pop_iter_mpc(mek_pop *pop, const double *mats, const double *uk_applied, double *uk, double *phise, int32_t *nexec,
                      uint32_t *active);

@@ -441,13 +441,93 @@ __device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, doub
   zk[d.nz + 1] = soc;       // the per-kind corrections (iterEKF.m:331-413) follow in k_iter_ekf
 }
 
-struct RowLists {            // output-row kinds for the full-zk corrections
+struct RowLists {            // output-row kinds for the full-zk corrections and the 3-sigma bounds
   int n_negtss, n_postss, n_thetae, n_negphise, n_posphise, n_phie, n_posphis, r_phise0;
   int negtss[16], postss[16], thetae[16], negphise[16], posphise[16], phie[16], posphis[16];
+  int r_ifdl0, r_ifdl3, r_if0, r_if3, r_tss0, r_tss3, r_the0, r_the3, r_phie_last;   // rows in the full output numbering
+  unsigned char kind[64];    // per output row: 0 plain, 1 posPhis, 2 negThetass, 3 posThetass, 4 negPhise, 5 posPhise, 6 Phie
 };
 
+// boundzk = 3*sqrt([diag(SigmaZ); SigmaV; SigmaSOC]) (iterEKF.m:185-205, getChatZ :523-602).  Function-level entry only:
+// the control path never reads the bounds.  zk is the corrected output vector of this call.
+__device__ void ekf_bounds(const Params& P, const BankSmem& bk, const RowLists& RL, const Cell& c, Scratch sc, const double* zk,
+                           double* bound) {
+  const Dims& d = P.d;
+  const double* p = P.cp;
+  const double Tk = c.f(S_TC) + 273.15;
+  const double rpa = d.Ts / (3600.0 * p[P_Q]);
+  const double sx0 = c.f(S_SIGX0);
+  const double xSOC = c.f(S_EKFSOC0) - c.f(S_X0) * rpa;              // :576
+  const double sn = soc_e(p, P_NEG, xSOC), sp = soc_e(p, P_POS, xSOC);
+  // ---- getChatV(Xind, zk, Tk) (:421-519) ----
+  const double Rfn = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
+  const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
+  const double th0 = zk[RL.r_tss0], th3 = zk[RL.r_tss3];
+  const double i0n = k0n * sqrt((zk[RL.r_the0] * (1.0 - th0)) * th0);
+  const double i0p = k0p * sqrt((zk[RL.r_the3] * (1.0 - th3)) * th3);
+  const double Rctn = (p[P_R] * Tk) / (p[P_F] * i0n), Rctp = (p[P_R] * Tk) / (p[P_F] * i0p);
+  const double dUn0 = duocp_n(p, th0), dUp3 = duocp_p(p, th3);
+  const double dsn = soc_e(p, P_NEG, 1.0) - soc_e(p, P_NEG, 0.0), dsp = soc_e(p, P_POS, 1.0) - soc_e(p, P_POS, 0.0);
+  const double ChatV0 = (((-dUp3) * d.Ts) * dsp) / (3600.0 * p[P_Q]) - (((-dUn0) * d.Ts) * dsn) / (3600.0 * p[P_Q]);   // :497-501
+  const double res0n = ((-d.Ts) * dsn) / (3600.0 * p[P_Q]), res0p = ((-d.Ts) * dsp) / (3600.0 * p[P_Q]);              // :562-565
+  const double dUn = duocp_n(p, sn), dUp = duocp_p(p, sp);           // :579-580
+  double S1[NSYM], ChatV[4][N5], g[4];
+  int mk[4];
+  for (int k = 0; k < 4; ++k) { mk[k] = (int)sc[SC_M + k]; g[k] = sc[SC_GAMMA + k]; }
+  for (int q = 0; q < NSYM; ++q) S1[q] = c.sig(mk[0], q);            // :192 (Q4): neighbour #1's SigmaX for all four terms
+  auto quad = [&](const double* row) {                                // row*SigmaX*row'
+    double t = 0.0;
+    for (int i = 0; i < N5; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < N5; ++j) acc += S1[sym_idx(i, j)] * row[j];
+      t += row[i] * acc;
+    }
+    return t;
+  };
+  double sigV = 0.0;
+  for (int k = 0; k < 4; ++k) {
+    const double* Cm = P.Cfull + (size_t)mk[k] * d.nz * 6;
+    for (int j = 0; j < N5; ++j) {
+      double v = Rfp * (g[k] * Cm[RL.r_ifdl3 * 6 + j]) - Rfn * (g[k] * Cm[RL.r_ifdl0 * 6 + j]);
+      v = (v + Rctp * (g[k] * Cm[RL.r_if3 * 6 + j])) - Rctn * (g[k] * Cm[RL.r_if0 * 6 + j]);
+      v = v + g[k] * Cm[RL.r_phie_last * 6 + j];
+      v = v + (dUp3 * (g[k] * Cm[RL.r_tss3 * 6 + j]) - dUn0 * (g[k] * Cm[RL.r_tss0 * 6 + j]));
+      ChatV[k][j] = v;
+    }
+    sigV += quad(ChatV[k]);                                          // :194
+  }
+  sigV += (ChatV0 * sx0) * ChatV0;                                   // :197
+  for (int r = 0; r < d.nz; ++r) {
+    const int kind = RL.kind[r];
+    double c0 = 0.0;                                                 // ChatZ0(r) (:540-586)
+    if (kind == 1) c0 = ChatV0;
+    else if (kind == 2) c0 = res0n;
+    else if (kind == 3) c0 = res0p;
+    else if (kind == 4) c0 = dUn * res0n;
+    else if (kind == 5) c0 = dUp * res0p;
+    else if (kind == 6) c0 = -dUn * res0n;
+    double acc = 0.0;
+    for (int k = 0; k < 4; ++k) {
+      const double* Cm = P.Cfull + (size_t)mk[k] * d.nz * 6;
+      double row[N5];
+      for (int j = 0; j < N5; ++j) {
+        double v = g[k] * Cm[r * 6 + j];
+        if (kind == 1) v += ChatV[k][j];                             // :546-552 posPhis carries the cell voltage
+        if (kind == 6) v -= g[k] * Cm[RL.r_phise0 * 6 + j];          // :589-595 Phie is referred to Phise(0)
+        row[j] = v;
+      }
+      acc += quad(row);                                              // :193
+    }
+    acc += (c0 * sx0) * c0;                                          // :196
+    bound[r] = 3.0 * sqrt(acc);                                      // :205
+  }
+  bound[d.nz] = 3.0 * sqrt(sigV);
+  const double res = -d.Ts / (3600.0 * p[P_Q]);
+  bound[d.nz + 1] = 3.0 * sqrt((res * sx0) * res);                   // :198
+}
+
 __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params P, const __grid_constant__ RowLists RL, const double* vk,
-                                                   const double* ik, double* zk, double* mats) {
+                                                   const double* ik, double* zk, double* mats, double* bounds) {
   extern __shared__ __align__(16) double sm[];
   BankSmem bk;
   stage_bank(sm, P, bk);
@@ -464,7 +544,7 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
     if (zk) {
       double* z = zk + id * (d.nz + 2);
       if (e.lost) {
-        for (int r = 0; r < d.nz + 2; ++r) z[r] = NAN;
+        for (int r = 0; r < d.nz + 2; ++r) { z[r] = NAN; if (bounds) bounds[id * (d.nz + 2) + r] = NAN; }
         continue;
       }
       full_zk(P, bk, c, ik[id], e.vhat, e.soc, z);
@@ -499,6 +579,7 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
         z[RL.thetae[k]] = v;
       }
       for (int k = 0; k < RL.n_posphis; ++k) z[RL.posphis[k]] = z[RL.posphis[k]] + e.vhat;
+      if (bounds) ekf_bounds(P, bk, RL, c, Scratch{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x}, z, bounds + id * (d.nz + 2));
     }
   }
 }
@@ -802,6 +883,14 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   fill(bank->negphise, RL.negphise, RL.n_negphise); fill(bank->posphise, RL.posphise, RL.n_posphise);
   fill(bank->phie, RL.phie, RL.n_phie); fill(bank->posphis, RL.posphis, RL.n_posphis);
   RL.r_phise0 = bank->r_phise0;
+  RL.r_ifdl0 = bank->r_ifdl0; RL.r_ifdl3 = bank->r_ifdl3; RL.r_if0 = bank->r_if0; RL.r_if3 = bank->r_if3;
+  RL.r_tss0 = bank->r_tss0; RL.r_tss3 = bank->r_tss3; RL.r_the0 = bank->r_the0; RL.r_the3 = bank->r_the3; RL.r_phie_last = bank->r_phie_last;
+  for (int r : bank->posphis) RL.kind[r] = 1;
+  for (int r : bank->negtss) RL.kind[r] = 2;
+  for (int r : bank->postss) RL.kind[r] = 3;
+  for (int r : bank->negphise) RL.kind[r] = 4;
+  for (int r : bank->posphise) RL.kind[r] = 5;
+  for (int r : bank->phie) RL.kind[r] = 6;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   p->sms = prop.multiProcessorCount;
@@ -850,7 +939,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     const int mask = (d.useCurrent ? 1 : 0) | (d.useVoltage ? 2 : 0) | (d.useEta ? 4 : 0) | (d.useZmax ? 8 : 0);
     if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path) {
       p->cons = mask;
-      p->run_threads = (cfg->threads_per_block == 256) ? 256 : 384;
+      p->run_threads = (cfg->threads_per_block == 384) ? 384 : 256;   // 256 threads x 255 registers: fewest spills, least DRAM traffic
       const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
       p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
@@ -1099,23 +1188,26 @@ extern "C" int mek_pop_ob_step(mek_pop* p, const double* Iapp, double* Vcell) {
   return MEK_OK;
 }
 
-extern "C" int mek_pop_iter_ekf(mek_pop* p, const double* vk, const double* ik, double* zk, double* mats) {
+extern "C" int mek_pop_iter_ekf(mek_pop* p, const double* vk, const double* ik, double* zk, double* boundzk, double* mats) {
   if (!p || !vk || !ik) return fail(MEK_ERR_ARG, "null argument");
   if (!p->inited) return fail(MEK_ERR_STATE, "mek_pop_iter_ekf before mek_pop_init");
   CUDA_TRY(cudaSetDevice(p->device));
   const size_t B = (size_t)p->P.d.B, nzk = (size_t)p->P.d.nz + 2;
-  int rc = ensure_scratch(p, 8 * B * (2 + nzk + MEK_NMATS));
+  if (boundzk && !zk) return fail(MEK_ERR_ARG, "boundzk needs zk");
+  int rc = ensure_scratch(p, 8 * B * (2 + 2 * nzk + MEK_NMATS));
   if (rc != MEK_OK) return rc;
   double* dv = p->d_scratch;
   double* di = dv + B;
   double* dz = di + B;
-  double* dm = dz + B * nzk;
+  double* db = dz + B * nzk;
+  double* dm = db + B * nzk;
   CUDA_TRY(cudaMemcpyAsync(dv, vk, 8 * B, cudaMemcpyHostToDevice, p->stream));
   CUDA_TRY(cudaMemcpyAsync(di, ik, 8 * B, cudaMemcpyHostToDevice, p->stream));
-  k_iter_ekf<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, dv, di, zk ? dz : nullptr, dm);
+  k_iter_ekf<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, dv, di, zk ? dz : nullptr, dm, boundzk ? db : nullptr);
   CUDA_TRY(cudaGetLastError());
   p->launches++;
   if (zk) CUDA_TRY(cudaMemcpyAsync(zk, dz, 8 * B * nzk, cudaMemcpyDeviceToHost, p->stream));
+  if (boundzk) CUDA_TRY(cudaMemcpyAsync(boundzk, db, 8 * B * nzk, cudaMemcpyDeviceToHost, p->stream));
   if (mats) CUDA_TRY(cudaMemcpyAsync(mats, dm, 8 * B * MEK_NMATS, cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MEK_OK;

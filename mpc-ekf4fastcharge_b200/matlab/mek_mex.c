@@ -74,12 +74,13 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     mek_pop *p = (mek_pop *)get_handle(prhs[1]);
     plhs[0] = mxCreateDoubleMatrix(1, mxGetNumberOfElements(prhs[2]), mxREAL);
     chk(mek_pop_ob_step(p, mxGetPr(prhs[2]), mxGetPr(plhs[0])));
-  } else if (!strcmp(cmd, "iter_ekf")) {                 /* [zk,mats] = mek_mex('iter_ekf', pop, vk, ik, nz)  <- iterEKF.m:30 + EKFmatsHandler.m:1 */
+  } else if (!strcmp(cmd, "iter_ekf")) {                 /* [zk,boundzk,mats] = mek_mex('iter_ekf', pop, vk, ik, nz)  <- iterEKF.m:30 + EKFmatsHandler.m:1 */
     mek_pop *p = (mek_pop *)get_handle(prhs[1]);
     mwSize B = mxGetNumberOfElements(prhs[2]), nz = (mwSize)mxGetScalar(prhs[4]);
     plhs[0] = mxCreateDoubleMatrix(nz + 2, B, mxREAL);
-    plhs[1] = mxCreateDoubleMatrix(MEK_NMATS, B, mxREAL);
-    chk(mek_pop_iter_ekf(p, mxGetPr(prhs[2]), mxGetPr(prhs[3]), mxGetPr(plhs[0]), mxGetPr(plhs[1])));
+    plhs[1] = mxCreateDoubleMatrix(nz + 2, B, mxREAL);
+    plhs[2] = mxCreateDoubleMatrix(MEK_NMATS, B, mxREAL);
+    chk(mek_pop_iter_ekf(p, mxGetPr(prhs[2]), mxGetPr(prhs[3]), mxGetPr(plhs[0]), mxGetPr(plhs[1]), mxGetPr(plhs[2])));
   } else if (!strcmp(cmd, "iter_mpc")) {                 /* [uk,phise,nexec] = mek_mex('iter_mpc', pop, mats, uk_applied)  <- iterMPC.m:1 */
     mek_pop *p = (mek_pop *)get_handle(prhs[1]);
     mwSize B = mxGetNumberOfElements(prhs[3]);

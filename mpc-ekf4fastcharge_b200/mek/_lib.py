@@ -75,7 +75,7 @@ def lib():
         L.mek_write_state.argtypes = [C.c_void_p, C.c_void_p]
         L.mek_summary.argtypes = [C.c_void_p, C.c_void_p]
         L.mek_pop_ob_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.mek_pop_iter_ekf.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.mek_pop_iter_ekf.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.mek_pop_iter_mpc.argtypes = [C.c_void_p] + [C.c_void_p] * 6
         L.mek_hildreth.argtypes = [C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int]
         L.mek_pred_mat.argtypes = [C.c_int64] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 2 + [C.c_int]

@@ -182,13 +182,15 @@ class CellBatch:
         check(_lib.lib().mek_pop_ob_step(self.h, _p(I), _p(V)))
         return V
 
-    def iter_ekf(self, vk, ik, want_zk=True):
+    def iter_ekf(self, vk, ik, want_zk=True, want_bounds=False):
+        """[zk, boundzk, ekfData, Xind] = iterEKF(vk, ik, Tk, ekfData) + EKFmatsHandler: returns (zk, mats) or (zk, boundzk, mats)."""
         v = _f64(np.broadcast_to(np.asarray(vk, float), (self.B,)))
         i = _f64(np.broadcast_to(np.asarray(ik, float), (self.B,)))
-        zk = np.empty((self.B, self.nz + 2)) if want_zk else None
+        zk = np.empty((self.B, self.nz + 2)) if (want_zk or want_bounds) else None
+        bz = np.empty((self.B, self.nz + 2)) if want_bounds else None
         mats = np.empty((self.B, NMATS))
-        check(_lib.lib().mek_pop_iter_ekf(self.h, _p(v), _p(i), _p(zk), _p(mats)))
-        return zk, mats
+        check(_lib.lib().mek_pop_iter_ekf(self.h, _p(v), _p(i), _p(zk), _p(bz), _p(mats)))
+        return (zk, bz, mats) if want_bounds else (zk, mats)
 
     def iter_mpc(self, mats, uk_applied):
         mats = _f64(mats, (self.B, NMATS))
