@@ -149,3 +149,27 @@ def api_fp64_ok():
     from mek import api
     tf = api.fp64_peak_tflops(0)
     return 5.0 < tf < 100.0
+
+
+def test_boundzk_three_sigma_bounds_vs_literal(bank):
+    """iterEKF's second output (iterEKF.m:185-205, getChatZ) from mek_pop_iter_ekf against the literal restatement."""
+    from mek import api, population as P
+    from oracle import literal as L
+    ROM = L.build_rom(bank)
+    SigmaX0 = np.diag([1.0] * 5 + [2e6])
+    for SOC0, T in ((22.0, 30.0), (10.0, 25.0), (61.0, 17.0)):
+        kf = L.initKF(SOC0, T, SigmaX0, 1e-3, 1e2, "OutB", ROM)
+        V, obs, cs = L.OB_step(0.0, T, None, ROM, dict(SOC0=SOC0, warnOff=True))
+        rom = api.RomBank(bank)
+        cb = api.CellBatch(rom, 1)
+        cb.init([SOC0], [T], SigmaX0, P.default_limits(bank.params[2]))
+        rng = np.random.default_rng(1)
+        for k in range(30):
+            I = float(rng.uniform(-60, 2))
+            V, obs, cs = L.OB_step(I, T, cs, ROM)
+            zk, zb, kf, X = L.iterEKF(V, I, T, kf)
+            cb.ob_step([I])
+            gz, gb, mats = cb.iter_ekf([V], [I], want_bounds=True)
+            assert np.allclose(gz[0], zk, rtol=1e-9, atol=1e-12)
+            assert np.all(np.isfinite(gb[0])) and np.all(gb[0] >= 0)
+            assert np.allclose(gb[0], zb, rtol=1e-8, atol=1e-13), (k, np.max(np.abs(gb[0] - zb) / np.maximum(zb, 1e-300)))
