@@ -43,7 +43,10 @@ def test_c3_one_million_cells_subsample_parity_and_population_properties(bank, c
     cb.run(1000, N_SIM)
     s2 = cb.summary()
     for k in s:
-        assert s[k] == s2[k], k
+        if k == "sum_soc":                      # floating-point sum over 1 Mi cells, accumulated with atomics: order is not fixed
+            assert abs(s[k] - s2[k]) < 1e-6
+        else:
+            assert s[k] == s2[k], k
     g2 = cb.logs()
     assert np.array_equal(g["u"], g2["u"]) and np.array_equal(g["active"], g2["active"])
 
