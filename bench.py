@@ -248,7 +248,7 @@ def main_mek(a):
                        "what": "mek_pop_init (pinned host inputs) + mek_run + mek_summary + mek_read_logs of %d cells' trajectories" % nlog},
                "gpu_launches": launches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                            "traffic": traffic, "kernel": "k_run_population<5,2,15,384,1>", "peak_source": "measured" if peaks else "fallback",
+                            "traffic": traffic, "kernel": "k_run_population<5,2,15,256,1>", "peak_source": "measured" if peaks else "fallback",
                             "bytes_per_cellstep": bytes_per_cellstep, "kernel_ms": kern_avg_ms},
                "fp64": {"peak_tflops_measured": fp64_tf},
                "qp_solves_per_s": value * qps, "hildreth_sweeps_per_s": value * sweeps, "mean_sweeps_per_step": sweeps,
