@@ -202,22 +202,21 @@ __device__ __forceinline__ void prefetch_models(const Dims& d, const Cell& c, in
 template <bool PLANT, bool EKF, int BATCH = 2>   // BATCH models' loads in flight per thread before the first store
 __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk, const Cell& c, double Iapp, double prior) {
   const double Sw = d.SigmaW;
-  constexpr int PD = 6;                                               // prefetch distance in models
+  constexpr int PD = 2 * BATCH + 2;                                   // prefetch distance in models
   int m = 0;
 #pragma unroll 1
-  for (; BATCH == 2 && m + 1 < d.M; m += 2) {
-    prefetch_models(d, c, m + PD, 2, PLANT, EKF);
-    ModelRegs<PLANT, EKF> r0, r1;
-    model_load<PLANT, EKF>(c, m, r0);
-    model_load<PLANT, EKF>(c, m + 1, r1);
-    model_update<PLANT, EKF>(bk.mdl + m * d.mstride, Iapp, prior, Sw, r0);
-    model_update<PLANT, EKF>(bk.mdl + (m + 1) * d.mstride, Iapp, prior, Sw, r1);
-    model_store<PLANT, EKF>(c, m, r0);
-    model_store<PLANT, EKF>(c, m + 1, r1);
+  for (; m + BATCH <= d.M; m += BATCH) {
+    prefetch_models(d, c, m + PD, BATCH, PLANT, EKF);
+    ModelRegs<PLANT, EKF> r[BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) model_load<PLANT, EKF>(c, m + b, r[b]);
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) model_update<PLANT, EKF>(bk.mdl + (m + b) * d.mstride, Iapp, prior, Sw, r[b]);
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) model_store<PLANT, EKF>(c, m + b, r[b]);
   }
 #pragma unroll 1
   for (; m < d.M; ++m) {
-    if (BATCH == 1) prefetch_models(d, c, m + PD, 1, PLANT, EKF);
     ModelRegs<PLANT, EKF> r0;
     model_load<PLANT, EKF>(c, m, r0);
     model_update<PLANT, EKF>(bk.mdl + m * d.mstride, Iapp, prior, Sw, r0);

@@ -20,6 +20,10 @@
 
 using namespace mek;
 
+#ifndef MEK_STREAM_BATCH
+#define MEK_STREAM_BATCH 2   // models whose loads are in flight per thread in the HBM stream
+#endif
+
 // ------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
       if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
       if (!active) continue;
       StepLog lg;
-      cell_step<NPM, NCM, CONS, 2>(P, bk, c, lg, smt, sms, tt);
+      cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt);
       // per-cell summary, kept in the state header (not in registers: they are the scarce resource of this kernel)
       if (lg.nexec > 0) {
         c.f(S_SUM_NEXEC) += (double)lg.nexec;
