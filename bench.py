@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--nsim", type=int, default=N_SIM)
     ap.add_argument("--log-cells", type=int, default=4096, help="cells per GPU whose full trajectory is logged and read back in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-cells-per-core", type=int, default=96)
+    ap.add_argument("--cpu-cells-per-core", type=int, default=1024, help="CPU sample: cells per host core (full charges); ~10-15 s of CPU work on the GPU box")
     return ap.parse_args()
 
 
@@ -119,7 +119,7 @@ def main_reference(a):
     from mek import bank as Bk
     bank = Bk.Bank.load(Bk.default_bank_path())
     cores = os.cpu_count() or 1
-    cells = max(cores * a.cpu_cells_per_core // 4, cores)
+    cells = max(cores * a.cpu_cells_per_core, cores)
     vals = []
     for i in range(a.warmup + a.steps):
         v = cpu_run(bank, cells, a.nsim, cores)
