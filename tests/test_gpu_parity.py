@@ -119,3 +119,21 @@ def test_cell_ordering_is_invisible_to_the_caller(bank):
     assert outs[0][0]["u"].shape == (500, 150)
     assert np.array_equal(outs[0][1], outs[1][1])
     assert outs[0][2]["sum_nexec"] == outs[1][2]["sum_nexec"] and outs[0][2]["min_phise"] == outs[1][2]["min_phise"]
+
+
+def test_lost_filter_latch_q19(bank, coracle_mod):
+    """Q19: more than 10 EKF warnings latch the filter 'lost' (iterEKF.m:55-59): NaN outputs from then on, status bit set,
+    the cell idles; healthy cells in the same warp are unaffected."""
+    from mek import api, population as P
+    pop = P.make_population(bank.params[2], 64, seed=14)
+    pop.ekf_SOC0[::7] = 150.0                       # EKF initialised at 150 % SOC: SOCnAvg > 1 on every getVariables call
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 60)
+    _assert_bit_exact(g, c)
+    lost = np.isnan(g["u"][-1])
+    assert lost[::7].all() and not lost[1::7].any()
+    first_nan = np.argmax(np.isnan(g["u"][:, 0]))
+    assert 3 <= first_nan <= 8                       # two warnings per iterEKF call -> latched after ~6 calls
+    s = cb.summary()
+    assert s["n_lost"] == lost.sum() and s["n_warn"] >= 11 * lost.sum()
+    st = cb.read_state()
+    assert ((st[:, 18].astype(int) & 1) == lost).all()          # S_STATUS bit MEK_ST_LOST
