@@ -78,6 +78,10 @@ typedef struct {
   int generic_path;         /* 1: never use the static-shape fast instances           */
   int sync_steps;           /* CTA-wide barrier before every sample instant: 0/1 = on (default), -1 = off */
   int keep_cell_order;      /* 1: do not reorder cells by (T, SOC0) inside the state block             */
+  int defer_block;          /* sample instants per deferral block of mek_run: local models outside a cell's present
+                               set-point neighbourhood are advanced once per block by replaying the block's currents
+                               (bit-identical to advancing them every instant).  0 = default (16), -1 = off        */
+  int defer_stagger;        /* 1: warps of a CTA start their deferral blocks at different instants                */
 } mek_config;
 
 /* ---- bank ---- */

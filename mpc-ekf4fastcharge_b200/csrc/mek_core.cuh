@@ -139,20 +139,25 @@ struct ModelRegs {
   double bx[PLANT ? 6 : 1], x[EKF ? N5 : 1], s[EKF ? NSYM : 1];
 };
 
-template <bool PLANT, bool EKF>
+// KEEP=false: evict-first accesses (.cs) for rows that are touched once and not again soon (the cold stream);
+// KEEP=true: L2-cached accesses (.cg) for the models a cell advances every instant, which stay resident in L2.
+template <bool KEEP> __device__ __forceinline__ double ld_state(const double* q) { return KEEP ? __ldcg(q) : __ldcs(q); }
+template <bool KEEP> __device__ __forceinline__ void st_state(double* q, double v) { if (KEEP) __stcg(q, v); else __stcs(q, v); }
+
+template <bool PLANT, bool EKF, bool KEEP = false>
 __device__ __forceinline__ void model_load(const Cell& c, int m, ModelRegs<PLANT, EKF>& r) {
   if (PLANT) {
     const double* q = &c.bigx(m, 0);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) r.bx[j] = __ldcs(q + j * TILE);
+    for (int j = 0; j < 6; ++j) r.bx[j] = ld_state<KEEP>(q + j * TILE);
   }
   if (EKF) {
     const double* q = &c.xhat(m, 0);
 #pragma unroll
-    for (int j = 0; j < N5; ++j) r.x[j] = __ldcs(q + j * TILE);
+    for (int j = 0; j < N5; ++j) r.x[j] = ld_state<KEEP>(q + j * TILE);
     const double* w = &c.sig(m, 0);
 #pragma unroll
-    for (int k = 0; k < NSYM; ++k) r.s[k] = __ldcs(w + k * TILE);
+    for (int k = 0; k < NSYM; ++k) r.s[k] = ld_state<KEEP>(w + k * TILE);
   }
 }
 template <bool PLANT, bool EKF>
@@ -171,20 +176,20 @@ __device__ __forceinline__ void model_update(const double* a, double Iapp, doubl
       for (int j = i; j < N5; ++j, ++q) r.s[q] = fma(a[i] * r.s[q], a[j], Sw);   // iterEKF.m:81 (Q12)
   }
 }
-template <bool PLANT, bool EKF>
+template <bool PLANT, bool EKF, bool KEEP = false>
 __device__ __forceinline__ void model_store(const Cell& c, int m, const ModelRegs<PLANT, EKF>& r) {
   if (PLANT) {
     double* q = &c.bigx(m, 0);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) __stcs(q + j * TILE, r.bx[j]);
+    for (int j = 0; j < 6; ++j) st_state<KEEP>(q + j * TILE, r.bx[j]);
   }
   if (EKF) {
     double* q = &c.xhat(m, 0);
 #pragma unroll
-    for (int j = 0; j < N5; ++j) __stcs(q + j * TILE, r.x[j]);
+    for (int j = 0; j < N5; ++j) st_state<KEEP>(q + j * TILE, r.x[j]);
     double* w = &c.sig(m, 0);
 #pragma unroll
-    for (int k = 0; k < NSYM; ++k) __stcs(w + k * TILE, r.s[k]);
+    for (int k = 0; k < NSYM; ++k) st_state<KEEP>(w + k * TILE, r.s[k]);
   }
 }
 // L2 prefetch of the state rows of models [m, m+cnt) of this warp's tile: in the AoSoA layout each of the three
@@ -225,11 +230,124 @@ __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk,
 }
 
 // ------------------------------------------------------------------------------------------
+// Deferred advance of the models a cell is not reading (temporal blocking of the HBM stream).
+//
+// OB_step.m:278 and iterEKF.m:73-84 advance ALL M local models every sample instant, but one instant only READS the
+// plant's four set-point neighbours and the EKF's four, and only the EKF's four receive a measurement update.  For every
+// other model the instant is the data-independent recurrence x <- a.*x + u_k, S <- a.*S.*a' + SigmaW, driven by the cell's
+// current history alone.  The fused kernel therefore works in blocks of KB instants: the models around the cell's
+// present SOC ("hot", a warp-uniform bit mask) are advanced every instant as the reference does; the others are brought
+// up to date once per block by replaying the block's recorded currents through the same recurrence, in registers —
+// one HBM round trip per block instead of one per instant.  A model outside the hot set that a cell turns out to need
+// (plant or EKF neighbour) is replayed on the spot and joins that cell's own set (`mine`).  Every model sees the same
+// operations in the same order as in the instant-by-instant form, so results are bit-identical.
+// History column in shared memory: h[0] = priorI at the start of the block, h[1+j] = u applied at block instant j;
+// the EKF time update of instant j uses h[j] (iterEKF.m:210: priorI = previous ik), the plant advance h[j+1].
+// ------------------------------------------------------------------------------------------
+struct Defer {
+  unsigned long long hot;    // warp-uniform
+  unsigned long long mine;   // this cell's on-demand additions inside the current block
+  int n;                     // instants recorded in the current block = advances applied to this cell's hot models
+  double* h;                 // this thread's history column
+  int hs;                    // column stride
+};
+
+__device__ __noinline__ void defer_catch_up(const Dims& d, const BankSmem& bk, const Cell& c, int m, int n, const double* h, int hs) {
+  ModelRegs<true, true> r;
+  model_load<true, true>(c, m, r);
+  double a[6];
+  const double* am = bk.mdl + m * d.mstride;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = am[j];
+  const double Sw = d.SigmaW;
+#pragma unroll 1
+  for (int j = 0; j < n; ++j) model_update<true, true>(a, h[(j + 1) * hs], h[j * hs], Sw, r);
+  model_store<true, true>(c, m, r);
+}
+
+__device__ __forceinline__ void defer_ensure(const Dims& d, const BankSmem& bk, const Cell& c, Defer* df, int m) {
+  if (!df) return;
+  if (((df->hot | df->mine) >> m) & 1ull) return;
+  if (df->n > 0) defer_catch_up(d, bk, c, m, df->n, df->h, df->hs);
+  df->mine |= 1ull << m;
+}
+
+// models this cell is expected to read during the coming block: both temperature rows x the SOC set-points around the
+// plant's and the EKF's present SOC, widened by the largest SOC change the current limits allow over `span` instants
+__device__ __noinline__ unsigned long long defer_hot_set(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
+                                                         int tt, int span) {
+  const double th0n = p[P_NEG + E_THETA0], th100n = p[P_NEG + E_THETA100];
+  const double rpa = d.Ts / (3600.0 * p[P_Q]);
+  const double zp = (c.f(S_SOCN) - th0n) / (th100n - th0n);
+  const double ze = c.f(S_EKFSOC0) - (c.f(S_X0) + c.f(S_PRIORI)) * rpa;
+  const double margin = 1.25 * (double)span * rpa * fmax(fabs(c.f(S_UMAX)), fabs(c.f(S_UMIN))) + 1e-4;
+  const int a = two_nearest(fmin(zp, ze) - margin, bk.Zpts, d.nZ), b = two_nearest(fmax(zp, ze) + margin, bk.Zpts, d.nZ);
+  int zl = (a & 0xffff) < (a >> 16) ? (a & 0xffff) : (a >> 16);
+  int zh = (b & 0xffff) > (b >> 16) ? (b & 0xffff) : (b >> 16);
+  if (zl > zh) { const int t = zl; zl = zh; zh = t; }
+  const int t1 = tt & 0xffff, t2 = tt >> 16;
+  unsigned long long mask = 0ull;
+  for (int z = zl; z <= zh; ++z) mask |= (1ull << (t1 * d.nZ + z)) | (1ull << (t2 * d.nZ + z));
+  return mask;
+}
+
+// one instant's advance (plant with u_k, EKF time update with priorI) of the hot models; records u_k in the history
+__device__ __forceinline__ void defer_stream(const Dims& d, const BankSmem& bk, const Cell& c, Defer& df, double Iapp, double prior) {
+  const double Sw = d.SigmaW;
+  df.h[(df.n + 1) * df.hs] = Iapp;
+  unsigned long long w = df.hot;
+#pragma unroll 1
+  while (w) {                                                        // warp-uniform: coalesced rows, two models' loads in flight
+    const int m0 = __ffsll((long long)w) - 1;
+    w &= w - 1;
+    if (w) {
+      const int m1 = __ffsll((long long)w) - 1;
+      w &= w - 1;
+      ModelRegs<true, true> r0, r1;
+      model_load<true, true, true>(c, m0, r0);
+      model_load<true, true, true>(c, m1, r1);
+      model_update<true, true>(bk.mdl + m0 * d.mstride, Iapp, prior, Sw, r0);
+      model_update<true, true>(bk.mdl + m1 * d.mstride, Iapp, prior, Sw, r1);
+      model_store<true, true, true>(c, m0, r0);
+      model_store<true, true, true>(c, m1, r1);
+    } else {
+      ModelRegs<true, true> r0;
+      model_load<true, true, true>(c, m0, r0);
+      model_update<true, true>(bk.mdl + m0 * d.mstride, Iapp, prior, Sw, r0);
+      model_store<true, true, true>(c, m0, r0);
+    }
+  }
+  unsigned long long x = df.mine & ~df.hot;                          // this cell's own additions (rare)
+#pragma unroll 1
+  while (x) {
+    const int m0 = __ffsll((long long)x) - 1;
+    x &= x - 1;
+    ModelRegs<true, true> r0;
+    model_load<true, true, true>(c, m0, r0);
+    model_update<true, true>(bk.mdl + m0 * d.mstride, Iapp, prior, Sw, r0);
+    model_store<true, true, true>(c, m0, r0);
+  }
+  df.n += 1;
+}
+
+// end of a block: replay the block's history through every model outside the hot set (one HBM round trip per block)
+__device__ __forceinline__ void defer_flush(const Dims& d, const BankSmem& bk, const Cell& c, Defer& df) {
+#pragma unroll 1
+  for (int m = 0; m < d.M; ++m) {
+    if ((df.hot >> m) & 1ull) continue;                              // warp-uniform
+    prefetch_models(d, c, m + 2, 1, true, true);
+    if (df.n > 0 && !((df.mine >> m) & 1ull)) defer_catch_up(d, bk, c, m, df.n, df.h, df.hs);
+  }
+  df.n = 0;
+  df.mine = 0ull;
+}
+
+// ------------------------------------------------------------------------------------------
 // plant: OB_step.m simStep (:188-357).  Returns Vcell.
 // ------------------------------------------------------------------------------------------
 template <bool ADVANCE>   // ADVANCE=false: the caller runs stream_models<true,...> right after (fused pass)
 __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
-                                             double Iapp, int tt_cached) {
+                                             double Iapp, int tt_cached, Defer* df = nullptr) {
   const double T = c.f(S_TC) + 273.15;                               // OB_step.m:75
   const double th0n = p[P_NEG + E_THETA0], th100n = p[P_NEG + E_THETA100];
   const double th0p = p[P_POS + E_THETA0], th100p = p[P_POS + E_THETA100];
@@ -266,6 +384,8 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
     const int ma = iT * d.nZ + iZlo, mb = iT * d.nZ + iZup;
     const double* ra = bk.mdl + ma * d.mstride + 6;
     const double* rb = bk.mdl + mb * d.mstride + 6;
+    defer_ensure(d, bk, c, df, ma);
+    defer_ensure(d, bk, c, df, mb);
     double xa[6], xb[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) { xa[j] = c.bigx(ma, j); xb[j] = c.bigx(mb, j); }
@@ -495,7 +615,7 @@ struct EkfOut {          // what EKFmatsHandler hands to the MPC (EKFmatsHandler
 // iterEKF (OB mode, iterEKF.m:55-210) followed by EKFmatsHandler (EKFmatsHandler.m:26-114)
 template <bool TIME_UPDATE>   // TIME_UPDATE=false: the caller already ran stream_models<...,true> with priorI
 __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double vk,
-                                         double ik, EkfOut& o, Scratch sc, int tt_cached) {
+                                         double ik, EkfOut& o, Scratch sc, int tt_cached, Defer* df = nullptr) {
   o.lost = 0;
   if (c.f(S_WARN) > 10.0) {                                          // iterEKF.m:55-59 (Q19)
     c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_LOST);
@@ -511,6 +631,10 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
   double SOC = c.f(S_EKFSOC0) - x0 * rpa;                            // :89
   get_xind(d, bk, Tk, SOC, sc, tt_cached);                           // :107
+  if (df) {
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
+  }
   double vhat = get_variables(d, bk, p, c, ik, Tk, sc);              // :108
   // ---- getChatV scalars (:421-519) ----
   const double tss0 = sc[SC_Z + HR_TSS0], tss3 = sc[SC_Z + HR_TSS3];
@@ -595,6 +719,10 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   c.f(S_SIGX0) = sx0;
   SOC = c.f(S_EKFSOC0) - x0 * rpa;                                   // :159
   get_xind(d, bk, Tk, SOC, sc, tt_cached);                           // :181
+  if (df) {                                                          // the estimate may have moved to other set-points
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
+  }
   vhat = get_variables(d, bk, p, c, ik, Tk, sc);                     // :182
   const double Zsoc = c.f(S_EKFSOC0) - x0 * rpa;                     // :416
   c.f(S_PRIORI) = ik;                                                // :210

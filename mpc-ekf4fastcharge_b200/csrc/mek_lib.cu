@@ -17,6 +17,9 @@
 
 #include "../../include/mek.h"
 #include "mek_core.cuh"
+#ifndef MEK_DEFER_DEFAULT
+#define MEK_DEFER_DEFAULT 16     // sample instants per deferral block when mek_config.defer_block == 0
+#endif
 
 using namespace mek;
 
@@ -222,6 +225,9 @@ struct Params {
   double* log_u; double* log_V; double* log_soc; double* log_phise;
   unsigned char* log_iT; unsigned char* log_iZ; unsigned short* log_nexec; unsigned* log_active; int log_words;
   int sync_steps;             // 1: CTA-wide barrier before every sample instant
+  int defer_k;                // > 0: sample instants per deferral block (models outside a cell's hot set are advanced once per block); 0: off
+  int defer_stagger;          // 1: the warps of a CTA start their blocks at different instants (spreads the block-end HBM bursts)
+  int hist_off;               // doubles from the start of dynamic shared memory to the history columns [defer_k + 1][threads]
   const int* slot2cell;       // state slot -> caller's cell index (cells are ordered by initial SOC inside the block), or null
 };
 
@@ -273,19 +279,22 @@ struct StepLog {
 };
 
 template <int NPM, int NCM, int CONS, int BATCH>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
-__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms, int tt) {
+__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms, int tt,
+                                          Defer* df) {
   const Dims& d = P.d;
   lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) lg.active[w] = 0u;
   if ((unsigned)c.f(S_STATUS) & ST_LOST) return;                     // Q19: a lost cell idles
   const double uk = c.f(S_UK);
-  prefetch_models(d, c, 0, 6, true, true);                           // first rows of this instant's HBM stream -> L2 while the plant outputs are computed
-  const double V = plant_step<false>(d, bk, P.cp, c, uk, tt);        // runMPC.m:85 (outputs; the state advance is fused below)
-  // one HBM pass over the M local models: OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}
-  stream_models<true, true, BATCH>(d, bk, c, uk, c.f(S_PRIORI));
+  if (!df) prefetch_models(d, c, 0, 6, true, true);                  // first rows of this instant's HBM stream -> L2 while the plant outputs are computed
+  const double V = plant_step<false>(d, bk, P.cp, c, uk, tt, df);    // runMPC.m:85 (outputs; the state advance is fused below)
+  // OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}: one HBM pass over all M local models, or (deferral
+  // on) over the cell's hot models only -- the rest catch up at the end of the block
+  if (df) defer_stream(d, bk, c, *df, uk, c.f(S_PRIORI));
+  else stream_models<true, true, BATCH>(d, bk, c, uk, c.f(S_PRIORI));
   EkfOut e;
-  ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms}, tt);  // runMPC.m:88,92
+  ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms}, tt, df);  // runMPC.m:88,92
   if (e.lost) return;
   MpcOut o;
   if constexpr (CONS >= 0) mpc_step_fast<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, smt, sms);   // runMPC.m:94-103
@@ -294,6 +303,11 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   lg.iT = e.iT + 1; lg.iZ = e.iZ + 1; lg.nexec = o.nexec;
 #pragma unroll
   for (int w = 0; w < 4; ++w) lg.active[w] = o.active[w];
+}
+
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+  const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v), hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+  return ((unsigned long long)hi << 32) | lo;
 }
 
 // ---- k_run_population: the fused persistent kernel ----
@@ -307,6 +321,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
   const Dims& d = P.d;
   const long long stride = (long long)gridDim.x * THREADS;
   const long long first = (long long)blockIdx.x * THREADS;
+  const int KB = P.defer_k;                          // 0: every model is advanced every instant
+  Defer df{0ull, 0ull, 0, sm + P.hist_off + threadIdx.x, THREADS};
+  // block boundaries of this warp: instants with (k - k0 + off) % KB == 0 (and k0 itself)
+  const int off = (KB > 0 && P.defer_stagger) ? (int)(((threadIdx.x >> 5) * KB) / (THREADS / 32)) : 0;
   // every thread of the CTA walks the same number of rounds so that the optional per-instant barrier is legal
   for (long long base = first; base < d.B; base += stride) {
     const long long cell = base + threadIdx.x;
@@ -318,9 +336,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
 #pragma unroll 1
     for (int k = k0; k < k1; ++k) {
       if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
+      if (KB > 0 && (k == k0 || (k - k0 + off) % KB == 0)) {           // warp-uniform: start of a deferral block
+        if (k != k0 && active) defer_flush(d, bk, c, df);
+        const bool run = active && !((unsigned)c.f(S_STATUS) & ST_LOST);
+        int left = KB - (k - k0 + off) % KB;
+        df.hot = warp_or64(run ? defer_hot_set(d, bk, P.cp, c, tt, left) : 0ull);
+        df.mine = 0ull;
+        df.n = 0;
+        if (run) df.h[0] = c.f(S_PRIORI);
+      }
       if (!active) continue;
       StepLog lg;
-      cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt);
+      cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt, KB > 0 ? &df : nullptr);
       // per-cell summary, kept in the state header (not in registers: they are the scarce resource of this kernel)
       if (lg.nexec > 0) {
         c.f(S_SUM_NEXEC) += (double)lg.nexec;
@@ -338,6 +365,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
         for (int w = 0; w < P.log_words; ++w) P.log_active[o * P.log_words + w] = lg.active[w];
       }
     }
+    if (KB > 0 && active && k1 > k0) defer_flush(d, bk, c, df);      // the state block leaves the kernel fully advanced
     if (active) c.f(S_STEPS) += (double)(k1 - k0);
   }
 }
@@ -948,6 +976,18 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
       p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
     }
+  }
+  // deferral blocks (temporal blocking of the model stream): history columns behind the scratch columns
+  {
+    int kb = cfg->defer_block == 0 ? MEK_DEFER_DEFAULT : cfg->defer_block;
+    if (kb < 2 || d.M > 64) kb = 0;                  // the hot set is a 64-bit mask
+    if (kb > 64) kb = 64;
+    while (kb > 0 && p->run_smem + sizeof(double) * (size_t)(kb + 1) * (size_t)p->run_threads > 227 * 1024) kb /= 2;
+    if (kb < 2) kb = 0;
+    p->P.defer_k = kb;
+    p->P.defer_stagger = cfg->defer_stagger > 0 ? 1 : 0;
+    p->P.hist_off = (int)(p->run_smem / sizeof(double));
+    if (kb > 0) p->run_smem += sizeof(double) * (size_t)(kb + 1) * (size_t)p->run_threads;
   }
 #define MEK_PREP(KERN)                                                                                          \
   do {                                                                                                          \
