@@ -218,7 +218,10 @@ def main_mek(a):
         nC = cb.nC
         M = bank.M
         state_bytes = 8 * (26 * M + 40 + nC)                       # SoA state block per cell
-        bytes_per_cellstep = 2 * state_bytes + 40                  # state streamed once in, once out, + log record
+        kdef = cb.defer_block                                      # sample instants per deferral block (0: every model every instant)
+        streamed_bytes = 2 * state_bytes + 40                      # instant-by-instant design: state once in, once out, + log record
+        # with deferral every model row crosses HBM at most once each way per block of kdef instants
+        bytes_per_cellstep = (2 * 8 * 26 * M) / kdef + 40 if kdef > 0 else streamed_bytes
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -226,13 +229,19 @@ def main_mek(a):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_per_cellstep * float(B) * a.nsim / (kern_avg_ms * 1e-3) / 1e9
-        # DRAM bytes per cell-step measured by `ncu --set full` on this kernel (profiles/r01_final_ncu_summary.csv),
-        # scaled to the units one launch of this run processes
-        traffic = None
+        # DRAM bytes per cell-step and issue-slot / FP64-pipe utilisation measured by `ncu --set full` on this kernel
+        # (profiles/r01_defer_ncu_summary.csv); traffic is scaled to the units one launch of this run processes
+        traffic, prof = None, {}
         try:
-            for line in open(os.path.join(ROOT, "profiles", "r01_final_ncu_summary.csv")):
+            for line in open(os.path.join(ROOT, "profiles", "r01_defer_ncu_summary.csv" if kdef > 0 else "r01_final_ncu_summary.csv")):
                 if line.startswith("# DRAM traffic per cell-step"):
                     traffic = float(line.split("=")[1].split("B")[0].replace(" ", "")) * float(B) * a.nsim
+                elif not line.startswith("#") and line.count(",") == 2:
+                    k_, _, v_ = line.strip().split(",")
+                    try:
+                        prof[k_] = float(v_)
+                    except ValueError:
+                        pass
         except Exception:
             pass
         fp64_tf = api.fp64_peak_tflops(local)
@@ -242,14 +251,22 @@ def main_mek(a):
                "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": {"workload": workload_name(B, a.nsim), "cells_total": B * world, "nsim": a.nsim,
-                          "l2": "inputs larger than L2: per-GPU state block %.2f GB streamed every sample instant" % (state_bytes * B / 1e9)},
+                          "l2": "inputs larger than L2: per-GPU state block %.2f GB, resident working set of the 37888 cells in flight 256 MB" % (state_bytes * B / 1e9)},
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "what": "mek_pop_init (pinned host inputs) + mek_run + mek_summary + mek_read_logs of %d cells' trajectories" % nlog},
                "gpu_launches": launches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                             "traffic": traffic, "kernel": "k_run_population<5,2,15,256,1>", "peak_source": "measured" if peaks else "fallback",
-                            "bytes_per_cellstep": bytes_per_cellstep, "kernel_ms": kern_avg_ms},
+                            "bytes_per_cellstep": bytes_per_cellstep, "kernel_ms": kern_avg_ms, "defer_block": kdef,
+                            "note": "deferral blocks took the kernel off the HBM roofline (see roofline_streamed and issue): it is bound by "
+                                    "FP64 dependency latency at 2 warps per scheduler, not by bytes"},
+               # the HBM bound of the instant-by-instant form of the same loop (every model streamed every instant)
+               "roofline_streamed": {"bytes_per_cellstep": streamed_bytes, "bound_cellsteps_per_s": hbm_peak * 1e9 / streamed_bytes,
+                                     "value_over_bound": (float(B) * a.nsim / (kern_avg_ms * 1e-3)) / (hbm_peak * 1e9 / streamed_bytes)},
+               "issue": {"issue_slots_active_pct": prof.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                         "fp64_pipe_active_pct": prof.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                         "source": "ncu capture in profiles/ (37888-cell stretch of the same kernel), not measured in this run"},
                "fp64": {"peak_tflops_measured": fp64_tf},
                "qp_solves_per_s": value * qps, "hildreth_sweeps_per_s": value * sweeps, "mean_sweeps_per_step": sweeps,
                "summary": {k: summ[k] for k in ("n_reached", "n_cap", "n_lost", "n_nonfinite", "min_phise", "max_V")}}

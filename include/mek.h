@@ -109,6 +109,7 @@ int mek_sync(mek_pop *pop);
 void *mek_pop_stream(mek_pop *pop);                              /* cudaStream_t                  */
 int64_t mek_pop_launches(const mek_pop *pop);                    /* kernels launched so far       */
 int mek_pop_ncon(const mek_pop *pop);                            /* constraint rows nC            */
+int mek_pop_defer_block(const mek_pop *pop);                     /* deferral block length in use (0 = off) */
 int mek_pop_state_len(const mek_pop *pop);                       /* doubles per cell in read/write_state */
 /* logs for instants [k0,k1) x first n_log_cells cells, [step][cell] row-major.  Any pointer may be NULL.
  * u = command computed at k (applied at k+1, runMPC.m:106), V = voltage_store, soc = zk(end),

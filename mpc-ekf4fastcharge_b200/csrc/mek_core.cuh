@@ -270,6 +270,7 @@ __device__ __forceinline__ void defer_ensure(const Dims& d, const BankSmem& bk, 
   if (((df->hot | df->mine) >> m) & 1ull) return;
   if (df->n > 0) defer_catch_up(d, bk, c, m, df->n, df->h, df->hs);
   df->mine |= 1ull << m;
+  c.f(S_SPARE) += 1.0;                                               // diagnostic: on-demand catch-ups of this cell
 }
 
 // models this cell is expected to read during the coming block: both temperature rows x the SOC set-points around the

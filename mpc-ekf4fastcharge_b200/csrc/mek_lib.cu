@@ -1140,6 +1140,7 @@ extern "C" int mek_sync(mek_pop* p) {
 extern "C" void* mek_pop_stream(mek_pop* p) { return p ? (void*)p->stream : nullptr; }
 extern "C" int64_t mek_pop_launches(const mek_pop* p) { return p ? p->launches : 0; }
 extern "C" int mek_pop_ncon(const mek_pop* p) { return p ? p->P.d.nC : 0; }
+extern "C" int mek_pop_defer_block(const mek_pop* p) { return p ? p->P.defer_k : 0; }
 extern "C" int mek_pop_state_len(const mek_pop* p) { return p ? p->P.d.nfields : 0; }
 
 extern "C" int mek_read_logs(mek_pop* p, int k0, int k1, double* u, double* V, double* soc, double* phise, int32_t* iT, int32_t* iZ,

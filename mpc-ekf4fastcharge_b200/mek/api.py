@@ -89,6 +89,7 @@ class CellBatch:
         self.h = C.c_void_p()
         check(L.mek_pop_create(rom.h, C.byref(cfg), self.B, int(device), C.byref(self.h)))
         self.nC = L.mek_pop_ncon(self.h)
+        self.defer_block = L.mek_pop_defer_block(self.h)      # what the library settled on (0 = off)
         self.state_len = L.mek_pop_state_len(self.h)
         self.nz = rom.bank.nz
         self.nlog = 0

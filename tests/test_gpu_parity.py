@@ -137,3 +137,65 @@ def test_lost_filter_latch_q19(bank, coracle_mod):
     assert s["n_lost"] == lost.sum() and s["n_warn"] >= 11 * lost.sum()
     st = cb.read_state()
     assert ((st[:, 18].astype(int) & 1) == lost).all()          # S_STATUS bit MEK_ST_LOST
+
+
+# ---- deferral blocks (temporal blocking of the model stream) ----
+def _oracle_state_in_gpu_layout(co, nC, M):
+    """The C oracle's per-cell state rearranged into mek_read_state's layout (header 0..28, lambda, bigX, xhat, SigmaX)."""
+    ncm = co.L.mko_ncon_max()
+    st = co.state
+    return np.concatenate([st[:, :29], st[:, 30:30 + nC], st[:, 30 + ncm:30 + ncm + 26 * M]], axis=1)
+
+
+def _gpu_state_comparable(cb, M):
+    st = cb.read_state()
+    return np.concatenate([st[:, :29], st[:, 40:40 + cb.nC], st[:, 40 + cb.nC:40 + cb.nC + 26 * M]], axis=1)
+
+
+def test_deferral_final_state_of_every_model_matches_oracle(bank, coracle_mod):
+    """Logs only see the models a cell reads; the state block after the run holds all M models of every cell.  With
+    deferral blocks the models outside the hot set are advanced by replay -- their final bigX / xhat / SigmaX must
+    equal the instant-by-instant oracle's bit for bit (also across launches that cut blocks short)."""
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 160, seed=21, heterogeneous=True, ekf_soc_error=3.0)
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 700, chunks=[(0, 5), (5, 37), (37, 38), (38, 700)])
+    assert cb.defer_block == 16
+    _assert_bit_exact(g, c)
+    a, b = _gpu_state_comparable(cb, bank.M), _oracle_state_in_gpu_layout(co, cb.nC, bank.M)
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), "state differs in %d entries (first columns %s)" % ((~same).sum(), np.unique(np.nonzero(~same)[1])[:10])
+
+
+@pytest.mark.parametrize("kblock", [2, 5, 16, 32])
+def test_deferral_block_length_does_not_change_anything(bank, kblock):
+    from mek import api, population as P
+    pop = P.make_population(bank.params[2], 224, seed=22, heterogeneous=True, ekf_soc_error=4.0)
+    rom = api.RomBank(bank)
+    outs = []
+    for kb in (-1, kblock):
+        cb = api.CellBatch(rom, len(pop), defer_block=kb)
+        assert cb.defer_block == (0 if kb < 0 else kb)
+        cb.set_logging(len(pop), 450)
+        cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        cb.run(0, 211)
+        cb.run(211, 450)
+        st = cb.read_state()
+        st[:, 29] = 0.0                               # S_SPARE: diagnostic counter of on-demand catch-ups
+        outs.append((cb.logs(0, 450), st))
+    for k in ("u", "V", "SOC", "phise", "iT", "iZ", "nexec", "active"):
+        assert np.array_equal(outs[0][0][k], outs[1][0][k], equal_nan=k in ("u", "V", "SOC", "phise")), k
+    assert np.array_equal(outs[0][1], outs[1][1], equal_nan=True)
+
+
+def test_deferral_on_demand_catch_up(bank, coracle_mod):
+    """An EKF started 20-35 % SOC away from the truth walks across several SOC set-points within a few instants: models
+    outside the block's hot set are needed mid-block and are replayed on the spot (S_SPARE counts those)."""
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 96, seed=23)
+    pop.ekf_SOC0[:] = pop.SOC0 + np.where(np.arange(96) % 2 == 0, 35.0, -4.0)
+    pop.SigmaX0[:, 5, 5] = 2e8                        # loose integrator covariance: the estimate snaps back within a block
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 400)
+    _assert_bit_exact(g, c)
+    a, b = _gpu_state_comparable(cb, bank.M), _oracle_state_in_gpu_layout(co, cb.nC, bank.M)
+    assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
+    assert cb.read_state()[:, 29].sum() > 0, "the on-demand path was not exercised"
