@@ -82,6 +82,8 @@ typedef struct {
                                set-point neighbourhood are advanced once per block by replaying the block's currents
                                (bit-identical to advancing them every instant).  0 = default (16), -1 = off        */
   int defer_stagger;        /* 1: warps of a CTA start their deferral blocks at different instants                */
+  int defer_narrow_test;    /* test hook, 1: shrink the per-block model set to the EKF estimate's own neighbours so
+                               that the plant's models take the on-demand replay path (results are unchanged)    */
 } mek_config;
 
 /* ---- bank ---- */

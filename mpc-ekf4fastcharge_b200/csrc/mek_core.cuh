@@ -276,13 +276,15 @@ __device__ __forceinline__ void defer_ensure(const Dims& d, const BankSmem& bk, 
 // models this cell is expected to read during the coming block: both temperature rows x the SOC set-points around the
 // plant's and the EKF's present SOC, widened by the largest SOC change the current limits allow over `span` instants
 __device__ __noinline__ unsigned long long defer_hot_set(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
-                                                         int tt, int span) {
+                                                         int tt, int span, int narrow) {
   const double th0n = p[P_NEG + E_THETA0], th100n = p[P_NEG + E_THETA100];
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
   const double zp = (c.f(S_SOCN) - th0n) / (th100n - th0n);
   const double ze = c.f(S_EKFSOC0) - (c.f(S_X0) + c.f(S_PRIORI)) * rpa;
-  const double margin = 1.25 * (double)span * rpa * fmax(fabs(c.f(S_UMAX)), fabs(c.f(S_UMIN))) + 1e-4;
-  const int a = two_nearest(fmin(zp, ze) - margin, bk.Zpts, d.nZ), b = two_nearest(fmax(zp, ze) + margin, bk.Zpts, d.nZ);
+  double margin = 1.25 * (double)span * rpa * fmax(fabs(c.f(S_UMAX)), fabs(c.f(S_UMIN))) + 1e-4;
+  double lo = fmin(zp, ze), hi = fmax(zp, ze);
+  if (narrow) { lo = ze; hi = ze; margin = 0.0; }                    // test hook: everything else goes through defer_ensure
+  const int a = two_nearest(lo - margin, bk.Zpts, d.nZ), b = two_nearest(hi + margin, bk.Zpts, d.nZ);
   int zl = (a & 0xffff) < (a >> 16) ? (a & 0xffff) : (a >> 16);
   int zh = (b & 0xffff) > (b >> 16) ? (b & 0xffff) : (b >> 16);
   if (zl > zh) { const int t = zl; zl = zh; zh = t; }
@@ -1377,5 +1379,304 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
   o.u = uk;
   if (!is_finite(uk)) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_NONFINITE);
 }
+
+// ------------------------------------------------------------------------------------------
+// Static-shape path of iterMPC for long horizons (config C4: Np = 20, Nc = 5, 80 constraint rows).
+// The dual is too large for registers; per thread it keeps in shared-memory columns only
+//   - the three impulse-response tables h_v, -h_eta, h_soc (Np entries each): every row of the voltage / eta / SOC
+//     blocks of M is a window [h(i-1), h(i-2), ..., h(i-Nc)] of one of them (constraintsMPC.m:47-53,68-75,92-99), and
+//     the current rows are +-1 / +-0 patterns (:23-42), so M itself is never stored;
+//   - K_i, 1/H_ii and lambda_i per row.
+// Column i of E\M' is recomputed as inv(E)*M(i,:)' where it is needed -- and it is needed only when lambda_i moves:
+// a row whose lambda stays put adds P*0 to v, which leaves v unchanged bit for bit as long as P is finite (v is
+// never -0: it starts at +0 and only ever receives sums).  Rows are walked in the reference's order by rolled loops
+// with a sliding window over the tables.  Same arithmetic, in the same order, as mpc_setup / hildreth_core.
+// ------------------------------------------------------------------------------------------
+template <int NP, int NC, int CONS>
+struct WideShape {
+  static constexpr bool UC = (CONS & 1) != 0, UV = (CONS & 2) != 0, UE = (CONS & 4) != 0, UZ = (CONS & 8) != 0;
+  static constexpr int nC = (UC ? 4 * NC : 0) + NP * ((UV ? 1 : 0) + (UE ? 1 : 0) + (UZ ? 1 : 0));
+  // read-mostly columns (written once per QP, read once per row and sweep): tables, K, 1/H
+  static constexpr int T_V = 0, T_E = NP, T_S = 2 * NP;              // table slots (Np entries each)
+  static constexpr int W_K = 3 * NP, W_H = W_K + nC;
+  static constexpr int WSLOTS = W_H + nC;
+  static constexpr int LSLOTS = nC;                                  // lambda column (read and written every row)
+  static constexpr int SLOTS = WSLOTS + LSLOTS;                      // all of it in shared memory (small CTAs)
+};
+
+// calls f(row, M[NC]) for every constraint row in the reference's order (constraintsMPC.m:99: [current; V; eta; SOC]).
+// The table entry of the next row is loaded one row ahead (the columns may live in L2).
+template <int NP, int NC, int CONS, typename F>
+__device__ __forceinline__ void wide_rows(const double* tab, int ts, F&& f) {
+  using WS = WideShape<NP, NC, CONS>;
+  int row = 0;
+  if (WS::UC) {
+#pragma unroll 1
+    for (int q = 0; q < 4 * NC; ++q) {                               // [prefix +; prefix -; identity +; identity -]
+      const int blk = q / NC, i = q - blk * NC;
+      const bool neg = (blk & 1) != 0, ident = blk >= 2;
+      double M[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const bool on = ident ? (j == i) : (j <= i);
+        M[j] = on ? (neg ? -1.0 : 1.0) : (neg ? -0.0 : 0.0);
+      }
+      f(row, M);
+      ++row;
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const bool use = b == 0 ? WS::UV : (b == 1 ? WS::UE : WS::UZ);
+    if (!use) continue;
+    const int toff = b == 0 ? WS::T_V : (b == 1 ? WS::T_E : WS::T_S);
+    double M[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) M[j] = (b == 1) ? -0.0 : 0.0;
+    double nxt = tab[toff * ts];
+#pragma unroll 1
+    for (int i = 0; i < NP; ++i) {
+#pragma unroll
+      for (int j = NC - 1; j > 0; --j) M[j] = M[j - 1];
+      M[0] = nxt;
+      nxt = tab[(toff + (i + 1 < NP ? i + 1 : i)) * ts];
+      f(row, M);
+      ++row;
+    }
+  }
+}
+
+template <int NP, int NC, int CONS>
+__device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __restrict__ p, const Cell& c, const EkfOut& e, double uk_applied,
+                                              MpcOut& o, double* lc, int ls, double* wc, int wst) {
+  // lc/ls: this thread's lambda column (shared memory); wc/wst: its read-mostly column (shared memory or the L2-resident workspace)
+  using WS = WideShape<NP, NC, CONS>;
+  constexpr int nC = WS::nC;
+  static_assert(nC <= 96, "row flags are kept in three words");
+  const double uk_1 = c.f(S_UK);                                     // iterMPC.m:19
+  {                                                                  // runMPC.m:94-95 (Q24)
+    double acc = e.Cphi[0] * e.xhat[0];
+#pragma unroll
+    for (int j = 1; j < N5; ++j) acc = fma(e.Cphi[j], e.xhat[j], acc);
+    acc = acc + 0.0 * e.xhat[5];
+    o.phise = (acc + uk_applied * e.Dphi) + e.bphi;
+  }
+  const double r = -d.Ts / (3600.0 * p[P_Q]);                        // EKFmatsHandler.m:43
+  double F[NC], LU[NC * NC], DU[NC], x[NC];
+  {
+    const double zero5[N5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double hs[NP + 1], pxs[NP];
+    pred_row<NP>(e.a, zero5, r, 0.0, e.xhat, NP, hs, pxs);           // iterMPC.m:33
+    {
+      double err[NP];
+#pragma unroll
+      for (int i = 1; i <= NP; ++i) err[i - 1] = d.ref - (pxs[i - 1] + hs[i] * uk_1);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {                                 // iterMPC.m:38
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 1; i <= NP; ++i) {
+          if (i - 1 - j >= 0) {
+            const double t = hs[i - 1 - j] * err[i - 1];
+            acc = (i == 1) ? t : acc + t;
+          } else {
+            const double t = 0.0 * err[i - 1];
+            acc = (i == 1) ? t : acc + t;
+          }
+        }
+        F[j] = -2.0 * acc;
+      }
+    }
+    double nf = F[0] * F[0];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) nf = nf + F[j] * F[j];
+    const double Ru = sqrt(nf) / ((2.0 * c.f(S_DUMAX)) * sqrt((double)NC)) - d.sigmin;   // iterMPC.m:43 (Q10)
+    double E[NC * NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+#pragma unroll
+      for (int l = 0; l < NC; ++l) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 1; i <= NP; ++i) {
+          const double gj = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0, gl = (i - 1 - l >= 0) ? hs[i - 1 - l] : 0.0;
+          const double t = gj * gl;
+          acc = (i == 1) ? t : acc + t;
+        }
+        E[j * NC + l] = 2.0 * (acc + ((j == l) ? Ru : 0.0));         // iterMPC.m:47
+      }
+    spd_factor<NC>(NC, E, LU);
+    spd_solve<NC>(NC, LU, F, x);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) DU[j] = -x[j];                      // iterMPC.m:48
+    // tables and gamma (kept in the K slots until the QP set-up turns them into K_i)
+    int row = 0;
+    if (WS::UC) {                                                    // constraintsMPC.m:23-42
+      const double umax = c.f(S_UMAX), umin = c.f(S_UMIN), dumax = c.f(S_DUMAX), dumin = c.f(S_DUMIN);
+#pragma unroll
+      for (int q = 0; q < 4 * NC; ++q) {
+        const int blk = q / NC;
+        wc[(WS::W_K + row) * wst] = blk == 0 ? (umax - uk_1) : (blk == 1 ? -(umin - uk_1) : (blk == 2 ? dumax : -dumin));
+        ++row;
+      }
+    }
+    if (WS::UV) {                                                    // constraintsMPC.m:45-63
+      double hv[NP + 1], pxv[NP];
+      pred_row<NP>(e.a, e.Cv, 0.0, e.Dv, e.xhat, NP, hv, pxv);
+      const double vmax = c.f(S_VMAX);
+#pragma unroll
+      for (int i = 1; i <= NP; ++i) {
+        wc[(WS::T_V + i - 1) * wst] = hv[i - 1];
+        wc[(WS::W_K + row) * wst] = vmax - ((pxv[i - 1] + hv[i] * uk_1) + e.bv);
+        ++row;
+      }
+    }
+    if (WS::UE) {                                                    // constraintsMPC.m:66-85
+      double he[NP + 1], pxe[NP];
+      pred_row<NP>(e.a, e.Cphi, 0.0, e.Dphi, e.xhat, NP, he, pxe);
+      const double pmin = c.f(S_PHIMIN);
+#pragma unroll
+      for (int i = 1; i <= NP; ++i) {
+        wc[(WS::T_E + i - 1) * wst] = -he[i - 1];
+        wc[(WS::W_K + row) * wst] = -pmin + ((pxe[i - 1] + he[i] * uk_1) + e.bphi);
+        ++row;
+      }
+    }
+    if (WS::UZ) {                                                    // constraintsMPC.m:89-101
+      const double zmax = c.f(S_ZMAX);
+#pragma unroll
+      for (int i = 1; i <= NP; ++i) {
+        wc[(WS::T_S + i - 1) * wst] = hs[i - 1];
+        wc[(WS::W_K + row) * wst] = zmax - ((pxs[i - 1] + hs[i] * uk_1) + e.soc);
+        ++row;
+      }
+    }
+  }
+  bool viol = false;                                                 // iterMPC.m:66 (Q8)
+  wide_rows<NP, NC, CONS>(wc, wst, [&](int i, const double (&M)[NC]) {
+    double acc = M[0] * DU[0];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) acc = fma(M[j], DU[j], acc);
+    if (acc - wc[(WS::W_K + i) * wst] > 0.0) viol = true;
+  });
+  o.nexec = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) o.active[w] = 0u;
+  if (viol) {                                                        // hildreth.m:16-46 (see hildreth_core)
+    const bool warm = c.f(S_LAMVALID) != 0.0;                        // Q11
+#pragma unroll 4
+    for (int i = 0; i < nC; ++i) lc[i * ls] = warm ? c.lam(i) : 0.0;
+    spd_solve<NC>(NC, LU, F, x);                                     // E\F
+    double Ei[NC][NC];                                               // inv(E)
+#pragma unroll
+    for (int l = 0; l < NC; ++l) {
+      double el[NC], col[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) el[j] = (j == l) ? 1.0 : 0.0;
+      spd_solve<NC>(NC, LU, el, col);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) Ei[j][l] = col[j];
+    }
+    double v[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = 0.0;
+    unsigned z0 = 0u, z1 = 0u, z2 = 0u;                              // rows with H_ii == 0 (all-zero M rows, Q7)
+    int npoison = 0;
+    bool pfin = true;                                                // every entry of E\M' is finite
+    wide_rows<NP, NC, CONS>(wc, wst, [&](int i, const double (&M)[NC]) {
+      double P[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        double acc = Ei[j][0] * M[0];
+#pragma unroll
+        for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], M[l], acc);
+        P[j] = acc;
+        pfin = pfin && is_finite(acc);
+      }
+      double hd = M[0] * P[0], k = M[0] * x[0];
+#pragma unroll
+      for (int j = 1; j < NC; ++j) { hd = fma(M[j], P[j], hd); k = fma(M[j], x[j], k); }
+      const double li = lc[i * ls];
+      wc[(WS::W_K + i) * wst] = k + wc[(WS::W_K + i) * wst];     // K(i) = M(i,:)*(E\F) + gamma(i)
+      wc[(WS::W_H + i) * wst] = rcp_d(hd);                         // 1/H(i,i)
+      if (hd == 0.0) {
+        const unsigned bit = 1u << (i & 31);
+        if (i < 32) z0 |= bit; else if (i < 64) z1 |= bit; else z2 |= bit;
+        if (!is_finite(li)) ++npoison;
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] = fma(P[j], li, v[j]);
+      }
+    });
+    int k = 1;
+    double kn = wc[WS::W_K * wst], hn = wc[WS::W_H * wst];           // K, 1/H of the next row, loaded one row ahead
+    for (; k <= d.maxHild; ++k) {                                    // hildreth.m:32
+      bool notconv = false;
+      wide_rows<NP, NC, CONS>(wc, wst, [&](int i, const double (&M)[NC]) {   // hildreth.m:34-37
+        const double li = lc[i * ls];
+        const double Ki = kn, rHi = hn;
+        {
+          const int ni = (i + 1 < nC) ? i + 1 : 0;
+          kn = wc[(WS::W_K + ni) * wst];
+          hn = wc[(WS::W_H + ni) * wst];
+        }
+        double w;
+        if (npoison > 0) {
+          w = NAN;
+        } else {
+          double hl = M[0] * v[0];
+#pragma unroll
+          for (int j = 1; j < NC; ++j) hl = fma(M[j], v[j], hl);
+          w = fma(-(Ki + hl), rHi, li);
+        }
+        const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
+        const double dl = nl - li;
+        const unsigned zw = i < 32 ? z0 : (i < 64 ? z1 : z2);
+        if ((zw >> (i & 31)) & 1u) {
+          npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li));
+        } else if (dl != 0.0 || !pfin) {                             // P*0 leaves v as it is
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            double acc = Ei[j][0] * M[0];
+#pragma unroll
+            for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], M[l], acc);
+            v[j] = fma(acc, dl, v[j]);
+          }
+        }
+        lc[i * ls] = nl;
+        if (!(fabs(dl) < 1e-6)) notconv = true;                      // hildreth.m:39 norm(.,Inf) < 1e-6, NaN-propagating
+      });
+      if (!notconv) break;
+    }
+    if (k > d.maxHild) k = d.maxHild;
+    double rhs[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) rhs[j] = 0.0;
+    unsigned a0 = 0u, a1 = 0u, a2 = 0u;
+    wide_rows<NP, NC, CONS>(wc, wst, [&](int i, const double (&M)[NC]) {     // hildreth.m:46  M'*lambda, rows in order
+      const double li = lc[i * ls];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) rhs[j] = (i == 0) ? M[j] * li : fma(M[j], li, rhs[j]);
+      c.lam(i) = li;                                                 // iterMPC.m:68
+      if (li > 0.0) {
+        const unsigned bit = 1u << (i & 31);
+        if (i < 32) a0 |= bit; else if (i < 64) a1 |= bit; else a2 |= bit;
+      }
+    });
+#pragma unroll
+    for (int j = 0; j < NC; ++j) rhs[j] = F[j] + rhs[j];
+    spd_solve<NC>(NC, LU, rhs, x);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) DU[j] = -x[j];
+    o.nexec = k;                                                     // iterMPC.m:67-69
+    o.active[0] = a0; o.active[1] = a1; o.active[2] = a2;
+    c.f(S_LAMVALID) = 1.0;
+  }
+  const double uk = DU[0] + uk_1;                                    // iterMPC.m:75-76
+  c.f(S_UK) = uk;
+  o.u = uk;
+  if (!is_finite(uk)) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_NONFINITE);
+}
+
 
 }  // namespace mek

@@ -227,6 +227,8 @@ struct Params {
   int sync_steps;             // 1: CTA-wide barrier before every sample instant
   int defer_k;                // > 0: sample instants per deferral block (models outside a cell's hot set are advanced once per block); 0: off
   int defer_stagger;          // 1: the warps of a CTA start their blocks at different instants (spreads the block-end HBM bursts)
+  double* wide_ws;            // long-horizon instance: per-CTA workspace [WSLOTS][threads] for tables, K, 1/H (null: shared memory)
+  int defer_narrow;           // test hook: hot set = the EKF estimate's neighbours only, no margin
   int hist_off;               // doubles from the start of dynamic shared memory to the history columns [defer_k + 1][threads]
   const int* slot2cell;       // state slot -> caller's cell index (cells are ordered by initial SOC inside the block), or null
 };
@@ -297,7 +299,14 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms}, tt, df);  // runMPC.m:88,92
   if (e.lost) return;
   MpcOut o;
-  if constexpr (CONS >= 0) mpc_step_fast<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, smt, sms);   // runMPC.m:94-103
+  if constexpr (CONS >= 0 && NPM == 5 && NCM == 2) mpc_step_fast<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, smt, sms);   // runMPC.m:94-103
+  else if constexpr (CONS >= 0) {
+    using WS = WideShape<NPM, NCM, CONS>;
+    // lambda column in shared memory; tables, K, 1/H in this CTA's slice of the L2-resident workspace, or (small CTAs) in shared memory too
+    double* lc = P.wide_ws ? smt : smt + WS::WSLOTS * sms;
+    double* wc = P.wide_ws ? P.wide_ws + (long long)blockIdx.x * WS::WSLOTS * sms + threadIdx.x : smt;
+    mpc_step_wide<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, lc, sms, wc, sms);
+  }
   else mpc_step<NPM, NCM>(d, P.cp, c, e, uk, o);
   lg.u = o.u; lg.V = V; lg.soc = e.soc; lg.phise = o.phise;          // runMPC.m:106-109
   lg.iT = e.iT + 1; lg.iZ = e.iZ + 1; lg.nexec = o.nexec;
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
         if (k != k0 && active) defer_flush(d, bk, c, df);
         const bool run = active && !((unsigned)c.f(S_STATUS) & ST_LOST);
         int left = KB - (k - k0 + off) % KB;
-        df.hot = warp_or64(run ? defer_hot_set(d, bk, P.cp, c, tt, left) : 0ull);
+        df.hot = warp_or64(run ? defer_hot_set(d, bk, P.cp, c, tt, left, P.defer_narrow) : 0ull);
         df.mine = 0ull;
         df.n = 0;
         if (run) df.h[0] = c.f(S_PRIORI);
@@ -814,6 +823,8 @@ struct mek_pop {
   int minb;     // register cap variant of the <5,2> instance (CTAs per SM)
   int cons;     // >= 0: static-shape fast instance with these constraint switches
   size_t run_smem; int run_threads;
+  int wide_ws_slots;           // > 0: doubles per thread of the long-horizon workspace in global memory
+  double* d_wide_ws;
 };
 
 static double sigma_min_gtg(int Np, int Nc, double r) {
@@ -882,6 +893,8 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   p->launches = 0;
   p->d_logs = nullptr;
   p->d_slot2cell = nullptr;
+  p->d_wide_ws = nullptr;
+  p->wide_ws_slots = 0;
   p->d_scratch = nullptr;
   p->scratch_bytes = 0;
   int Np = cfg->Np < 1 ? 1 : cfg->Np;                               // initMPC.m:32-33 (Q23)
@@ -976,6 +989,15 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
       p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
     }
+    if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path) {   // config C4: long-horizon static-shape instance
+      using WS = WideShape<20, 5, 15>;
+      p->cons = mask;
+      // 64 threads: every column in shared memory; 128 / 256 threads: lambda in shared memory, the read-mostly columns in L2
+      p->run_threads = (cfg->threads_per_block == 64 || cfg->threads_per_block == 128) ? cfg->threads_per_block : 256;
+      const int slots = p->run_threads == 64 ? WS::SLOTS : WS::LSLOTS;
+      p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
+      p->wide_ws_slots = p->run_threads == 64 ? 0 : WS::WSLOTS;
+    }
   }
   // deferral blocks (temporal blocking of the model stream): history columns behind the scratch columns
   {
@@ -986,6 +1008,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     if (kb < 2) kb = 0;
     p->P.defer_k = kb;
     p->P.defer_stagger = cfg->defer_stagger > 0 ? 1 : 0;
+    p->P.defer_narrow = cfg->defer_narrow_test > 0 ? 1 : 0;
     p->P.hist_off = (int)(p->run_smem / sizeof(double));
     if (kb > 0) p->run_smem += sizeof(double) * (size_t)(kb + 1) * (size_t)p->run_threads;
   }
@@ -994,7 +1017,10 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     rc |= prep_kernel(KERN, p->run_smem);                                                                       \
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, p->run_threads, p->run_smem));           \
   } while (0)
-  if (p->cons == 15 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 15, 384, 1>));
+  if (p->inst == 1 && p->cons == 15 && p->run_threads == 64) MEK_PREP((k_run_population<20, 5, 15, 64, 1>));
+  else if (p->inst == 1 && p->cons == 15 && p->run_threads == 128) MEK_PREP((k_run_population<20, 5, 15, 128, 1>));
+  else if (p->inst == 1 && p->cons == 15) MEK_PREP((k_run_population<20, 5, 15, 256, 1>));
+  else if (p->cons == 15 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 15, 384, 1>));
   else if (p->cons == 11 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 11, 384, 1>));
   else if (p->cons == 15) MEK_PREP((k_run_population<5, 2, 15, 256, 1>));
   else if (p->cons == 11) MEK_PREP((k_run_population<5, 2, 11, 256, 1>));
@@ -1006,6 +1032,12 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   if (occ < 1) occ = 1;
   if (cfg->blocks_per_sm == 1) occ = 1;
   p->blocks = p->sms * occ;
+  if (p->wide_ws_slots > 0) {
+    const size_t bytes = sizeof(double) * (size_t)p->wide_ws_slots * (size_t)p->run_threads * (size_t)p->blocks;
+    CUDA_TRY(cudaMalloc(&p->d_wide_ws, bytes));
+    CUDA_TRY(cudaMemset(p->d_wide_ws, 0, bytes));
+    p->P.wide_ws = p->d_wide_ws;
+  }
   *out = p;
   return MEK_OK;
 }
@@ -1015,6 +1047,7 @@ extern "C" void mek_pop_destroy(mek_pop* p) {
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->stream);
   if (p->d_slot2cell) cudaFree(p->d_slot2cell);
+  if (p->d_wide_ws) cudaFree(p->d_wide_ws);
   cudaFree(p->d_blob); cudaFree(p->d_Cfull); cudaFree(p->d_Dfull); cudaFree(p->d_st); cudaFree(p->d_in); cudaFree(p->d_totals);
   if (p->d_logs) cudaFree(p->d_logs);
   if (p->d_scratch) cudaFree(p->d_scratch);
@@ -1099,7 +1132,10 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 
 static int launch_run(mek_pop* p, int k0, int k1) {
   const int g = grid_for(p, p->P.d.B, p->run_threads);
-  if (p->cons == 15 && p->run_threads == 384) k_run_population<5, 2, 15, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  if (p->inst == 1 && p->cons == 15 && p->run_threads == 64) k_run_population<20, 5, 15, 64, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->inst == 1 && p->cons == 15 && p->run_threads == 128) k_run_population<20, 5, 15, 128, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->inst == 1 && p->cons == 15) k_run_population<20, 5, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  else if (p->cons == 15 && p->run_threads == 384) k_run_population<5, 2, 15, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->cons == 11 && p->run_threads == 384) k_run_population<5, 2, 11, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->cons == 15) k_run_population<5, 2, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->cons == 11) k_run_population<5, 2, 11, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
