@@ -1392,6 +1392,9 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 // never -0: it starts at +0 and only ever receives sums).  Rows are walked in the reference's order by rolled loops
 // with a sliding window over the tables.  Same arithmetic, in the same order, as mpc_setup / hildreth_core.
 // ------------------------------------------------------------------------------------------
+#ifndef WIDE_UNROLL
+#define WIDE_UNROLL 5            // Toeplitz rows per loop trip in the long-horizon sweep
+#endif
 template <int NP, int NC, int CONS>
 struct WideShape {
   static constexpr bool UC = (CONS & 1) != 0, UV = (CONS & 2) != 0, UE = (CONS & 4) != 0, UZ = (CONS & 8) != 0;
@@ -1399,47 +1402,53 @@ struct WideShape {
   // read-mostly columns (written once per QP, read once per row and sweep): tables, K, 1/H
   static constexpr int T_V = 0, T_E = NP, T_S = 2 * NP;              // table slots (Np entries each)
   static constexpr int W_K = 3 * NP, W_H = W_K + nC;
-  static constexpr int WSLOTS = W_H + nC;
+  static constexpr int W_LU = W_H + nC, W_F = W_LU + NC * NC;        // factor of E and F parked here during the sweeps
+  static constexpr int WSLOTS = W_F + NC;
   static constexpr int LSLOTS = nC;                                  // lambda column (read and written every row)
   static constexpr int SLOTS = WSLOTS + LSLOTS;                      // all of it in shared memory (small CTAs)
 };
 
 // calls f(row, M[NC]) for every constraint row in the reference's order (constraintsMPC.m:99: [current; V; eta; SOC]).
-// The table entry of the next row is loaded one row ahead (the columns may live in L2).
-template <int NP, int NC, int CONS, typename F>
-__device__ __forceinline__ void wide_rows(const double* tab, int ts, F&& f) {
+// The current rows are compile-time patterns (fully unrolled); the Toeplitz blocks slide a window over their table,
+// whose entries are loaded four rows ahead (the column may live in L2), UNR rows per loop trip.
+template <int NP, int NC, int CONS, int UNR, typename F>
+__device__ __forceinline__ void wide_rows(const double* __restrict__ tab, int ts, F&& f) {
   using WS = WideShape<NP, NC, CONS>;
   int row = 0;
   if (WS::UC) {
-#pragma unroll 1
-    for (int q = 0; q < 4 * NC; ++q) {                               // [prefix +; prefix -; identity +; identity -]
-      const int blk = q / NC, i = q - blk * NC;
-      const bool neg = (blk & 1) != 0, ident = blk >= 2;
-      double M[NC];
 #pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const bool on = ident ? (j == i) : (j <= i);
-        M[j] = on ? (neg ? -1.0 : 1.0) : (neg ? -0.0 : 0.0);
+    for (int blk = 0; blk < 4; ++blk) {                              // [prefix +; prefix -; identity +; identity -]
+      const bool neg = (blk & 1) != 0, ident = blk >= 2;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        double M[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const bool on = ident ? (j == i) : (j <= i);
+          M[j] = on ? (neg ? -1.0 : 1.0) : (neg ? -0.0 : 0.0);
+        }
+        f(row, M);
+        ++row;
       }
-      f(row, M);
-      ++row;
     }
   }
 #pragma unroll
   for (int b = 0; b < 3; ++b) {
     const bool use = b == 0 ? WS::UV : (b == 1 ? WS::UE : WS::UZ);
     if (!use) continue;
-    const int toff = b == 0 ? WS::T_V : (b == 1 ? WS::T_E : WS::T_S);
+    const double* t = tab + (b == 0 ? WS::T_V : (b == 1 ? WS::T_E : WS::T_S)) * ts;
     double M[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) M[j] = (b == 1) ? -0.0 : 0.0;
-    double nxt = tab[toff * ts];
-#pragma unroll 1
+    static_assert(NP >= 4, "table prefetch depth");
+    double n0 = t[0], n1 = t[ts], n2 = t[2 * ts], n3 = t[3 * ts];
+#pragma unroll UNR
     for (int i = 0; i < NP; ++i) {
 #pragma unroll
       for (int j = NC - 1; j > 0; --j) M[j] = M[j - 1];
-      M[0] = nxt;
-      nxt = tab[(toff + (i + 1 < NP ? i + 1 : i)) * ts];
+      M[0] = n0;
+      n0 = n1; n1 = n2; n2 = n3;
+      n3 = t[(i + 4 < NP ? i + 4 : NP - 1) * ts];
       f(row, M);
       ++row;
     }
@@ -1553,7 +1562,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
     }
   }
   bool viol = false;                                                 // iterMPC.m:66 (Q8)
-  wide_rows<NP, NC, CONS>(wc, wst, [&](int i, const double (&M)[NC]) {
+  wide_rows<NP, NC, CONS, 1>(wc, wst, [&](int i, const double (&M)[NC]) {
     double acc = M[0] * DU[0];
 #pragma unroll
     for (int j = 1; j < NC; ++j) acc = fma(M[j], DU[j], acc);
@@ -1583,7 +1592,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
     unsigned z0 = 0u, z1 = 0u, z2 = 0u;                              // rows with H_ii == 0 (all-zero M rows, Q7)
     int npoison = 0;
     bool pfin = true;                                                // every entry of E\M' is finite
-    wide_rows<NP, NC, CONS>(wc, wst, [&](int i, const double (&M)[NC]) {
+    wide_rows<NP, NC, CONS, 1>(wc, wst, [&](int i, const double (&M)[NC]) {
       double P[NC];
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
@@ -1608,17 +1617,26 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
         for (int j = 0; j < NC; ++j) v[j] = fma(P[j], li, v[j]);
       }
     });
+    // the factor of E and F are not needed until the sweeps are over: park them (registers are what the sweep is short of)
+#pragma unroll
+    for (int q = 0; q < NC * NC; ++q) wc[(WS::W_LU + q) * wst] = LU[q];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) wc[(WS::W_F + q) * wst] = F[q];
     int k = 1;
-    double kn = wc[WS::W_K * wst], hn = wc[WS::W_H * wst];           // K, 1/H of the next row, loaded one row ahead
+    // K, 1/H of the coming rows, loaded four rows ahead of their use (L2 latency)
+    double kq0 = wc[WS::W_K * wst], kq1 = wc[(WS::W_K + 1) * wst], kq2 = wc[(WS::W_K + 2) * wst], kq3 = wc[(WS::W_K + 3) * wst];
+    double hq0 = wc[WS::W_H * wst], hq1 = wc[(WS::W_H + 1) * wst], hq2 = wc[(WS::W_H + 2) * wst], hq3 = wc[(WS::W_H + 3) * wst];
     for (; k <= d.maxHild; ++k) {                                    // hildreth.m:32
       bool notconv = false;
-      wide_rows<NP, NC, CONS>(wc, wst, [&](int i, const double (&M)[NC]) {   // hildreth.m:34-37
+      wide_rows<NP, NC, CONS, WIDE_UNROLL>(wc, wst, [&](int i, const double (&M)[NC]) {   // hildreth.m:34-37
         const double li = lc[i * ls];
-        const double Ki = kn, rHi = hn;
+        const double Ki = kq0, rHi = hq0;
         {
-          const int ni = (i + 1 < nC) ? i + 1 : 0;
-          kn = wc[(WS::W_K + ni) * wst];
-          hn = wc[(WS::W_H + ni) * wst];
+          int ni = i + 4;
+          if (ni >= nC) ni -= nC;
+          kq0 = kq1; kq1 = kq2; kq2 = kq3; hq0 = hq1; hq1 = hq2; hq2 = hq3;
+          kq3 = wc[(WS::W_K + ni) * wst];
+          hq3 = wc[(WS::W_H + ni) * wst];
         }
         double w;
         if (npoison > 0) {
@@ -1649,11 +1667,18 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
       if (!notconv) break;
     }
     if (k > d.maxHild) k = d.maxHild;
+    {
+      const volatile double* wv = wc;
+#pragma unroll
+      for (int q = 0; q < NC * NC; ++q) LU[q] = wv[(WS::W_LU + q) * wst];
+#pragma unroll
+      for (int q = 0; q < NC; ++q) F[q] = wv[(WS::W_F + q) * wst];
+    }
     double rhs[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) rhs[j] = 0.0;
     unsigned a0 = 0u, a1 = 0u, a2 = 0u;
-    wide_rows<NP, NC, CONS>(wc, wst, [&](int i, const double (&M)[NC]) {     // hildreth.m:46  M'*lambda, rows in order
+    wide_rows<NP, NC, CONS, 1>(wc, wst, [&](int i, const double (&M)[NC]) {     // hildreth.m:46  M'*lambda, rows in order
       const double li = lc[i * ls];
 #pragma unroll
       for (int j = 0; j < NC; ++j) rhs[j] = (i == 0) ? M[j] * li : fma(M[j], li, rhs[j]);

@@ -992,8 +992,8 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path) {   // config C4: long-horizon static-shape instance
       using WS = WideShape<20, 5, 15>;
       p->cons = mask;
-      // 64 threads: every column in shared memory; 128 / 256 threads: lambda in shared memory, the read-mostly columns in L2
-      p->run_threads = (cfg->threads_per_block == 64 || cfg->threads_per_block == 128) ? cfg->threads_per_block : 256;
+      // 256 threads (default): lambda in shared memory, the read-mostly columns in L2; 64 threads: every column in shared memory
+      p->run_threads = cfg->threads_per_block == 64 ? 64 : 256;
       const int slots = p->run_threads == 64 ? WS::SLOTS : WS::LSLOTS;
       p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       p->wide_ws_slots = p->run_threads == 64 ? 0 : WS::WSLOTS;
@@ -1018,7 +1018,6 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, p->run_threads, p->run_smem));           \
   } while (0)
   if (p->inst == 1 && p->cons == 15 && p->run_threads == 64) MEK_PREP((k_run_population<20, 5, 15, 64, 1>));
-  else if (p->inst == 1 && p->cons == 15 && p->run_threads == 128) MEK_PREP((k_run_population<20, 5, 15, 128, 1>));
   else if (p->inst == 1 && p->cons == 15) MEK_PREP((k_run_population<20, 5, 15, 256, 1>));
   else if (p->cons == 15 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 15, 384, 1>));
   else if (p->cons == 11 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 11, 384, 1>));
@@ -1133,7 +1132,6 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 static int launch_run(mek_pop* p, int k0, int k1) {
   const int g = grid_for(p, p->P.d.B, p->run_threads);
   if (p->inst == 1 && p->cons == 15 && p->run_threads == 64) k_run_population<20, 5, 15, 64, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->inst == 1 && p->cons == 15 && p->run_threads == 128) k_run_population<20, 5, 15, 128, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->inst == 1 && p->cons == 15) k_run_population<20, 5, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->cons == 15 && p->run_threads == 384) k_run_population<5, 2, 15, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->cons == 11 && p->run_threads == 384) k_run_population<5, 2, 11, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
