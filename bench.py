@@ -31,6 +31,15 @@ METRIC = "cell-steps/sec (ROM+EKF+MPC)"
 UNIT = "cell-steps/s"
 SEED = 2                # C3
 
+# The configurations BASELINE.json names.  The default bench line is C3 = the configuration the metric is
+# quoted on ("cell-steps/sec at 1M cells"); the others are run with --config for the results table in BASELINE.md.
+CONFIGS = {
+    "C3":   dict(kernel="k_run_population<5,2,15,256,1>", profile="r01_defer_ncu_summary.csv", seed=2, Np=5, Nc=2, constraints=(1, 1, 1), het=False, cells=1 << 20, what="limits 2C/4.1V/80mV, constraints [1 1 1]"),
+    "C3v":  dict(kernel="k_run_population<5,2,11,256,1>", profile=None, seed=2, Np=5, Nc=2, constraints=(1, 1, 0), het=False, cells=1 << 20, what="limits 2C/4.1V, constraints [1 1 0] (no side-reaction constraint)"),
+    "C4":   dict(kernel="k_run_population<20,5,15,256,1>", profile="r01_c4_ncu_summary.csv", seed=3, Np=20, Nc=5, constraints=(1, 1, 1), het=False, cells=65536, what="extended horizon, 80 constraint rows, limits 2C/4.1V/80mV"),
+    "C5":   dict(kernel="k_run_population<5,2,15,256,1>", profile=None, seed=4, Np=5, Nc=2, constraints=(1, 1, 1), het=True, cells=1 << 20, what="heterogeneous per-cell limits and temperature 15..35 C"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -38,17 +47,23 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mek", choices=["mek", "reference"])
-    ap.add_argument("--cells", type=int, default=1 << 20, help="cells per GPU")
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--cells", type=int, default=0, help="cells per GPU (default: the configuration's size)")
     ap.add_argument("--nsim", type=int, default=N_SIM)
     ap.add_argument("--log-cells", type=int, default=4096, help="cells per GPU whose full trajectory is logged and read back in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells-per-core", type=int, default=1024, help="CPU sample: cells per host core (full charges); ~10-15 s of CPU work on the GPU box")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.cfg = CONFIGS[a.config]
+    if a.cells <= 0:
+        a.cells = a.cfg["cells"]
+    return a
 
 
-def workload_name(cells, nsim):
-    return ("C3: %d NMC30 cells per GPU x %d sample instants (10..30%% -> 95%% SOC), limits 2C/4.1V/80mV, "
-            "constraints [1 1 1], Np=5, Nc=2, seed %d" % (cells, nsim, SEED))
+def workload_name(a):
+    c = a.cfg
+    return ("%s: %d NMC30 cells per GPU x %d sample instants (5..30%% -> 95%% SOC), %s, Np=%d, Nc=%d, seed %d"
+            % (a.config, a.cells, a.nsim, c["what"], c["Np"], c["Nc"], c["seed"]))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -98,14 +113,15 @@ class ClockSampler:
 # CPU arm: the oracle's C restatement on the host cores (the only CPU implementation that exists:
 # the reference is MATLAB and cannot run here)
 # ------------------------------------------------------------------------------------------------
-def cpu_run(bank, cells, nsim, nthreads, first_cell=0):
+def cpu_run(bank, cells, nsim, nthreads, cfg, first_cell=0):
     from mek import population as P
     from oracle import coracle
-    pop = P.make_population(bank.params[2], cells, SEED, first_cell=first_cell)
-    warm = coracle.COracle(bank)                                   # spin the OpenMP team up outside the timed region
+    pop = P.make_population(bank.params[2], cells, cfg["seed"], heterogeneous=cfg["het"], first_cell=first_cell)
+    kw = dict(Np=cfg["Np"], Nc=cfg["Nc"], constraints=cfg["constraints"])
+    warm = coracle.COracle(bank, **kw)                             # spin the OpenMP team up outside the timed region
     warm.init(pop.SOC0[:nthreads], pop.T[:nthreads], pop.SigmaX0[:nthreads], pop.limits[:nthreads])
     warm.run(0, 20, logs=False, nthreads=nthreads)
-    co = coracle.COracle(bank)
+    co = coracle.COracle(bank, **kw)
     co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
     t0 = time.perf_counter()
     co.run(0, nsim, logs=False, nthreads=nthreads)
@@ -119,17 +135,17 @@ def main_reference(a):
     from mek import bank as Bk
     bank = Bk.Bank.load(Bk.default_bank_path())
     cores = os.cpu_count() or 1
-    cells = max(cores * a.cpu_cells_per_core, cores)
+    cells = max(cores * a.cpu_cells_per_core // (8 if a.cfg["Np"] > 5 else 1), cores)
     vals = []
     for i in range(a.warmup + a.steps):
-        v = cpu_run(bank, cells, a.nsim, cores)
+        v = cpu_run(bank, cells, a.nsim, cores, a.cfg)
         if i >= a.warmup:
             vals.append(v)
     value = float(np.mean(vals))
     sample = "%d cells x %d instants per step (first cells of the same population), C restatement oracle/mek_oracle.c, OpenMP over cells" % (cells, a.nsim)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": 1e3 * cells * a.nsim / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": {"workload": workload_name(a.cells, a.nsim)},
+           "data": "synthetic", "config": {"workload": workload_name(a)},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "the reference is MATLAB (no MATLAB/Octave here, ROM .mat missing): this arm times the plain-C restatement of its loop"}
@@ -162,13 +178,14 @@ def main_mek(a):
     bank = Bk.Bank.load(Bk.default_bank_path())
     rom = api.RomBank(bank)
     B = a.cells
-    pop = P.make_population(bank.params[2], B, SEED, first_cell=rank * B)       # weak scaling: B cells on every rank
+    cfg = a.cfg
+    pop = P.make_population(bank.params[2], B, cfg["seed"], heterogeneous=cfg["het"], first_cell=rank * B)   # weak scaling: B cells on every rank
     # pinned host inputs (what a user hands to the ABI)
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
     h_soc, h_ekf, h_T = pin(pop.SOC0), pin(pop.ekf_SOC0), pin(pop.T)
     h_sx, h_lim = pin(np.swapaxes(pop.SigmaX0, 1, 2)), pin(pop.limits)
     h2d = sum(t.numel() * 8 for t in (h_soc, h_ekf, h_T, h_sx, h_lim))
-    cb = api.CellBatch(rom, B, device=local)
+    cb = api.CellBatch(rom, B, Np=cfg["Np"], Nc=cfg["Nc"], constraints=cfg["constraints"], device=local)
     nlog = min(a.log_cells, B)
     cb.set_logging(nlog, a.nsim)
     cb.init_raw(h_soc.data_ptr(), h_ekf.data_ptr(), h_T.data_ptr(), h_sx.data_ptr(), h_lim.data_ptr())
@@ -233,7 +250,7 @@ def main_mek(a):
         # (profiles/r01_defer_ncu_summary.csv); traffic is scaled to the units one launch of this run processes
         traffic, prof = None, {}
         try:
-            for line in open(os.path.join(ROOT, "profiles", "r01_defer_ncu_summary.csv" if kdef > 0 else "r01_final_ncu_summary.csv")):
+            for line in open(os.path.join(ROOT, "profiles", (cfg["profile"] or "none") if kdef > 0 else "r01_final_ncu_summary.csv")):
                 if line.startswith("# DRAM traffic per cell-step"):
                     traffic = float(line.split("=")[1].split("B")[0].replace(" ", "")) * float(B) * a.nsim
                 elif not line.startswith("#") and line.count(",") == 2:
@@ -250,14 +267,14 @@ def main_mek(a):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": {"workload": workload_name(B, a.nsim), "cells_total": B * world, "nsim": a.nsim,
+               "config": {"workload": workload_name(a), "cells_total": B * world, "nsim": a.nsim,
                           "l2": "inputs larger than L2: per-GPU state block %.2f GB, resident working set of the 37888 cells in flight 256 MB" % (state_bytes * B / 1e9)},
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "what": "mek_pop_init (pinned host inputs) + mek_run + mek_summary + mek_read_logs of %d cells' trajectories" % nlog},
                "gpu_launches": launches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                            "traffic": traffic, "kernel": "k_run_population<5,2,15,256,1>", "peak_source": "measured" if peaks else "fallback",
+                            "traffic": traffic, "kernel": cfg["kernel"], "peak_source": "measured" if peaks else "fallback",
                             "bytes_per_cellstep": bytes_per_cellstep, "kernel_ms": kern_avg_ms, "defer_block": kdef,
                             "note": "deferral blocks took the kernel off the HBM roofline (see roofline_streamed and issue): it is bound by "
                                     "FP64 dependency latency at 2 warps per scheduler, not by bytes"},
@@ -272,8 +289,8 @@ def main_mek(a):
                "summary": {k: summ[k] for k in ("n_reached", "n_cap", "n_lost", "n_nonfinite", "min_phise", "max_V")}}
         if not a.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cells = cores * a.cpu_cells_per_core
-            v = cpu_run(bank, cells, a.nsim, cores)
+            cells = max(cores * a.cpu_cells_per_core // (8 if cfg["Np"] > 5 else 1), cores)
+            v = cpu_run(bank, cells, a.nsim, cores, cfg)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "first %d cells of the same population x %d instants, oracle/mek_oracle.c with OpenMP over cells" % (cells, a.nsim)}
         print(json.dumps(out))

@@ -82,6 +82,10 @@ typedef struct {
                                set-point neighbourhood are advanced once per block by replaying the block's currents
                                (bit-identical to advancing them every instant).  0 = default (16), -1 = off        */
   int defer_stagger;        /* 1: warps of a CTA start their deferral blocks at different instants                */
+  int regroup_every;        /* mek_run re-sorts the state block by (temperature bracket, present SOC, C-rate) every this
+                               many sample instants, so that the cells of a warp stay in the same phase of the charge.
+                               Scheduling only (results and the caller's cell indices are unchanged).  0 = automatic
+                               (128 when temperatures or limits differ between cells, else off), -1 = off           */
   int defer_narrow_test;    /* test hook, 1: shrink the per-block model set to the EKF estimate's own neighbours so
                                that the plant's models take the on-demand replay path (results are unchanged)    */
 } mek_config;

@@ -6,6 +6,7 @@
 // copy (cp.async.bulk + mbarrier); per-cell state, covariance and trajectory logs are
 // structure-of-arrays in HBM with the cell index fastest, so each warp access is coalesced.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
 #include <cstdio>
@@ -17,6 +18,9 @@
 
 #include "../../include/mek.h"
 #include "mek_core.cuh"
+#ifndef MEK_REGROUP_DEFAULT
+#define MEK_REGROUP_DEFAULT 128  // sample instants between regroupings of a heterogeneous population (mek_config.regroup_every == 0)
+#endif
 #ifndef MEK_DEFER_DEFAULT
 #define MEK_DEFER_DEFAULT 16     // sample instants per deferral block when mek_config.defer_block == 0
 #endif
@@ -801,6 +805,57 @@ __global__ void k_state_gather(const __grid_constant__ Params P, double* aos, in
   }
 }
 
+// ---- dynamic regrouping: cells of a warp should be in the same phase of the charge ----
+// mek_pop_init orders the cells by (T, SOC0) once; in a heterogeneous population (per-cell C-rate, limits, temperature)
+// the cells of a warp drift apart as the charge proceeds: different local models (a wide hot set), different Hildreth
+// sweep counts, different branches.  Between two launches of the fused kernel the state block is therefore re-sorted
+// by (temperature bracket, present SOC, C-rate): a key per slot, a radix sort, one gather pass over the AoSoA tiles.
+// Pure scheduling -- the caller's cell indices are kept by slot2cell.
+__global__ void k_regroup_keys(const __grid_constant__ Params P, unsigned* keys, int* idx) {
+  const Dims& d = P.d;
+  const double* Tpts = P.bank_blob;                                  // blob layout: Tpts[nT] (K), Zpts[nZ], ...
+  const double th0n = P.cp[P_NEG + E_THETA0], th100n = P.cp[P_NEG + E_THETA100];
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < d.B; s += (long long)gridDim.x * blockDim.x) {
+    const double* b = P.st + (s >> 5) * ((long long)d.nfields * TILE) + (s & 31);
+    const int tt = two_nearest(b[S_TC * TILE] + 273.15, Tpts, d.nT), t1 = tt & 0xffff, t2 = tt >> 16;
+    const unsigned bracket = (unsigned)((t1 < t2 ? t1 : t2) * d.nT + (t1 < t2 ? t2 : t1)) & 0xffu;
+    double soc = (b[S_SOCN * TILE] - th0n) / (th100n - th0n);
+    soc = soc > 0.0 ? (soc < 1.2 ? soc : 1.2) : 0.0;                 // also maps NaN to 0
+    const unsigned bin = (unsigned)(soc * 400.0);                    // 0.25 % SOC
+    const double um = fabs(b[S_UMIN * TILE]);
+    const unsigned rate = (unsigned)((um < 255.0 ? um : 255.0) * 16.0) & 0xfffu;
+    const unsigned lost = ((unsigned)b[S_STATUS * TILE] & ST_LOST) ? 1u : 0u;
+    keys[s] = (lost << 31) | (bracket << 23) | ((bin & 0x7ffu) << 12) | rate;
+    idx[s] = (int)s;
+  }
+}
+
+// st_new[slot j] = st_old[slot perm[j]] for every field; one warp per destination tile
+__global__ void __launch_bounds__(256) k_regroup_move(const __grid_constant__ Params P, const int* __restrict__ perm, double* __restrict__ st_new,
+                                                      const int* __restrict__ s2c_old, int* __restrict__ s2c_new) {
+  const Dims& d = P.d;
+  const long long ntiles = d.ld / TILE;
+  const int lane = threadIdx.x & 31;
+  const long long tsz = (long long)d.nfields * TILE;
+  for (long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const long long j = tile * TILE + lane;
+    const bool live = j < d.B;
+    const long long src = live ? (long long)perm[j] : 0;
+    const double* q = P.st + (src >> 5) * tsz + (src & 31);
+    double* o = st_new + tile * tsz + lane;
+    if (live) s2c_new[j] = s2c_old[src];
+    int f = 0;
+    for (; f + 8 <= d.nfields; f += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = live ? __ldcs(q + (long long)(f + u) * TILE) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) __stcs(o + (long long)(f + u) * TILE, v[u]);
+    }
+    for (; f < d.nfields; ++f) __stcs(o + (long long)f * TILE, live ? __ldcs(q + (long long)f * TILE) : 0.0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // population (host object)
 // ------------------------------------------------------------------------------------------
@@ -825,6 +880,14 @@ struct mek_pop {
   size_t run_smem; int run_threads;
   int wide_ws_slots;           // > 0: doubles per thread of the long-horizon workspace in global memory
   double* d_wide_ws;
+  // dynamic regrouping (k_regroup_*): second state block, key / permutation buffers, the order chosen at init
+  int regroup_every;           // sample instants between regroupings inside mek_run (0: off)
+  bool heterogeneous;          // set by mek_pop_init: temperatures or limits differ between cells
+  double* d_st2;
+  int *d_slot2cell0, *d_slot2cell2, *d_idx, *d_perm;
+  unsigned *d_keys, *d_keys2;
+  void* d_cubtmp; size_t cubtmp_bytes;
+  int64_t regroups;
 };
 
 static double sigma_min_gtg(int Np, int Nc, double r) {
@@ -895,6 +958,10 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   p->d_slot2cell = nullptr;
   p->d_wide_ws = nullptr;
   p->wide_ws_slots = 0;
+  p->regroup_every = cfg->regroup_every;      // resolved in mek_pop_init (0 = automatic)
+  p->heterogeneous = false;
+  p->d_st2 = nullptr; p->d_slot2cell0 = nullptr; p->d_slot2cell2 = nullptr; p->d_idx = nullptr; p->d_perm = nullptr;
+  p->d_keys = nullptr; p->d_keys2 = nullptr; p->d_cubtmp = nullptr; p->cubtmp_bytes = 0; p->regroups = 0;
   p->d_scratch = nullptr;
   p->scratch_bytes = 0;
   int Np = cfg->Np < 1 ? 1 : cfg->Np;                               // initMPC.m:32-33 (Q23)
@@ -1047,6 +1114,14 @@ extern "C" void mek_pop_destroy(mek_pop* p) {
   cudaStreamSynchronize(p->stream);
   if (p->d_slot2cell) cudaFree(p->d_slot2cell);
   if (p->d_wide_ws) cudaFree(p->d_wide_ws);
+  if (p->d_st2) cudaFree(p->d_st2);
+  if (p->d_slot2cell0) cudaFree(p->d_slot2cell0);
+  if (p->d_slot2cell2) cudaFree(p->d_slot2cell2);
+  if (p->d_idx) cudaFree(p->d_idx);
+  if (p->d_perm) cudaFree(p->d_perm);
+  if (p->d_keys) cudaFree(p->d_keys);
+  if (p->d_keys2) cudaFree(p->d_keys2);
+  if (p->d_cubtmp) cudaFree(p->d_cubtmp);
   cudaFree(p->d_blob); cudaFree(p->d_Cfull); cudaFree(p->d_Dfull); cudaFree(p->d_st); cudaFree(p->d_in); cudaFree(p->d_totals);
   if (p->d_logs) cudaFree(p->d_logs);
   if (p->d_scratch) cudaFree(p->d_scratch);
@@ -1093,6 +1168,8 @@ extern "C" int mek_pop_set_logging(mek_pop* p, int64_t n_log_cells, int max_step
 extern "C" int mek_pop_reset(mek_pop* p) {
   if (!p) return fail(MEK_ERR_ARG, "null pop");
   CUDA_TRY(cudaSetDevice(p->device));
+  if (p->d_slot2cell0 && p->P.slot2cell)      // regrouping has permuted the slots: go back to the order chosen at init
+    CUDA_TRY(cudaMemcpyAsync(p->d_slot2cell, p->d_slot2cell0, sizeof(int) * (size_t)p->P.d.B, cudaMemcpyDeviceToDevice, p->stream));
   k_pop_init<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P);
   CUDA_TRY(cudaGetLastError());
   p->launches++;
@@ -1125,11 +1202,28 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
     CUDA_TRY(cudaMemcpyAsync(p->d_slot2cell, order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));        // `order` is a pageable temporary
     p->P.slot2cell = p->d_slot2cell;
+    // regrouping (automatic: only where it pays, i.e. when the cells do not all share temperature and limits)
+    bool het = false;
+    for (size_t i = 1; i < B && !het; ++i) {
+      if (Tc[i] != Tc[0]) het = true;
+      for (int q = 0; q < 7 && !het; ++q)
+        if (limits[7 * i + q] != limits[q]) het = true;
+    }
+    p->heterogeneous = het;
+    int every = p->cfg.regroup_every;
+    if (every == 0) every = het ? MEK_REGROUP_DEFAULT : -1;
+    p->regroup_every = every > 0 ? every : 0;
+    if (p->regroup_every > 0) {
+      if (!p->d_slot2cell0) CUDA_TRY(cudaMalloc(&p->d_slot2cell0, sizeof(int) * B));
+      CUDA_TRY(cudaMemcpyAsync(p->d_slot2cell0, p->d_slot2cell, sizeof(int) * B, cudaMemcpyDeviceToDevice, p->stream));
+    }
+  } else {
+    p->regroup_every = 0;
   }
   return mek_pop_reset(p);
 }
 
-static int launch_run(mek_pop* p, int k0, int k1) {
+static int launch_segment(mek_pop* p, int k0, int k1) {
   const int g = grid_for(p, p->P.d.B, p->run_threads);
   if (p->inst == 1 && p->cons == 15 && p->run_threads == 64) k_run_population<20, 5, 15, 64, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   else if (p->inst == 1 && p->cons == 15) k_run_population<20, 5, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
@@ -1142,6 +1236,50 @@ static int launch_run(mek_pop* p, int k0, int k1) {
   else k_run_population<32, 8, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
   CUDA_TRY(cudaGetLastError());
   p->launches++;
+  return MEK_OK;
+}
+
+
+// re-sort the state block by (temperature bracket, present SOC, C-rate); see k_regroup_keys
+static int regroup(mek_pop* p) {
+  const size_t B = (size_t)p->P.d.B;
+  const size_t st_bytes = sizeof(double) * (size_t)p->P.d.nfields * (size_t)p->P.d.ld;
+  if (!p->d_st2) {
+    CUDA_TRY(cudaMalloc(&p->d_st2, st_bytes));
+    CUDA_TRY(cudaMalloc(&p->d_slot2cell2, sizeof(int) * B));
+    CUDA_TRY(cudaMalloc(&p->d_idx, sizeof(int) * B));
+    CUDA_TRY(cudaMalloc(&p->d_perm, sizeof(int) * B));
+    CUDA_TRY(cudaMalloc(&p->d_keys, sizeof(unsigned) * B));
+    CUDA_TRY(cudaMalloc(&p->d_keys2, sizeof(unsigned) * B));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, p->cubtmp_bytes, p->d_keys, p->d_keys2, p->d_idx, p->d_perm, (int)B, 0, 32, p->stream));
+    CUDA_TRY(cudaMalloc(&p->d_cubtmp, p->cubtmp_bytes));
+  }
+  k_regroup_keys<<<p->sms * 4, 256, 0, p->stream>>>(p->P, p->d_keys, p->d_idx);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(p->d_cubtmp, p->cubtmp_bytes, p->d_keys, p->d_keys2, p->d_idx, p->d_perm, (int)B, 0, 32, p->stream));
+  k_regroup_move<<<p->sms * 8, 256, 0, p->stream>>>(p->P, p->d_perm, p->d_st2, p->d_slot2cell, p->d_slot2cell2);
+  CUDA_TRY(cudaGetLastError());
+  std::swap(p->d_st, p->d_st2);
+  std::swap(p->d_slot2cell, p->d_slot2cell2);
+  p->P.st = p->d_st;
+  p->P.slot2cell = p->d_slot2cell;
+  p->launches += 3;            // keys, sort (one or more library kernels), move
+  p->regroups++;
+  return MEK_OK;
+}
+
+static int launch_run(mek_pop* p, int k0, int k1) {
+  const int every = (p->regroup_every > 0 && p->P.slot2cell) ? p->regroup_every : 0;
+  if (every == 0 || k1 - k0 <= every) return launch_segment(p, k0, k1);
+  for (int s = k0; s < k1; s += every) {
+    const int e = s + every < k1 ? s + every : k1;
+    int rc = launch_segment(p, s, e);
+    if (rc != MEK_OK) return rc;
+    if (e < k1) {
+      rc = regroup(p);
+      if (rc != MEK_OK) return rc;
+    }
+  }
   return MEK_OK;
 }
 

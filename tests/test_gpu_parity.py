@@ -200,3 +200,35 @@ def test_deferral_on_demand_catch_up(bank, coracle_mod):
     assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
     n_on_demand = cb.read_state()[:, 29]
     assert n_on_demand.sum() >= 20, "the on-demand path was not exercised"
+
+
+# ---- dynamic regrouping of a heterogeneous population ----
+def test_regrouping_is_invisible_to_the_caller(bank, coracle_mod):
+    """mek_run re-sorts the state block by (temperature bracket, SOC, C-rate) between launches of the fused kernel; logs,
+    state read-back, summaries and a later reset keep the caller's indices and stay bit-identical to the oracle."""
+    from mek import api, population as P
+    pop = P.make_population(bank.params[2], 333, seed=31, heterogeneous=True, ekf_soc_error=2.0)
+    rom = api.RomBank(bank)
+    outs = []
+    for every in (-1, 37, 0):                       # off, every 37 instants, automatic (128: the population is heterogeneous)
+        cb = api.CellBatch(rom, len(pop), regroup_every=every)
+        cb.set_logging(len(pop), 600)
+        cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        cb.run(0, 250)
+        cb.run(250, 600)
+        st = cb.read_state(); st[:, 29] = 0.0
+        outs.append((cb.logs(0, 600), st, cb.summary()))
+        if every == 37:                             # reset goes back to the order chosen at init and reproduces the run
+            cb.reset()
+            cb.run(0, 600)
+            g2 = cb.logs(0, 600)
+            for k in ("u", "V", "SOC", "phise", "nexec"):
+                assert np.array_equal(g2[k], outs[-1][0][k], equal_nan=True), k
+    for o in outs[1:]:
+        for k in ("u", "V", "SOC", "phise", "iT", "iZ", "nexec", "active"):
+            assert np.array_equal(outs[0][0][k], o[0][k], equal_nan=k in ("u", "V", "SOC", "phise")), k
+        assert np.array_equal(outs[0][1], o[1], equal_nan=True)
+        assert outs[0][2]["sum_nexec"] == o[2]["sum_nexec"] and outs[0][2]["min_phise"] == o[2]["min_phise"]
+    co = coracle_mod.COracle(bank)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    _assert_bit_exact(outs[1][0], co.run(0, 600, nthreads=8))

@@ -10,7 +10,8 @@ bps = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 tpb = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 bk = B.Bank.load(B.default_bank_path())
 rom = api.RomBank(bk)
-pop = P.make_population(bk.params[2], cells, seed=2)
+het = os.environ.get("MEK_HET", "0") == "1"
+pop = P.make_population(bk.params[2], cells, seed=4 if het else 2, heterogeneous=het)
 cb = api.CellBatch(rom, cells, Np=Np, Nc=Nc, blocks_per_sm=0, threads_per_block=(bps if bps > 100 else 0), generic_path=(bps == 9), sync_steps=(tpb != 2))
 cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits)
 ksplit = int(sys.argv[7]) if len(sys.argv) > 7 else 0
