@@ -38,6 +38,7 @@ struct Dims {
   int useCurrent, useVoltage, useEta, useZmax;
   int force_jacobi;
   double Ts, ref, SigmaV, SigmaW, sigmin;
+  double zinv;       // (nZ-1)/(Zpts[nZ-1]-Zpts[0]): bracket guess of two_nearest_z
   long long B, ld;   // cells in this shard, cells rounded up to whole 32-cell tiles
   int f_lambda, f_bigx, f_xhat, f_sig, nfields;
 };
@@ -73,7 +74,8 @@ struct Scratch {
   int s;
   __device__ __forceinline__ double& operator[](int i) const { return p[i * s]; }
 };
-enum : int { SC_GAMMA = 0, SC_M = 4, SC_IT = 8, SC_IZ = 12, SC_Z = 16, SC_TOTAL = SC_Z + HR_MAX };
+// SC_X: what getVariables leaves for EKFmatsHandler (negEta0, posEta3, Uocp_neg(thetass0), Uocp_pos(thetass3), SOC-clamp flag)
+enum : int { SC_GAMMA = 0, SC_M = 4, SC_IT = 8, SC_IZ = 12, SC_Z = 16, SC_X = SC_Z + HR_MAX, SC_TOTAL = SC_X + 5 };
 
 __device__ __forceinline__ int sym_idx(int i, int j) {
   // upper triangle, row-major: (0,0..4)=0..4, (1,1..4)=5..8, (2,2..4)=9..11, (3,3..4)=12,13, (4,4)=14
@@ -96,10 +98,32 @@ __device__ __noinline__ int two_nearest(double v, const double* pts, int n) {
   return a | (b << 16);
 }
 
+// Same result as two_nearest(v, Zpts, nZ) without the scan: guess the bracket [lo, lo+1] from the grid's mean spacing, then
+// PROVE the guess with the sort's own rule -- the nearer of the two (ties: lower index) comes first, and both outer
+// neighbours sort after the farther one (left: strictly farther, it has the lower index; right: farther or tied).
+// On an ascending grid |v - pts[i]| cannot decrease away from the bracket (rounding is monotonic), so the neighbours
+// stand for everything beyond them.  Any doubt (NaN, guess off by one, v beyond a neighbour) falls back to the scan.
+__device__ __forceinline__ int two_nearest_z(const Dims& d, double v, const double* pts) {
+  const int n = d.nZ;
+  if (n >= 2) {
+    int lo = (int)((v - pts[0]) * d.zinv);                           // NaN / out of range -> clamped, then rejected below if wrong
+    lo = lo < 0 ? 0 : (lo > n - 2 ? n - 2 : lo);
+    const int hi = lo + 1;
+    const double dl = fabs(v - pts[lo]), dh = fabs(v - pts[hi]);
+    const bool lo_first = dl <= dh;
+    const double db = lo_first ? dh : dl;
+    bool ok = (dl == dl) && (dh == dh);
+    if (lo > 0) ok = ok && (v >= pts[lo - 1]) && (fabs(v - pts[lo - 1]) > db);
+    if (hi < n - 1) ok = ok && (v <= pts[hi + 1]) && (fabs(v - pts[hi + 1]) >= db);
+    if (ok) return lo_first ? (lo | (hi << 16)) : (hi | (lo << 16));
+  }
+  return two_nearest(v, pts, n);
+}
+
 // getXind (iterEKF.m:219-255): ordering by value with swap, alphas not clamped (Q14).
 // Writes gamma[4], model column m[4] = iT*nZ+iZ, iT[4], iZ[4] into the scratch column.
 __device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc, int tt_cached) {
-  const int zz = two_nearest(SOC, bk.Zpts, d.nZ), z1 = zz & 0xffff, z2 = zz >> 16;
+  const int zz = two_nearest_z(d, SOC, bk.Zpts), z1 = zz & 0xffff, z2 = zz >> 16;
   int iZup = z1, iZlo = z1;
   double Zup = bk.Zpts[z1], Zlo = bk.Zpts[z1];
   if (d.nZ > 1) {
@@ -370,7 +394,7 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   if (SOCp < 0.0) { SOCp = 0.0; ++nw; }
   if (SOCp > 1.0) { SOCp = 1.0; ++nw; }
   if (nw) c.f(S_PLANTWARN) += (double)nw;
-  const int zz = two_nearest(cellSOC, bk.Zpts, d.nZ), z1 = zz & 0xffff, z2 = zz >> 16;   // :251-259 (ordering by index, Q15)
+  const int zz = two_nearest_z(d, cellSOC, bk.Zpts), z1 = zz & 0xffff, z2 = zz >> 16;   // :251-259 (ordering by index, Q15)
   const int iZup = z1 > z2 ? z1 : z2, iZlo = z1 < z2 ? z1 : z2;
   const int tt = (tt_cached >= 0) ? tt_cached : two_nearest(T, bk.Tpts, d.nT), t1 = tt & 0xffff, t2 = tt >> 16;   // :261-269
   const int iTup = t1 > t2 ? t1 : t2, iTlo = t1 < t2 ? t1 : t2;
@@ -454,6 +478,7 @@ __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, 
   if (SOCn > 1.0) { ++nwarn; SOCn = 1.0 - 1e-6; }
   if (SOCp < 0.0) { ++nwarn; SOCp = 1e-6; }
   if (SOCp > 0.998) { ++nwarn; SOCp = 0.998; }
+  const bool soc_clamped = nwarn != 0;
 #pragma unroll 1
   for (int r = 0; r < d.R; ++r) {                                    // :302-313  Z = [C1*x1+D1*i, ...]*gamma, hot rows only
     if (r == HR_PHI) continue;
@@ -527,6 +552,8 @@ __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, 
   const double Rfn = rf_e(p, P_NEG, SOCn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, SOCp, c.f(S_ARRRFP));
   if (nwarn) c.f(S_WARN) += (double)nwarn;                           // shortWarn -> warnCount (:749)
   if (status) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | status);
+  sc[SC_X + 0] = negEta0; sc[SC_X + 1] = posEta3; sc[SC_X + 2] = Un0; sc[SC_X + 3] = Up3;
+  sc[SC_X + 4] = soc_clamped ? 1.0 : 0.0;
   return ((((posEta3 - negEta0) + sc[SC_Z + HR_PHIE]) + Up3) - Un0) + (Rfp * sc[SC_Z + HR_IFDL3] - Rfn * sc[SC_Z + HR_IFDL0]);   // :409-410 (Q5)
 }
 
@@ -756,19 +783,26 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     const double ztss0 = sc[SC_Z + HR_TSS0], ztss3 = sc[SC_Z + HR_TSS3];
     const double TK = c.f(S_TC) + 273.15;                            // :53
     const double sn = soc_e(p, P_NEG, Zsoc), sp = soc_e(p, P_POS, Zsoc);   // :56-58
-    const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
-    const double i0n = k0n * sqrt((sc[SC_Z + HR_THE0] * (1.0 - ztss0)) * ztss0);   // :63-66
-    const double i0p = k0p * sqrt((sc[SC_Z + HR_THE3] * (1.0 - ztss3)) * ztss3);
     const double Rfn2 = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)), Rfp2 = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
     const double* mm = am + 6;
 #pragma unroll
     for (int j = 0; j < N5; ++j)                                     // :75-76
       o.Cv[j] = (Rfp2 * mm[HR_IFDL3 * 7 + j] - Rfn2 * mm[HR_IFDL0 * 7 + j]) + mm[HR_PHIE * 7 + j];
     o.Dv = (Rfp2 * mm[HR_IFDL3 * 7 + 6] - Rfn2 * mm[HR_IFDL0 * 7 + 6]) + mm[HR_PHIE * 7 + 6];   // :79-80
-    const double Upos = uocp_p(p, ztss3), Uneg = uocp_n(p, ztss0);   // :84-85
-    const double pref = ((2.0 * p[P_R]) * TK) / p[P_F];
-    const double negEta0 = pref * asinh_d(sc[SC_Z + HR_IF0] / (2.0 * i0n));   // :88-89
-    const double posEta3 = pref * asinh_d(sc[SC_Z + HR_IF3] / (2.0 * i0p));
+    // :57-69,84-89 evaluate, at zk's SOC and the corrected thetass / thetae, exactly what the getVariables call above (:182)
+    // just evaluated -- unless that call clamped its electrode SOCs (Q17), in which case its k0 arguments differ
+    double Upos, Uneg, negEta0, posEta3;
+    if (sc[SC_X + 4] == 0.0) {
+      negEta0 = sc[SC_X + 0]; posEta3 = sc[SC_X + 1]; Uneg = sc[SC_X + 2]; Upos = sc[SC_X + 3];
+    } else {
+      const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
+      const double i0n = k0n * sqrt((sc[SC_Z + HR_THE0] * (1.0 - ztss0)) * ztss0);   // :63-66
+      const double i0p = k0p * sqrt((sc[SC_Z + HR_THE3] * (1.0 - ztss3)) * ztss3);
+      Upos = uocp_p(p, ztss3); Uneg = uocp_n(p, ztss0);              // :84-85
+      const double pref = ((2.0 * p[P_R]) * TK) / p[P_F];
+      negEta0 = pref * asinh_d(sc[SC_Z + HR_IF0] / (2.0 * i0n));     // :88-89
+      posEta3 = pref * asinh_d(sc[SC_Z + HR_IF3] / (2.0 * i0p));
+    }
     o.bv = ((Upos - Uneg) + (posEta3 - negEta0)) + 0.0;              // :92
     o.bphi = uocp_n(p, sn);                                          // :96 (Q21)
 #pragma unroll

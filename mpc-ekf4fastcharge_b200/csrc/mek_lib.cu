@@ -982,6 +982,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   d.force_jacobi = cfg->force_jacobi;
   d.Ts = bank->Tsamp; d.ref = cfg->ref; d.SigmaV = cfg->SigmaV; d.SigmaW = cfg->SigmaW;
   d.sigmin = sigma_min_gtg(Np, Nc, -bank->Tsamp / (3600.0 * bank->params[P_Q]));
+  d.zinv = bank->nZ > 1 ? (double)(bank->nZ - 1) / (bank->Zpts[bank->nZ - 1] - bank->Zpts[0]) : 0.0;
   d.B = B;
   d.ld = (B + 31) / 32 * 32;
   d.f_lambda = S_HDR; d.f_bigx = d.f_lambda + d.nC; d.f_xhat = d.f_bigx + 6 * d.M; d.f_sig = d.f_xhat + N5 * d.M;
