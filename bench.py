@@ -264,6 +264,20 @@ def main_mek(a):
         fp64_tf = api.fp64_peak_tflops(local)
         qps = summ["n_qp"] / summ["cellsteps"]
         sweeps = summ["sum_nexec"] / summ["cellsteps"]
+        # FP64 roofline: exact algorithmic flops from the frozen op-count table (profiles/r01_flop_tally.json, made by
+        # oracle/opcount_run.py) x this run's own QP and sweep counters, over the kernel time
+        fp64 = {"peak_tflops_measured": fp64_tf}
+        try:
+            tl = json.load(open(os.path.join(ROOT, "profiles", "r01_flop_tally.json")))["configs"][a.config]
+            fl = tl["F_fixed"] + qps * tl["F_qp_setup"] + sweeps * tl["F_sweep"]
+            ins = tl["fp64_instr_per_cellstep"] + (sweeps - tl["mean_sweeps_per_step"]) * tl["F_sweep"] * (tl["blocks"][8]["fp64_instr_per_cellstep"] / tl["blocks"][8]["flops_per_cellstep"])
+            rate = float(B) * a.nsim / (kern_avg_ms * 1e-3)
+            fp64.update({"flops_per_cellstep": fl, "achieved_tflops": fl * rate / 1e12, "frac": fl * rate / 1e12 / fp64_tf,
+                         "fp64_instr_per_cellstep": ins, "pipe_frac": ins * rate / (fp64_tf * 1e12 / 2),
+                         "F_fixed": tl["F_fixed"], "F_qp_setup": tl["F_qp_setup"], "F_sweep": tl["F_sweep"],
+                         "rule": "add/mul/div/sqrt = 1, fma = 2 (SURVEY.md 8d); pipe_frac counts one pipe slot per FP64 instruction against peak/2 DFMA/s"})
+        except Exception:
+            pass
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
@@ -284,7 +298,7 @@ def main_mek(a):
                "issue": {"issue_slots_active_pct": prof.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                          "fp64_pipe_active_pct": prof.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                          "source": "ncu capture in profiles/ (37888-cell stretch of the same kernel), not measured in this run"},
-               "fp64": {"peak_tflops_measured": fp64_tf},
+               "fp64": fp64,
                "qp_solves_per_s": value * qps, "hildreth_sweeps_per_s": value * sweeps, "mean_sweeps_per_step": sweeps,
                "summary": {k: summ[k] for k in ("n_reached", "n_cap", "n_lost", "n_nonfinite", "min_phise", "max_V")}}
         if not a.no_cpu_baseline:

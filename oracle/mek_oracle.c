@@ -28,6 +28,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* The op-counting build (oracle/opcount.cpp) marks the blocks of BASELINE.md section 3 with OPC_BLOCK(id):
+   0 plant, 1 EKF time update, 2 EKF measurement path, 3 PSD check/repair, 4 EKFmatsHandler, 5 iterMPC fixed part,
+   6 constraintsMPC, 7 QP set-up + recovery, 8 Hildreth sweeps, 9 everything else.  A no-op in the normal build. */
+#ifndef OPC_BLOCK
+#define OPC_BLOCK(id) ((void)0)
+#endif
+
 #define N5 5
 #define NSYM 15
 #define NP_MAX 32
@@ -235,6 +242,7 @@ static int sym_idx(int i, int j) { /* upper triangle, row-major, i <= j */
 /* plant: OB_step.m simStep                                                                   */
 /* ------------------------------------------------------------------------------------------ */
 static double plant_step(const mko_bank *bk, double *st, double Iapp) {
+  OPC_BLOCK(0);
   const double *p = bk->params;
   const int M = bk->nT * bk->nZ, nz = bk->nz;
   double *bigX = st + st_off_bigx();
@@ -485,6 +493,7 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
   const int M = bk->nT * bk->nZ, nz = bk->nz;
   double *xhat = st + st_off_xhat(M), *Sig = st + st_off_sig(M);
   double Z[64 + 2];
+  OPC_BLOCK(1);
   o->lost = 0;
   if (st[S_WARN] > 10.0) {                                         /* iterEKF.m:55-59 (Q19) */
     st[S_STATUS] = (double)((unsigned)st[S_STATUS] | ST_LOST);
@@ -502,6 +511,7 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
     for (int i = 0; i < N5; ++i)
       for (int j = i; j < N5; ++j, ++q) S[q] = fma(a[i] * S[q], a[j], Sw); /* :81 (Q12) */
   }
+  OPC_BLOCK(2);
   st[S_X0] = st[S_X0] + prior;                                     /* :85 */
   st[S_SIGX0] = st[S_SIGX0] + Sw;                                  /* :86 */
   const double rpa = bk->Ts / (3600.0 * p[P_Q]);
@@ -565,7 +575,10 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
     int q = 0;
     for (int i = 0; i < N5; ++i)
       for (int j = i; j < N5; ++j, ++q) S[q] = fma(-(L[c][i] * svt[c]), L[c][j], S[q]); /* :142 */
-    if (psd_repair(S, cf->force_jacobi)) st[S_NJAC] += 1.0;        /* :143-145 */
+    OPC_BLOCK(3);
+    const int jac = psd_repair(S, cf->force_jacobi);               /* :143-145 */
+    OPC_BLOCK(2);
+    if (jac) st[S_NJAC] += 1.0;
     if (resid * resid > 9.0 * svt[c]) {                            /* :148-151 */
       for (int k = 0; k < NSYM; ++k) S[k] = S[k] * 2.0;
       st[S_NBUMP] += 1.0;
@@ -591,6 +604,7 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
   o->vhat = vhat;
   o->soc = Zsoc;
   /* ---- EKFmatsHandler (EKFmatsHandler.m:26-114) ---- */
+  OPC_BLOCK(4);
   int imax = 0;                                                    /* :26 first max, NaN ignored */
   {
     int have = 0;
@@ -693,6 +707,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
                  const double *lam0, int maxIter, double *DU, double *lam, int *nexec) {
   double LU[NC_MAX * NC_MAX], Ei[NC_MAX][NC_MAX], P[NCON_MAX][NC_MAX], K[NCON_MAX], Hd[NCON_MAX], rH[NCON_MAX], v[NC_MAX], x[NC_MAX];
   if (Nc > NC_MAX || nC > NCON_MAX) return -1;
+  OPC_BLOCK(7);
   spd_factor(Nc, E, LU);
   spd_solve(Nc, LU, F, x);                                         /* E\F */
   for (int l = 0; l < Nc; ++l) {                                   /* inv(E), column by column: E\M' = inv(E)*M' */
@@ -721,6 +736,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
     for (int j = 0; j < Nc; ++j) v[j] = fma(P[i][j], lam[i], v[j]);
   }
   int k = 0;
+  OPC_BLOCK(8);
   for (k = 1; k <= maxIter; ++k) {                                 /* :32 */
     int notconv = 0;
     for (int i = 0; i < nC; ++i) {                                 /* :34-37 */
@@ -746,6 +762,7 @@ int mko_hildreth(int Nc, int nC, const double *E, const double *F, const double 
     }
     if (!notconv) break;
   }
+  OPC_BLOCK(7);
   if (k > maxIter) k = maxIter;
   *nexec = k;                                                      /* :43 */
   double rhs[NC_MAX];
@@ -804,6 +821,7 @@ static void mpc_step(const mko_bank *bk, const mko_config *cf, double sigmin, do
                      mpc_out *o) {
   const int Np = cf->Np, Nc = cf->Nc;
   const double *p = bk->params;
+  OPC_BLOCK(5);
   const double uk_1 = st[S_UK];                                    /* iterMPC.m:19 */
   const double r = -bk->Ts / (3600.0 * p[P_Q]);                    /* EKFmatsHandler.m:43 */
   const double zero5[N5] = {0, 0, 0, 0, 0};
@@ -852,6 +870,7 @@ static void mpc_step(const mko_bank *bk, const mko_config *cf, double sigmin, do
   spd_solve(Nc, LU, F, x);
   for (int j = 0; j < Nc; ++j) DU[j] = -x[j];                      /* :48 */
   /* ---- constraintsMPC.m ---- */
+  OPC_BLOCK(6);
   double Mm[NCON_MAX * NC_MAX], gam[NCON_MAX];
   int nC = 0;
   if (cf->useCurrent) {                                            /* :23-42 */
@@ -886,6 +905,7 @@ static void mpc_step(const mko_bank *bk, const mko_config *cf, double sigmin, do
       gam[nC] = st[S_ZMAX] - ((pxs[i - 1] + hs[i] * uk_1) + e->soc);
     }
   }
+  OPC_BLOCK(5);
   int viol = 0;                                                    /* iterMPC.m:66 (Q8) */
   for (int i = 0; i < nC; ++i) {
     double acc = Mm[i * Nc] * DU[0];
@@ -902,6 +922,7 @@ static void mpc_step(const mko_bank *bk, const mko_config *cf, double sigmin, do
       st[S_LAMBDA + i] = lam[i];                                   /* :68 (Q11) */
       if (lam[i] > 0.0) o->active[i >> 5] |= (1u << (i & 31));
     }
+    OPC_BLOCK(5);
     st[S_LAMVALID] = 1.0;
     o->nexec = nexec;
   }
@@ -968,6 +989,7 @@ void mko_cell_step(const mko_bank *bk, const mko_config *cf, double sigmin, doub
   }
   mpc_out o;
   mpc_step(bk, cf, sigmin, st, &e, uk, &o);                        /* :94-103 */
+  OPC_BLOCK(9);
   *log_u = o.u; *log_V = V; *log_soc = e.soc; *log_phise = o.phise; /* :106-109 */
   *log_iT = e.iT + 1; *log_iZ = e.iZ + 1; *log_nexec = o.nexec;
   for (int w = 0; w < 4; ++w) log_active[w] = o.active[w];
