@@ -37,6 +37,7 @@ struct Dims {
   int Np, Nc, maxHild;
   int useCurrent, useVoltage, useEta, useZmax;
   int force_jacobi;
+  int no_lean_sweep;  // test hook: static-shape instances always take the general Hildreth sweep
   double Ts, ref, SigmaV, SigmaW, sigmin;
   double zinv;       // (nZ-1)/(Zpts[nZ-1]-Zpts[0]): bracket guess of two_nearest_z
   long long B, ld;   // cells in this shard, cells rounded up to whole 32-cell tiles
@@ -1361,6 +1362,42 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     for (int i = 0; i < nC; ++i)
       if (((zmask >> i) & 1u) && !is_finite(lam[i])) pmask |= 1u << i;
     int k = 1;
+    // Lean sweep: the only all-zero row is the first z_max row (h_soc(0) = 0 always, quirk Q7), it holds a finite lambda and
+    // its K (= gamma_i) is not negative.  Then that row's update is max(0, -K*Inf) = 0 on every sweep (K = 0: NaN -> 0), it
+    // never touches v, no lambda ever becomes non-finite ("poison"), and every other row is the plain update -- the masks
+    // of the general loop below are all constant and drop out.  Bit-identical to the general loop by construction
+    // (tests/test_gpu_parity.py::test_lean_sweep_equals_general_sweep forces the general loop for comparison).
+    constexpr unsigned ZEXP = FS::UZ ? (1u << FS::O_Z) : 0u;
+    bool lean = (zmask == ZEXP) && (pmask == 0u) && !d.no_lean_sweep;
+    if (FS::UZ) lean = lean && !(vs[(FS::O_Z * 2 + 0) * sms] < 0.0);
+    if (lean) {
+      bool first_nc = false;
+      if (FS::UZ) { first_nc = !(lam[FS::O_Z] < 1e-6); lam[FS::O_Z] = 0.0; }
+      for (; k <= d.maxHild; ++k) {                                  // hildreth.m:32
+        bool notconv = (k == 1) && first_nc;
+#pragma unroll
+        for (int i = 0; i < nC; ++i) {                               // hildreth.m:34-37
+          if (FS::UZ && i == FS::O_Z) continue;
+          const double li = lam[i];
+          double hl = Mm[i][0] * v[0];
+#pragma unroll
+          for (int j = 1; j < NC; ++j) hl = fma(Mm[i][j], v[j], hl);
+          const double w = fma(-(vs[(i * 2 + 0) * sms] + hl), vs[(i * 2 + 1) * sms], li);
+          const double nl = pos_or_zero(w);                          // max(0,w); max(0,NaN) = 0
+          const double dl = nl - li;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            double acc = Ei[j][0] * Mm[i][0];
+#pragma unroll
+            for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
+            v[j] = fma(acc, dl, v[j]);
+          }
+          lam[i] = nl;
+          notconv = notconv || !(fabs(dl) < 1e-6);                   // hildreth.m:39
+        }
+        if (!notconv) break;
+      }
+    } else
     for (; k <= d.maxHild; ++k) {                                    // hildreth.m:32
       bool notconv = false;
 #pragma unroll

@@ -980,6 +980,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax);
   if (d.nC > 128) { delete p; return fail(MEK_ERR_UNSUPPORTED, "more than 128 constraint rows"); }
   d.force_jacobi = cfg->force_jacobi;
+  d.no_lean_sweep = cfg->general_sweep_test > 0 ? 1 : 0;
   d.Ts = bank->Tsamp; d.ref = cfg->ref; d.SigmaV = cfg->SigmaV; d.SigmaW = cfg->SigmaW;
   d.sigmin = sigma_min_gtg(Np, Nc, -bank->Tsamp / (3600.0 * bank->params[P_Q]));
   d.zinv = bank->nZ > 1 ? (double)(bank->nZ - 1) / (bank->Zpts[bank->nZ - 1] - bank->Zpts[0]) : 0.0;

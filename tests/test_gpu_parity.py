@@ -232,3 +232,24 @@ def test_regrouping_is_invisible_to_the_caller(bank, coracle_mod):
     co = coracle_mod.COracle(bank)
     co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
     _assert_bit_exact(outs[1][0], co.run(0, 600, nthreads=8))
+
+
+# ---- lean Hildreth sweep of the static-shape instances ----
+@pytest.mark.parametrize("constraints", [(1, 1, 1), (1, 1, 0)])
+def test_lean_sweep_equals_general_sweep(bank, coracle_mod, constraints):
+    """The static-shape instances run a lean sweep when the only all-zero row of M is the first z_max row, its lambda is
+    finite and its K is not negative, and the general masked sweep otherwise (a QP that drives the zero row to +Inf: the
+    cap-hit cases).  Both must give the oracle's bits; the test hook forces the general sweep everywhere for comparison.
+    The population includes cells that start above z_max - a few percent so that the +Inf / NaN pattern occurs."""
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 160, seed=41, heterogeneous=True, ekf_soc_error=1.0)
+    pop.SOC0[::5] = 93.5                                  # reach z_max within the run: K of the zero row changes sign
+    pop.ekf_SOC0[::5] = 94.5
+    outs = []
+    for hook in (False, True):
+        cb, g, co, c = _run_both(bank, coracle_mod, pop, 700, constraints=constraints, general_sweep_test=hook)
+        _assert_bit_exact(g, c)
+        outs.append((g, cb.summary()))
+    assert outs[0][1]["n_cap"] > 0, "no QP hit the sweep cap: the general sweep was not exercised by the lean build"
+    for k in ("u", "nexec", "active"):
+        assert np.array_equal(outs[0][0][k], outs[1][0][k], equal_nan=(k == "u")), k
