@@ -667,6 +667,14 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     for (int k = 0; k < 4; ++k) defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
   }
   double vhat = get_variables(d, bk, p, c, ik, Tk, sc);              // :108
+  // SigmaX of neighbour #1 *before* any update: every gain uses it (:117, Q1).  Loaded here so that the L2 round trip
+  // overlaps the scalar block below.
+  double S1[NSYM];
+  {
+    const int m0 = (int)sc[SC_M + 0];
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) S1[q] = c.sig(m0, q);
+  }
   // ---- getChatV scalars (:421-519) ----
   const double tss0 = sc[SC_Z + HR_TSS0], tss3 = sc[SC_Z + HR_TSS3];
   double Rfn, Rfp, Rctn, Rctp, dUn0, dUp3, C0;
@@ -687,20 +695,19 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   const double svt0 = (C0 * sx0) * C0 + d.SigmaV;                    // :123
   const double L0 = (sx0 * C0) / svt0;                               // :124
   const double resid = vk - vhat;                                    // :133
-  // SigmaX of neighbour #1 *before* any update: every gain uses it (:117, Q1)
-  double S1[NSYM];
-  {
-    const int m0 = (int)sc[SC_M + 0];
-#pragma unroll
-    for (int q = 0; q < NSYM; ++q) S1[q] = c.sig(m0, q);
-  }
   int njac = 0, nbump = 0;
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {                                      // :116-121 gain, :136-154 update; sequential (Q2)
     const int mo = (int)sc[SC_M + k];
     const double g = sc[SC_GAMMA + k];
     const double* mm = bk.mdl + mo * d.mstride + 6;
-    double Chat[N5], v[N5], L[N5], S[NSYM];
+    double Chat[N5], v[N5], L[N5], S[NSYM], xs[N5];
+    // this neighbour's state, requested before the gain is computed (the loads overlap it); after the previous
+    // neighbour's stores in program order, so a duplicate neighbour sees its own update (Q2)
+#pragma unroll
+    for (int j = 0; j < N5; ++j) xs[j] = c.xhat(mo, j);
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) S[q] = c.sig(mo, q);
 #pragma unroll
     for (int j = 0; j < N5; ++j) {                                   // getChatV for this neighbour
       double t = Rfp * (g * mm[HR_IFDL3 * 7 + j]) - Rfn * (g * mm[HR_IFDL0 * 7 + j]);    // :444
@@ -724,12 +731,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
 #pragma unroll
     for (int i = 0; i < N5; ++i) L[i] = v[i] * isv;                  // :120
 #pragma unroll
-    for (int j = 0; j < N5; ++j) {
-      double& x = c.xhat(mo, j);
-      x = fma(L[j], resid, x);                                       // :138
-    }
-#pragma unroll
-    for (int q = 0; q < NSYM; ++q) S[q] = c.sig(mo, q);
+    for (int j = 0; j < N5; ++j) c.xhat(mo, j) = fma(L[j], resid, xs[j]);   // :138
     int q = 0;
 #pragma unroll
     for (int i = 0; i < N5; ++i)
