@@ -295,3 +295,96 @@ def make_synthetic_bank():
 def default_bank_path():
     import os
     return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "bank_nmc30_synth.bin")
+
+
+# ------------------------------------------------------------------------------------------------
+# MATLAB .mat import / export of the numeric part of the reference's ROM file
+# ------------------------------------------------------------------------------------------------
+def from_mat(path, params=None, var="ROM"):
+    """Build a Bank from the reference's ``ROM_NMC30_HRA.mat`` (loaded at runMPC.m:4-5) or any file with the same
+    structure (MATLAB v5..v7; v7.3/HDF5 is not readable without h5py).
+
+    Read: ``ROM.ROMmdls(iT,iZ).{A,B,C,D}`` (OB_step.m:171-181, initKF.m:60-92), ``ROM.xraData.{T,SOC,Tsamp}``
+    (OB_step.m:50,166-167; initKF.m:132), ``ROM.tfData.{names,xLoc}`` (OB_step.m:88-89) and, when present,
+    ``ROM.cellData.const.{F,R}``.  The structural checks are the reference's own (initKF.m:74-88: integrator state,
+    B = ones; diagonal A as every line of the hot path assumes).
+
+    NOT read: ``cellData.function.*`` -- MATLAB function handles, which a .mat file stores as opaque objects.  The closed
+    forms are supplied as the parameter vector ``params`` (layout P_*/E_* above; ``default_params()`` when None, with F and
+    R taken from the file).  Fitting that vector to a real cell's handles is the user's step: sample the handles in
+    MATLAB, fit, pass the result here.
+    """
+    import scipy.io
+    try:
+        m = scipy.io.loadmat(path, struct_as_record=False, squeeze_me=False)
+    except NotImplementedError as e:                              # v7.3
+        raise BankError("cannot read %s: %s (save with -v7, or convert)" % (path, e))
+    if var not in m:
+        raise BankError("variable %r not found in %s" % (var, path))
+
+    def one(x):                                                   # 1x1 struct array -> its element
+        while isinstance(x, np.ndarray) and x.dtype == object and x.size == 1:
+            x = x.reshape(-1)[0]
+        return x
+    rom = one(m[var])
+    for f in ("ROMmdls", "xraData", "tfData"):
+        if not hasattr(rom, f):
+            raise BankError("ROM.%s missing" % f)
+    xra, tf = one(rom.xraData), one(rom.tfData)
+    Tpts = np.asarray(xra.T, float).reshape(-1); Zpts = np.asarray(xra.SOC, float).reshape(-1)
+    Tsamp = float(np.asarray(xra.Tsamp).reshape(-1)[0])
+    names = [str(one(s)) if not isinstance(one(s), np.ndarray) else "".join(one(s).reshape(-1).tolist())
+             for s in np.asarray(tf.names, dtype=object).reshape(-1)]
+    xloc = np.asarray(tf.xLoc, float).reshape(-1)
+    mdls = np.asarray(rom.ROMmdls, dtype=object)
+    nT, nZ = len(Tpts), len(Zpts)
+    if mdls.size != nT * nZ:
+        raise BankError("ROMmdls has %d models, xraData grids give %d x %d" % (mdls.size, nT, nZ))
+    mdls = mdls.reshape(nT, nZ)
+    A0 = np.asarray(mdls[0, 0].A, float)
+    n = A0.shape[0] - 1
+    nz = np.asarray(mdls[0, 0].C, float).shape[0]
+    if len(names) != nz or len(xloc) != nz:
+        raise BankError("tfData.names/xLoc do not match the %d output rows of C" % nz)
+    A = np.zeros((nT, nZ, n + 1)); C = np.zeros((nT, nZ, nz, n + 1)); D = np.zeros((nT, nZ, nz))
+    T_K = np.zeros((nT, nZ)); Z = np.zeros((nT, nZ))
+    for i in range(nT):
+        for j in range(nZ):
+            md = mdls[i, j]
+            Am = np.asarray(md.A, float)
+            if Am.shape != (n + 1, n + 1) or np.any(Am - np.diag(np.diag(Am)) != 0.0):
+                raise BankError("ROMmdls(%d,%d).A is not diagonal %dx%d" % (i + 1, j + 1, n + 1, n + 1))
+            if Am[-1, -1] != 1.0:                                 # initKF.m:74-77
+                raise BankError("A does not have integrator state")
+            if hasattr(md, "B") and np.any(np.asarray(md.B, float).reshape(-1) != 1.0):   # initKF.m:84-88
+                raise BankError("B is not all ones")
+            A[i, j] = np.diag(Am)
+            C[i, j] = np.asarray(md.C, float).reshape(nz, n + 1)
+            D[i, j] = np.asarray(md.D, float).reshape(nz)
+            T_K[i, j] = float(np.asarray(md.T).reshape(-1)[0]) if hasattr(md, "T") else Tpts[i] + 273.15
+            Z[i, j] = float(np.asarray(md.SOC).reshape(-1)[0]) if hasattr(md, "SOC") else Zpts[j] / 100.0
+    if params is None:
+        params = default_params()
+        cd = one(getattr(rom, "cellData", None))
+        cst = one(getattr(cd, "const", None)) if cd is not None else None
+        if cst is not None and hasattr(cst, "F") and hasattr(cst, "R"):
+            params[P_F] = float(np.asarray(cst.F).reshape(-1)[0]); params[P_R] = float(np.asarray(cst.R).reshape(-1)[0])
+    return Bank(n, nz, Tpts, Zpts, Tsamp, names, xloc, A, C, D, np.asarray(params, float), T_K, Z).validate()
+
+
+def to_mat(bank, path, var="ROM"):
+    """Write the numeric part of a Bank in the structure ``from_mat`` reads (and the reference's loader expects), so a
+    MATLAB user can inspect the synthetic bank; cellData.function.* cannot be written (function handles)."""
+    import scipy.io
+    nT, nZ, n, nz = bank.nT, bank.nZ, bank.n, bank.nz
+    dt = [(k, object) for k in ("A", "B", "C", "D", "T", "SOC")]
+    mdls = np.empty((nT, nZ), dtype=dt)
+    for i in range(nT):
+        for j in range(nZ):
+            mdls[i, j] = (np.diag(bank.A[i, j]), np.ones((n + 1, 1)), bank.C[i, j], bank.D[i, j].reshape(nz, 1),
+                          float(bank.T_K[i, j]), float(bank.Z[i, j]))
+    rom = {"ROMmdls": mdls,
+           "xraData": {"T": bank.Tpts_C.reshape(1, -1), "SOC": bank.Zpts_pct.reshape(1, -1), "Tsamp": float(bank.Tsamp)},
+           "tfData": {"names": np.array(list(bank.names), dtype=object).reshape(-1, 1), "xLoc": bank.xloc.reshape(-1, 1)},
+           "cellData": {"const": {"F": float(bank.params[P_F]), "R": float(bank.params[P_R])}}}
+    scipy.io.savemat(path, {var: rom}, oned_as="column")
