@@ -148,6 +148,11 @@ int mek_pop_iter_ekf(mek_pop *pop, const double *vk, const double *ik, double *z
 /* consumes mats (from mek_pop_iter_ekf) and the applied current; returns the new command and diagnostics */
 int mek_pop_iter_mpc(mek_pop *pop, const double *mats, const double *uk_applied, double *uk, double *phise, int32_t *nexec,
                      uint32_t *active);
+/* the same call with iterMPC's cost log (iterMPC.m:50-51,82-95): cost[MEK_NCOST*B] cell-major =
+ *   mpcData.cost.J_uncon, .J_final, .norm_DU, .viol  (t = (k-1)*Ts and nexec are the caller's / returned above) */
+#define MEK_NCOST 4
+int mek_pop_iter_mpc_cost(mek_pop *pop, const double *mats, const double *uk_applied, double *uk, double *phise, int32_t *nexec,
+                          uint32_t *active, double *cost);
 
 /* ---- stateless batched entry points ---- */
 /* hildreth.m: E[Nc*Nc*B], F[Nc*B], M[nC*Nc*B] (row-major per problem), gamma[nC*B], lambda0[nC*B] or NULL */

@@ -1017,6 +1017,7 @@ struct MpcProblem {
   double F[NCM], E[NCM * NCM], LU[NCM * NCM], DU[NCM];
   double Mm[NCONM * NCM], gam[NCONM];
   int nC;
+  double hs[NPM + 1], err[NPM], Ru;   // impulse response of the SOC row (G_soc entries), Ref - Phi_soc*dx, control weight
 };
 
 struct Limits {
@@ -1029,9 +1030,11 @@ __device__ __forceinline__ void mpc_setup(const Dims& d, double r /* Csoc(end), 
                                           double uk_1, MpcProblem<NPM, NCM>& q) {
   const int Np = d.Np, Nc = d.Nc;
   const double zero5[N5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  double hs[NPM + 1], pxs[NPM];
+  double pxs[NPM];
+  double (&hs)[NPM + 1] = q.hs;
+  double (&err)[NPM] = q.err;
   pred_row<NPM>(e.a, zero5, r, 0.0, e.xhat, Np, hs, pxs);            // iterMPC.m:33
-  double err[NPM], x[NCM];
+  double x[NCM];
 #pragma unroll
   for (int i = 1; i <= NPM; ++i)
     if (i <= Np) err[i - 1] = d.ref - (pxs[i - 1] + hs[i] * uk_1);   // Ref - Phi_soc*dx
@@ -1055,6 +1058,7 @@ __device__ __forceinline__ void mpc_setup(const Dims& d, double r /* Csoc(end), 
   for (int j = 1; j < NCM; ++j)
     if (j < Nc) nf = nf + q.F[j] * q.F[j];
   const double Ru = sqrt(nf) / ((2.0 * lim.du_max) * sqrt((double)Nc)) - d.sigmin;   // iterMPC.m:43 (Q10)
+  q.Ru = Ru;
 #pragma unroll
   for (int j = 0; j < NCM; ++j)
 #pragma unroll
@@ -1130,10 +1134,24 @@ struct MpcOut {
   unsigned active[4];
 };
 
+// mpcData.cost (iterMPC.m:50-51,82-95): J = (Ref - Phi*dx - G*DU)'*(Ref - Phi*dx - G*DU) + DU'*Ru*DU
+template <int NPM, int NCM>
+__device__ __forceinline__ double mpc_cost_J(int Np, int Nc, const MpcProblem<NPM, NCM>& q) {
+  double J = 0.0, n2 = 0.0;
+  for (int i = 1; i <= Np; ++i) {
+    double y = q.err[i - 1];
+    for (int j = 0; j < Nc; ++j)
+      if (i - 1 - j >= 0) y = y - q.hs[i - 1 - j] * q.DU[j];
+    J = J + y * y;
+  }
+  for (int j = 0; j < Nc; ++j) n2 = n2 + q.DU[j] * q.DU[j];
+  return J + q.Ru * n2;
+}
+
 // iterMPC.m:17-95 with constraintsMPC.m and hildreth.m inlined; the dual warm start lives in the cell state
 template <int NPM, int NCM>
 __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict__ p, const Cell& c, const EkfOut& e, double uk_applied,
-                                         MpcOut& o) {
+                                         MpcOut& o, double* cost = nullptr /* J_uncon, J_final, norm_DU, viol */) {
   constexpr int NCONM = 4 * NCM + 3 * NPM;
   const int Nc = d.Nc;
   const double uk_1 = c.f(S_UK);                                     // iterMPC.m:19
@@ -1149,6 +1167,7 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
   const double r = -d.Ts / (3600.0 * p[P_Q]);                        // EKFmatsHandler.m:43
   mpc_setup<NPM, NCM>(d, r, lim, e, uk_1, q);
   const int nC = q.nC;
+  if (cost) cost[0] = mpc_cost_J<NPM, NCM>(d.Np, Nc, q);             // iterMPC.m:50-51
   bool viol = false;                                                 // iterMPC.m:66 (Q8)
   for (int i = 0; i < nC; ++i) {
     double acc = q.Mm[i * NCM] * q.DU[0];
@@ -1177,6 +1196,19 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
       }
     c.f(S_LAMVALID) = 1.0;
   }
+  if (cost) {                                                        // iterMPC.m:82-95
+    int nviol = 0;
+    double n2 = 0.0;
+    for (int i = 0; i < nC; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < Nc; ++j) acc = acc + q.Mm[i * NCM + j] * q.DU[j];
+      if (acc - q.gam[i] > 1e-9) ++nviol;
+    }
+    for (int j = 0; j < Nc; ++j) n2 = n2 + q.DU[j] * q.DU[j];
+    cost[1] = mpc_cost_J<NPM, NCM>(d.Np, Nc, q);
+    cost[2] = sqrt(n2);
+    cost[3] = (double)nviol;
+  }
   const double uk = q.DU[0] + uk_1;                                  // iterMPC.m:75-76
   c.f(S_UK) = uk;                                                    // iterMPC.m:78
   o.u = uk;
@@ -1190,6 +1222,9 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
 // in this thread's column of shared memory ([slot][thread] layout: conflict-free, no local memory).
 // Same arithmetic, in the same order, as mpc_step / hildreth_core.
 // ------------------------------------------------------------------------------------------
+#ifndef LEAN_AHEAD
+#define LEAN_AHEAD 3             // rows of look-ahead of the K_i, 1/H_ii loads in the lean Hildreth sweep
+#endif
 template <int NP, int NC, int CONS>
 struct FastShape {
   static constexpr bool UC = (CONS & 1) != 0, UV = (CONS & 2) != 0, UE = (CONS & 4) != 0, UZ = (CONS & 8) != 0;
@@ -1375,16 +1410,27 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     if (lean) {
       bool first_nc = false;
       if (FS::UZ) { first_nc = !(lam[FS::O_Z] < 1e-6); lam[FS::O_Z] = 0.0; }
+      // K_i and 1/H_ii are read from shared memory LEAN_AHEAD rows before their use (a ring of registers), so the load
+      // latency is off the row-to-row dependency chain
+      constexpr int RING = LEAN_AHEAD < nC ? LEAN_AHEAD : nC;
       for (; k <= d.maxHild; ++k) {                                  // hildreth.m:32
         bool notconv = (k == 1) && first_nc;
+        double kq[RING], hq[RING];
+#pragma unroll
+        for (int t = 0; t < RING; ++t) { kq[t] = vs[(t * 2 + 0) * sms]; hq[t] = vs[(t * 2 + 1) * sms]; }
 #pragma unroll
         for (int i = 0; i < nC; ++i) {                               // hildreth.m:34-37
+          const double Ki = kq[i % RING], rHi = hq[i % RING];
+          if (i + RING < nC) {
+            kq[i % RING] = vs[((i + RING) * 2 + 0) * sms];
+            hq[i % RING] = vs[((i + RING) * 2 + 1) * sms];
+          }
           if (FS::UZ && i == FS::O_Z) continue;
           const double li = lam[i];
           double hl = Mm[i][0] * v[0];
 #pragma unroll
           for (int j = 1; j < NC; ++j) hl = fma(Mm[i][j], v[j], hl);
-          const double w = fma(-(vs[(i * 2 + 0) * sms] + hl), vs[(i * 2 + 1) * sms], li);
+          const double w = fma(-(Ki + hl), rHi, li);
           const double nl = pos_or_zero(w);                          // max(0,w); max(0,NaN) = 0
           const double dl = nl - li;
 #pragma unroll

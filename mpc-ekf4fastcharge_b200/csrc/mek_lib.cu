@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
 
 template <int NPM, int NCM>
 __global__ void __launch_bounds__(128) k_iter_mpc(const __grid_constant__ Params P, const double* mats, const double* uk_applied, double* uk,
-                                                   double* phise, int* nexec, unsigned* active) {
+                                                   double* phise, int* nexec, unsigned* active, double* cost) {
   const Dims& d = P.d;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
@@ -642,10 +642,13 @@ __global__ void __launch_bounds__(128) k_iter_mpc(const __grid_constant__ Params
     if (e.lost) {
       uk[id] = NAN; if (phise) phise[id] = NAN; if (nexec) nexec[id] = 0;
       if (active) for (int w = 0; w < 4; ++w) active[id * 4 + w] = 0u;
+      if (cost) for (int w = 0; w < MEK_NCOST; ++w) cost[id * MEK_NCOST + w] = NAN;
       continue;
     }
     MpcOut o;
-    mpc_step<NPM, NCM>(d, P.cp, c, e, uk_applied[id], o);
+    double cj[MEK_NCOST];
+    mpc_step<NPM, NCM>(d, P.cp, c, e, uk_applied[id], o, cost ? cj : nullptr);
+    if (cost) for (int w = 0; w < MEK_NCOST; ++w) cost[id * MEK_NCOST + w] = cj[w];
     uk[id] = o.u;
     if (phise) phise[id] = o.phise;
     if (nexec) nexec[id] = o.nexec;
@@ -1434,30 +1437,37 @@ extern "C" int mek_pop_iter_ekf(mek_pop* p, const double* vk, const double* ik, 
 
 extern "C" int mek_pop_iter_mpc(mek_pop* p, const double* mats, const double* uk_applied, double* uk, double* phise, int32_t* nexec,
                                 uint32_t* active) {
+  return mek_pop_iter_mpc_cost(p, mats, uk_applied, uk, phise, nexec, active, nullptr);
+}
+
+extern "C" int mek_pop_iter_mpc_cost(mek_pop* p, const double* mats, const double* uk_applied, double* uk, double* phise, int32_t* nexec,
+                                     uint32_t* active, double* cost) {
   if (!p || !mats || !uk_applied || !uk) return fail(MEK_ERR_ARG, "null argument");
   if (!p->inited) return fail(MEK_ERR_STATE, "mek_pop_iter_mpc before mek_pop_init");
   CUDA_TRY(cudaSetDevice(p->device));
   const size_t B = (size_t)p->P.d.B;
-  int rc = ensure_scratch(p, 8 * B * (MEK_NMATS + 3) + 4 * B * 5);
+  int rc = ensure_scratch(p, 8 * B * (MEK_NMATS + 3 + MEK_NCOST) + 4 * B * 5);
   if (rc != MEK_OK) return rc;
   double* dm = p->d_scratch;
   double* du_in = dm + B * MEK_NMATS;
   double* du = du_in + B;
   double* dph = du + B;
-  int* dn = reinterpret_cast<int*>(dph + B);
+  double* dc = dph + B;
+  int* dn = reinterpret_cast<int*>(dc + B * MEK_NCOST);
   unsigned* da = reinterpret_cast<unsigned*>(dn + B);
   CUDA_TRY(cudaMemcpyAsync(dm, mats, 8 * B * MEK_NMATS, cudaMemcpyHostToDevice, p->stream));
   CUDA_TRY(cudaMemcpyAsync(du_in, uk_applied, 8 * B, cudaMemcpyHostToDevice, p->stream));
   const int g = grid_for(p, p->P.d.B, p->threads);
-  if (p->inst == 0) k_iter_mpc<5, 2><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da);
-  else if (p->inst == 1) k_iter_mpc<20, 5><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da);
-  else k_iter_mpc<32, 8><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da);
+  if (p->inst == 0) k_iter_mpc<5, 2><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da, cost ? dc : nullptr);
+  else if (p->inst == 1) k_iter_mpc<20, 5><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da, cost ? dc : nullptr);
+  else k_iter_mpc<32, 8><<<g, p->threads, 0, p->stream>>>(p->P, dm, du_in, du, dph, dn, da, cost ? dc : nullptr);
   CUDA_TRY(cudaGetLastError());
   p->launches++;
   CUDA_TRY(cudaMemcpyAsync(uk, du, 8 * B, cudaMemcpyDeviceToHost, p->stream));
   if (phise) CUDA_TRY(cudaMemcpyAsync(phise, dph, 8 * B, cudaMemcpyDeviceToHost, p->stream));
   if (nexec) CUDA_TRY(cudaMemcpyAsync(nexec, dn, 4 * B, cudaMemcpyDeviceToHost, p->stream));
   if (active) CUDA_TRY(cudaMemcpyAsync(active, da, 16 * B, cudaMemcpyDeviceToHost, p->stream));
+  if (cost) CUDA_TRY(cudaMemcpyAsync(cost, dc, 8 * B * MEK_NCOST, cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MEK_OK;
 }

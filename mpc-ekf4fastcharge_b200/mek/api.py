@@ -198,10 +198,16 @@ class CellBatch:
         check(_lib.lib().mek_pop_iter_ekf(self.h, _p(v), _p(i), _p(zk), _p(bz), _p(mats)))
         return (zk, bz, mats) if want_bounds else (zk, mats)
 
-    def iter_mpc(self, mats, uk_applied):
+    def iter_mpc(self, mats, uk_applied, want_cost=False):
+        """iterMPC.m for every cell.  want_cost: also return mpcData.cost's columns J_uncon, J_final, norm_DU, viol [B,4]
+        (iterMPC.m:50-51,82-95)."""
         mats = _f64(mats, (self.B, NMATS))
         ua = _f64(np.broadcast_to(np.asarray(uk_applied, float), (self.B,)))
         uk = np.empty(self.B); ph = np.empty(self.B); nx = np.empty(self.B, np.int32); act = np.empty((self.B, 4), np.uint32)
+        if want_cost:
+            cost = np.empty((self.B, 4))
+            check(_lib.lib().mek_pop_iter_mpc_cost(self.h, _p(mats), _p(ua), _p(uk), _p(ph), _p(nx), _p(act), _p(cost)))
+            return uk, ph, nx, act, cost
         check(_lib.lib().mek_pop_iter_mpc(self.h, _p(mats), _p(ua), _p(uk), _p(ph), _p(nx), _p(act)))
         return uk, ph, nx, act
 

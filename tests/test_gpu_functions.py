@@ -173,3 +173,30 @@ def test_boundzk_three_sigma_bounds_vs_literal(bank):
             assert np.allclose(gz[0], zk, rtol=1e-9, atol=1e-12)
             assert np.all(np.isfinite(gb[0])) and np.all(gb[0] >= 0)
             assert np.allclose(gb[0], zb, rtol=1e-8, atol=1e-13), (k, np.max(np.abs(gb[0] - zb) / np.maximum(zb, 1e-300)))
+
+
+def test_iter_mpc_cost_log_vs_literal(bank):
+    """mpcData.cost (iterMPC.m:50-51,82-95: J_uncon, J_final, norm_DU, viol) from mek_pop_iter_mpc_cost against the literal
+    restatement's run of runMPC, through the ramp, the constant-current phase and the first constraint-riding steps."""
+    from mek import api, population as P
+    from oracle import literal as L
+    N = 900
+    lit = L.run_mpc(bank, SOC0=10.0, TC=25.0, N=N)
+    rom = api.RomBank(bank)
+    cb = api.CellBatch(rom, 1)
+    cb.init([10.0], [25.0], np.diag([1.0] * 5 + [2e6]), P.default_limits(bank.params[2]))
+    uk = np.zeros(1)
+    cost = np.zeros((N, 4)); nx = np.zeros(N, np.int32); u = np.zeros(N)
+    for k in range(N):
+        V = cb.ob_step(uk)
+        zk, mats = cb.iter_ekf(V, uk)
+        uk, ph, n1, act, cj = cb.iter_mpc(mats, uk, want_cost=True)
+        cost[k] = cj[0]; nx[k] = n1[0]; u[k] = uk[0]
+    c = lit["cost"]
+    assert np.array_equal(nx, lit["nexec"]) and np.allclose(u, lit["u"], rtol=1e-9, atol=1e-9)
+    assert (nx > 0).sum() > 100 and (c["viol"][:N] > 0).sum() >= 0
+    for j, key in enumerate(("J_uncon", "J_final", "norm_DU")):
+        ref = c[key][:N]
+        assert np.allclose(cost[:, j], ref, rtol=1e-9, atol=1e-12 * np.max(np.abs(ref))), (key, np.max(np.abs(cost[:, j] - ref) / np.abs(ref)))
+    assert np.array_equal(cost[:, 3], c["viol"][:N])
+    assert np.all(cost[:, 1] >= cost[:, 0] * (1 - 1e-12))          # a constrained optimum never beats the unconstrained one
