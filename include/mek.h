@@ -137,6 +137,12 @@ enum {
   MEK_STAT_N_JACOBI, MEK_STAT_N_BUMP, MEK_STAT_N_WARN, MEK_STAT_N_Q18
 };
 int mek_summary(mek_pop *pop, double *totals);
+/* per-cell summary columns, cell-major [B][MEK_NCELLSUM], caller's cell order (population analytics; the reference plots
+ * one cell's traces in plot4Figures.m, a population needs distributions):
+ *   status bits, EKF warnCount (iterEKF.m:741-751), sum nexec, #QP runs, #QPs at the sweep cap, min phise_store, max voltage_store,
+ *   first instant with SOC >= z_max - 1e-3 (-1: not reached), instants run, last SOC estimate, last voltage, last phise */
+#define MEK_NCELLSUM 12
+int mek_read_cell_summaries(mek_pop *pop, double *out);
 
 /* ---- function-level batched entry points on a population's state (one call = one line of the loop body) ---- */
 int mek_pop_ob_step(mek_pop *pop, const double *Iapp, double *Vcell);

@@ -167,6 +167,16 @@ struct ModelRegs {
 // KEEP=false: evict-first accesses (.cs) for rows that are touched once and not again soon (the cold stream);
 // KEEP=true: L2-cached accesses (.cg) for the models a cell advances every instant, which stay resident in L2.
 template <bool KEEP> __device__ __forceinline__ double ld_state(const double* q) { return KEEP ? __ldcg(q) : __ldcs(q); }
+// model rows and multipliers read or written between the streams: L2 only (.cg) as well, so that L1 is left to the header
+// fields and the register spills (a row is touched once or twice per instant; 8 warps x 8 models x 26 rows of 256 B = 425 KB
+// would only evict them)
+#ifndef ROW_VIA_L1
+__device__ __forceinline__ double ld_row(const double* q) { return __ldcg(q); }
+__device__ __forceinline__ void st_row(double* q, double v) { __stcg(q, v); }
+#else
+__device__ __forceinline__ double ld_row(const double* q) { return *q; }
+__device__ __forceinline__ void st_row(double* q, double v) { *q = v; }
+#endif
 template <bool KEEP> __device__ __forceinline__ void st_state(double* q, double v) { if (KEEP) __stcg(q, v); else __stcs(q, v); }
 
 template <bool PLANT, bool EKF, bool KEEP = false>
@@ -416,7 +426,7 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
     defer_ensure(d, bk, c, df, mb);
     double xa[6], xb[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { xa[j] = c.bigx(ma, j); xb[j] = c.bigx(mb, j); }
+    for (int j = 0; j < 6; ++j) { xa[j] = ld_row(&c.bigx(ma, j)); xb[j] = ld_row(&c.bigx(mb, j)); }
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const double* ca = ra + r * 7;
@@ -468,7 +478,7 @@ __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, 
     g[k] = sc[SC_GAMMA + k];
     mm[k] = bk.mdl + m * d.mstride + 6;
 #pragma unroll
-    for (int j = 0; j < N5; ++j) xk[k][j] = c.xhat(m, j);            // :267-270
+    for (int j = 0; j < N5; ++j) xk[k][j] = ld_row(&c.xhat(m, j));   // :267-270
   }
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
   const double xSOC = c.f(S_EKFSOC0) - c.f(S_X0) * rpa;              // :277
@@ -673,7 +683,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   {
     const int m0 = (int)sc[SC_M + 0];
 #pragma unroll
-    for (int q = 0; q < NSYM; ++q) S1[q] = c.sig(m0, q);
+    for (int q = 0; q < NSYM; ++q) S1[q] = ld_row(&c.sig(m0, q));
   }
   // ---- getChatV scalars (:421-519) ----
   const double tss0 = sc[SC_Z + HR_TSS0], tss3 = sc[SC_Z + HR_TSS3];
@@ -705,9 +715,9 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     // this neighbour's state, requested before the gain is computed (the loads overlap it); after the previous
     // neighbour's stores in program order, so a duplicate neighbour sees its own update (Q2)
 #pragma unroll
-    for (int j = 0; j < N5; ++j) xs[j] = c.xhat(mo, j);
+    for (int j = 0; j < N5; ++j) xs[j] = ld_row(&c.xhat(mo, j));
 #pragma unroll
-    for (int q = 0; q < NSYM; ++q) S[q] = c.sig(mo, q);
+    for (int q = 0; q < NSYM; ++q) S[q] = ld_row(&c.sig(mo, q));
 #pragma unroll
     for (int j = 0; j < N5; ++j) {                                   // getChatV for this neighbour
       double t = Rfp * (g * mm[HR_IFDL3 * 7 + j]) - Rfn * (g * mm[HR_IFDL0 * 7 + j]);    // :444
@@ -731,7 +741,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
 #pragma unroll
     for (int i = 0; i < N5; ++i) L[i] = v[i] * isv;                  // :120
 #pragma unroll
-    for (int j = 0; j < N5; ++j) c.xhat(mo, j) = fma(L[j], resid, xs[j]);   // :138
+    for (int j = 0; j < N5; ++j) st_row(&c.xhat(mo, j), fma(L[j], resid, xs[j]));   // :138
     int q = 0;
 #pragma unroll
     for (int i = 0; i < N5; ++i)
@@ -744,7 +754,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
       ++nbump;
     }
 #pragma unroll
-    for (int q2 = 0; q2 < NSYM; ++q2) c.sig(mo, q2) = S[q2];
+    for (int q2 = 0; q2 < NSYM; ++q2) st_row(&c.sig(mo, q2), S[q2]);
   }
   x0 = x0 + L0 * resid;                                              // :155
   sx0 = sx0 - (L0 * svt0) * L0;                                      // :156
@@ -780,7 +790,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   o.iZ = (int)sc[SC_IZ + imax];
   const double* am = bk.mdl + mp * d.mstride;
 #pragma unroll
-  for (int j = 0; j < N5; ++j) { o.xhat[j] = c.xhat(mp, j); o.a[j] = am[j]; }   // :33-35
+  for (int j = 0; j < N5; ++j) { o.xhat[j] = ld_row(&c.xhat(mp, j)); o.a[j] = am[j]; }   // :33-35
   o.xhat[5] = 0.0;                                                   // :33 (Q3)
   {
     const double ztss0 = sc[SC_Z + HR_TSS0], ztss3 = sc[SC_Z + HR_TSS3];
@@ -1355,7 +1365,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     double lam[nC], v[NC];
     const bool warm = c.f(S_LAMVALID) != 0.0;                        // Q11
 #pragma unroll
-    for (int i = 0; i < nC; ++i) lam[i] = warm ? c.lam(i) : 0.0;
+    for (int i = 0; i < nC; ++i) lam[i] = warm ? ld_row(&c.lam(i)) : 0.0;
     spd_solve<NC>(NC, LU, F, x);                                     // E\F
     double Ei[NC][NC];                                               // inv(E): column i of E\M' is recomputed as inv(E)*M(i,:)'
 #pragma unroll
@@ -1488,7 +1498,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     o.nexec = k;                                                     // iterMPC.m:67-69
 #pragma unroll
     for (int i = 0; i < nC; ++i) {
-      c.lam(i) = lam[i];
+      st_row(&c.lam(i), lam[i]);
       if (lam[i] > 0.0) o.active[i >> 5] |= (1u << (i & 31));
     }
     c.f(S_LAMVALID) = 1.0;

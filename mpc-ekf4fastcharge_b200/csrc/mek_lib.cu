@@ -1375,6 +1375,33 @@ extern "C" int mek_write_state(mek_pop* p, const double* state) {
   return rc;
 }
 
+// per-cell summary columns in the caller's cell order (population analytics: histograms of charge time, min phise, ...)
+__global__ void k_cell_summaries(const __grid_constant__ Params P, double* out) {
+  const Dims& d = P.d;
+  const long long total = d.B * (long long)MEK_NCELLSUM;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long j = i / d.B, cell = i % d.B, id = cell_id(P, cell);   // consecutive threads: consecutive slots of one field
+    const int f = j == 0 ? S_STATUS : (j == 1 ? S_WARN : S_SUM_NEXEC + (int)(j - 2));
+    out[id * MEK_NCELLSUM + j] = P.st[(cell >> 5) * ((long long)d.nfields * TILE) + (long long)f * TILE + (cell & 31)];
+  }
+}
+
+extern "C" int mek_read_cell_summaries(mek_pop* p, double* out) {
+  if (!p || !out) return fail(MEK_ERR_ARG, "null argument");
+  if (!p->inited) return fail(MEK_ERR_STATE, "mek_read_cell_summaries before mek_pop_init");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const size_t bytes = sizeof(double) * (size_t)p->P.d.B * MEK_NCELLSUM;
+  int rc = ensure_scratch(p, bytes);
+  if (rc != MEK_OK) return rc;
+  k_cell_summaries<<<p->sms * 4, 256, 0, p->stream>>>(p->P, p->d_scratch);
+  CUDA_TRY(cudaGetLastError());
+  p->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out, p->d_scratch, bytes, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MEK_OK;
+}
+
 extern "C" int mek_summary(mek_pop* p, double* totals) {
   if (!p || !totals) return fail(MEK_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(p->device));

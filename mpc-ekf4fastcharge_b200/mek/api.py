@@ -176,6 +176,15 @@ class CellBatch:
         st = _f64(st, (self.B, self.state_len))
         check(_lib.lib().mek_write_state(self.h, _p(st)))
 
+    CELLSUM_NAMES = ("status", "warn_count", "sum_nexec", "n_qp", "n_cap", "min_phise", "max_V", "t_reach", "steps",
+                     "last_soc", "last_V", "last_phise")
+
+    def cell_summaries(self):
+        """Per-cell summary columns (caller's cell order) as a dict of [B] arrays; see mek_read_cell_summaries."""
+        a = np.empty((self.B, len(self.CELLSUM_NAMES)))
+        check(_lib.lib().mek_read_cell_summaries(self.h, _p(a)))
+        return {k: a[:, i].copy() for i, k in enumerate(self.CELLSUM_NAMES)}
+
     def summary(self):
         t = np.empty(NSTAT)
         check(_lib.lib().mek_summary(self.h, _p(t)))

@@ -1,5 +1,7 @@
 """GPU tests at BASELINE.json's full size (config C3: 1 Mi cells, one GPU): parity on a sub-sample of cells against the
 oracle plus size-independent properties of the whole population."""
+import os
+
 import numpy as np
 import pytest
 
@@ -15,17 +17,17 @@ def test_c3_one_million_cells_subsample_parity_and_population_properties(bank, c
     pop = P.make_population(Q, B_FULL, seed=2)
     rom = api.RomBank(bank)
     cb = api.CellBatch(rom, B_FULL)
-    nlog = 384
+    nlog = 4096                                   # parity on a 4 096-cell sub-sample
     cb.set_logging(nlog, N_SIM)
     cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
     cb.run(0, N_SIM)
     g = cb.logs()
     s = cb.summary()
-    # (1) the first 384 cells (caller's indices; they are scattered over the SOC-ordered state block) match the oracle bit for bit
+    # (1) the first 4 096 cells (caller's indices; they are scattered over the SOC-ordered state block) match the oracle bit for bit
     sub = pop.slice(0, nlog)
     co = coracle_mod.COracle(bank)
     co.init(sub.SOC0, sub.T, sub.SigmaX0, sub.limits, sub.ekf_SOC0)
-    c = co.run(0, N_SIM, nthreads=8)
+    c = co.run(0, N_SIM, nthreads=max(8, os.cpu_count() or 8))
     for k in ("u", "V", "SOC", "phise", "iT", "iZ", "nexec", "active"):
         assert np.array_equal(g[k], c[k]), k
     # (2) population-level properties

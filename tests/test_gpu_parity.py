@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI) against the C oracle on the same seeded inputs.
 The bar is bit-exact for every logged quantity (integers and doubles): both sides evaluate the same
 correctly rounded IEEE-754 operations in the same order (numerics contract)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -23,7 +25,7 @@ def _run_both(bank, coracle_mod, pop, N, Np=5, Nc=2, constraints=(1, 1, 1), forc
     g = cb.logs(0, N)
     co = coracle_mod.COracle(bank, Np=Np, Nc=Nc, constraints=constraints, force_jacobi=force_jacobi)
     co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
-    c = co.run(0, N, nthreads=8)
+    c = co.run(0, N, nthreads=max(8, os.cpu_count() or 8))
     return cb, g, co, c
 
 
@@ -45,13 +47,16 @@ def test_c1_single_cell_full_charge(bank, coracle_mod):
 
 
 def test_c2_population_full_charge(bank, coracle_mod):
+    """Config C2 of SURVEY.md 8(d) in full: all 4 096 cells, all 3 001 instants, every logged quantity bit for bit."""
     from mek import population as P
-    pop = P.make_population(bank.params[2], 256, seed=1)
+    B = 4096
+    pop = P.make_population(bank.params[2], B, seed=1)
     cb, g, co, c = _run_both(bank, coracle_mod, pop, 3001)
     _assert_bit_exact(g, c)
     s = cb.summary()
-    assert s["cells"] == 256 and s["cellsteps"] == 256 * 3001
+    assert s["cells"] == B and s["cellsteps"] == B * 3001
     assert s["sum_nexec"] == c["nexec"].sum()
+    assert s["n_reached"] == B and s["n_lost"] == 0
 
 
 def test_c5_heterogeneous(bank, coracle_mod):
