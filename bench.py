@@ -219,13 +219,14 @@ def main_mek(a):
 
     # ---- e2e: the public API with HOST buffers, H2D of the inputs and D2H of the results inside the timed region ----
     d2h = 16 * 8 + nlog * a.nsim * (4 * 8 + 3 * 4 + 16)
+    cb.logs(0, a.nsim, reuse=True)                                  # one-time allocation of the page-locked result buffers (like `pin` above)
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         cb.init_raw(h_soc.data_ptr(), h_ekf.data_ptr(), h_T.data_ptr(), h_sx.data_ptr(), h_lim.data_ptr())
         cb.run(0, a.nsim, sync=False)
         s_e2e = cb.summary()
-        lg = cb.logs(0, a.nsim)
+        lg = cb.logs(0, a.nsim, reuse=True)          # page-locked result buffers owned by the batch
     barrier()
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, device=dev)
     e2e_value = cellsteps * a.steps / e2e_s

@@ -23,6 +23,7 @@
 #ifndef MEK_H
 #define MEK_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -126,6 +127,10 @@ int mek_pop_state_len(const mek_pop *pop);                       /* doubles per 
  * active[step][cell][4] = bit i set <=> lambda_i > 0 on exit of hildreth. */
 int mek_read_logs(mek_pop *pop, int k0, int k1, double *u, double *V, double *soc, double *phise, int32_t *iT, int32_t *iZ,
                   int32_t *nexec, uint32_t *active);
+/* page-locked host memory for the caller's input and result buffers: copies into it run at link speed (a pageable buffer
+ * is staged by the driver at a fraction of that).  The reference has no counterpart (MATLAB owns its arrays). */
+int mek_host_alloc(size_t bytes, void **out);
+int mek_host_free(void *ptr);
 /* full per-cell state, cell-major: [B][state_len] (layout: DESIGN.md "state block") */
 int mek_read_state(mek_pop *pop, double *state);
 int mek_write_state(mek_pop *pop, const double *state);

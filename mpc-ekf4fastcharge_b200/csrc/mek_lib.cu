@@ -795,6 +795,49 @@ __global__ void __launch_bounds__(256) k_summary(const __grid_constant__ Params 
   }
 }
 
+// ---- initial cell order and heterogeneity test on the device (mek_pop_init) ----
+// order-preserving 64-bit image of a double (NaN last): radix-sortable
+__device__ __forceinline__ unsigned long long orderable(double x) {
+  if (x != x) return ~0ull;
+  if (x == 0.0) x = 0.0;                                             // -0 and +0 compare equal
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void k_order_keys(long long B, const double* v, const int* idx_in, unsigned long long* keys, int* idx) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+    const int c = idx_in ? idx_in[i] : (int)i;
+    keys[i] = orderable(v[c]);
+    idx[i] = c;
+  }
+}
+__global__ void k_heterogeneous(long long B, const double* Tc, const double* lim, int* flag) {
+  bool het = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+    if (Tc[i] != Tc[0]) het = true;
+    for (int q = 0; q < 7; ++q)
+      if (lim[7 * i + q] != lim[q]) het = true;
+  }
+  if (het) atomicOr(flag, 1);
+}
+
+// log read-back: the compact on-device records (u8 / u16 / u32 x words) widened to the ABI's int32 / uint32[4] columns
+__global__ void k_widen_logs(size_t n, int W, const unsigned char* iT, const unsigned char* iZ, const unsigned short* nexec,
+                             const unsigned* active, int* oT, int* oZ, int* on, unsigned* oa) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (oT) oT[i] = iT[i];
+    if (oZ) oZ[i] = iZ[i];
+    if (on) on[i] = nexec[i];
+    if (oa) {
+      uint4 a = make_uint4(0u, 0u, 0u, 0u);
+      a.x = active[i * W];
+      if (W > 1) a.y = active[i * W + 1];
+      if (W > 2) a.z = active[i * W + 2];
+      if (W > 3) a.w = active[i * W + 3];
+      reinterpret_cast<uint4*>(oa)[i] = a;
+    }
+  }
+}
+
 // AoS <-> SoA transposition for mek_read_state / mek_write_state
 __global__ void k_state_gather(const __grid_constant__ Params P, double* aos, int to_aos) {
   const Dims& d = P.d;
@@ -1197,30 +1240,46 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
   // charge (same local models, similar Hildreth sweep counts), which removes most of the warp divergence.  Pure
   // scheduling: every per-cell input/output of the ABI keeps the caller's index (slot2cell).
   if (!p->cfg.keep_cell_order) {
-    std::vector<int> order(B);
-    for (size_t i = 0; i < B; ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      if (Tc[a] != Tc[b]) return Tc[a] < Tc[b];
-      return SOC0pct[a] < SOC0pct[b];
-    });
+    // stable radix sort by SOC0, then by temperature (LSD): the order of a host stable_sort on (T, SOC0), without the host
     if (!p->d_slot2cell) CUDA_TRY(cudaMalloc(&p->d_slot2cell, sizeof(int) * B));
-    CUDA_TRY(cudaMemcpyAsync(p->d_slot2cell, order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, p->stream));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));        // `order` is a pageable temporary
-    p->P.slot2cell = p->d_slot2cell;
-    // regrouping (automatic: only where it pays, i.e. when the cells do not all share temperature and limits)
-    bool het = false;
-    for (size_t i = 1; i < B && !het; ++i) {
-      if (Tc[i] != Tc[0]) het = true;
-      for (int q = 0; q < 7 && !het; ++q)
-        if (limits[7 * i + q] != limits[q]) het = true;
-    }
-    p->heterogeneous = het;
-    int every = p->cfg.regroup_every;
-    if (every == 0) every = het ? MEK_REGROUP_DEFAULT : -1;
-    p->regroup_every = every > 0 ? every : 0;
-    if (p->regroup_every > 0) {
-      if (!p->d_slot2cell0) CUDA_TRY(cudaMalloc(&p->d_slot2cell0, sizeof(int) * B));
-      CUDA_TRY(cudaMemcpyAsync(p->d_slot2cell0, p->d_slot2cell, sizeof(int) * B, cudaMemcpyDeviceToDevice, p->stream));
+    {
+      const size_t kb = (sizeof(unsigned long long) * B + 255) / 256 * 256, ib = (sizeof(int) * B + 255) / 256 * 256;
+      size_t tmpb = 0;
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmpb, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr,
+                                               (int*)nullptr, (int)B, 0, 64, p->stream));
+      tmpb = (tmpb + 255) / 256 * 256;
+      int rc0 = ensure_scratch(p, 2 * kb + 2 * ib + tmpb + 256);
+      if (rc0 != MEK_OK) return rc0;
+      char* base = reinterpret_cast<char*>(p->d_scratch);
+      unsigned long long* k1 = reinterpret_cast<unsigned long long*>(base);
+      unsigned long long* k2 = reinterpret_cast<unsigned long long*>(base + kb);
+      int* i1 = reinterpret_cast<int*>(base + 2 * kb);
+      int* i2 = reinterpret_cast<int*>(base + 2 * kb + ib);
+      void* tmp = base + 2 * kb + 2 * ib;
+      int* flag = reinterpret_cast<int*>(base + 2 * kb + 2 * ib + tmpb);
+      const int g = p->sms * 4;
+      k_order_keys<<<g, 256, 0, p->stream>>>((long long)B, in, nullptr, k1, i1);                   // by SOC0
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmpb, k1, k2, i1, i2, (int)B, 0, 64, p->stream));
+      k_order_keys<<<g, 256, 0, p->stream>>>((long long)B, in + 2 * B, i2, k1, i1);                // then by T (stable)
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmpb, k1, k2, i1, p->d_slot2cell, (int)B, 0, 64, p->stream));
+      CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), p->stream));
+      k_heterogeneous<<<g, 256, 0, p->stream>>>((long long)B, in + 2 * B, in + 39 * B, flag);
+      CUDA_TRY(cudaGetLastError());
+      p->launches += 5;
+      int hflag = 0;
+      CUDA_TRY(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+      CUDA_TRY(cudaStreamSynchronize(p->stream));
+      p->P.slot2cell = p->d_slot2cell;
+      // regrouping (automatic: only where it pays, i.e. when the cells do not all share temperature and limits)
+      const bool het = hflag != 0;
+      p->heterogeneous = het;
+      int every = p->cfg.regroup_every;
+      if (every == 0) every = het ? MEK_REGROUP_DEFAULT : -1;
+      p->regroup_every = every > 0 ? every : 0;
+      if (p->regroup_every > 0) {
+        if (!p->d_slot2cell0) CUDA_TRY(cudaMalloc(&p->d_slot2cell0, sizeof(int) * B));
+        CUDA_TRY(cudaMemcpyAsync(p->d_slot2cell0, p->d_slot2cell, sizeof(int) * B, cudaMemcpyDeviceToDevice, p->stream));
+      }
     }
   } else {
     p->regroup_every = 0;
@@ -1327,27 +1386,43 @@ extern "C" int mek_read_logs(mek_pop* p, int k0, int k1, double* u, double* V, d
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   const size_t nl = (size_t)p->P.nlog, n = nl * (size_t)(k1 - k0), o = nl * (size_t)k0;
   if (n == 0) return MEK_OK;
-  if (u) CUDA_TRY(cudaMemcpy(u, p->P.log_u + o, 8 * n, cudaMemcpyDeviceToHost));
-  if (V) CUDA_TRY(cudaMemcpy(V, p->P.log_V + o, 8 * n, cudaMemcpyDeviceToHost));
-  if (soc) CUDA_TRY(cudaMemcpy(soc, p->P.log_soc + o, 8 * n, cudaMemcpyDeviceToHost));
-  if (phise) CUDA_TRY(cudaMemcpy(phise, p->P.log_phise + o, 8 * n, cudaMemcpyDeviceToHost));
-  if (iT || iZ) {
-    std::vector<unsigned char> tmp(n);
-    if (iT) { CUDA_TRY(cudaMemcpy(tmp.data(), p->P.log_iT + o, n, cudaMemcpyDeviceToHost)); for (size_t i = 0; i < n; ++i) iT[i] = tmp[i]; }
-    if (iZ) { CUDA_TRY(cudaMemcpy(tmp.data(), p->P.log_iZ + o, n, cudaMemcpyDeviceToHost)); for (size_t i = 0; i < n; ++i) iZ[i] = tmp[i]; }
-  }
-  if (nexec) {
-    std::vector<unsigned short> tmp(n);
-    CUDA_TRY(cudaMemcpy(tmp.data(), p->P.log_nexec + o, 2 * n, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i) nexec[i] = tmp[i];
-  }
-  if (active) {
+  // doubles straight from the log block; the compact integer records are widened on the device first.  All copies are
+  // queued on the population's stream and waited for once: into pinned memory (mek_host_alloc) they run at link speed
+  if (iT || iZ || nexec || active) {
+    const size_t ib = (4 * n + 255) / 256 * 256;
+    int rc = ensure_scratch(p, 3 * ib + 16 * n);
+    if (rc != MEK_OK) return rc;
+    char* base = reinterpret_cast<char*>(p->d_scratch);
+    int* dT = reinterpret_cast<int*>(base);
+    int* dZ = reinterpret_cast<int*>(base + ib);
+    int* dn = reinterpret_cast<int*>(base + 2 * ib);
+    unsigned* da = reinterpret_cast<unsigned*>(base + 3 * ib);
     const int W = p->P.log_words;
-    std::vector<unsigned> tmp(n * W);
-    CUDA_TRY(cudaMemcpy(tmp.data(), p->P.log_active + o * W, 4 * n * W, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i)
-      for (int w = 0; w < 4; ++w) active[i * 4 + w] = (w < W) ? tmp[i * W + w] : 0u;
+    k_widen_logs<<<p->sms * 8, 256, 0, p->stream>>>(n, W, p->P.log_iT + o, p->P.log_iZ + o, p->P.log_nexec + o, p->P.log_active + o * W,
+                                                  iT ? dT : nullptr, iZ ? dZ : nullptr, nexec ? dn : nullptr, active ? da : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    p->launches++;
+    if (iT) CUDA_TRY(cudaMemcpyAsync(iT, dT, 4 * n, cudaMemcpyDeviceToHost, p->stream));
+    if (iZ) CUDA_TRY(cudaMemcpyAsync(iZ, dZ, 4 * n, cudaMemcpyDeviceToHost, p->stream));
+    if (nexec) CUDA_TRY(cudaMemcpyAsync(nexec, dn, 4 * n, cudaMemcpyDeviceToHost, p->stream));
+    if (active) CUDA_TRY(cudaMemcpyAsync(active, da, 16 * n, cudaMemcpyDeviceToHost, p->stream));
   }
+  if (u) CUDA_TRY(cudaMemcpyAsync(u, p->P.log_u + o, 8 * n, cudaMemcpyDeviceToHost, p->stream));
+  if (V) CUDA_TRY(cudaMemcpyAsync(V, p->P.log_V + o, 8 * n, cudaMemcpyDeviceToHost, p->stream));
+  if (soc) CUDA_TRY(cudaMemcpyAsync(soc, p->P.log_soc + o, 8 * n, cudaMemcpyDeviceToHost, p->stream));
+  if (phise) CUDA_TRY(cudaMemcpyAsync(phise, p->P.log_phise + o, 8 * n, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MEK_OK;
+}
+
+// page-locked host memory for the caller's input / result buffers (transfers then run at link speed and asynchronously)
+extern "C" int mek_host_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) return fail(MEK_ERR_ARG, "bad argument to mek_host_alloc");
+  CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return MEK_OK;
+}
+extern "C" int mek_host_free(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
   return MEK_OK;
 }
 

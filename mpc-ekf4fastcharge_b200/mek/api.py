@@ -89,6 +89,7 @@ class CellBatch:
         cfg.general_sweep_test = int(bool(general_sweep_test))
         cfg.regroup_every = int(regroup_every)
         self.cfg = cfg
+        self._log_cache, self._pinned_ptrs = {}, []
         self.h = C.c_void_p()
         check(L.mek_pop_create(rom.h, C.byref(cfg), self.B, int(device), C.byref(self.h)))
         self.nC = L.mek_pop_ncon(self.h)
@@ -99,6 +100,10 @@ class CellBatch:
         self.log_steps = 0
 
     def close(self):
+        self._log_cache = {}
+        for ptr in getattr(self, "_pinned_ptrs", []):
+            _lib.lib().mek_host_free(ptr)
+        self._pinned_ptrs = []
         if self.h:
             _lib.lib().mek_pop_destroy(self.h)
             self.h = C.c_void_p()
@@ -158,12 +163,30 @@ class CellBatch:
     def stream(self):
         return _lib.lib().mek_pop_stream(self.h)
 
-    def logs(self, k0=0, k1=None):
+    def _pinned(self, shape, dtype):
+        """A page-locked NumPy array owned by this batch (freed in close())."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        check(_lib.lib().mek_host_alloc(max(n, 1), C.byref(ptr)))
+        self._pinned_ptrs.append(ptr)
+        buf = (C.c_char * max(n, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def logs(self, k0=0, k1=None, reuse=False):
+        """Trajectory logs of the first `nlog` cells for instants [k0, k1): dict of [step][cell] arrays.
+        reuse=True returns page-locked arrays owned by this batch (allocated once per range, overwritten by the next call
+        with the same range): the device-to-host copies then run at link speed with no page faults on fresh memory."""
         k1 = self.log_steps if k1 is None else k1
         n, nl = k1 - k0, self.nlog
-        out = dict(u=np.empty((n, nl)), V=np.empty((n, nl)), SOC=np.empty((n, nl)), phise=np.empty((n, nl)),
-                   iT=np.empty((n, nl), np.int32), iZ=np.empty((n, nl), np.int32), nexec=np.empty((n, nl), np.int32),
-                   active=np.empty((n, nl, 4), np.uint32))
+        spec = (("u", (n, nl), np.float64), ("V", (n, nl), np.float64), ("SOC", (n, nl), np.float64), ("phise", (n, nl), np.float64),
+                ("iT", (n, nl), np.int32), ("iZ", (n, nl), np.int32), ("nexec", (n, nl), np.int32), ("active", (n, nl, 4), np.uint32))
+        if reuse:
+            key = (int(k0), int(k1), nl)
+            if key not in self._log_cache:
+                self._log_cache[key] = {k: self._pinned(sh, dt) for k, sh, dt in spec}
+            out = self._log_cache[key]
+        else:
+            out = {k: np.empty(sh, dt) for k, sh, dt in spec}
         check(_lib.lib().mek_read_logs(self.h, int(k0), int(k1), *[_p(out[k]) for k in ("u", "V", "SOC", "phise", "iT", "iZ", "nexec", "active")]))
         return out
 
