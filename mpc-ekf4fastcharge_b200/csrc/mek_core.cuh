@@ -1232,9 +1232,20 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
 // in this thread's column of shared memory ([slot][thread] layout: conflict-free, no local memory).
 // Same arithmetic, in the same order, as mpc_step / hildreth_core.
 // ------------------------------------------------------------------------------------------
-#ifndef LEAN_AHEAD
-#define LEAN_AHEAD 3             // rows of look-ahead of the K_i, 1/H_ii loads in the lean Hildreth sweep
-#endif
+// Shared-memory load that the compiler neither keeps in a register across sweeps (asm volatile: re-executed every time)
+// nor pins to its program point (a C++ volatile access becomes ld.volatile, which ptxas leaves right in front of its use).
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double x;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr) : "memory");
+  return x;
+}
+// K_i and 1/H_ii of one row as a 16-byte pair: one LDS.128, one exposed shared-memory latency per row instead of two
+__device__ __forceinline__ void lds_pair(unsigned addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts_pair(unsigned addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
 template <int NP, int NC, int CONS>
 struct FastShape {
   static constexpr bool UC = (CONS & 1) != 0, UV = (CONS & 2) != 0, UE = (CONS & 4) != 0, UZ = (CONS & 8) != 0;
@@ -1380,7 +1391,14 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
     unsigned zmask = 0u;
-    volatile double* vs = smt;                                       // re-read K, 1/H from shared memory (keeps them out of registers)
+    // (K_i, 1/H_ii) as 16-byte pairs, re-read from shared memory every sweep (keeps them out of registers).  Row i lives
+    // in scratch slots 2i and 2i+1 as before, but inside the slots a WARP's 64 doubles are dealt out as 32 pairs: lanes
+    // 0-15 take slot 2i, lanes 16-31 slot 2i+1, each the two columns 2(l mod 16), +1 of its own warp.  A warp therefore
+    // still touches only its own columns (other warps may be in another phase of the instant and use theirs as scratch),
+    // every quarter-warp reads 128 contiguous bytes, and the region starts 16-byte aligned (the bank blob is padded).
+    const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
+    const unsigned kra = (unsigned)__cvta_generic_to_shared(smt - threadIdx.x) + ((lane >> 4) * (unsigned)sms + wbase + 2u * (lane & 15u)) * 8u;
+    const unsigned krs = (unsigned)sms * 16u;
 #pragma unroll
     for (int i = 0; i < nC; ++i) {
       double P[NC];
@@ -1394,8 +1412,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
       double hd = Mm[i][0] * P[0], k = Mm[i][0] * x[0];
 #pragma unroll
       for (int j = 1; j < NC; ++j) { hd = fma(Mm[i][j], P[j], hd); k = fma(Mm[i][j], x[j], k); }
-      vs[(i * 2 + 0) * sms] = k + gam[i];                            // K(i)
-      vs[(i * 2 + 1) * sms] = rcp_d(hd);                             // 1/H(i,i)
+      sts_pair(kra + (unsigned)i * krs, k + gam[i], rcp_d(hd));      // K(i), 1/H(i,i)
       if (hd == 0.0) {
         zmask |= 1u << i;
       } else {
@@ -1416,26 +1433,21 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     // (tests/test_gpu_parity.py::test_lean_sweep_equals_general_sweep forces the general loop for comparison).
     constexpr unsigned ZEXP = FS::UZ ? (1u << FS::O_Z) : 0u;
     bool lean = (zmask == ZEXP) && (pmask == 0u) && !d.no_lean_sweep;
-    if (FS::UZ) lean = lean && !(vs[(FS::O_Z * 2 + 0) * sms] < 0.0);
+    if (FS::UZ) {
+      double kz, hz;
+      lds_pair(kra + (unsigned)FS::O_Z * krs, kz, hz);
+      lean = lean && !(kz < 0.0);
+    }
     if (lean) {
       bool first_nc = false;
       if (FS::UZ) { first_nc = !(lam[FS::O_Z] < 1e-6); lam[FS::O_Z] = 0.0; }
-      // K_i and 1/H_ii are read from shared memory LEAN_AHEAD rows before their use (a ring of registers), so the load
-      // latency is off the row-to-row dependency chain
-      constexpr int RING = LEAN_AHEAD < nC ? LEAN_AHEAD : nC;
       for (; k <= d.maxHild; ++k) {                                  // hildreth.m:32
         bool notconv = (k == 1) && first_nc;
-        double kq[RING], hq[RING];
-#pragma unroll
-        for (int t = 0; t < RING; ++t) { kq[t] = vs[(t * 2 + 0) * sms]; hq[t] = vs[(t * 2 + 1) * sms]; }
 #pragma unroll
         for (int i = 0; i < nC; ++i) {                               // hildreth.m:34-37
-          const double Ki = kq[i % RING], rHi = hq[i % RING];
-          if (i + RING < nC) {
-            kq[i % RING] = vs[((i + RING) * 2 + 0) * sms];
-            hq[i % RING] = vs[((i + RING) * 2 + 1) * sms];
-          }
           if (FS::UZ && i == FS::O_Z) continue;
+          double Ki, rHi;
+          lds_pair(kra + (unsigned)i * krs, Ki, rHi);
           const double li = lam[i];
           double hl = Mm[i][0] * v[0];
 #pragma unroll
@@ -1464,7 +1476,9 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
         double hl = Mm[i][0] * v[0];
 #pragma unroll
         for (int j = 1; j < NC; ++j) hl = fma(Mm[i][j], v[j], hl);
-        double w = fma(-(vs[(i * 2 + 0) * sms] + hl), vs[(i * 2 + 1) * sms], li);
+        double Kg, rHg;
+        lds_pair(kra + (unsigned)i * krs, Kg, rHg);
+        double w = fma(-(Kg + hl), rHg, li);
         w = (pmask != 0u) ? NAN : w;
         const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
         const double dl = nl - li;
