@@ -81,13 +81,19 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     plhs[1] = mxCreateDoubleMatrix(nz + 2, B, mxREAL);
     plhs[2] = mxCreateDoubleMatrix(MEK_NMATS, B, mxREAL);
     chk(mek_pop_iter_ekf(p, mxGetPr(prhs[2]), mxGetPr(prhs[3]), mxGetPr(plhs[0]), mxGetPr(plhs[1]), mxGetPr(plhs[2])));
-  } else if (!strcmp(cmd, "iter_mpc")) {                 /* [uk,phise,nexec] = mek_mex('iter_mpc', pop, mats, uk_applied)  <- iterMPC.m:1 */
-    mek_pop *p = (mek_pop *)get_handle(prhs[1]);
+  } else if (!strcmp(cmd, "iter_mpc")) {                 /* [uk,phise,nexec,cost] = mek_mex('iter_mpc', pop, mats, uk_applied)  <- iterMPC.m:1 */
+    mek_pop *p = (mek_pop *)get_handle(prhs[1]);          /* cost(:,b) = [J_uncon; J_final; norm_DU; viol]  (iterMPC.m:88-95) */
     mwSize B = mxGetNumberOfElements(prhs[3]);
     plhs[0] = mxCreateDoubleMatrix(1, B, mxREAL);
     plhs[1] = mxCreateDoubleMatrix(1, B, mxREAL);
     plhs[2] = mxCreateNumericMatrix(1, B, mxINT32_CLASS, mxREAL);
-    chk(mek_pop_iter_mpc(p, mxGetPr(prhs[2]), mxGetPr(prhs[3]), mxGetPr(plhs[0]), mxGetPr(plhs[1]), (int32_t *)mxGetData(plhs[2]), NULL));
+    plhs[3] = mxCreateDoubleMatrix(MEK_NCOST, B, mxREAL);
+    chk(mek_pop_iter_mpc_cost(p, mxGetPr(prhs[2]), mxGetPr(prhs[3]), mxGetPr(plhs[0]), mxGetPr(plhs[1]), (int32_t *)mxGetData(plhs[2]), NULL,
+                              mxGetPr(plhs[3])));
+  } else if (!strcmp(cmd, "cell_summaries")) {           /* S = mek_mex('cell_summaries', pop, B): 12 x B per-cell outcomes */
+    mek_pop *p = (mek_pop *)get_handle(prhs[1]);
+    plhs[0] = mxCreateDoubleMatrix(MEK_NCELLSUM, (mwSize)mxGetScalar(prhs[2]), mxREAL);
+    chk(mek_read_cell_summaries(p, mxGetPr(plhs[0])));
   } else if (!strcmp(cmd, "hildreth")) {                 /* [DU,lambda,nexec] = mek_mex('hildreth', Et, F, Mt, gamma, lambda0, maxIter) */
     /* Et = E.' and Mt = M.' (column-major MATLAB -> row-major ABI), one problem */
     int Nc = (int)mxGetM(prhs[1]), nC = (int)mxGetN(prhs[3]);
