@@ -7,6 +7,8 @@
 // "numerics contract".
 #pragma once
 #include <cstdint>
+#include <type_traits>
+
 #include "mek_cellfn.cuh"
 
 namespace mek {
@@ -1246,6 +1248,9 @@ __device__ __forceinline__ void lds_pair(unsigned addr, double& a, double& b) {
 __device__ __forceinline__ void sts_pair(unsigned addr, double a, double b) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
 }
+#ifndef LEAN_GROUPS
+#define LEAN_GROUPS 0            // 1: evaluate a constraint block from one v first, run it in sequence only if a row moves (measured neutral)
+#endif
 template <int NP, int NC, int CONS>
 struct FastShape {
   static constexpr bool UC = (CONS & 1) != 0, UV = (CONS & 2) != 0, UE = (CONS & 4) != 0, UZ = (CONS & 8) != 0;
@@ -1391,6 +1396,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
     unsigned zmask = 0u;
+    bool pfin = true;                                                // every entry of E\M' is finite
     // (K_i, 1/H_ii) as 16-byte pairs, re-read from shared memory every sweep (keeps them out of registers).  Row i lives
     // in scratch slots 2i and 2i+1 as before, but inside the slots a WARP's 64 doubles are dealt out as 32 pairs: lanes
     // 0-15 take slot 2i, lanes 16-31 slot 2i+1, each the two columns 2(l mod 16), +1 of its own warp.  A warp therefore
@@ -1408,6 +1414,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 #pragma unroll
         for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
         P[j] = acc;
+        pfin = pfin && is_finite(acc);
       }
       double hd = Mm[i][0] * P[0], k = Mm[i][0] * x[0];
 #pragma unroll
@@ -1441,30 +1448,57 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     if (lean) {
       bool first_nc = false;
       if (FS::UZ) { first_nc = !(lam[FS::O_Z] < 1e-6); lam[FS::O_Z] = 0.0; }
+      // One row of hildreth.m:34-37.  APPLY = false: evaluate only (no state is written) and report whether lambda_i
+      // would move.
+      auto row = [&](const int i, const bool APPLY, bool& flag) {
+        double Ki, rHi;
+        lds_pair(kra + (unsigned)i * krs, Ki, rHi);
+        const double li = lam[i];
+        double hl = Mm[i][0] * v[0];
+#pragma unroll
+        for (int j = 1; j < NC; ++j) hl = fma(Mm[i][j], v[j], hl);
+        const double w = fma(-(Ki + hl), rHi, li);
+        const double nl = pos_or_zero(w);                            // max(0,w); max(0,NaN) = 0
+        const double dl = nl - li;
+        if (!APPLY) { flag = flag || (dl != 0.0); return; }
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          double acc = Ei[j][0] * Mm[i][0];
+#pragma unroll
+          for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
+          v[j] = fma(acc, dl, v[j]);
+        }
+        lam[i] = nl;
+        flag = flag || !(fabs(dl) < 1e-6);                           // hildreth.m:39
+      };
+      // Row groups (the constraint blocks of constraintsMPC.m), LEAN_GROUPS = 1 only.  Most rows are inactive most of the time: lambda_i = 0 and
+      // w <= 0, so the update leaves lambda_i and v exactly as they were (v + P*0 = v for finite P; v is never -0).  A
+      // group is therefore first evaluated row by row from the SAME v -- independent chains instead of one chain through
+      // v -- and only if some lane of the warp finds a row that would move is it run again in sequence, exactly as
+      // written in the reference.  If no row moves the sequential pass would have seen the same v in every row, computed
+      // the same w and changed nothing: skipping it is exact.
+      auto group = [&](auto a_c, auto b_c, bool& notconv) {       // rows [A, B) of M, compile-time bounds
+        constexpr int A = decltype(a_c)::value, B = decltype(b_c)::value;
+        if (A == B) return;
+#if LEAN_GROUPS
+        bool moves = !pfin;
+#pragma unroll
+        for (int i = A; i < B; ++i)
+          if (!(FS::UZ && i == FS::O_Z)) row(i, false, moves);
+        if (!__any_sync(__activemask(), moves)) return;
+#endif
+#pragma unroll
+        for (int i = A; i < B; ++i)
+          if (!(FS::UZ && i == FS::O_Z)) row(i, true, notconv);
+      };
+      using std::integral_constant;
       for (; k <= d.maxHild; ++k) {                                  // hildreth.m:32
         bool notconv = (k == 1) && first_nc;
-#pragma unroll
-        for (int i = 0; i < nC; ++i) {                               // hildreth.m:34-37
-          if (FS::UZ && i == FS::O_Z) continue;
-          double Ki, rHi;
-          lds_pair(kra + (unsigned)i * krs, Ki, rHi);
-          const double li = lam[i];
-          double hl = Mm[i][0] * v[0];
-#pragma unroll
-          for (int j = 1; j < NC; ++j) hl = fma(Mm[i][j], v[j], hl);
-          const double w = fma(-(Ki + hl), rHi, li);
-          const double nl = pos_or_zero(w);                          // max(0,w); max(0,NaN) = 0
-          const double dl = nl - li;
-#pragma unroll
-          for (int j = 0; j < NC; ++j) {
-            double acc = Ei[j][0] * Mm[i][0];
-#pragma unroll
-            for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
-            v[j] = fma(acc, dl, v[j]);
-          }
-          lam[i] = nl;
-          notconv = notconv || !(fabs(dl) < 1e-6);                   // hildreth.m:39
-        }
+        group(integral_constant<int, 0>{}, integral_constant<int, (FS::UC ? 2 * NC : 0)>{}, notconv);            // u_max, u_min
+        group(integral_constant<int, (FS::UC ? 2 * NC : 0)>{}, integral_constant<int, FS::O_V>{}, notconv);      // du_max, du_min
+        group(integral_constant<int, FS::O_V>{}, integral_constant<int, FS::O_E>{}, notconv);                    // voltage
+        group(integral_constant<int, FS::O_E>{}, integral_constant<int, FS::O_Z>{}, notconv);                    // eta
+        group(integral_constant<int, FS::O_Z>{}, integral_constant<int, nC>{}, notconv);                         // z_max
         if (!notconv) break;
       }
     } else
