@@ -149,7 +149,7 @@ def main_reference(a):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "the reference is MATLAB (no MATLAB/Octave here, ROM .mat missing): this arm times the plain-C restatement of its loop"}
-    print(json.dumps(out))
+    print(json.dumps(out), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -308,14 +308,24 @@ def main_mek(a):
             v = cpu_run(bank, cells, a.nsim, cores, cfg)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "first %d cells of the same population x %d instants, oracle/mek_oracle.c with OpenMP over cells" % (cells, a.nsim)}
-        print(json.dumps(out))
+        print(json.dumps(out), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that libraries write to file descriptor 1 (NCCL prints its version
+    banner there) goes to stderr.  Returns a text stream on the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 if __name__ == "__main__":
     args = parse()
+    _OUT = _claim_stdout()
     if args.impl == "reference":
         main_reference(args)
     else:

@@ -1234,13 +1234,8 @@ __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict
 // in this thread's column of shared memory ([slot][thread] layout: conflict-free, no local memory).
 // Same arithmetic, in the same order, as mpc_step / hildreth_core.
 // ------------------------------------------------------------------------------------------
-// Shared-memory load that the compiler neither keeps in a register across sweeps (asm volatile: re-executed every time)
-// nor pins to its program point (a C++ volatile access becomes ld.volatile, which ptxas leaves right in front of its use).
-__device__ __forceinline__ double lds_f64(unsigned addr) {
-  double x;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr) : "memory");
-  return x;
-}
+// Shared-memory accesses as asm volatile: re-executed every sweep (never cached in a register across sweeps) without the
+// ld.volatile / st.volatile semantics a C++ volatile access would carry.
 // K_i and 1/H_ii of one row as a 16-byte pair: one LDS.128, one exposed shared-memory latency per row instead of two
 __device__ __forceinline__ void lds_pair(unsigned addr, double& a, double& b) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr) : "memory");
