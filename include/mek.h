@@ -89,9 +89,6 @@ typedef struct {
                                (128 when temperatures or limits differ between cells, else off), -1 = off           */
   int defer_narrow_test;    /* test hook, 1: shrink the per-block model set to the EKF estimate's own neighbours so
                                that the plant's models take the on-demand replay path (results are unchanged)    */
-  int smem_header;          /* 1: stage a cell's state header (40 scalars) in shared memory for the length of a launch of the
-                               fused kernel (256-thread static-shape instances; the default deferral block becomes 12 instants
-                               to make room).  Off by default: measured neutral */
   int general_sweep_test;   /* test hook, 1: the static-shape instances always run the general (masked) Hildreth sweep
                                instead of the lean one that applies when the only all-zero row is the first z_max row
                                (results are unchanged)                                                             */

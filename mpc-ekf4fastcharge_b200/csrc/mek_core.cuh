@@ -58,7 +58,12 @@ constexpr int TILE = 32;
 struct Cell {
   double* base;          // &st[tile][0][lane]
   double *bx, *xh, *sg, *lm;   // first bigX / xhat / SigmaX / lambda field of this cell
-  __device__ __forceinline__ double& f(int field) const { return base[field * TILE]; }
+  __device__ __forceinline__ double& f(int field) const {
+#if defined(__CUDA_ARCH__) && defined(MEK_HINT_GLOBAL)
+    __builtin_assume(__isGlobal(base));          // address-space hint: the state block is global memory (LDG/STG, no generic path)
+#endif
+    return base[field * TILE];
+  }
   __device__ __forceinline__ double& bigx(int m, int j) const { return bx[(m * 6 + j) * TILE]; }
   __device__ __forceinline__ double& xhat(int m, int j) const { return xh[(m * N5 + j) * TILE]; }
   __device__ __forceinline__ double& sig(int m, int q) const { return sg[(m * NSYM + q) * TILE]; }
@@ -472,6 +477,9 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
 // outputs in sc[SC_Z + HR_*] and returns Vcell.  Warnings go straight to the cell's counters.
 __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double ik,
                                              double T, Scratch sc) {
+#ifdef __CUDA_ARCH__
+  __builtin_assume(__isShared(sc.p));              // address-space hint: LDS/STS for the scratch column, not generic LD/ST
+#endif
   double xk[4][N5], g[4];
   const double* mm[4];
 #pragma unroll
@@ -659,6 +667,9 @@ struct EkfOut {          // what EKFmatsHandler hands to the MPC (EKFmatsHandler
 template <bool TIME_UPDATE>   // TIME_UPDATE=false: the caller already ran stream_models<...,true> with priorI
 __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double vk,
                                          double ik, EkfOut& o, Scratch sc, int tt_cached, Defer* df = nullptr) {
+#ifdef __CUDA_ARCH__
+  __builtin_assume(__isShared(sc.p));              // address-space hint (see get_variables)
+#endif
   o.lost = 0;
   if (c.f(S_WARN) > 10.0) {                                          // iterEKF.m:55-59 (Q19)
     c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | ST_LOST);

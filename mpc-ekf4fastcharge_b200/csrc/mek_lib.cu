@@ -234,7 +234,6 @@ struct Params {
   double* wide_ws;            // long-horizon instance: per-CTA workspace [WSLOTS][threads] for tables, K, 1/H (null: shared memory)
   int defer_narrow;           // test hook: hot set = the EKF estimate's neighbours only, no margin
   int hist_off;               // doubles from the start of dynamic shared memory to the history columns [defer_k + 1][threads]
-  int hdr_off;                // > 0: doubles from the start of dynamic shared memory to the per-warp copies of the state header; 0: header stays in global memory
   const int* slot2cell;       // state slot -> caller's cell index (cells are ordered by initial SOC inside the block), or null
 };
 
@@ -344,17 +343,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
     const long long cell = base + threadIdx.x;
     const bool active = cell < d.B;
     Cell c = cell_ref(P.st, d, active ? cell : 0);
-    // The 40 header fields of the cell (plant SOCs, EKF integrator, limits, counters, summaries) are read and written all
-    // over the instant, one dependent L2 round trip each (L1 is thrashed by the spills).  They are staged into shared
-    // memory for the whole launch -- [warp][field][lane], the tile's own layout, so Cell::f() indexes it unchanged -- and
-    // written back when the cell's last instant is done.
-    double* const ghdr = c.base;
-    if (P.hdr_off > 0) {
-      double* h = sm + P.hdr_off + (threadIdx.x >> 5) * (S_HDR * TILE) + (threadIdx.x & 31);
-#pragma unroll 8
-      for (int f = 0; f < S_HDR; ++f) h[f * TILE] = __ldcg(ghdr + f * TILE);
-      c.base = h;
-    }
     // the cell temperature is constant over a run: its two nearest set-points are looked up once (same rule as every step)
     const int tt = active ? two_nearest(c.f(S_TC) + 273.15, bk.Tpts, d.nT) : 0;
     const long long id = active ? cell_id(P, cell) : 0;   // the caller's index of this cell (logs are addressed by it)
@@ -392,10 +380,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
     }
     if (KB > 0 && active && k1 > k0) defer_flush(d, bk, c, df);      // the state block leaves the kernel fully advanced
     if (active) c.f(S_STEPS) += (double)(k1 - k0);
-    if (P.hdr_off > 0 && active) {
-#pragma unroll 8
-      for (int f = 0; f < S_HDR; ++f) __stcg(ghdr + f * TILE, c.base[f * TILE]);
-    }
   }
 }
 
@@ -1135,22 +1119,6 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     int kb = cfg->defer_block == 0 ? MEK_DEFER_DEFAULT : cfg->defer_block;
     if (kb < 2 || d.M > 64) kb = 0;                  // the hot set is a 64-bit mask
     if (kb > 64) kb = 64;
-    // state header in shared memory (k_run_population; opt-in, measured neutral: profiles/r01_optimisation_log.csv x9): the
-    // 256-thread static-shape <5,2> instances have the room if the default block length gives up four instants (16 -> 12);
-    // a block length the caller asked for wins over the header
-    p->P.hdr_off = 0;
-    if (cfg->smem_header > 0 && p->cons >= 0 && p->inst == 0 && p->run_threads == 256) {
-      const size_t room = 227 * 1024 - p->run_smem, hdr_bytes = sizeof(double) * S_HDR * (size_t)p->run_threads;
-      auto hist_bytes = [&](int k) { return k > 0 ? sizeof(double) * (size_t)(k + 1) * (size_t)p->run_threads : (size_t)0; };
-      if (cfg->defer_block == 0)
-        while (kb > 8 && hdr_bytes + hist_bytes(kb) > room) kb -= 4;
-      if (hdr_bytes + hist_bytes(kb) <= room) {
-        p->P.hdr_off = (int)(p->run_smem / sizeof(double));
-        p->run_smem += hdr_bytes;
-      } else if (cfg->defer_block == 0) {
-        kb = MEK_DEFER_DEFAULT;
-      }
-    }
     while (kb > 0 && p->run_smem + sizeof(double) * (size_t)(kb + 1) * (size_t)p->run_threads > 227 * 1024) kb /= 2;
     if (kb < 2) kb = 0;
     p->P.defer_k = kb;

@@ -69,7 +69,7 @@ class CellBatch:
 
     def __init__(self, rom: RomBank, B, Np=5, Nc=2, constraints=(1, 1, 1), ref=95.0, SigmaV=1e-3, SigmaW=1e2, maxHild=100,
                  use_zmax=True, force_jacobi=False, device=0, threads_per_block=0, blocks_per_sm=0, generic_path=False, sync_steps=True, keep_cell_order=False,
-                 defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=False, smem_header=0):
+                 defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=False):
         L = _lib.lib()
         self.rom = rom
         self.B = int(B)
@@ -87,7 +87,6 @@ class CellBatch:
         cfg.defer_block, cfg.defer_stagger = int(defer_block), int(bool(defer_stagger))
         cfg.defer_narrow_test = int(bool(defer_narrow_test))
         cfg.general_sweep_test = int(bool(general_sweep_test))
-        cfg.smem_header = int(smem_header)
         cfg.regroup_every = int(regroup_every)
         self.cfg = cfg
         self._log_cache, self._pinned_ptrs = {}, []
