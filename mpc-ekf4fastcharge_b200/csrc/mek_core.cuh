@@ -58,12 +58,7 @@ constexpr int TILE = 32;
 struct Cell {
   double* base;          // &st[tile][0][lane]
   double *bx, *xh, *sg, *lm;   // first bigX / xhat / SigmaX / lambda field of this cell
-  __device__ __forceinline__ double& f(int field) const {
-#if defined(__CUDA_ARCH__) && defined(MEK_HINT_GLOBAL)
-    __builtin_assume(__isGlobal(base));          // address-space hint: the state block is global memory (LDG/STG, no generic path)
-#endif
-    return base[field * TILE];
-  }
+  __device__ __forceinline__ double& f(int field) const { return base[field * TILE]; }
   __device__ __forceinline__ double& bigx(int m, int j) const { return bx[(m * 6 + j) * TILE]; }
   __device__ __forceinline__ double& xhat(int m, int j) const { return xh[(m * N5 + j) * TILE]; }
   __device__ __forceinline__ double& sig(int m, int q) const { return sg[(m * NSYM + q) * TILE]; }
