@@ -27,6 +27,9 @@ constexpr int N5 = 5, NSYM = 15;
 // ---- hot rows of the bank kept in shared memory (subset of ROMmdls(iT,iZ).C/.D the control path reads) ----
 enum : int { HR_IFDL0 = 0, HR_IFDL3, HR_IF0, HR_IF3, HR_TSS0, HR_TSS3, HR_THE0, HR_THE3, HR_PHIE, HR_PHI, HR_FIXED = 10 };
 constexpr int HR_MAX = 24;
+// One hot row of a local model in the shared-memory bank: 8 doubles, 16-byte aligned, [C(1..5) | D | C(6) | pad], so that the
+// EKF's row (five transient states + feed-through) is three 16-byte loads and the plant's (all six states) four.
+constexpr int HRS = 8, HR_D = 5, HR_C6 = 6;
 
 struct Dims {
   int M, nT, nZ, nz;
@@ -34,7 +37,7 @@ struct Dims {
   int nx_negtss;     // extra negThetass rows (beyond Thetass0), then extra posThetass, then extra Thetae
   int nx_postss;
   int nx_thetae;
-  int mstride;       // doubles per model in the hot bank: 6 (diag A) + R*7 (C row 6 + D)
+  int mstride;       // doubles per model in the hot bank: 6 (diag A) + R*HRS
   int nC;            // constraint rows
   int Np, Nc, maxHild;
   int useCurrent, useVoltage, useEta, useZmax;
@@ -431,8 +434,11 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
     for (int j = 0; j < 6; ++j) { xa[j] = ld_row(&c.bigx(ma, j)); xb[j] = ld_row(&c.bigx(mb, j)); }
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
-      const double* ca = ra + r * 7;
-      const double* cb = rb + r * 7;
+      const double2* pa = reinterpret_cast<const double2*>(ra + r * HRS);
+      const double2* pb = reinterpret_cast<const double2*>(rb + r * HRS);
+      const double2 a01 = pa[0], a23 = pa[1], a4d = pa[2], a6p = pa[3], b01 = pb[0], b23 = pb[1], b4d = pb[2], b6p = pb[3];
+      const double ca[7] = {a01.x, a01.y, a23.x, a23.y, a4d.x, a6p.x, a4d.y};   // C(1..6), D
+      const double cb[7] = {b01.x, b01.y, b23.x, b23.y, b4d.x, b6p.x, b4d.y};
       double ya = ca[0] * xa[0], yb = cb[0] * xb[0];
 #pragma unroll
       for (int j = 1; j < 6; ++j) { ya = fma(ca[j], xa[j], ya); yb = fma(cb[j], xb[j], yb); }
@@ -501,11 +507,13 @@ __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, 
     double yc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const double* cr = mm[k] + r * 7;
+      const double2* pr = reinterpret_cast<const double2*>(mm[k] + r * HRS);
+      const double2 c01 = pr[0], c23 = pr[1], c4d = pr[2];
+      const double cr[N5] = {c01.x, c01.y, c23.x, c23.y, c4d.x};
       double acc = cr[0] * xk[k][0];
 #pragma unroll
       for (int j = 1; j < N5; ++j) acc = fma(cr[j], xk[k][j], acc);
-      yc[k] = fma(cr[6], ik, acc);
+      yc[k] = fma(c4d.y, ik, acc);
     }
     sc[SC_Z + r] = fma(yc[3], g[3], fma(yc[2], g[2], fma(yc[1], g[1], yc[0] * g[0])));
   }
@@ -728,10 +736,10 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     for (int q = 0; q < NSYM; ++q) S[q] = ld_row(&c.sig(mo, q));
 #pragma unroll
     for (int j = 0; j < N5; ++j) {                                   // getChatV for this neighbour
-      double t = Rfp * (g * mm[HR_IFDL3 * 7 + j]) - Rfn * (g * mm[HR_IFDL0 * 7 + j]);    // :444
-      t = (t + Rctp * (g * mm[HR_IF3 * 7 + j])) - Rctn * (g * mm[HR_IF0 * 7 + j]);       // :471
-      t = t + g * mm[HR_PHIE * 7 + j];                                                    // :485
-      t = t + (dUp3 * (g * mm[HR_TSS3 * 7 + j]) - dUn0 * (g * mm[HR_TSS0 * 7 + j]));      // :504
+      double t = Rfp * (g * mm[HR_IFDL3 * HRS + j]) - Rfn * (g * mm[HR_IFDL0 * HRS + j]);    // :444
+      t = (t + Rctp * (g * mm[HR_IF3 * HRS + j])) - Rctn * (g * mm[HR_IF0 * HRS + j]);       // :471
+      t = t + g * mm[HR_PHIE * HRS + j];                                                    // :485
+      t = t + (dUp3 * (g * mm[HR_TSS3 * HRS + j]) - dUn0 * (g * mm[HR_TSS0 * HRS + j]));      // :504
       Chat[j] = t;
     }
 #pragma unroll
@@ -808,8 +816,8 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     const double* mm = am + 6;
 #pragma unroll
     for (int j = 0; j < N5; ++j)                                     // :75-76
-      o.Cv[j] = (Rfp2 * mm[HR_IFDL3 * 7 + j] - Rfn2 * mm[HR_IFDL0 * 7 + j]) + mm[HR_PHIE * 7 + j];
-    o.Dv = (Rfp2 * mm[HR_IFDL3 * 7 + 6] - Rfn2 * mm[HR_IFDL0 * 7 + 6]) + mm[HR_PHIE * 7 + 6];   // :79-80
+      o.Cv[j] = (Rfp2 * mm[HR_IFDL3 * HRS + j] - Rfn2 * mm[HR_IFDL0 * HRS + j]) + mm[HR_PHIE * HRS + j];
+    o.Dv = (Rfp2 * mm[HR_IFDL3 * HRS + HR_D] - Rfn2 * mm[HR_IFDL0 * HRS + HR_D]) + mm[HR_PHIE * HRS + HR_D];   // :79-80
     // :57-69,84-89 evaluate, at zk's SOC and the corrected thetass / thetae, exactly what the getVariables call above (:182)
     // just evaluated -- unless that call clamped its electrode SOCs (Q17), in which case its k0 arguments differ
     double Upos, Uneg, negEta0, posEta3;
@@ -827,8 +835,8 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     o.bv = ((Upos - Uneg) + (posEta3 - negEta0)) + 0.0;              // :92
     o.bphi = uocp_n(p, sn);                                          // :96 (Q21)
 #pragma unroll
-    for (int j = 0; j < N5; ++j) o.Cphi[j] = mm[HR_PHI * 7 + j];     // :97
-    o.Dphi = mm[HR_PHI * 7 + 6];                                     // :98
+    for (int j = 0; j < N5; ++j) o.Cphi[j] = mm[HR_PHI * HRS + j];     // :97
+    o.Dphi = mm[HR_PHI * HRS + HR_D];                                     // :98
   }
 }
 

@@ -120,7 +120,7 @@ static int bank_finalize(mek_bank* b) {
   for (int r : b->thetae) if (r != b->r_the0 && r != b->r_the3) { hot.push_back(r); b->nx_thetae++; }
   b->R = (int)hot.size();
   if (b->R > HR_MAX) return fail(MEK_ERR_UNSUPPORTED, "too many Thetass/Thetae rows for the shared-memory hot bank");
-  b->mstride = 6 + b->R * 7;
+  b->mstride = 6 + b->R * HRS;
   int head = b->nT + b->nZ;
   if (head & 1) head++;                                      // keep the model block 16-byte aligned
   b->off_mdl = head;
@@ -133,8 +133,12 @@ static int bank_finalize(mek_bank* b) {
     double* dst = &b->blob[(size_t)b->off_mdl + (size_t)m * b->mstride];
     for (int j = 0; j < 6; ++j) dst[j] = b->A[(size_t)m * 6 + j];
     for (int r = 0; r < b->R; ++r) {
-      for (int j = 0; j < 6; ++j) dst[6 + r * 7 + j] = b->C[((size_t)m * b->nz + hot[r]) * 6 + j];
-      dst[6 + r * 7 + 6] = b->D[(size_t)m * b->nz + hot[r]];
+      const double* Cr = &b->C[((size_t)m * b->nz + hot[r]) * 6];
+      double* row = dst + 6 + r * HRS;                         // [C(1..5) | D | C(6) | pad]  (mek_core.cuh HRS)
+      for (int j = 0; j < 5; ++j) row[j] = Cr[j];
+      row[HR_D] = b->D[(size_t)m * b->nz + hot[r]];
+      row[HR_C6] = Cr[5];
+      row[7] = 0.0;
     }
   }
   return MEK_OK;
