@@ -66,6 +66,15 @@ def workload_name(a):
             % (a.config, a.cells, a.nsim, c["what"], c["Np"], c["Nc"], c["seed"]))
 
 
+def config_dict(a, bank, world):
+    """The `config` object of the JSON line -- the same for both arms (the driver compares them)."""
+    c = a.cfg
+    nC = 4 * c["Nc"] * int(c["constraints"][0] == 1) + c["Np"] * (int(c["constraints"][1] == 1) + int(c["constraints"][2] == 1) + 1)
+    state_bytes = 8 * (26 * bank.M + 40 + nC)                      # DESIGN.md: SoA state block per cell
+    return {"workload": workload_name(a), "cells_total": a.cells * world, "nsim": a.nsim,
+            "l2": "inputs larger than L2: per-GPU state block %.2f GB of HBM-resident per-cell state" % (state_bytes * a.cells / 1e9)}
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks: sampled during the timed region through NVML
 # ------------------------------------------------------------------------------------------------
@@ -145,7 +154,7 @@ def main_reference(a):
     sample = "%d cells x %d instants per step (first cells of the same population), C restatement oracle/mek_oracle.c, OpenMP over cells" % (cells, a.nsim)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": 1e3 * cells * a.nsim / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": {"workload": workload_name(a)},
+           "data": "synthetic", "config": config_dict(a, bank, a.gpus),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "the reference is MATLAB (no MATLAB/Octave here, ROM .mat missing): this arm times the plain-C restatement of its loop"}
@@ -282,8 +291,7 @@ def main_mek(a):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": {"workload": workload_name(a), "cells_total": B * world, "nsim": a.nsim,
-                          "l2": "inputs larger than L2: per-GPU state block %.2f GB, resident working set of the 37888 cells in flight 256 MB" % (state_bytes * B / 1e9)},
+               "config": config_dict(a, bank, world),
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "what": "mek_pop_init (pinned host inputs) + mek_run + mek_summary + mek_read_logs of %d cells' trajectories" % nlog},

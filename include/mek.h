@@ -108,7 +108,10 @@ void mek_pop_destroy(mek_pop *pop);
 int mek_pop_set_logging(mek_pop *pop, int64_t n_log_cells, int max_steps);
 /* initKF + initMPC + first OB_step call.  SOC0pct[B] (plant), ekfSOC0pct[B] or NULL (= SOC0pct),
  * Tc[B] deg C, SigmaX0[36*B] (6x6 column-major per cell, symmetric), limits[7*B] =
- * u_max,u_min,du_max,du_min,v_max,phise_min,z_max+z_tol per cell (runMPC.m:36-44, initMPC.m:66-67). */
+ * u_max,u_min,du_max,du_min,v_max,phise_min,z_max+z_tol per cell (runMPC.m:36-44, initMPC.m:66-67).
+ * Tc is degrees Celsius ONLY: the reference's "T > 100 means Kelvin" heuristic (initKF.m:38-41, iterEKF.m:62-66; absent
+ * from OB_step.m:75 and EKFmatsHandler.m:53) is not reproduced, any Tc > 100 is rejected with MEK_ERR_ARG.
+ * Synchronous with respect to its arguments: every input buffer may be reused or freed as soon as the call returns. */
 int mek_pop_init(mek_pop *pop, const double *SOC0pct, const double *ekfSOC0pct, const double *Tc, const double *SigmaX0,
                  const double *limits);
 int mek_pop_reset(mek_pop *pop);    /* re-run the initialisation from the inputs already on the device */
@@ -120,6 +123,7 @@ void *mek_pop_stream(mek_pop *pop);                              /* cudaStream_t
 int64_t mek_pop_launches(const mek_pop *pop);                    /* kernels launched so far       */
 int mek_pop_ncon(const mek_pop *pop);                            /* constraint rows nC            */
 int mek_pop_defer_block(const mek_pop *pop);                     /* deferral block length in use (0 = off) */
+int64_t mek_pop_regroups(const mek_pop *pop);                    /* regroupings of the state block so far (scheduling only) */
 int mek_pop_state_len(const mek_pop *pop);                       /* doubles per cell in read/write_state */
 /* logs for instants [k0,k1) x first n_log_cells cells, [step][cell] row-major.  Any pointer may be NULL.
  * u = command computed at k (applied at k+1, runMPC.m:106), V = voltage_store, soc = zk(end),

@@ -492,7 +492,7 @@ __device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, doub
 
 struct RowLists {            // output-row kinds for the full-zk corrections and the 3-sigma bounds
   int n_negtss, n_postss, n_thetae, n_negphise, n_posphise, n_phie, n_posphis, r_phise0;
-  int negtss[16], postss[16], thetae[16], negphise[16], posphise[16], phie[16], posphis[16];
+  int negtss[64], postss[64], thetae[64], negphise[64], posphise[64], phie[64], posphis[64];   // nz <= 64 (mek_bank_create): no group can overflow
   int r_ifdl0, r_ifdl3, r_if0, r_if3, r_tss0, r_tss3, r_the0, r_the3, r_phie_last;   // rows in the full output numbering
   unsigned char kind[64];    // per output row: 0 plain, 1 posPhis, 2 negThetass, 3 posThetass, 4 negPhise, 5 posPhise, 6 Phie
 };
@@ -938,6 +938,7 @@ struct mek_pop {
   unsigned *d_keys, *d_keys2;
   void* d_cubtmp; size_t cubtmp_bytes;
   int64_t regroups;
+  int since_regroup;           // sample instants run since the last regrouping (or the initialisation): kept across mek_run calls
 };
 
 static double sigma_min_gtg(int Np, int Nc, double r) {
@@ -989,15 +990,10 @@ static int grid_for(const mek_pop* p, long long B, int threads) {
   return (int)blocks;
 }
 
-extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64_t B, int device, mek_pop** out) {
-  if (!bank || !cfg || !out || B < 1) return fail(MEK_ERR_ARG, "bad argument to mek_pop_create");
-  int ndev = 0;
-  cudaError_t e0 = cudaGetDeviceCount(&ndev);
-  if (e0 != cudaSuccess || ndev < 1)
-    return fail(MEK_ERR_CUDA, "no CUDA device: libmek has no CPU path (the oracle under oracle/ is test infrastructure only)");
-  if (device < 0 || device >= ndev) return fail(MEK_ERR_ARG, "bad device index");
-  CUDA_TRY(cudaSetDevice(device));
-  mek_pop* p = new mek_pop();
+extern "C" void mek_pop_destroy(mek_pop* p);
+// fills a zero-initialised mek_pop; on any failure the caller (mek_pop_create) hands the partly built object to
+// mek_pop_destroy, which releases whatever was allocated so far
+static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, int64_t B, int device) {
   memset(&p->P, 0, sizeof(Params));
   p->bank = bank;
   p->cfg = *cfg;
@@ -1019,7 +1015,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   if (Np == 5 && Nc == 2) p->inst = 0;
   else if (Np <= 20 && Nc <= 5) p->inst = 1;
   else if (Np <= 32 && Nc <= 8) p->inst = 2;
-  else { delete p; return fail(MEK_ERR_UNSUPPORTED, "Np > 32 or Nc > 8 is outside the built kernel instances"); }
+  else { return fail(MEK_ERR_UNSUPPORTED, "Np > 32 or Nc > 8 is outside the built kernel instances"); }
   Dims& d = p->P.d;
   d.M = bank->M; d.nT = bank->nT; d.nZ = bank->nZ; d.nz = bank->nz;
   d.R = bank->R; d.nx_negtss = bank->nx_negtss; d.nx_postss = bank->nx_postss; d.nx_thetae = bank->nx_thetae;
@@ -1028,7 +1024,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   d.useCurrent = cfg->constraints[0] == 1; d.useVoltage = cfg->constraints[1] == 1; d.useEta = cfg->constraints[2] == 1;
   d.useZmax = cfg->use_zmax != 0;
   d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax);
-  if (d.nC > 128) { delete p; return fail(MEK_ERR_UNSUPPORTED, "more than 128 constraint rows"); }
+  if (d.nC > 128) { return fail(MEK_ERR_UNSUPPORTED, "more than 128 constraint rows"); }
   d.force_jacobi = cfg->force_jacobi;
   d.no_lean_sweep = cfg->general_sweep_test > 0 ? 1 : 0;
   d.Ts = bank->Tsamp; d.ref = cfg->ref; d.SigmaV = cfg->SigmaV; d.SigmaW = cfg->SigmaW;
@@ -1042,7 +1038,9 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   // row lists for the full-zk corrections
   RowLists& RL = p->RL;
   memset(&RL, 0, sizeof(RL));
-  auto fill = [](const std::vector<int>& v, int* dst, int& n) { n = (int)(v.size() > 16 ? 16 : v.size()); for (int i = 0; i < n; ++i) dst[i] = v[i]; };
+  auto fill = [](const std::vector<int>& v, int* dst, int& n) { n = (int)(v.size() > 64 ? 64 : v.size()); for (int i = 0; i < n; ++i) dst[i] = v[i]; };
+  for (const std::vector<int>* v : {&bank->negtss, &bank->postss, &bank->thetae, &bank->negphise, &bank->posphise, &bank->phie, &bank->posphis})
+    if (v->size() > 64) { return fail(MEK_ERR_UNSUPPORTED, "more than 64 output rows of one kind"); }
   fill(bank->negtss, RL.negtss, RL.n_negtss); fill(bank->postss, RL.postss, RL.n_postss); fill(bank->thetae, RL.thetae, RL.n_thetae);
   fill(bank->negphise, RL.negphise, RL.n_negphise); fill(bank->posphise, RL.posphise, RL.n_posphise);
   fill(bank->phie, RL.phie, RL.n_phie); fill(bank->posphis, RL.posphis, RL.n_posphis);
@@ -1061,7 +1059,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
   p->threads = 128;   // the fused kernels are compiled for a fixed CTA size (their shared-memory columns use it as a constant stride)
   p->blob_bytes = bank->blob.size() * sizeof(double);
   p->smem_bytes = p->blob_bytes + sizeof(double) * (size_t)SC_TOTAL * (size_t)p->threads;   // hot bank + per-thread scratch columns
-  if (p->smem_bytes > 200 * 1024) { delete p; return fail(MEK_ERR_UNSUPPORTED, "hot bank does not fit in shared memory"); }
+  if (p->smem_bytes > 200 * 1024) { return fail(MEK_ERR_UNSUPPORTED, "hot bank does not fit in shared memory"); }
   CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&p->ev0));
   CUDA_TRY(cudaEventCreate(&p->ev1));
@@ -1156,6 +1154,25 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
     CUDA_TRY(cudaMemset(p->d_wide_ws, 0, bytes));
     p->P.wide_ws = p->d_wide_ws;
   }
+  return MEK_OK;
+}
+
+extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64_t B, int device, mek_pop** out) {
+  if (!bank || !cfg || !out || B < 1) return fail(MEK_ERR_ARG, "bad argument to mek_pop_create");
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev < 1)
+    return fail(MEK_ERR_CUDA, "no CUDA device: libmek has no CPU path (the oracle under oracle/ is test infrastructure only)");
+  if (device < 0 || device >= ndev) return fail(MEK_ERR_ARG, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  mek_pop* p = new mek_pop();                  // value-initialised: every pointer / handle starts null
+  const int rc = pop_build(p, bank, cfg, B, device);
+  if (rc != MEK_OK) {
+    const std::string msg = g_err;             // mek_pop_destroy must not lose the reason
+    mek_pop_destroy(p);
+    g_err = msg;
+    return rc;
+  }
   *out = p;
   return MEK_OK;
 }
@@ -1163,7 +1180,7 @@ extern "C" int mek_pop_create(const mek_bank* bank, const mek_config* cfg, int64
 extern "C" void mek_pop_destroy(mek_pop* p) {
   if (!p) return;
   cudaSetDevice(p->device);
-  cudaStreamSynchronize(p->stream);
+  if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->d_slot2cell) cudaFree(p->d_slot2cell);
   if (p->d_wide_ws) cudaFree(p->d_wide_ws);
   if (p->d_st2) cudaFree(p->d_st2);
@@ -1177,8 +1194,9 @@ extern "C" void mek_pop_destroy(mek_pop* p) {
   cudaFree(p->d_blob); cudaFree(p->d_Cfull); cudaFree(p->d_Dfull); cudaFree(p->d_st); cudaFree(p->d_in); cudaFree(p->d_totals);
   if (p->d_logs) cudaFree(p->d_logs);
   if (p->d_scratch) cudaFree(p->d_scratch);
-  cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
-  cudaStreamDestroy(p->stream);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
 
@@ -1225,6 +1243,7 @@ extern "C" int mek_pop_reset(mek_pop* p) {
   k_pop_init<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P);
   CUDA_TRY(cudaGetLastError());
   p->launches++;
+  p->since_regroup = 0;
   p->inited = true;
   return MEK_OK;
 }
@@ -1234,6 +1253,11 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
   if (!p || !SOC0pct || !Tc || !SigmaX0 || !limits) return fail(MEK_ERR_ARG, "null argument to mek_pop_init");
   CUDA_TRY(cudaSetDevice(p->device));
   const size_t B = (size_t)p->P.d.B;
+  // The reference treats a temperature above 100 as Kelvin in initKF.m:38-41 and iterEKF.m:62-66 but adds 273.15 to it
+  // unconditionally in OB_step.m:75 and EKFmatsHandler.m:53: with such an input its three functions run at three
+  // different temperatures.  libmek takes degrees Celsius only and says so instead of reproducing that.
+  for (size_t i = 0; i < B; ++i)
+    if (Tc[i] > 100.0) return fail(MEK_ERR_ARG, "Tc must be in degrees Celsius (<= 100); the reference's Kelvin heuristic (initKF.m:38-41, iterEKF.m:62-66) is not reproduced");
   double* in = p->d_in;
   CUDA_TRY(cudaMemcpyAsync(in, SOC0pct, 8 * B, cudaMemcpyHostToDevice, p->stream));
   CUDA_TRY(cudaMemcpyAsync(in + B, ekfSOC0pct ? ekfSOC0pct : SOC0pct, 8 * B, cudaMemcpyHostToDevice, p->stream));
@@ -1287,6 +1311,7 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
     }
   } else {
     p->regroup_every = 0;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));    // the caller's buffers are free to reuse when mek_pop_init returns, in both branches
   }
   return mek_pop_reset(p);
 }
@@ -1338,15 +1363,21 @@ static int regroup(mek_pop* p) {
 
 static int launch_run(mek_pop* p, int k0, int k1) {
   const int every = (p->regroup_every > 0 && p->P.slot2cell) ? p->regroup_every : 0;
-  if (every == 0 || k1 - k0 <= every) return launch_segment(p, k0, k1);
-  for (int s = k0; s < k1; s += every) {
-    const int e = s + every < k1 ? s + every : k1;
-    int rc = launch_segment(p, s, e);
-    if (rc != MEK_OK) return rc;
-    if (e < k1) {
-      rc = regroup(p);
+  if (every == 0) return launch_segment(p, k0, k1);
+  // The instants since the last regrouping are counted across calls, so a caller that runs the charge in chunks no longer
+  // than regroup_every is regrouped exactly like one that runs it in a single call.
+  for (int s = k0; s < k1;) {
+    if (p->since_regroup >= every) {
+      const int rc = regroup(p);
       if (rc != MEK_OK) return rc;
+      p->since_regroup = 0;
     }
+    const int room = every - p->since_regroup;
+    const int e = s + room < k1 ? s + room : k1;
+    const int rc = launch_segment(p, s, e);
+    if (rc != MEK_OK) return rc;
+    p->since_regroup += e - s;
+    s = e;
   }
   return MEK_OK;
 }
@@ -1381,6 +1412,7 @@ extern "C" void* mek_pop_stream(mek_pop* p) { return p ? (void*)p->stream : null
 extern "C" int64_t mek_pop_launches(const mek_pop* p) { return p ? p->launches : 0; }
 extern "C" int mek_pop_ncon(const mek_pop* p) { return p ? p->P.d.nC : 0; }
 extern "C" int mek_pop_defer_block(const mek_pop* p) { return p ? p->P.defer_k : 0; }
+extern "C" int64_t mek_pop_regroups(const mek_pop* p) { return p ? p->regroups : 0; }
 extern "C" int mek_pop_state_len(const mek_pop* p) { return p ? p->P.d.nfields : 0; }
 
 extern "C" int mek_read_logs(mek_pop* p, int k0, int k1, double* u, double* V, double* soc, double* phise, int32_t* iT, int32_t* iZ,

@@ -160,6 +160,11 @@ class CellBatch:
         return int(_lib.lib().mek_pop_launches(self.h))
 
     @property
+    def regroups(self):
+        """Regroupings of the state block so far (scheduling only; results do not depend on it)."""
+        return int(_lib.lib().mek_pop_regroups(self.h))
+
+    @property
     def stream(self):
         return _lib.lib().mek_pop_stream(self.h)
 

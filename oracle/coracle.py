@@ -26,7 +26,7 @@ def _has_fma():
 
 
 _SO = os.path.join(_HERE, "_build", "libmek_oracle_fma.so" if _has_fma() else "libmek_oracle.so")
-MAXROWS = 16
+MAXROWS = 64
 
 # state-vector field offsets (enum in mek_oracle.c)
 (S_SOCN, S_SOCP, S_SOC0N, S_SOC0P, S_CDLN, S_CDLP, S_TC, S_ARRK0N, S_ARRK0P, S_ARRRFN, S_ARRRFP,

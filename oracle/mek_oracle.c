@@ -40,7 +40,7 @@
 #define NP_MAX 32
 #define NC_MAX 8
 #define NCON_MAX (4 * NC_MAX + 3 * NP_MAX)
-#define MAXROWS 16
+#define MAXROWS 64   /* nz <= 64: no group of output rows can overflow */
 
 /* parameter vector layout (restated; equals mek/bank.py) */
 enum { P_F = 0, P_R, P_Q, P_RC, P_TREF, P_NEG = 5, P_POS = 16, P_UN = 27, P_UP = 33, P_UP_COEF = 36, N_PARAMS = 44 };

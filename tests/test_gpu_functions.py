@@ -200,3 +200,51 @@ def test_iter_mpc_cost_log_vs_literal(bank):
         assert np.allclose(cost[:, j], ref, rtol=1e-9, atol=1e-12 * np.max(np.abs(ref))), (key, np.max(np.abs(cost[:, j] - ref) / np.abs(ref)))
     assert np.array_equal(cost[:, 3], c["viol"][:N])
     assert np.all(cost[:, 1] >= cost[:, 0] * (1 - 1e-12))          # a constrained optimum never beats the unconstrained one
+
+
+def test_full_zk_with_more_than_16_rows_of_one_kind(bank, coracle_mod):
+    """A bank with 19 posPhis rows (the per-kind row lists used to be cut at 16 entries): every row of zk must still get
+    its correction (+vhat for posPhis, iterEKF.m:411-413) and its 3-sigma bound, bit for bit like the oracle."""
+    from mek import api, bank as Bk, population as P
+    extra = 17
+    src = bank.names.index("posPhis") if "posPhis" in bank.names else None
+    assert src is not None
+    names = list(bank.names) + ["posPhis"] * extra
+    xloc = np.concatenate([bank.xloc, np.full(extra, 3.0)])
+    scale = 1.0 + 0.01 * np.arange(1, extra + 1)
+    C = np.concatenate([bank.C, bank.C[:, :, src:src + 1, :] * scale[None, None, :, None]], axis=2)
+    D = np.concatenate([bank.D, bank.D[:, :, src:src + 1] * scale[None, None, :]], axis=2)
+    big = Bk.Bank(bank.n, bank.nz + extra, bank.Tpts_C, bank.Zpts_pct, bank.Tsamp, names, xloc, bank.A, C, D, bank.params).validate()
+    B = 16
+    pop = P.make_population(big.params[2], B, seed=12, heterogeneous=True)
+    cb = api.CellBatch(api.RomBank(big), B)
+    cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    co = coracle_mod.COracle(big)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    rng = np.random.default_rng(5)
+    for k in range(6):
+        I = rng.uniform(-60, 5, B)
+        V = cb.ob_step(I)
+        zk, mats = cb.iter_ekf(V, I)
+        for c in range(B):
+            assert V[c] == co.ob_step(c, I[c])
+            zkc, matsc = co.iter_ekf(c, V[c], I[c])
+            assert np.array_equal(zk[c], zkc), (k, c, np.nonzero(zk[c] != zkc)[0])
+    # the duplicated rows differ from their source row only by the linear part's scale: all carry +vhat
+    vhat = zk[:, big.nz]
+    lin_src = zk[:, src] - vhat
+    for j in range(extra):
+        assert np.allclose(zk[:, bank.nz + j] - vhat, lin_src * scale[j], rtol=1e-9, atol=1e-15)
+
+
+def test_kelvin_temperature_is_rejected(bank):
+    """initKF.m:38-41 / iterEKF.m:62-66 guess Kelvin when T > 100 (OB_step.m:75 and EKFmatsHandler.m:53 do not): libmek takes
+    degrees Celsius only and refuses anything else instead of silently running a different filter than the reference."""
+    from mek import api, population as P
+    pop = P.make_population(bank.params[2], 8, seed=3)
+    cb = api.CellBatch(api.RomBank(bank), 8)
+    T = pop.T.copy(); T[5] = 298.15
+    with pytest.raises(api.MekError, match="Celsius"):
+        cb.init(pop.SOC0, T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)        # the batch is still usable
+    assert np.isfinite(cb.ob_step(np.zeros(8))).all()

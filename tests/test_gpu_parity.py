@@ -258,3 +258,57 @@ def test_lean_sweep_equals_general_sweep(bank, coracle_mod, constraints):
     assert outs[0][1]["n_cap"] > 0, "no QP hit the sweep cap: the general sweep was not exercised by the lean build"
     for k in ("u", "nexec", "active"):
         assert np.array_equal(outs[0][0][k], outs[1][0][k], equal_nan=(k == "u")), k
+
+
+def test_regrouping_also_happens_when_the_run_is_chunked(bank, coracle_mod):
+    """The instants since the last regrouping are counted across mek_run calls: a caller that advances the charge in chunks
+    shorter than regroup_every is regrouped like one that runs it in one call (it used to never regroup)."""
+    from mek import api, population as P
+    pop = P.make_population(bank.params[2], 200, seed=32, heterogeneous=True)
+    rom = api.RomBank(bank)
+    cb = api.CellBatch(rom, len(pop), regroup_every=50)
+    cb.set_logging(len(pop), 400)
+    cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    for k in range(0, 400, 20):
+        cb.run(k, k + 20)
+    assert cb.regroups == 7                          # after instants 50, 100, ..., 350
+    one = api.CellBatch(rom, len(pop), regroup_every=50)
+    one.set_logging(len(pop), 400)
+    one.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    one.run(0, 400)
+    assert one.regroups == 7
+    co = coracle_mod.COracle(bank)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    c = co.run(0, 400, nthreads=8)
+    _assert_bit_exact(cb.logs(0, 400), c)
+    _assert_bit_exact(one.logs(0, 400), c)
+    cb.reset()                                       # a reset starts the count again
+    cb.run(0, 49)
+    assert cb.regroups == 7
+    cb.run(49, 51)
+    assert cb.regroups == 8
+
+
+# ---- the product against the LITERAL restatement (committed golden trajectories made by oracle/literal.py) ----
+import glob as _glob
+_GOLD = sorted(_glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _GOLD, ids=[os.path.basename(p)[:-4] for p in _GOLD])
+def test_cuda_matches_literal_golden(bank, path):
+    """CUDA (through the C ABI) against the line-by-line NumPy restatement of the reference, without the C oracle in
+    between: <= 1e-9 relative on u, V, SOC, phi_se (north_star's FP64 tolerance), identical local-ROM indices, Hildreth sweep
+    counts and active sets.  The golden files were made by tests/golden/make_golden.py from oracle/literal.py."""
+    from mek import api
+    g = np.load(path)
+    B, N = len(g["SOC0"]), int(g["N"])
+    cb = api.CellBatch(api.RomBank(bank), B, Np=int(g["Np"]), Nc=int(g["Nc"]), constraints=tuple(int(c) for c in g["constraints"]))
+    cb.set_logging(B, N)
+    cb.init(g["SOC0"], g["T"], g["SigmaX0"], g["limits"], g["ekf_SOC0"])
+    cb.run(0, N)
+    o = cb.logs(0, N)
+    for k in ("iT", "iZ", "nexec"):
+        assert np.array_equal(o[k], g[k]), "%s: %d mismatches" % (k, (o[k] != g[k]).sum())
+    assert np.array_equal(o["active"], g["active"])
+    for k in ("u", "V", "SOC", "phise"):
+        assert rel_err(o[k], g[k], SCALE[k]) <= 1e-9, k
