@@ -81,7 +81,9 @@ struct Scratch {
   __device__ __forceinline__ double& operator[](int i) const { return p[i * s]; }
 };
 // SC_X: what getVariables leaves for EKFmatsHandler (negEta0, posEta3, Uocp_neg(thetass0), Uocp_pos(thetass3), SOC-clamp flag)
-enum : int { SC_GAMMA = 0, SC_M = 4, SC_IT = 8, SC_IZ = 12, SC_Z = 16, SC_X = SC_Z + HR_MAX, SC_TOTAL = SC_X + 5 };
+// SC_Z comes last so that a launch only has to provide SC_Z + R slots (sc_slots) for the bank at hand
+enum : int { SC_GAMMA = 0, SC_M = 4, SC_IT = 8, SC_IZ = 12, SC_X = 16, SC_Z = SC_X + 5, SC_TOTAL = SC_Z + HR_MAX };
+__host__ __device__ constexpr int sc_slots(int R) { return SC_Z + R; }
 
 __device__ __forceinline__ int sym_idx(int i, int j) {
   // upper triangle, row-major: (0,0..4)=0..4, (1,1..4)=5..8, (2,2..4)=9..11, (3,3..4)=12,13, (4,4)=14
@@ -90,7 +92,7 @@ __device__ __forceinline__ int sym_idx(int i, int j) {
 }
 
 // first two entries of a stable ascending sort of |v - pts| (OB_step.m:251,261; iterEKF.m:221,234); returns i1 | i2 << 16
-__device__ __noinline__ int two_nearest(double v, const double* pts, int n) {
+static __device__ __noinline__ int two_nearest(double v, const double* pts, int n) {
   int a = -1, b = -1;
   double b1 = INFINITY, b2 = INFINITY;
 #pragma unroll 1
@@ -128,7 +130,7 @@ __device__ __forceinline__ int two_nearest_z(const Dims& d, double v, const doub
 
 // getXind (iterEKF.m:219-255): ordering by value with swap, alphas not clamped (Q14).
 // Writes gamma[4], model column m[4] = iT*nZ+iZ, iT[4], iZ[4] into the scratch column.
-__device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc, int tt_cached) {
+static __device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc, int tt_cached) {
   const int zz = two_nearest_z(d, SOC, bk.Zpts), z1 = zz & 0xffff, z2 = zz >> 16;
   int iZup = z1, iZlo = z1;
   double Zup = bk.Zpts[z1], Zlo = bk.Zpts[z1];
@@ -292,7 +294,7 @@ struct Defer {
   int hs;                    // column stride
 };
 
-__device__ __noinline__ void defer_catch_up(const Dims& d, const BankSmem& bk, const Cell& c, int m, int n, const double* h, int hs) {
+static __device__ __noinline__ void defer_catch_up(const Dims& d, const BankSmem& bk, const Cell& c, int m, int n, const double* h, int hs) {
   ModelRegs<true, true> r;
   model_load<true, true>(c, m, r);
   double a[6];
@@ -315,7 +317,7 @@ __device__ __forceinline__ void defer_ensure(const Dims& d, const BankSmem& bk, 
 
 // models this cell is expected to read during the coming block: both temperature rows x the SOC set-points around the
 // plant's and the EKF's present SOC, widened by the largest SOC change the current limits allow over `span` instants
-__device__ __noinline__ unsigned long long defer_hot_set(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
+static __device__ __noinline__ unsigned long long defer_hot_set(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
                                                          int tt, int span, int narrow) {
   const double th0n = p[P_NEG + E_THETA0], th100n = p[P_NEG + E_THETA100];
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
@@ -476,7 +478,7 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
 // getVariables (iterEKF.m:259-417) restricted to the rows that feed Vcell, the warnings and
 // EKFmatsHandler.  Reads the neighbour set from the scratch column (get_xind), leaves the corrected
 // outputs in sc[SC_Z + HR_*] and returns Vcell.  Warnings go straight to the cell's counters.
-__device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double ik,
+static __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double ik,
                                              double T, Scratch sc) {
 #ifdef __CUDA_ARCH__
   __builtin_assume(__isShared(sc.p));              // address-space hint: LDS/STS for the scratch column, not generic LD/ST
@@ -584,7 +586,7 @@ __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, 
 // PSD repair (iterEKF.m:143-145) on the symmetric 15-entry storage.  If an LDL^T sweep finds every
 // pivot > 0 the matrix is positive definite, V*S*V' equals SigmaX and line 145 is the identity;
 // otherwise a cyclic Jacobi eigen-decomposition gives HH = V|w|V'.  Returns 1 if the eigen path ran.
-__device__ __noinline__ int psd_repair_jacobi(double* S) {
+static __device__ __noinline__ int psd_repair_jacobi(double* S) {
   double A[5][5], V[5][5];
   for (int i = 0; i < 5; ++i)
     for (int j = 0; j < 5; ++j) { A[i][j] = S[sym_idx(i, j)]; V[i][j] = (i == j) ? 1.0 : 0.0; }
@@ -657,7 +659,15 @@ __device__ __forceinline__ int psd_repair(double* S, int force) {
     }
     if (pd) return 0;
   }
-  return psd_repair_jacobi(S);
+  // rare path, out of line: it works on a copy so that S itself never has its address taken (an array whose address
+  // escapes lives in local memory on the common path too)
+  double T[NSYM];
+#pragma unroll
+  for (int q = 0; q < NSYM; ++q) T[q] = S[q];
+  const int r = psd_repair_jacobi(T);
+#pragma unroll
+  for (int q = 0; q < NSYM; ++q) S[q] = T[q];
+  return r;
 }
 
 struct EkfOut {          // what EKFmatsHandler hands to the MPC (EKFmatsHandler.m:101-114) + zk(end), vhat
@@ -1257,9 +1267,6 @@ __device__ __forceinline__ void lds_pair(unsigned addr, double& a, double& b) {
 __device__ __forceinline__ void sts_pair(unsigned addr, double a, double b) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
 }
-#ifndef LEAN_GROUPS
-#define LEAN_GROUPS 0            // 1: evaluate a constraint block from one v first, run it in sequence only if a row moves (measured neutral)
-#endif
 template <int NP, int NC, int CONS>
 struct FastShape {
   static constexpr bool UC = (CONS & 1) != 0, UV = (CONS & 2) != 0, UE = (CONS & 4) != 0, UZ = (CONS & 8) != 0;
@@ -1269,6 +1276,27 @@ struct FastShape {
   static constexpr int nC = O_Z + (UZ ? NP : 0);
   static constexpr int SLOTS = nC * 2;                               // doubles of shared memory per thread: K_i, 1/H_ii
 };
+
+// Tells the compiler that inv(E) may have changed: column i of E\M' = inv(E)*M(i,:)' is then RECOMPUTED in every sweep
+// (four FP64 operations per row) instead of being computed once for all rows and kept -- 44 values that do not fit the
+// register file and would be spilled and re-read from local memory in every sweep.
+template <int N>
+__device__ __forceinline__ void opaque(double (&A)[N][N]) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) asm volatile("" : "+d"(A[i][j]));
+#endif
+}
+
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
 
 template <int NP, int NC, int CONS>
 __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __restrict__ p, const Cell& c, const EkfOut& e, double uk_applied,
@@ -1285,103 +1313,128 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     o.phise = (acc + uk_applied * e.Dphi) + e.bphi;
   }
   const double r = -d.Ts / (3600.0 * p[P_Q]);                        // EKFmatsHandler.m:43
-  const double zero5[N5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  double hs[NP + 1], pxs[NP];
-  pred_row<NP>(e.a, zero5, r, 0.0, e.xhat, NP, hs, pxs);             // iterMPC.m:33
-  double err[NP], F[NC], E[NC * NC], LU[NC * NC], DU[NC], x[NC];
+  // The stacked constraint matrix M (constraintsMPC.m:99) is never stored: the current rows are +-1 / +-0 patterns
+  // (:23-42) and every row of the voltage / eta / SOC blocks is a window [h(i-1) ... h(i-Nc)] of that output's impulse
+  // response (:47-53,68-75,92-99), so three tables of Np entries stand for all of it -- 15 registers instead of 46 for M
+  // plus 23 for gamma, which waits in the K slots of shared memory until the QP set-up turns it into K_i.
+  double hs[NP + 1], hv[NP + 1], nhe[NP + 1];                        // h_soc, h_v, -h_eta
+  double F[NC], LU[NC * NC], DU[NC], x[NC];
+  // (K_i, 1/H_ii) as 16-byte pairs, re-read from shared memory every sweep (keeps them out of registers).  Row i lives
+  // in scratch slots 2i and 2i+1, but inside the slots a WARP's 64 doubles are dealt out as 32 pairs: lanes
+  // 0-15 take slot 2i, lanes 16-31 slot 2i+1, each the two columns 2(l mod 16), +1 of its own warp.  A warp therefore
+  // still touches only its own columns (other warps may be in another phase of the instant and use theirs as scratch),
+  // every quarter-warp reads 128 contiguous bytes, and the region starts 16-byte aligned (the bank blob is padded).
+  const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
+  const unsigned kra = (unsigned)__cvta_generic_to_shared(smt - threadIdx.x) + ((lane >> 4) * (unsigned)sms + wbase + 2u * (lane & 15u)) * 8u;
+  const unsigned krs = (unsigned)sms * 16u;
+  // row i of M from the tables (i is a compile-time constant: every entry is a register or an immediate)
+  auto mrow = [&](auto ic, double (&Mi)[NC]) {
+    constexpr int i = decltype(ic)::value;
 #pragma unroll
-  for (int i = 1; i <= NP; ++i) err[i - 1] = d.ref - (pxs[i - 1] + hs[i] * uk_1);
-#pragma unroll
-  for (int j = 0; j < NC; ++j) {                                     // iterMPC.m:38
-    double acc = 0.0;
-#pragma unroll
-    for (int i = 1; i <= NP; ++i) {
-      const double g = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0;
-      const double t = g * err[i - 1];
-      acc = (i == 1) ? t : acc + t;
+    for (int j = 0; j < NC; ++j) {
+      if constexpr (FS::UC && i < 2 * NC) {                          // [Cu; -Cu], Cu lower-triangular ones (:23-32)
+        constexpr int s = i / NC, q = i % NC;
+        Mi[j] = (j <= q) ? (s ? -1.0 : 1.0) : (s ? -0.0 : 0.0);
+      } else if constexpr (FS::UC && i < 4 * NC) {                   // [I; -I] (:33-42)
+        constexpr int s = (i - 2 * NC) / NC, q = (i - 2 * NC) % NC;
+        Mi[j] = (j == q) ? (s ? -1.0 : 1.0) : (s ? -0.0 : 0.0);
+      } else if constexpr (FS::UV && i >= FS::O_V && i < FS::O_E) {
+        constexpr int q = i - FS::O_V;
+        Mi[j] = (q - j >= 0) ? hv[q - j >= 0 ? q - j : 0] : 0.0;
+      } else if constexpr (FS::UE && i >= FS::O_E && i < FS::O_Z) {
+        constexpr int q = i - FS::O_E;
+        Mi[j] = (q - j >= 0) ? nhe[q - j >= 0 ? q - j : 0] : -0.0;
+      } else {
+        constexpr int q = i - FS::O_Z;
+        Mi[j] = (q - j >= 0) ? hs[q - j >= 0 ? q - j : 0] : 0.0;
+      }
     }
-    F[j] = -2.0 * acc;
-  }
-  double nf = F[0] * F[0];
+  };
+  bool viol = false;                                                 // iterMPC.m:66 (Q8)
+  {
+    const double zero5[N5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double pxs[NP], err[NP], E[NC * NC];
+    pred_row<NP>(e.a, zero5, r, 0.0, e.xhat, NP, hs, pxs);           // iterMPC.m:33
 #pragma unroll
-  for (int j = 1; j < NC; ++j) nf = nf + F[j] * F[j];
-  const double Ru = sqrt(nf) / ((2.0 * c.f(S_DUMAX)) * sqrt((double)NC)) - d.sigmin;   // iterMPC.m:43 (Q10)
+    for (int i = 1; i <= NP; ++i) err[i - 1] = d.ref - (pxs[i - 1] + hs[i] * uk_1);
 #pragma unroll
-  for (int j = 0; j < NC; ++j)
-#pragma unroll
-    for (int l = 0; l < NC; ++l) {
+    for (int j = 0; j < NC; ++j) {                                   // iterMPC.m:38
       double acc = 0.0;
 #pragma unroll
       for (int i = 1; i <= NP; ++i) {
-        const double gj = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0, gl = (i - 1 - l >= 0) ? hs[i - 1 - l] : 0.0;
-        const double t = gj * gl;
+        const double g = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0;
+        const double t = g * err[i - 1];
         acc = (i == 1) ? t : acc + t;
       }
-      E[j * NC + l] = 2.0 * (acc + ((j == l) ? Ru : 0.0));           // iterMPC.m:47
+      F[j] = -2.0 * acc;
     }
-  spd_factor<NC>(NC, E, LU);
-  spd_solve<NC>(NC, LU, F, x);
+    double nf = F[0] * F[0];
 #pragma unroll
-  for (int j = 0; j < NC; ++j) DU[j] = -x[j];                        // iterMPC.m:48
-  // ---- constraintsMPC.m rows, static indices ----
-  double Mm[nC][NC], gam[nC];
-  if (FS::UC) {                                                      // constraintsMPC.m:23-42
-    const double umax = c.f(S_UMAX), umin = c.f(S_UMIN), dumax = c.f(S_DUMAX), dumin = c.f(S_DUMIN);
+    for (int j = 1; j < NC; ++j) nf = nf + F[j] * F[j];
+    const double Ru = sqrt(nf) / ((2.0 * c.f(S_DUMAX)) * sqrt((double)NC)) - d.sigmin;   // iterMPC.m:43 (Q10)
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int j = 0; j < NC; ++j)
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
+      for (int l = 0; l < NC; ++l) {
+        double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < NC; ++j) Mm[s * NC + i][j] = (j <= i) ? (s ? -1.0 : 1.0) : (s ? -0.0 : 0.0);
-        gam[s * NC + i] = s ? -(umin - uk_1) : (umax - uk_1);
+        for (int i = 1; i <= NP; ++i) {
+          const double gj = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0, gl = (i - 1 - l >= 0) ? hs[i - 1 - l] : 0.0;
+          const double t = gj * gl;
+          acc = (i == 1) ? t : acc + t;
+        }
+        E[j * NC + l] = 2.0 * (acc + ((j == l) ? Ru : 0.0));         // iterMPC.m:47
       }
+    spd_factor<NC>(NC, E, LU);
+    spd_solve<NC>(NC, LU, F, x);
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int j = 0; j < NC; ++j) DU[j] = -x[j];                      // iterMPC.m:48
+    // ---- constraintsMPC.m: gamma row by row; each row is tested against the unconstrained DU at once (iterMPC.m:66) and
+    //      its gamma parked in the row's K slot ----
+    auto park = [&](auto ic, double gam) {
+      constexpr int i = decltype(ic)::value;
+      double Mi[NC];
+      mrow(ic, Mi);
+      double acc = Mi[0] * DU[0];
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
-#pragma unroll
-        for (int j = 0; j < NC; ++j) Mm[2 * NC + s * NC + i][j] = (j == i) ? (s ? -1.0 : 1.0) : (s ? -0.0 : 0.0);
-        gam[2 * NC + s * NC + i] = s ? -dumin : dumax;
-      }
-  }
-  if (FS::UV) {                                                      // constraintsMPC.m:45-63
-    double hv[NP + 1], pxv[NP];
-    pred_row<NP>(e.a, e.Cv, 0.0, e.Dv, e.xhat, NP, hv, pxv);
-    const double vmax = c.f(S_VMAX);
-#pragma unroll
-    for (int i = 1; i <= NP; ++i) {
-#pragma unroll
-      for (int j = 0; j < NC; ++j) Mm[FS::O_V + i - 1][j] = (i - 1 - j >= 0) ? hv[i - 1 - j] : 0.0;
-      gam[FS::O_V + i - 1] = vmax - ((pxv[i - 1] + hv[i] * uk_1) + e.bv);
+      for (int j = 1; j < NC; ++j) acc = fma(Mi[j], DU[j], acc);
+      if (acc - gam > 0.0) viol = true;
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(kra + (unsigned)i * krs), "d"(gam) : "memory");
+    };
+    if constexpr (FS::UC) {                                          // constraintsMPC.m:23-42
+      const double umax = c.f(S_UMAX), umin = c.f(S_UMIN), dumax = c.f(S_DUMAX), dumin = c.f(S_DUMIN);
+      static_for<0, 4 * NC>([&](auto ic) {
+        constexpr int blk = decltype(ic)::value / NC;
+        park(ic, blk == 0 ? (umax - uk_1) : (blk == 1 ? -(umin - uk_1) : (blk == 2 ? dumax : -dumin)));
+      });
     }
-  }
-  if (FS::UE) {                                                      // constraintsMPC.m:66-85
-    double he[NP + 1], pxe[NP];
-    pred_row<NP>(e.a, e.Cphi, 0.0, e.Dphi, e.xhat, NP, he, pxe);
-    const double pmin = c.f(S_PHIMIN);
-#pragma unroll
-    for (int i = 1; i <= NP; ++i) {
-#pragma unroll
-      for (int j = 0; j < NC; ++j) Mm[FS::O_E + i - 1][j] = (i - 1 - j >= 0) ? -he[i - 1 - j] : -0.0;
-      gam[FS::O_E + i - 1] = -pmin + ((pxe[i - 1] + he[i] * uk_1) + e.bphi);
+    if constexpr (FS::UV) {                                          // constraintsMPC.m:45-63
+      double pxv[NP];
+      pred_row<NP>(e.a, e.Cv, 0.0, e.Dv, e.xhat, NP, hv, pxv);
+      const double vmax = c.f(S_VMAX);
+      static_for<0, NP>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        park(std::integral_constant<int, FS::O_V + q>{}, vmax - ((pxv[q] + hv[q + 1] * uk_1) + e.bv));
+      });
     }
-  }
-  if (FS::UZ) {                                                      // constraintsMPC.m:89-101
-    const double zmax = c.f(S_ZMAX);
+    if constexpr (FS::UE) {                                          // constraintsMPC.m:66-85
+      double he[NP + 1], pxe[NP];
+      pred_row<NP>(e.a, e.Cphi, 0.0, e.Dphi, e.xhat, NP, he, pxe);
+      const double pmin = c.f(S_PHIMIN);
 #pragma unroll
-    for (int i = 1; i <= NP; ++i) {
-#pragma unroll
-      for (int j = 0; j < NC; ++j) Mm[FS::O_Z + i - 1][j] = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0;
-      gam[FS::O_Z + i - 1] = zmax - ((pxs[i - 1] + hs[i] * uk_1) + e.soc);
+      for (int i = 0; i <= NP; ++i) nhe[i] = -he[i];
+      static_for<0, NP>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        park(std::integral_constant<int, FS::O_E + q>{}, -pmin + ((pxe[q] + he[q + 1] * uk_1) + e.bphi));
+      });
     }
-  }
-  bool viol = false;                                                 // iterMPC.m:66 (Q8)
-#pragma unroll
-  for (int i = 0; i < nC; ++i) {
-    double acc = Mm[i][0] * DU[0];
-#pragma unroll
-    for (int j = 1; j < NC; ++j) acc = fma(Mm[i][j], DU[j], acc);
-    if (acc - gam[i] > 0.0) viol = true;
+    if constexpr (FS::UZ) {                                          // constraintsMPC.m:89-101
+      const double zmax = c.f(S_ZMAX);
+      static_for<0, NP>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        park(std::integral_constant<int, FS::O_Z + q>{}, zmax - ((pxs[q] + hs[q + 1] * uk_1) + e.soc));
+      });
+    }
   }
   o.nexec = 0;
 #pragma unroll
@@ -1406,36 +1459,31 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
     unsigned zmask = 0u;
     bool pfin = true;                                                // every entry of E\M' is finite
-    // (K_i, 1/H_ii) as 16-byte pairs, re-read from shared memory every sweep (keeps them out of registers).  Row i lives
-    // in scratch slots 2i and 2i+1 as before, but inside the slots a WARP's 64 doubles are dealt out as 32 pairs: lanes
-    // 0-15 take slot 2i, lanes 16-31 slot 2i+1, each the two columns 2(l mod 16), +1 of its own warp.  A warp therefore
-    // still touches only its own columns (other warps may be in another phase of the instant and use theirs as scratch),
-    // every quarter-warp reads 128 contiguous bytes, and the region starts 16-byte aligned (the bank blob is padded).
-    const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
-    const unsigned kra = (unsigned)__cvta_generic_to_shared(smt - threadIdx.x) + ((lane >> 4) * (unsigned)sms + wbase + 2u * (lane & 15u)) * 8u;
-    const unsigned krs = (unsigned)sms * 16u;
-#pragma unroll
-    for (int i = 0; i < nC; ++i) {
-      double P[NC];
+    static_for<0, nC>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      double Mi[NC], P[NC];
+      mrow(ic, Mi);
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
-        double acc = Ei[j][0] * Mm[i][0];
+        double acc = Ei[j][0] * Mi[0];
 #pragma unroll
-        for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
+        for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mi[l], acc);
         P[j] = acc;
         pfin = pfin && is_finite(acc);
       }
-      double hd = Mm[i][0] * P[0], k = Mm[i][0] * x[0];
+      double hd = Mi[0] * P[0], k = Mi[0] * x[0];
 #pragma unroll
-      for (int j = 1; j < NC; ++j) { hd = fma(Mm[i][j], P[j], hd); k = fma(Mm[i][j], x[j], k); }
-      sts_pair(kra + (unsigned)i * krs, k + gam[i], rcp_d(hd));      // K(i), 1/H(i,i)
+      for (int j = 1; j < NC; ++j) { hd = fma(Mi[j], P[j], hd); k = fma(Mi[j], x[j], k); }
+      double gam;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(gam) : "r"(kra + (unsigned)i * krs) : "memory");
+      sts_pair(kra + (unsigned)i * krs, k + gam, rcp_d(hd));         // K(i), 1/H(i,i)
       if (hd == 0.0) {
         zmask |= 1u << i;
       } else {
 #pragma unroll
         for (int j = 0; j < NC; ++j) v[j] = fma(P[j], lam[i], v[j]);
       }
-    }
+    });
     // rows whose lambda is non-finite (only all-zero rows can get there): while any is set every row product is NaN
     unsigned pmask = 0u;
 #pragma unroll
@@ -1457,68 +1505,48 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     if (lean) {
       bool first_nc = false;
       if (FS::UZ) { first_nc = !(lam[FS::O_Z] < 1e-6); lam[FS::O_Z] = 0.0; }
-      // One row of hildreth.m:34-37.  APPLY = false: evaluate only (no state is written) and report whether lambda_i
-      // would move.
-      auto row = [&](const int i, const bool APPLY, bool& flag) {
-        double Ki, rHi;
-        lds_pair(kra + (unsigned)i * krs, Ki, rHi);
-        const double li = lam[i];
-        double hl = Mm[i][0] * v[0];
-#pragma unroll
-        for (int j = 1; j < NC; ++j) hl = fma(Mm[i][j], v[j], hl);
-        const double w = fma(-(Ki + hl), rHi, li);
-        const double nl = pos_or_zero(w);                            // max(0,w); max(0,NaN) = 0
-        const double dl = nl - li;
-        if (!APPLY) { flag = flag || (dl != 0.0); return; }
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
-          double acc = Ei[j][0] * Mm[i][0];
-#pragma unroll
-          for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
-          v[j] = fma(acc, dl, v[j]);
-        }
-        lam[i] = nl;
-        flag = flag || !(fabs(dl) < 1e-6);                           // hildreth.m:39
-      };
-      // Row groups (the constraint blocks of constraintsMPC.m), LEAN_GROUPS = 1 only.  Most rows are inactive most of the time: lambda_i = 0 and
-      // w <= 0, so the update leaves lambda_i and v exactly as they were (v + P*0 = v for finite P; v is never -0).  A
-      // group is therefore first evaluated row by row from the SAME v -- independent chains instead of one chain through
-      // v -- and only if some lane of the warp finds a row that would move is it run again in sequence, exactly as
-      // written in the reference.  If no row moves the sequential pass would have seen the same v in every row, computed
-      // the same w and changed nothing: skipping it is exact.
-      auto group = [&](auto a_c, auto b_c, bool& notconv) {       // rows [A, B) of M, compile-time bounds
-        constexpr int A = decltype(a_c)::value, B = decltype(b_c)::value;
-        if (A == B) return;
-#if LEAN_GROUPS
-        bool moves = !pfin;
-#pragma unroll
-        for (int i = A; i < B; ++i)
-          if (!(FS::UZ && i == FS::O_Z)) row(i, false, moves);
-        if (!__any_sync(__activemask(), moves)) return;
-#endif
-#pragma unroll
-        for (int i = A; i < B; ++i)
-          if (!(FS::UZ && i == FS::O_Z)) row(i, true, notconv);
-      };
-      using std::integral_constant;
       for (; k <= d.maxHild; ++k) {                                  // hildreth.m:32
         bool notconv = (k == 1) && first_nc;
-        group(integral_constant<int, 0>{}, integral_constant<int, (FS::UC ? 2 * NC : 0)>{}, notconv);            // u_max, u_min
-        group(integral_constant<int, (FS::UC ? 2 * NC : 0)>{}, integral_constant<int, FS::O_V>{}, notconv);      // du_max, du_min
-        group(integral_constant<int, FS::O_V>{}, integral_constant<int, FS::O_E>{}, notconv);                    // voltage
-        group(integral_constant<int, FS::O_E>{}, integral_constant<int, FS::O_Z>{}, notconv);                    // eta
-        group(integral_constant<int, FS::O_Z>{}, integral_constant<int, nC>{}, notconv);                         // z_max
+        opaque(Ei);
+        static_for<0, nC>([&](auto ic) {                             // hildreth.m:34-37
+          constexpr int i = decltype(ic)::value;
+          if constexpr (!(FS::UZ && i == FS::O_Z)) {
+            double Mi[NC];
+            mrow(ic, Mi);
+            double Ki, rHi;
+            lds_pair(kra + (unsigned)i * krs, Ki, rHi);
+            const double li = lam[i];
+            double hl = Mi[0] * v[0];
+#pragma unroll
+            for (int j = 1; j < NC; ++j) hl = fma(Mi[j], v[j], hl);
+            const double w = fma(-(Ki + hl), rHi, li);
+            const double nl = pos_or_zero(w);                        // max(0,w); max(0,NaN) = 0
+            const double dl = nl - li;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+              double acc = Ei[j][0] * Mi[0];
+#pragma unroll
+              for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mi[l], acc);
+              v[j] = fma(acc, dl, v[j]);
+            }
+            lam[i] = nl;
+            notconv = notconv || !(fabs(dl) < 1e-6);                 // hildreth.m:39
+          }
+        });
         if (!notconv) break;
       }
     } else
     for (; k <= d.maxHild; ++k) {                                    // hildreth.m:32
       bool notconv = false;
-#pragma unroll
-      for (int i = 0; i < nC; ++i) {                                 // hildreth.m:34-37, branch-free
+      opaque(Ei);
+      static_for<0, nC>([&](auto ic) {                               // hildreth.m:34-37, branch-free
+        constexpr int i = decltype(ic)::value;
+        double Mi[NC];
+        mrow(ic, Mi);
         const double li = lam[i];
-        double hl = Mm[i][0] * v[0];
+        double hl = Mi[0] * v[0];
 #pragma unroll
-        for (int j = 1; j < NC; ++j) hl = fma(Mm[i][j], v[j], hl);
+        for (int j = 1; j < NC; ++j) hl = fma(Mi[j], v[j], hl);
         double Kg, rHg;
         lds_pair(kra + (unsigned)i * krs, Kg, rHg);
         double w = fma(-(Kg + hl), rHg, li);
@@ -1529,26 +1557,30 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
         const double pd = zr ? 0.0 : dl;                             // an all-zero row never touches v
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-          double acc = Ei[j][0] * Mm[i][0];
+          double acc = Ei[j][0] * Mi[0];
 #pragma unroll
-          for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mm[i][l], acc);
+          for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mi[l], acc);
           v[j] = fma(acc, pd, v[j]);
         }
         pmask = (zr && !(nl <= kDblMax)) ? (pmask | (1u << i)) : (pmask & ~(1u << i));
         lam[i] = nl;
         if (!(fabs(dl) < 1e-6)) notconv = true;                      // hildreth.m:39 norm(.,Inf) < 1e-6, NaN-propagating
-      }
+      });
       if (!notconv) break;
     }
     if (k > d.maxHild) k = d.maxHild;
     double rhs[NC];
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {                                   // hildreth.m:46
-      double acc = Mm[0][j] * lam[0];
+    for (int j = 0; j < NC; ++j) rhs[j] = 0.0;
+    static_for<0, nC>([&](auto ic) {                                 // hildreth.m:46  M'*lambda, rows in order
+      constexpr int i = decltype(ic)::value;
+      double Mi[NC];
+      mrow(ic, Mi);
 #pragma unroll
-      for (int i = 1; i < nC; ++i) acc = fma(Mm[i][j], lam[i], acc);
-      rhs[j] = F[j] + acc;
-    }
+      for (int j = 0; j < NC; ++j) rhs[j] = (i == 0) ? Mi[j] * lam[i] : fma(Mi[j], lam[i], rhs[j]);
+    });
+#pragma unroll
+    for (int j = 0; j < NC; ++j) rhs[j] = F[j] + rhs[j];
     spd_solve<NC>(NC, LU, rhs, x);
 #pragma unroll
     for (int j = 0; j < NC; ++j) DU[j] = -x[j];

@@ -21,15 +21,20 @@
 #ifndef MEK_REGROUP_DEFAULT
 #define MEK_REGROUP_DEFAULT 128  // sample instants between regroupings of a heterogeneous population (mek_config.regroup_every == 0)
 #endif
+#ifndef MEK_SPLIT_MIN_CELLS
+#define MEK_SPLIT_MIN_CELLS (1ll << 60)   // mek_config.split_phases == 0: populations at least this large run the phase-split form
+#endif
+#ifndef MEK_SPLIT_EST_THREADS
+#define MEK_SPLIT_EST_THREADS 256
+#endif
+#ifndef MEK_SPLIT_MPC_THREADS
+#define MEK_SPLIT_MPC_THREADS 256
+#endif
 #ifndef MEK_DEFER_DEFAULT
 #define MEK_DEFER_DEFAULT 16     // sample instants per deferral block when mek_config.defer_block == 0
 #endif
 
 using namespace mek;
-
-#ifndef MEK_STREAM_BATCH
-#define MEK_STREAM_BATCH 2   // models whose loads are in flight per thread in the HBM stream
-#endif
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -214,178 +219,9 @@ extern "C" int mek_bank_dims(const mek_bank* b, int* n, int* nz, int* nT, int* n
 }
 extern "C" double mek_bank_capacity_Ah(const mek_bank* b) { return b ? b->params[P_Q] : NAN; }
 
-// ------------------------------------------------------------------------------------------
-// kernel parameters
-// ------------------------------------------------------------------------------------------
-struct Params {
-  Dims d;
-  double cp[N_PARAMS];        // cellData closed-form parameters
-  double* st;                 // SoA state block [nfields][ld]
-  const double* bank_blob;    // hot bank in global memory (source of the TMA bulk copy)
-  int blob_doubles, off_mdl;
-  // full bank (function-level zk output only)
-  const double* Cfull;        // [M][nz][6]
-  const double* Dfull;        // [M][nz]
-  // inputs staged on the device (mek_pop_init / mek_pop_reset)
-  const double* in_soc0; const double* in_ekf; const double* in_T; const double* in_sigx0; const double* in_lim;
-  // trajectory logs [step][nlog]
-  long long nlog; int log_steps;
-  double* log_u; double* log_V; double* log_soc; double* log_phise;
-  unsigned char* log_iT; unsigned char* log_iZ; unsigned short* log_nexec; unsigned* log_active; int log_words;
-  int sync_steps;             // 1: CTA-wide barrier before every sample instant
-  int defer_k;                // > 0: sample instants per deferral block (models outside a cell's hot set are advanced once per block); 0: off
-  int defer_stagger;          // 1: the warps of a CTA start their blocks at different instants (spreads the block-end HBM bursts)
-  double* wide_ws;            // long-horizon instance: per-CTA workspace [WSLOTS][threads] for tables, K, 1/H (null: shared memory)
-  int defer_narrow;           // test hook: hot set = the EKF estimate's neighbours only, no margin
-  int hist_off;               // doubles from the start of dynamic shared memory to the history columns [defer_k + 1][threads]
-  const int* slot2cell;       // state slot -> caller's cell index (cells are ordered by initial SOC inside the block), or null
-};
-
-__device__ __forceinline__ long long cell_id(const Params& P, long long slot) { return P.slot2cell ? (long long)P.slot2cell[slot] : slot; }
-
-// ---- TMA bulk copy of the hot bank into shared memory ----
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void stage_bank(double* sm, const Params& P, BankSmem& bk) {
-  __shared__ __align__(8) unsigned long long mbar;
-  const unsigned bytes = (unsigned)P.blob_doubles * 8u;
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
-    unsigned done = 0;
-    while (done < bytes) {                                   // chunks keep each bulk request modest
-      const unsigned chunk = (bytes - done) < 32768u ? (bytes - done) : 32768u;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_u32(reinterpret_cast<char*>(sm) + done)),
-                   "l"(reinterpret_cast<const char*>(P.bank_blob) + done), "r"(chunk), "r"(smem_u32(&mbar))
-                   : "memory");
-      done += chunk;
-    }
-  }
-  unsigned ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(&mbar)), "r"(0u)
-        : "memory");
-  }
-  bk.Tpts = sm;
-  bk.Zpts = sm + P.d.nT;
-  bk.mdl = sm + P.off_mdl;
-}
-
-// ---- one pass of the loop body runMPC.m:83-112 for one cell ----
-struct StepLog {
-  double u, V, soc, phise;
-  int iT, iZ, nexec;
-  unsigned active[4];
-};
-
-template <int NPM, int NCM, int CONS, int BATCH>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
-__device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms, int tt,
-                                          Defer* df) {
-  const Dims& d = P.d;
-  lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
-#pragma unroll
-  for (int w = 0; w < 4; ++w) lg.active[w] = 0u;
-  if ((unsigned)c.f(S_STATUS) & ST_LOST) return;                     // Q19: a lost cell idles
-  const double uk = c.f(S_UK);
-  if (!df) prefetch_models(d, c, 0, 6, true, true);                  // first rows of this instant's HBM stream -> L2 while the plant outputs are computed
-  const double V = plant_step<false>(d, bk, P.cp, c, uk, tt, df);    // runMPC.m:85 (outputs; the state advance is fused below)
-  // OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}: one HBM pass over all M local models, or (deferral
-  // on) over the cell's hot models only -- the rest catch up at the end of the block
-  if (df) defer_stream(d, bk, c, *df, uk, c.f(S_PRIORI));
-  else stream_models<true, true, BATCH>(d, bk, c, uk, c.f(S_PRIORI));
-  EkfOut e;
-  ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms}, tt, df);  // runMPC.m:88,92
-  if (e.lost) return;
-  MpcOut o;
-  if constexpr (CONS >= 0 && NPM == 5 && NCM == 2) mpc_step_fast<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, smt, sms);   // runMPC.m:94-103
-  else if constexpr (CONS >= 0) {
-    using WS = WideShape<NPM, NCM, CONS>;
-    // lambda column in shared memory; tables, K, 1/H in this CTA's slice of the L2-resident workspace, or (small CTAs) in shared memory too
-    double* lc = P.wide_ws ? smt : smt + WS::WSLOTS * sms;
-    double* wc = P.wide_ws ? P.wide_ws + (long long)blockIdx.x * WS::WSLOTS * sms + threadIdx.x : smt;
-    mpc_step_wide<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, lc, sms, wc, sms);
-  }
-  else mpc_step<NPM, NCM>(d, P.cp, c, e, uk, o);
-  lg.u = o.u; lg.V = V; lg.soc = e.soc; lg.phise = o.phise;          // runMPC.m:106-109
-  lg.iT = e.iT + 1; lg.iZ = e.iZ + 1; lg.nexec = o.nexec;
-#pragma unroll
-  for (int w = 0; w < 4; ++w) lg.active[w] = o.active[w];
-}
-
-__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
-  const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v), hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-  return ((unsigned long long)hi << 32) | lo;
-}
-
-// ---- k_run_population: the fused persistent kernel ----
-template <int NPM, int NCM, int CONS, int THREADS, int MINB>   // THREADS/MINB: launch bounds (register cap)
-__global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_constant__ Params P, int k0, int k1) {
-  extern __shared__ __align__(16) double sm[];
-  BankSmem bk;
-  stage_bank(sm, P, bk);
-  double* smt = sm + P.blob_doubles + threadIdx.x;   // this thread's column of the per-thread shared arrays
-  constexpr int sms = THREADS;                       // launched with exactly THREADS threads per CTA
-  const Dims& d = P.d;
-  const long long stride = (long long)gridDim.x * THREADS;
-  const long long first = (long long)blockIdx.x * THREADS;
-  const int KB = P.defer_k;                          // 0: every model is advanced every instant
-  Defer df{0ull, 0ull, 0, sm + P.hist_off + threadIdx.x, THREADS};
-  // block boundaries of this warp: instants with (k - k0 + off) % KB == 0 (and k0 itself)
-  const int off = (KB > 0 && P.defer_stagger) ? (int)(((threadIdx.x >> 5) * KB) / (THREADS / 32)) : 0;
-  // every thread of the CTA walks the same number of rounds so that the optional per-instant barrier is legal
-  for (long long base = first; base < d.B; base += stride) {
-    const long long cell = base + threadIdx.x;
-    const bool active = cell < d.B;
-    Cell c = cell_ref(P.st, d, active ? cell : 0);
-    // the cell temperature is constant over a run: its two nearest set-points are looked up once (same rule as every step)
-    const int tt = active ? two_nearest(c.f(S_TC) + 273.15, bk.Tpts, d.nT) : 0;
-    const long long id = active ? cell_id(P, cell) : 0;   // the caller's index of this cell (logs are addressed by it)
-#pragma unroll 1
-    for (int k = k0; k < k1; ++k) {
-      if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
-      if (KB > 0 && (k == k0 || (k - k0 + off) % KB == 0)) {           // warp-uniform: start of a deferral block
-        if (k != k0 && active) defer_flush(d, bk, c, df);
-        const bool run = active && !((unsigned)c.f(S_STATUS) & ST_LOST);
-        int left = KB - (k - k0 + off) % KB;
-        df.hot = warp_or64(run ? defer_hot_set(d, bk, P.cp, c, tt, left, P.defer_narrow) : 0ull);
-        df.mine = 0ull;
-        df.n = 0;
-        if (run) df.h[0] = c.f(S_PRIORI);
-      }
-      if (!active) continue;
-      StepLog lg;
-      cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt, KB > 0 ? &df : nullptr);
-      // per-cell summary, kept in the state header (not in registers: they are the scarce resource of this kernel)
-      if (lg.nexec > 0) {
-        c.f(S_SUM_NEXEC) += (double)lg.nexec;
-        c.f(S_N_QP) += 1.0;
-        if (lg.nexec >= d.maxHild) c.f(S_N_CAP) += 1.0;
-      }
-      c.f(S_MIN_PHISE) = fmin(c.f(S_MIN_PHISE), lg.phise);
-      c.f(S_MAX_V) = fmax(c.f(S_MAX_V), lg.V);
-      if (c.f(S_T_REACH) < 0.0 && lg.soc >= c.f(S_ZMAX) - 1e-3) c.f(S_T_REACH) = (double)k;
-      c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
-      if (id < P.nlog && k < P.log_steps) {
-        const long long o = (long long)k * P.nlog + id;
-        P.log_u[o] = lg.u; P.log_V[o] = lg.V; P.log_soc[o] = lg.soc; P.log_phise[o] = lg.phise;
-        P.log_iT[o] = (unsigned char)lg.iT; P.log_iZ[o] = (unsigned char)lg.iZ; P.log_nexec[o] = (unsigned short)lg.nexec;
-        for (int w = 0; w < P.log_words; ++w) P.log_active[o * P.log_words + w] = lg.active[w];
-      }
-    }
-    if (KB > 0 && active && k1 > k0) defer_flush(d, bk, c, df);      // the state block leaves the kernel fully advanced
-    if (active) c.f(S_STEPS) += (double)(k1 - k0);
-  }
-}
+#include "mek_kernels.cuh"
+#include "mek_split.cuh"
+#include "mek_entry.h"
 
 // ---- initialisation: initKF.m:37-133, initMPC.m:32-72, OB_step.m:63-71 and the first I = 0 call (runMPC.m:72-74) ----
 __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params P) {
@@ -939,6 +775,12 @@ struct mek_pop {
   void* d_cubtmp; size_t cubtmp_bytes;
   int64_t regroups;
   int since_regroup;           // sample instants run since the last regrouping (or the initialisation): kept across mek_run calls
+  // phase-split form of the loop (mek_split.cuh): two launches per sample instant over all cells
+  bool split;
+  SplitArgs S;
+  int est_threads, mpc_threads, est_grid, mpc_grid, blk_grid;
+  size_t est_smem, mpc_smem, blk_smem;
+  const void *fn_run, *fn_est, *fn_mpc, *fn_blk;   // kernel entry points in use (mek_entry.h)
 };
 
 static double sigma_min_gtg(int Np, int Nc, double r) {
@@ -988,6 +830,77 @@ static int grid_for(const mek_pop* p, long long B, int threads) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
+}
+
+// ---- phase-split form (mek_split.cuh) ----
+static int launch_kernel(const void* fn, int grid, int threads, size_t smem, cudaStream_t st, void** args) {
+  CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)threads), args, smem, st));
+  return MEK_OK;
+}
+static int prep_fn(const void* fn, int threads, size_t smem, int* occ) {
+  if (!fn) return fail(MEK_ERR_UNSUPPORTED, "kernel instance not built");
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fn, threads, smem));
+  return MEK_OK;
+}
+
+static int split_prepare(mek_pop* p, const mek_config* cfg) {
+  const Dims& d = p->P.d;
+  auto pick = [](int want, int dflt) { return (want == 256 || want == 384 || want == 512) ? want : dflt; };
+  p->est_threads = pick(cfg->split_threads_est, MEK_SPLIT_EST_THREADS);
+  p->mpc_threads = pick(cfg->split_threads_mpc, MEK_SPLIT_MPC_THREADS);
+  const int mslots = p->cons == 15 ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
+  p->est_smem = p->blob_bytes + sizeof(double) * (size_t)sc_slots(d.R) * (size_t)p->est_threads;
+  p->mpc_smem = sizeof(double) * (size_t)mslots * (size_t)p->mpc_threads;
+  p->blk_smem = p->blob_bytes + sizeof(double) * (size_t)(p->P.defer_k + 1) * (size_t)SPLIT_BLK_THREADS;
+  if (p->est_smem > 227 * 1024 || p->mpc_smem > 227 * 1024 || p->blk_smem > 227 * 1024) return MEK_OK;   // stays on the fused kernel
+  int rc = MEK_OK, occ_e = 0, occ_m = 0, occ_b = 0;
+  p->fn_est = mek_split_est_kernel(p->est_threads);
+  p->fn_mpc = mek_split_mpc_kernel(p->cons, p->mpc_threads);
+  p->fn_blk = mek_split_block_kernel();
+  if ((rc = prep_fn(p->fn_est, p->est_threads, p->est_smem, &occ_e)) != MEK_OK) return rc;
+  if ((rc = prep_fn(p->fn_mpc, p->mpc_threads, p->mpc_smem, &occ_m)) != MEK_OK) return rc;
+  if ((rc = prep_fn(p->fn_blk, SPLIT_BLK_THREADS, p->blk_smem, &occ_b)) != MEK_OK) return rc;
+  auto grid = [&](int occ, int threads) {
+    long long need = (d.ld + threads - 1) / threads, cap = (long long)p->sms * (occ < 1 ? 1 : occ);
+    return (int)(need < cap ? need : cap);
+  };
+  p->est_grid = grid(occ_e, p->est_threads);
+  p->mpc_grid = grid(occ_m, p->mpc_threads);
+  p->blk_grid = grid(occ_b, SPLIT_BLK_THREADS);
+  p->S.xfields = split_xfields(p->P.defer_k);
+  const size_t ntiles = (size_t)(d.ld / TILE);
+  CUDA_TRY(cudaMalloc(&p->S.xt, sizeof(double) * ntiles * (size_t)p->S.xfields * TILE));
+  CUDA_TRY(cudaMemset(p->S.xt, 0, sizeof(double) * ntiles * (size_t)p->S.xfields * TILE));
+  CUDA_TRY(cudaMalloc(&p->S.tile_hot, sizeof(unsigned long long) * ntiles));
+  CUDA_TRY(cudaMemset(p->S.tile_hot, 0, sizeof(unsigned long long) * ntiles));
+  p->split = true;
+  return MEK_OK;
+}
+
+// sample instants [k0, k1) as two launches per instant plus one per deferral-block boundary
+static int split_segment(mek_pop* p, int k0, int k1) {
+  if (k1 <= k0) return MEK_OK;
+  int KB = p->P.defer_k, zero = 0, one = 1, k = k0, rc;
+  void* a_begin[] = {&p->P, &p->S, &zero, &KB};
+  void* a_next[] = {&p->P, &p->S, &one, &KB};
+  void* a_end[] = {&p->P, &p->S, &one, &zero};
+  void* a_est[] = {&p->P, &p->S};
+  void* a_mpc[] = {&p->P, &p->S, &k};
+  if ((rc = launch_kernel(p->fn_blk, p->blk_grid, SPLIT_BLK_THREADS, p->blk_smem, p->stream, a_begin)) != MEK_OK) return rc;
+  p->launches++;
+  for (k = k0; k < k1; ++k) {
+    if (k != k0 && (k - k0) % KB == 0) {
+      if ((rc = launch_kernel(p->fn_blk, p->blk_grid, SPLIT_BLK_THREADS, p->blk_smem, p->stream, a_next)) != MEK_OK) return rc;
+      p->launches++;
+    }
+    if ((rc = launch_kernel(p->fn_est, p->est_grid, p->est_threads, p->est_smem, p->stream, a_est)) != MEK_OK) return rc;
+    if ((rc = launch_kernel(p->fn_mpc, p->mpc_grid, p->mpc_threads, p->mpc_smem, p->stream, a_mpc)) != MEK_OK) return rc;
+    p->launches += 2;
+  }
+  if ((rc = launch_kernel(p->fn_blk, p->blk_grid, SPLIT_BLK_THREADS, p->blk_smem, p->stream, a_end)) != MEK_OK) return rc;
+  p->launches++;
+  return MEK_OK;
 }
 
 extern "C" void mek_pop_destroy(mek_pop* p);
@@ -1129,21 +1042,10 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
     p->P.hist_off = (int)(p->run_smem / sizeof(double));
     if (kb > 0) p->run_smem += sizeof(double) * (size_t)(kb + 1) * (size_t)p->run_threads;
   }
-#define MEK_PREP(KERN)                                                                                          \
-  do {                                                                                                          \
-    rc |= prep_kernel(KERN, p->run_smem);                                                                       \
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, p->run_threads, p->run_smem));           \
-  } while (0)
-  if (p->inst == 1 && p->cons == 15 && p->run_threads == 64) MEK_PREP((k_run_population<20, 5, 15, 64, 1>));
-  else if (p->inst == 1 && p->cons == 15) MEK_PREP((k_run_population<20, 5, 15, 256, 1>));
-  else if (p->cons == 15 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 15, 384, 1>));
-  else if (p->cons == 11 && p->run_threads == 384) MEK_PREP((k_run_population<5, 2, 11, 384, 1>));
-  else if (p->cons == 15) MEK_PREP((k_run_population<5, 2, 15, 256, 1>));
-  else if (p->cons == 11) MEK_PREP((k_run_population<5, 2, 11, 256, 1>));
-  else if (p->inst == 0) MEK_PREP((k_run_population<5, 2, -1, 128, 2>));
-  else if (p->inst == 1) MEK_PREP((k_run_population<20, 5, -1, 128, 2>));
-  else MEK_PREP((k_run_population<32, 8, -1, 128, 2>));
-#undef MEK_PREP
+  if (p->inst == 1 && p->cons == 15) p->fn_run = mek_fused_wide_kernel(p->run_threads);
+  else if (p->cons >= 0) p->fn_run = mek_fused_fast_kernel(p->cons, p->run_threads);
+  else p->fn_run = mek_fused_generic_kernel(p->inst);
+  rc |= prep_fn(p->fn_run, p->run_threads, p->run_smem, &occ);
   if (rc != MEK_OK) { return rc; }
   if (occ < 1) occ = 1;
   if (cfg->blocks_per_sm == 1) occ = 1;
@@ -1153,6 +1055,16 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
     CUDA_TRY(cudaMalloc(&p->d_wide_ws, bytes));
     CUDA_TRY(cudaMemset(p->d_wide_ws, 0, bytes));
     p->P.wide_ws = p->d_wide_ws;
+  }
+  // phase-split form: needs a static-shape short-horizon instance and deferral blocks
+  p->split = false;
+  {
+    int want = cfg->split_phases;
+    if (want == 0) want = (B >= (int64_t)MEK_SPLIT_MIN_CELLS) ? 1 : -1;
+    if (want > 0 && p->inst == 0 && p->cons >= 0 && p->P.defer_k > 0) {
+      int rc2 = split_prepare(p, cfg);
+      if (rc2 != MEK_OK) return rc2;
+    }
   }
   return MEK_OK;
 }
@@ -1183,6 +1095,8 @@ extern "C" void mek_pop_destroy(mek_pop* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->d_slot2cell) cudaFree(p->d_slot2cell);
   if (p->d_wide_ws) cudaFree(p->d_wide_ws);
+  if (p->S.xt) cudaFree(p->S.xt);
+  if (p->S.tile_hot) cudaFree(p->S.tile_hot);
   if (p->d_st2) cudaFree(p->d_st2);
   if (p->d_slot2cell0) cudaFree(p->d_slot2cell0);
   if (p->d_slot2cell2) cudaFree(p->d_slot2cell2);
@@ -1317,16 +1231,11 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 }
 
 static int launch_segment(mek_pop* p, int k0, int k1) {
+  if (p->split) return split_segment(p, k0, k1);
   const int g = grid_for(p, p->P.d.B, p->run_threads);
-  if (p->inst == 1 && p->cons == 15 && p->run_threads == 64) k_run_population<20, 5, 15, 64, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->inst == 1 && p->cons == 15) k_run_population<20, 5, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->cons == 15 && p->run_threads == 384) k_run_population<5, 2, 15, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->cons == 11 && p->run_threads == 384) k_run_population<5, 2, 11, 384, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->cons == 15) k_run_population<5, 2, 15, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->cons == 11) k_run_population<5, 2, 11, 256, 1><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->inst == 0) k_run_population<5, 2, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else if (p->inst == 1) k_run_population<20, 5, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
-  else k_run_population<32, 8, -1, 128, 2><<<g, p->run_threads, p->run_smem, p->stream>>>(p->P, k0, k1);
+  void* args[] = {&p->P, &k0, &k1};
+  const int rc = launch_kernel(p->fn_run, g, p->run_threads, p->run_smem, p->stream, args);
+  if (rc != MEK_OK) return rc;
   CUDA_TRY(cudaGetLastError());
   p->launches++;
   return MEK_OK;
@@ -1413,6 +1322,7 @@ extern "C" int64_t mek_pop_launches(const mek_pop* p) { return p ? p->launches :
 extern "C" int mek_pop_ncon(const mek_pop* p) { return p ? p->P.d.nC : 0; }
 extern "C" int mek_pop_defer_block(const mek_pop* p) { return p ? p->P.defer_k : 0; }
 extern "C" int64_t mek_pop_regroups(const mek_pop* p) { return p ? p->regroups : 0; }
+extern "C" int mek_pop_split(const mek_pop* p) { return (p && p->split) ? 1 : 0; }
 extern "C" int mek_pop_state_len(const mek_pop* p) { return p ? p->P.d.nfields : 0; }
 
 extern "C" int mek_read_logs(mek_pop* p, int k0, int k1, double* u, double* V, double* soc, double* phise, int32_t* iT, int32_t* iZ,

@@ -22,7 +22,7 @@ def _libmek_built():
     lib = os.path.join(PKG, "mek", "libmek.so")
     if not os.path.exists(lib):
         import subprocess
-        subprocess.call(["make", "-C", os.path.join(PKG, "csrc"), "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.call(["make", "-j8", "-C", os.path.join(PKG, "csrc"), "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return lib
 
 
