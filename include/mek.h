@@ -90,8 +90,9 @@ typedef struct {
   int defer_narrow_test;    /* test hook, 1: shrink the per-block model set to the EKF estimate's own neighbours so
                                that the plant's models take the on-demand replay path (results are unchanged)    */
   int general_sweep_test;   /* test hook, 1: the static-shape instances always run the general (masked) Hildreth sweep
-                               instead of the lean one that applies when the only all-zero row is the first z_max row
-                               (results are unchanged)                                                             */
+                               instead of the lean one that applies when the only all-zero row is the first z_max row;
+                               2: the lean sweep never skips the tail of a row that is idle in every cell of the warp
+                               (results are unchanged either way)                                                  */
   int split_phases;         /* large populations: run each sample instant as two launches over all cells (estimator, then
                                MPC) with their own register budgets instead of the one fused persistent kernel; results are
                                bit-identical.  0 = automatic (by population size), 1 = on, -1 = off.  Needs a static-shape

@@ -43,6 +43,7 @@ struct Dims {
   int useCurrent, useVoltage, useEta, useZmax;
   int force_jacobi;
   int no_lean_sweep;  // test hook: static-shape instances always take the general Hildreth sweep
+  int no_row_skip;    // test hook: the lean sweep never skips the tail of an idle row
   double Ts, ref, SigmaV, SigmaW, sigmin;
   double zinv;       // (nZ-1)/(Zpts[nZ-1]-Zpts[0]): bracket guess of two_nearest_z
   long long B, ld;   // cells in this shard, cells rounded up to whole 32-cell tiles
@@ -1459,6 +1460,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
     unsigned zmask = 0u;
     bool pfin = true;                                                // every entry of E\M' is finite
+    bool hpos = true;                                                // H_ii > 0 on every row that is not all-zero
     static_for<0, nC>([&](auto ic) {
       constexpr int i = decltype(ic)::value;
       double Mi[NC], P[NC];
@@ -1480,6 +1482,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
       if (hd == 0.0) {
         zmask |= 1u << i;
       } else {
+        hpos = hpos && (hd > 0.0);
 #pragma unroll
         for (int j = 0; j < NC; ++j) v[j] = fma(P[j], lam[i], v[j]);
       }
@@ -1503,6 +1506,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
       lean = lean && !(kz < 0.0);
     }
     if (lean) {
+      const bool skip_ok = pfin && hpos && !d.no_row_skip;
       bool first_nc = false;
       if (FS::UZ) { first_nc = !(lam[FS::O_Z] < 1e-6); lam[FS::O_Z] = 0.0; }
       for (; k <= d.maxHild; ++k) {                                  // hildreth.m:32
@@ -1519,18 +1523,25 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
             double hl = Mi[0] * v[0];
 #pragma unroll
             for (int j = 1; j < NC; ++j) hl = fma(Mi[j], v[j], hl);
-            const double w = fma(-(Ki + hl), rHi, li);
-            const double nl = pos_or_zero(w);                        // max(0,w); max(0,NaN) = 0
-            const double dl = nl - li;
+            const double t = Ki + hl;
+            // An inactive row that stays inactive: lambda_i = 0 and K_i + H(i,:)*lambda >= 0 give w = -t/H_ii <= 0 (H_ii > 0),
+            // max(0,w) = 0, lambda_i and v exactly as they were (v + P*0 = v for finite P; v is never -0).  Most rows of most
+            // sweeps are like that; when they are for every cell of the warp the rest of the row is skipped.
+            const bool idle = skip_ok && (li == 0.0) && (t >= 0.0);
+            if (!__all_sync(__activemask(), idle)) {
+              const double w = fma(-t, rHi, li);
+              const double nl = pos_or_zero(w);                      // max(0,w); max(0,NaN) = 0
+              const double dl = nl - li;
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-              double acc = Ei[j][0] * Mi[0];
+              for (int j = 0; j < NC; ++j) {
+                double acc = Ei[j][0] * Mi[0];
 #pragma unroll
-              for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mi[l], acc);
-              v[j] = fma(acc, dl, v[j]);
+                for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mi[l], acc);
+                v[j] = fma(acc, dl, v[j]);
+              }
+              lam[i] = nl;
+              notconv = notconv || !(fabs(dl) < 1e-6);               // hildreth.m:39
             }
-            lam[i] = nl;
-            notconv = notconv || !(fabs(dl) < 1e-6);                 // hildreth.m:39
           }
         });
         if (!notconv) break;

@@ -939,7 +939,8 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax);
   if (d.nC > 128) { return fail(MEK_ERR_UNSUPPORTED, "more than 128 constraint rows"); }
   d.force_jacobi = cfg->force_jacobi;
-  d.no_lean_sweep = cfg->general_sweep_test > 0 ? 1 : 0;
+  d.no_lean_sweep = cfg->general_sweep_test == 1 ? 1 : 0;
+  d.no_row_skip = cfg->general_sweep_test == 2 ? 1 : 0;
   d.Ts = bank->Tsamp; d.ref = cfg->ref; d.SigmaV = cfg->SigmaV; d.SigmaW = cfg->SigmaW;
   d.sigmin = sigma_min_gtg(Np, Nc, -bank->Tsamp / (3600.0 * bank->params[P_Q]));
   d.zinv = bank->nZ > 1 ? (double)(bank->nZ - 1) / (bank->Zpts[bank->nZ - 1] - bank->Zpts[0]) : 0.0;

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmek.so")
+LIB_PATH = os.environ.get("MEK_LIB_PATH") or os.path.join(_HERE, "libmek.so")   # MEK_LIB_PATH: an alternative build (tuning runs)
 NMATS = 31
 NSTAT = 16
 STAT_NAMES = ["cells", "cellsteps", "sum_nexec", "n_qp", "n_cap", "n_reached", "sum_t_reach", "min_phise", "max_V",

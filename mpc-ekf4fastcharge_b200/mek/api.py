@@ -87,7 +87,7 @@ class CellBatch:
         cfg.keep_cell_order = int(bool(keep_cell_order))
         cfg.defer_block, cfg.defer_stagger = int(defer_block), int(bool(defer_stagger))
         cfg.defer_narrow_test = int(bool(defer_narrow_test))
-        cfg.general_sweep_test = int(bool(general_sweep_test))
+        cfg.general_sweep_test = int(general_sweep_test)
         cfg.regroup_every = int(regroup_every)
         cfg.split_phases, cfg.split_threads_est, cfg.split_threads_mpc = int(split_phases), int(split_threads_est), int(split_threads_mpc)
         self.cfg = cfg

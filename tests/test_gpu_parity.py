@@ -251,13 +251,14 @@ def test_lean_sweep_equals_general_sweep(bank, coracle_mod, constraints):
     pop.SOC0[::5] = 93.5                                  # reach z_max within the run: K of the zero row changes sign
     pop.ekf_SOC0[::5] = 94.5
     outs = []
-    for hook in (False, True):
+    for hook in (0, 1, 2):                                # lean sweep with idle-row skipping, general sweep, lean without skipping
         cb, g, co, c = _run_both(bank, coracle_mod, pop, 700, constraints=constraints, general_sweep_test=hook)
         _assert_bit_exact(g, c)
         outs.append((g, cb.summary()))
     assert outs[0][1]["n_cap"] > 0, "no QP hit the sweep cap: the general sweep was not exercised by the lean build"
-    for k in ("u", "nexec", "active"):
-        assert np.array_equal(outs[0][0][k], outs[1][0][k], equal_nan=(k == "u")), k
+    for o in outs[1:]:
+        for k in ("u", "nexec", "active"):
+            assert np.array_equal(outs[0][0][k], o[0][k], equal_nan=(k == "u")), k
 
 
 def test_regrouping_also_happens_when_the_run_is_chunked(bank, coracle_mod):
