@@ -93,12 +93,6 @@ typedef struct {
                                instead of the lean one that applies when the only all-zero row is the first z_max row;
                                2: the lean sweep never skips the tail of a row that is idle in every cell of the warp
                                (results are unchanged either way)                                                  */
-  int split_phases;         /* large populations: run each sample instant as two launches over all cells (estimator, then
-                               MPC) with their own register budgets instead of the one fused persistent kernel; results are
-                               bit-identical.  0 = automatic (by population size), 1 = on, -1 = off.  Needs a static-shape
-                               short-horizon instance (Np 5, Nc 2, constraints [1 1 x] + z_max) and deferral blocks.        */
-  int split_threads_est;    /* tuning: CTA size of the estimator launch (256, 384, 512; 0 = default)                  */
-  int split_threads_mpc;    /* tuning: CTA size of the MPC launch (256, 384, 512; 0 = default)                        */
 } mek_config;
 
 /* ---- bank ---- */
@@ -130,7 +124,6 @@ void *mek_pop_stream(mek_pop *pop);                              /* cudaStream_t
 int64_t mek_pop_launches(const mek_pop *pop);                    /* kernels launched so far       */
 int mek_pop_ncon(const mek_pop *pop);                            /* constraint rows nC            */
 int mek_pop_defer_block(const mek_pop *pop);                     /* deferral block length in use (0 = off) */
-int mek_pop_split(const mek_pop *pop);                           /* 1: mek_run uses the phase-split form */
 int64_t mek_pop_regroups(const mek_pop *pop);                    /* regroupings of the state block so far (scheduling only) */
 int mek_pop_state_len(const mek_pop *pop);                       /* doubles per cell in read/write_state */
 /* logs for instants [k0,k1) x first n_log_cells cells, [step][cell] row-major.  Any pointer may be NULL.

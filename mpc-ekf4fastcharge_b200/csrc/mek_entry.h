@@ -1,4 +1,4 @@
-// Entry points of the fused / phase-split kernels, one translation unit per family so that they build in parallel.
+// Entry points of the fused kernels, one translation unit per family so that they build in parallel.
 // Each function returns the kernel's host-side function pointer (what cudaLaunchKernel, cudaFuncSetAttribute and the
 // occupancy calculator take) or nullptr when that shape is not built.
 #pragma once
@@ -7,8 +7,3 @@
 const void* mek_fused_fast_kernel(int cons, int threads);      // <5,2,cons,threads,1>: cons 15 | 11, threads 256 | 384
 const void* mek_fused_wide_kernel(int threads);                // <20,5,15,threads,1>: threads 256 | 64
 const void* mek_fused_generic_kernel(int inst);                // <5,2,-1,128,2>, <20,5,-1,128,2>, <32,8,-1,128,2>
-// mek_split.cuh
-const void* mek_split_est_kernel(int threads);                 // 256 | 384 | 512
-const void* mek_split_mpc_kernel(int cons, int threads);       // cons 15 | 11; threads 256 | 384 | 512
-const void* mek_split_block_kernel();                          // SPLIT_BLK_THREADS threads
-constexpr int SPLIT_BLK_THREADS = 256;

@@ -21,15 +21,6 @@
 #ifndef MEK_REGROUP_DEFAULT
 #define MEK_REGROUP_DEFAULT 128  // sample instants between regroupings of a heterogeneous population (mek_config.regroup_every == 0)
 #endif
-#ifndef MEK_SPLIT_MIN_CELLS
-#define MEK_SPLIT_MIN_CELLS (1ll << 60)   // mek_config.split_phases == 0: populations at least this large run the phase-split form
-#endif
-#ifndef MEK_SPLIT_EST_THREADS
-#define MEK_SPLIT_EST_THREADS 256
-#endif
-#ifndef MEK_SPLIT_MPC_THREADS
-#define MEK_SPLIT_MPC_THREADS 256
-#endif
 #ifndef MEK_DEFER_DEFAULT
 #define MEK_DEFER_DEFAULT 16     // sample instants per deferral block when mek_config.defer_block == 0
 #endif
@@ -220,7 +211,6 @@ extern "C" int mek_bank_dims(const mek_bank* b, int* n, int* nz, int* nT, int* n
 extern "C" double mek_bank_capacity_Ah(const mek_bank* b) { return b ? b->params[P_Q] : NAN; }
 
 #include "mek_kernels.cuh"
-#include "mek_split.cuh"
 #include "mek_entry.h"
 
 // ---- initialisation: initKF.m:37-133, initMPC.m:32-72, OB_step.m:63-71 and the first I = 0 call (runMPC.m:72-74) ----
@@ -775,12 +765,7 @@ struct mek_pop {
   void* d_cubtmp; size_t cubtmp_bytes;
   int64_t regroups;
   int since_regroup;           // sample instants run since the last regrouping (or the initialisation): kept across mek_run calls
-  // phase-split form of the loop (mek_split.cuh): two launches per sample instant over all cells
-  bool split;
-  SplitArgs S;
-  int est_threads, mpc_threads, est_grid, mpc_grid, blk_grid;
-  size_t est_smem, mpc_smem, blk_smem;
-  const void *fn_run, *fn_est, *fn_mpc, *fn_blk;   // kernel entry points in use (mek_entry.h)
+  const void* fn_run;          // entry point of the fused kernel instance in use (mek_entry.h)
 };
 
 static double sigma_min_gtg(int Np, int Nc, double r) {
@@ -832,7 +817,7 @@ static int grid_for(const mek_pop* p, long long B, int threads) {
   return (int)blocks;
 }
 
-// ---- phase-split form (mek_split.cuh) ----
+// ---- kernel launch / preparation through the entry points of mek_entry.h ----
 static int launch_kernel(const void* fn, int grid, int threads, size_t smem, cudaStream_t st, void** args) {
   CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)threads), args, smem, st));
   return MEK_OK;
@@ -841,65 +826,6 @@ static int prep_fn(const void* fn, int threads, size_t smem, int* occ) {
   if (!fn) return fail(MEK_ERR_UNSUPPORTED, "kernel instance not built");
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fn, threads, smem));
-  return MEK_OK;
-}
-
-static int split_prepare(mek_pop* p, const mek_config* cfg) {
-  const Dims& d = p->P.d;
-  auto pick = [](int want, int dflt) { return (want == 256 || want == 384 || want == 512) ? want : dflt; };
-  p->est_threads = pick(cfg->split_threads_est, MEK_SPLIT_EST_THREADS);
-  p->mpc_threads = pick(cfg->split_threads_mpc, MEK_SPLIT_MPC_THREADS);
-  const int mslots = p->cons == 15 ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
-  p->est_smem = p->blob_bytes + sizeof(double) * (size_t)sc_slots(d.R) * (size_t)p->est_threads;
-  p->mpc_smem = sizeof(double) * (size_t)mslots * (size_t)p->mpc_threads;
-  p->blk_smem = p->blob_bytes + sizeof(double) * (size_t)(p->P.defer_k + 1) * (size_t)SPLIT_BLK_THREADS;
-  if (p->est_smem > 227 * 1024 || p->mpc_smem > 227 * 1024 || p->blk_smem > 227 * 1024) return MEK_OK;   // stays on the fused kernel
-  int rc = MEK_OK, occ_e = 0, occ_m = 0, occ_b = 0;
-  p->fn_est = mek_split_est_kernel(p->est_threads);
-  p->fn_mpc = mek_split_mpc_kernel(p->cons, p->mpc_threads);
-  p->fn_blk = mek_split_block_kernel();
-  if ((rc = prep_fn(p->fn_est, p->est_threads, p->est_smem, &occ_e)) != MEK_OK) return rc;
-  if ((rc = prep_fn(p->fn_mpc, p->mpc_threads, p->mpc_smem, &occ_m)) != MEK_OK) return rc;
-  if ((rc = prep_fn(p->fn_blk, SPLIT_BLK_THREADS, p->blk_smem, &occ_b)) != MEK_OK) return rc;
-  auto grid = [&](int occ, int threads) {
-    long long need = (d.ld + threads - 1) / threads, cap = (long long)p->sms * (occ < 1 ? 1 : occ);
-    return (int)(need < cap ? need : cap);
-  };
-  p->est_grid = grid(occ_e, p->est_threads);
-  p->mpc_grid = grid(occ_m, p->mpc_threads);
-  p->blk_grid = grid(occ_b, SPLIT_BLK_THREADS);
-  p->S.xfields = split_xfields(p->P.defer_k);
-  const size_t ntiles = (size_t)(d.ld / TILE);
-  CUDA_TRY(cudaMalloc(&p->S.xt, sizeof(double) * ntiles * (size_t)p->S.xfields * TILE));
-  CUDA_TRY(cudaMemset(p->S.xt, 0, sizeof(double) * ntiles * (size_t)p->S.xfields * TILE));
-  CUDA_TRY(cudaMalloc(&p->S.tile_hot, sizeof(unsigned long long) * ntiles));
-  CUDA_TRY(cudaMemset(p->S.tile_hot, 0, sizeof(unsigned long long) * ntiles));
-  p->split = true;
-  return MEK_OK;
-}
-
-// sample instants [k0, k1) as two launches per instant plus one per deferral-block boundary
-static int split_segment(mek_pop* p, int k0, int k1) {
-  if (k1 <= k0) return MEK_OK;
-  int KB = p->P.defer_k, zero = 0, one = 1, k = k0, rc;
-  void* a_begin[] = {&p->P, &p->S, &zero, &KB};
-  void* a_next[] = {&p->P, &p->S, &one, &KB};
-  void* a_end[] = {&p->P, &p->S, &one, &zero};
-  void* a_est[] = {&p->P, &p->S};
-  void* a_mpc[] = {&p->P, &p->S, &k};
-  if ((rc = launch_kernel(p->fn_blk, p->blk_grid, SPLIT_BLK_THREADS, p->blk_smem, p->stream, a_begin)) != MEK_OK) return rc;
-  p->launches++;
-  for (k = k0; k < k1; ++k) {
-    if (k != k0 && (k - k0) % KB == 0) {
-      if ((rc = launch_kernel(p->fn_blk, p->blk_grid, SPLIT_BLK_THREADS, p->blk_smem, p->stream, a_next)) != MEK_OK) return rc;
-      p->launches++;
-    }
-    if ((rc = launch_kernel(p->fn_est, p->est_grid, p->est_threads, p->est_smem, p->stream, a_est)) != MEK_OK) return rc;
-    if ((rc = launch_kernel(p->fn_mpc, p->mpc_grid, p->mpc_threads, p->mpc_smem, p->stream, a_mpc)) != MEK_OK) return rc;
-    p->launches += 2;
-  }
-  if ((rc = launch_kernel(p->fn_blk, p->blk_grid, SPLIT_BLK_THREADS, p->blk_smem, p->stream, a_end)) != MEK_OK) return rc;
-  p->launches++;
   return MEK_OK;
 }
 
@@ -1057,16 +983,6 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
     CUDA_TRY(cudaMemset(p->d_wide_ws, 0, bytes));
     p->P.wide_ws = p->d_wide_ws;
   }
-  // phase-split form: needs a static-shape short-horizon instance and deferral blocks
-  p->split = false;
-  {
-    int want = cfg->split_phases;
-    if (want == 0) want = (B >= (int64_t)MEK_SPLIT_MIN_CELLS) ? 1 : -1;
-    if (want > 0 && p->inst == 0 && p->cons >= 0 && p->P.defer_k > 0) {
-      int rc2 = split_prepare(p, cfg);
-      if (rc2 != MEK_OK) return rc2;
-    }
-  }
   return MEK_OK;
 }
 
@@ -1096,8 +1012,6 @@ extern "C" void mek_pop_destroy(mek_pop* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->d_slot2cell) cudaFree(p->d_slot2cell);
   if (p->d_wide_ws) cudaFree(p->d_wide_ws);
-  if (p->S.xt) cudaFree(p->S.xt);
-  if (p->S.tile_hot) cudaFree(p->S.tile_hot);
   if (p->d_st2) cudaFree(p->d_st2);
   if (p->d_slot2cell0) cudaFree(p->d_slot2cell0);
   if (p->d_slot2cell2) cudaFree(p->d_slot2cell2);
@@ -1232,7 +1146,6 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 }
 
 static int launch_segment(mek_pop* p, int k0, int k1) {
-  if (p->split) return split_segment(p, k0, k1);
   const int g = grid_for(p, p->P.d.B, p->run_threads);
   void* args[] = {&p->P, &k0, &k1};
   const int rc = launch_kernel(p->fn_run, g, p->run_threads, p->run_smem, p->stream, args);
@@ -1323,7 +1236,6 @@ extern "C" int64_t mek_pop_launches(const mek_pop* p) { return p ? p->launches :
 extern "C" int mek_pop_ncon(const mek_pop* p) { return p ? p->P.d.nC : 0; }
 extern "C" int mek_pop_defer_block(const mek_pop* p) { return p ? p->P.defer_k : 0; }
 extern "C" int64_t mek_pop_regroups(const mek_pop* p) { return p ? p->regroups : 0; }
-extern "C" int mek_pop_split(const mek_pop* p) { return (p && p->split) ? 1 : 0; }
 extern "C" int mek_pop_state_len(const mek_pop* p) { return p ? p->P.d.nfields : 0; }
 
 extern "C" int mek_read_logs(mek_pop* p, int k0, int k1, double* u, double* V, double* soc, double* phise, int32_t* iT, int32_t* iZ,

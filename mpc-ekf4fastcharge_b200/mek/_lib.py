@@ -15,7 +15,7 @@ STAT_NAMES = ["cells", "cellsteps", "sum_nexec", "n_qp", "n_cap", "n_reached", "
 # every symbol include/mek.h declares (tests check that the library exports all of them)
 SYMBOLS = ["mek_bank_create", "mek_bank_load", "mek_bank_destroy", "mek_bank_dims", "mek_bank_capacity_Ah",
            "mek_pop_create", "mek_pop_destroy", "mek_pop_set_logging", "mek_pop_init", "mek_pop_reset", "mek_run",
-           "mek_run_timed", "mek_sync", "mek_pop_stream", "mek_pop_launches", "mek_pop_ncon", "mek_pop_defer_block", "mek_pop_regroups", "mek_pop_split", "mek_pop_state_len",
+           "mek_run_timed", "mek_sync", "mek_pop_stream", "mek_pop_launches", "mek_pop_ncon", "mek_pop_defer_block", "mek_pop_regroups", "mek_pop_state_len",
            "mek_read_logs", "mek_read_state", "mek_write_state", "mek_summary", "mek_pop_ob_step", "mek_pop_iter_ekf",
            "mek_pop_iter_mpc", "mek_pop_iter_mpc_cost", "mek_read_cell_summaries", "mek_host_alloc", "mek_host_free", "mek_hildreth", "mek_pred_mat", "mek_constraints", "mek_fp64_peak", "mek_last_error", "mek_version"]
 
@@ -28,8 +28,7 @@ class MekConfig(C.Structure):
     _fields_ = [("Np", C.c_int), ("Nc", C.c_int), ("maxHild", C.c_int), ("constraints", C.c_int * 3), ("use_zmax", C.c_int),
                 ("ref", C.c_double), ("SigmaV", C.c_double), ("SigmaW", C.c_double), ("force_jacobi", C.c_int),
                 ("threads_per_block", C.c_int), ("blocks_per_sm", C.c_int), ("generic_path", C.c_int), ("sync_steps", C.c_int), ("keep_cell_order", C.c_int),
-                ("defer_block", C.c_int), ("defer_stagger", C.c_int), ("regroup_every", C.c_int), ("defer_narrow_test", C.c_int), ("general_sweep_test", C.c_int),
-                ("split_phases", C.c_int), ("split_threads_est", C.c_int), ("split_threads_mpc", C.c_int)]
+                ("defer_block", C.c_int), ("defer_stagger", C.c_int), ("regroup_every", C.c_int), ("defer_narrow_test", C.c_int), ("general_sweep_test", C.c_int)]
 
 
 class MekBankDesc(C.Structure):
@@ -58,7 +57,6 @@ def lib():
         L.mek_pop_launches.argtypes = [C.c_void_p]
         L.mek_pop_ncon.argtypes = [C.c_void_p]
         L.mek_pop_defer_block.argtypes = [C.c_void_p]
-        L.mek_pop_split.argtypes = [C.c_void_p]
         L.mek_pop_regroups.restype = C.c_int64
         L.mek_pop_regroups.argtypes = [C.c_void_p]
         L.mek_pop_state_len.argtypes = [C.c_void_p]

@@ -69,8 +69,7 @@ class CellBatch:
 
     def __init__(self, rom: RomBank, B, Np=5, Nc=2, constraints=(1, 1, 1), ref=95.0, SigmaV=1e-3, SigmaW=1e2, maxHild=100,
                  use_zmax=True, force_jacobi=False, device=0, threads_per_block=0, blocks_per_sm=0, generic_path=False, sync_steps=True, keep_cell_order=False,
-                 defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=False,
-                 split_phases=0, split_threads_est=0, split_threads_mpc=0):
+                 defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=0):
         L = _lib.lib()
         self.rom = rom
         self.B = int(B)
@@ -89,7 +88,6 @@ class CellBatch:
         cfg.defer_narrow_test = int(bool(defer_narrow_test))
         cfg.general_sweep_test = int(general_sweep_test)
         cfg.regroup_every = int(regroup_every)
-        cfg.split_phases, cfg.split_threads_est, cfg.split_threads_mpc = int(split_phases), int(split_threads_est), int(split_threads_mpc)
         self.cfg = cfg
         self._log_cache, self._pinned_ptrs = {}, []
         self.h = C.c_void_p()
@@ -97,7 +95,6 @@ class CellBatch:
         self.nC = L.mek_pop_ncon(self.h)
         self.defer_block = L.mek_pop_defer_block(self.h)      # what the library settled on (0 = off)
         self.state_len = L.mek_pop_state_len(self.h)
-        self.split = bool(L.mek_pop_split(self.h))            # mek_run uses the phase-split form (two launches per instant)
         self.nz = rom.bank.nz
         self.nlog = 0
         self.log_steps = 0

@@ -314,49 +314,3 @@ def test_cuda_matches_literal_golden(bank, path):
     for k in ("u", "V", "SOC", "phise"):
         assert rel_err(o[k], g[k], SCALE[k]) <= 1e-9, k
 
-
-# ---- phase-split form of the loop (two launches per sample instant) ----
-@pytest.mark.parametrize("threads", [(256, 256), (384, 512), (512, 384)])
-def test_split_phases_bit_identical(bank, coracle_mod, threads):
-    """The phase-split form runs the same device functions as the fused kernel: logs, the final state of all M models of every
-    cell and the summaries must equal the oracle's bit for bit -- across launches that cut deferral blocks short, with a
-    heterogeneous population (on-demand catch-ups, Q19 lost cells included)."""
-    from mek import population as P
-    pop = P.make_population(bank.params[2], 300, seed=51, heterogeneous=True, ekf_soc_error=3.0)
-    pop.ekf_SOC0[::41] = 150.0                        # a few filters get lost (Q19) and idle
-    cb, g, co, c = _run_both(bank, coracle_mod, pop, 500, chunks=[(0, 3), (3, 40), (40, 41), (41, 500)], split_phases=1,
-                             split_threads_est=threads[0], split_threads_mpc=threads[1])
-    assert cb.split and cb.defer_block == 16
-    _assert_bit_exact(g, c)
-    a, b = _gpu_state_comparable(cb, bank.M), _oracle_state_in_gpu_layout(co, cb.nC, bank.M)
-    same = (a == b) | (np.isnan(a) & np.isnan(b))
-    # A cell whose filter got lost is dead from that instant on (NaN outputs, it idles).  On the instant of the latch the
-    # kernels have already given the models their EKF time update together with the plant advance, the reference's iterEKF
-    # returns before it (iterEKF.m:55-59): the dead filter's xhat / SigmaX differ by that one update and are never read again.
-    lost = np.isnan(g["u"][-1])
-    same[np.ix_(lost, np.arange(same.shape[1]) >= 29 + cb.nC + 6 * bank.M)] = True
-    assert lost.sum() == len(pop.ekf_SOC0[::41])
-    assert same.all(), "state differs in %d entries (first columns %s)" % ((~same).sum(), np.unique(np.nonzero(~same)[1])[:10])
-    s = cb.summary()
-    assert s["cellsteps"] == 300 * 500 and s["sum_nexec"] == c["nexec"].sum() and s["n_lost"] == len(pop.ekf_SOC0[::41])
-
-
-def test_split_phases_equals_fused_kernel(bank):
-    from mek import api, population as P
-    pop = P.make_population(bank.params[2], 777, seed=52, heterogeneous=True)
-    rom = api.RomBank(bank)
-    outs = []
-    for split in (-1, 1):
-        for cons in ((1, 1, 1), (1, 1, 0)):
-            cb = api.CellBatch(rom, len(pop), constraints=cons, split_phases=split)
-            assert cb.split == (split == 1)
-            cb.set_logging(len(pop), 300)
-            cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
-            cb.run(0, 300)
-            st = cb.read_state(); st[:, 29] = 0.0
-            outs.append((cb.logs(0, 300), st, cb.summary()))
-    for a, b in ((outs[0], outs[2]), (outs[1], outs[3])):
-        for k in ("u", "V", "SOC", "phise", "iT", "iZ", "nexec", "active"):
-            assert np.array_equal(a[0][k], b[0][k], equal_nan=k in ("u", "V", "SOC", "phise")), k
-        assert np.array_equal(a[1], b[1], equal_nan=True)
-        assert a[2] == b[2]
