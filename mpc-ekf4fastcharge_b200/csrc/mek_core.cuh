@@ -1459,7 +1459,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
     unsigned zmask = 0u;
-    bool pfin = true;                                                // every entry of E\M' is finite
+    double pchk = 0.0;                                               // stays (+-)0 while every entry of E\M' is finite: Inf*0 = NaN sticks
     bool hpos = true;                                                // H_ii > 0 on every row that is not all-zero
     static_for<0, nC>([&](auto ic) {
       constexpr int i = decltype(ic)::value;
@@ -1471,7 +1471,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
 #pragma unroll
         for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mi[l], acc);
         P[j] = acc;
-        pfin = pfin && is_finite(acc);
+        pchk = fma(acc, 0.0, pchk);
       }
       double hd = Mi[0] * P[0], k = Mi[0] * x[0];
 #pragma unroll
@@ -1489,16 +1489,20 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     });
     // rows whose lambda is non-finite (only all-zero rows can get there): while any is set every row product is NaN
     unsigned pmask = 0u;
+    constexpr unsigned ZEXP = FS::UZ ? (1u << FS::O_Z) : 0u;         // the one structurally all-zero row: first z_max row (Q7)
+    if (FS::UZ && (zmask & ZEXP) && !is_finite(lam[FS::O_Z])) pmask |= ZEXP;
+    if (zmask & ~ZEXP) {                                             // any other all-zero row (degenerate linearisation)
 #pragma unroll
-    for (int i = 0; i < nC; ++i)
-      if (((zmask >> i) & 1u) && !is_finite(lam[i])) pmask |= 1u << i;
+      for (int i = 0; i < nC; ++i)
+        if (((zmask >> i) & 1u) && !is_finite(lam[i])) pmask |= 1u << i;
+    }
+    const bool pfin = pchk == 0.0;
     int k = 1;
     // Lean sweep: the only all-zero row is the first z_max row (h_soc(0) = 0 always, quirk Q7), it holds a finite lambda and
     // its K (= gamma_i) is not negative.  Then that row's update is max(0, -K*Inf) = 0 on every sweep (K = 0: NaN -> 0), it
     // never touches v, no lambda ever becomes non-finite ("poison"), and every other row is the plain update -- the masks
     // of the general loop below are all constant and drop out.  Bit-identical to the general loop by construction
     // (tests/test_gpu_parity.py::test_lean_sweep_equals_general_sweep forces the general loop for comparison).
-    constexpr unsigned ZEXP = FS::UZ ? (1u << FS::O_Z) : 0u;
     bool lean = (zmask == ZEXP) && (pmask == 0u) && !d.no_lean_sweep;
     if (FS::UZ) {
       double kz, hz;
@@ -1820,7 +1824,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
     for (int j = 0; j < NC; ++j) v[j] = 0.0;
     unsigned z0 = 0u, z1 = 0u, z2 = 0u;                              // rows with H_ii == 0 (all-zero M rows, Q7)
     int npoison = 0;
-    bool pfin = true;                                                // every entry of E\M' is finite
+    double pchk = 0.0;                                               // stays (+-)0 while every entry of E\M' is finite
     wide_rows<NP, NC, CONS, 1>(wc, wst, [&](int i, const double (&M)[NC]) {
       double P[NC];
 #pragma unroll
@@ -1829,7 +1833,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
 #pragma unroll
         for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], M[l], acc);
         P[j] = acc;
-        pfin = pfin && is_finite(acc);
+        pchk = fma(acc, 0.0, pchk);
       }
       double hd = M[0] * P[0], k = M[0] * x[0];
 #pragma unroll
@@ -1846,6 +1850,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
         for (int j = 0; j < NC; ++j) v[j] = fma(P[j], li, v[j]);
       }
     });
+    const bool pfin = pchk == 0.0;
     // the factor of E and F are not needed until the sweeps are over: park them (registers are what the sweep is short of)
 #pragma unroll
     for (int q = 0; q < NC * NC; ++q) wc[(WS::W_LU + q) * wst] = LU[q];
