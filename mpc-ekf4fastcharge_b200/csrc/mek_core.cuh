@@ -1825,6 +1825,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
     unsigned z0 = 0u, z1 = 0u, z2 = 0u;                              // rows with H_ii == 0 (all-zero M rows, Q7)
     int npoison = 0;
     double pchk = 0.0;                                               // stays (+-)0 while every entry of E\M' is finite
+    bool hpos = true;                                                // H_ii > 0 on every row that is not all-zero
     wide_rows<NP, NC, CONS, 1>(wc, wst, [&](int i, const double (&M)[NC]) {
       double P[NC];
 #pragma unroll
@@ -1846,6 +1847,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
         if (i < 32) z0 |= bit; else if (i < 64) z1 |= bit; else z2 |= bit;
         if (!is_finite(li)) ++npoison;
       } else {
+        hpos = hpos && (hd > 0.0);
 #pragma unroll
         for (int j = 0; j < NC; ++j) v[j] = fma(P[j], li, v[j]);
       }
@@ -1857,47 +1859,100 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
 #pragma unroll
     for (int q = 0; q < NC; ++q) wc[(WS::W_F + q) * wst] = F[q];
     int k = 1;
-    // K, 1/H of the coming rows, loaded four rows ahead of their use (L2 latency)
-    double kq0 = wc[WS::W_K * wst], kq1 = wc[(WS::W_K + 1) * wst], kq2 = wc[(WS::W_K + 2) * wst], kq3 = wc[(WS::W_K + 3) * wst];
-    double hq0 = wc[WS::W_H * wst], hq1 = wc[(WS::W_H + 1) * wst], hq2 = wc[(WS::W_H + 2) * wst], hq3 = wc[(WS::W_H + 3) * wst];
+    // The 80 rows are walked in blocks of Nc rows; every block is a Toeplitz window [h(q) ... h(q-Nc+1)] over one table
+    // (the current rows too: prefix rows are the table [s s s ...], identity rows [s 0 0 ...]).  A block is first tested
+    // as a whole from the present v -- Nc independent short chains, their loads issued together one block ahead --
+    // and left alone when every row of it is idle in every cell of the warp: lambda_i = 0 and K_i + H(i,:)lambda >= 0
+    // give w <= 0 (or NaN on the all-zero row: 0*Inf), max(0,w) = 0, lambda and v exactly as they were, so the
+    // sequential pass of hildreth.m:34-37 would have seen that same v in every row of the block and changed nothing.
+    // Otherwise the block is walked row by row exactly as written there.
+    static_assert(NP % NC == 0, "blocked sweep: the horizon must be a multiple of the block length");
+    constexpr int BL = NC, BPT = NP / BL, NCUR = WS::UC ? 4 : 0, NBLK = nC / BL;
+    constexpr int TS0 = WS::UV ? WS::T_V : (WS::UE ? WS::T_E : WS::T_S);
+    constexpr int TS1 = (WS::UV && WS::UE) ? WS::T_E : WS::T_S;
+    constexpr int TS2 = WS::T_S;
+    const bool skip_base = pfin && hpos;
+    double win[2 * NC - 1];                                          // win[k] = table[q0 - (Nc-1) + k]; row r reads M(j) = win[Nc-1 + r - j]
+#pragma unroll
+    for (int q = 0; q < 2 * NC - 1; ++q) win[q] = 0.0;
+    double Kn[BL], Tn[BL];                                           // K and the new table entries of the coming block (in flight)
+    auto fetch = [&](int blk, double (&Kd)[BL], double (&Td)[BL]) {
+#pragma unroll
+      for (int r = 0; r < BL; ++r) Kd[r] = wc[(WS::W_K + blk * BL + r) * wst];
+      if (blk >= NCUR) {
+        const int tb = (blk - NCUR) / BPT, bb = (blk - NCUR) % BPT;
+        const double* t = wc + (tb == 0 ? TS0 : (tb == 1 ? TS1 : TS2)) * wst;
+#pragma unroll
+        for (int r = 0; r < BL; ++r) Td[r] = t[(bb * BL + r) * wst];
+      }
+    };
+    fetch(0, Kn, Tn);
     for (; k <= d.maxHild; ++k) {                                    // hildreth.m:32
       bool notconv = false;
-      wide_rows<NP, NC, CONS, WIDE_UNROLL>(wc, wst, [&](int i, const double (&M)[NC]) {   // hildreth.m:34-37
-        const double li = lc[i * ls];
-        const double Ki = kq0, rHi = hq0;
-        {
-          int ni = i + 4;
-          if (ni >= nC) ni -= nC;
-          kq0 = kq1; kq1 = kq2; kq2 = kq3; hq0 = hq1; hq1 = hq2; hq2 = hq3;
-          kq3 = wc[(WS::W_K + ni) * wst];
-          hq3 = wc[(WS::W_H + ni) * wst];
-        }
-        double w;
-        if (npoison > 0) {
-          w = NAN;
+#pragma unroll 1
+      for (int blk = 0; blk < NBLK; ++blk) {
+        double Kc[BL], Tc[BL];
+#pragma unroll
+        for (int r = 0; r < BL; ++r) { Kc[r] = Kn[r]; Tc[r] = Tn[r]; }
+        fetch(blk + 1 == NBLK ? 0 : blk + 1, Kn, Tn);
+        if (blk < NCUR) {                                            // constraintsMPC.m:23-42: [prefix +; prefix -; identity +; identity -]
+          const bool neg = (blk & 1) != 0, ident = blk >= 2;
+          const double one = neg ? -1.0 : 1.0, zer = neg ? -0.0 : 0.0;
+#pragma unroll
+          for (int q = 0; q < 2 * NC - 1; ++q) win[q] = (q < NC - 1) ? zer : ((q == NC - 1 || !ident) ? one : zer);
         } else {
-          double hl = M[0] * v[0];
+          const int tb = (blk - NCUR) / BPT, bb = (blk - NCUR) % BPT;
+          const bool neg = (tb == 0 ? TS0 : (tb == 1 ? TS1 : TS2)) == WS::T_E;
 #pragma unroll
-          for (int j = 1; j < NC; ++j) hl = fma(M[j], v[j], hl);
-          w = fma(-(Ki + hl), rHi, li);
+          for (int q = 0; q < NC - 1; ++q) win[q] = (bb == 0) ? (neg ? -0.0 : 0.0) : win[BL + q];
+#pragma unroll
+          for (int r = 0; r < BL; ++r) win[NC - 1 + r] = Tc[r];
         }
-        const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
-        const double dl = nl - li;
-        const unsigned zw = i < 32 ? z0 : (i < 64 ? z1 : z2);
-        if ((zw >> (i & 31)) & 1u) {
-          npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li));
-        } else if (dl != 0.0 || !pfin) {                             // P*0 leaves v as it is
+        const int i0 = blk * BL;
+        double li[BL];
+        bool idle = skip_base && (npoison == 0);
 #pragma unroll
-          for (int j = 0; j < NC; ++j) {
-            double acc = Ei[j][0] * M[0];
+        for (int r = 0; r < BL; ++r) {
+          li[r] = lc[(i0 + r) * ls];
+          double hl = win[NC - 1 + r] * v[0];
 #pragma unroll
-            for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], M[l], acc);
-            v[j] = fma(acc, dl, v[j]);
+          for (int j = 1; j < NC; ++j) hl = fma(win[NC - 1 + r - j], v[j], hl);
+          idle = idle && (li[r] == 0.0) && (Kc[r] + hl >= 0.0);
+        }
+        if (__all_sync(__activemask(), idle)) continue;
+        double rH[BL];
+#pragma unroll
+        for (int r = 0; r < BL; ++r) rH[r] = wc[(WS::W_H + i0 + r) * wst];
+#pragma unroll
+        for (int r = 0; r < BL; ++r) {                               // hildreth.m:34-37
+          const int i = i0 + r;
+          double w;
+          if (npoison > 0) {
+            w = NAN;
+          } else {
+            double hl = win[NC - 1 + r] * v[0];
+#pragma unroll
+            for (int j = 1; j < NC; ++j) hl = fma(win[NC - 1 + r - j], v[j], hl);
+            w = fma(-(Kc[r] + hl), rH[r], li[r]);
           }
+          const double nl = (w > 0.0) ? w : 0.0;                     // max(0,w); max(0,NaN) = 0
+          const double dl = nl - li[r];
+          const unsigned zw = i < 32 ? z0 : (i < 64 ? z1 : z2);
+          if ((zw >> (i & 31)) & 1u) {
+            npoison += (int)(!is_finite(nl)) - (int)(!is_finite(li[r]));
+          } else if (dl != 0.0 || !pfin) {                           // P*0 leaves v as it is
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+              double acc = Ei[j][0] * win[NC - 1 + r];
+#pragma unroll
+              for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], win[NC - 1 + r - l], acc);
+              v[j] = fma(acc, dl, v[j]);
+            }
+          }
+          lc[i * ls] = nl;
+          if (!(fabs(dl) < 1e-6)) notconv = true;                    // hildreth.m:39 norm(.,Inf) < 1e-6, NaN-propagating
         }
-        lc[i * ls] = nl;
-        if (!(fabs(dl) < 1e-6)) notconv = true;                      // hildreth.m:39 norm(.,Inf) < 1e-6, NaN-propagating
-      });
+      }
       if (!notconv) break;
     }
     if (k > d.maxHild) k = d.maxHild;
