@@ -699,9 +699,20 @@ __global__ void k_regroup_keys(const __grid_constant__ Params P, unsigned* keys,
     soc = soc > 0.0 ? (soc < 1.2 ? soc : 1.2) : 0.0;                 // also maps NaN to 0
     const unsigned bin = (unsigned)(soc * 400.0);                    // 0.25 % SOC
     const double um = fabs(b[S_UMIN * TILE]);
-    const unsigned rate = (unsigned)((um < 255.0 ? um : 255.0) * 16.0) & 0xfffu;
+    const unsigned rate = (unsigned)((um < 255.0 ? um : 255.0) * 4.0) & 0x3ffu;
     const unsigned lost = ((unsigned)b[S_STATUS * TILE] & ST_LOST) ? 1u : 0u;
-    keys[s] = (lost << 31) | (bracket << 23) | ((bin & 0x7ffu) << 12) | rate;
+    // which constraint blocks hold an active multiplier (constraintsMPC.m:99 [u; du; V; eta; SOC]): cells riding the same
+    // limits walk the same rows of the Hildreth sweep and need similar numbers of sweeps
+    unsigned act = 0u;
+    if (b[S_LAMVALID * TILE] != 0.0) {
+      const double* lam = b + (long long)d.f_lambda * TILE;
+      int row = 0;
+      const int len[5] = {d.useCurrent ? 2 * d.Nc : 0, d.useCurrent ? 2 * d.Nc : 0, d.useVoltage ? d.Np : 0, d.useEta ? d.Np : 0, d.useZmax ? d.Np : 0};
+      for (int blk = 0; blk < 5; ++blk)
+        for (int i = 0; i < len[blk]; ++i, ++row)
+          if (!(lam[(long long)row * TILE] <= 0.0)) act |= 1u << blk;
+    }
+    keys[s] = (lost << 31) | ((bracket & 0x1fu) << 26) | (act << 21) | ((bin & 0x7ffu) << 10) | rate;
     idx[s] = (int)s;
   }
 }
