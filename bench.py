@@ -34,9 +34,9 @@ SEED = 2                # C3
 # The configurations BASELINE.json names.  The default bench line is C3 = the configuration the metric is
 # quoted on ("cell-steps/sec at 1M cells"); the others are run with --config for the results table in BASELINE.md.
 CONFIGS = {
-    "C3":   dict(kernel="k_run_population<5,2,15,256,1>", profile="r01_final2_ncu_summary.csv", seed=2, Np=5, Nc=2, constraints=(1, 1, 1), het=False, cells=1 << 20, what="limits 2C/4.1V/80mV, constraints [1 1 1]"),
+    "C3":   dict(kernel="k_run_population<5,2,15,256,1>", profile="r02_c3_ncu_summary.csv", seed=2, Np=5, Nc=2, constraints=(1, 1, 1), het=False, cells=1 << 20, what="limits 2C/4.1V/80mV, constraints [1 1 1]"),
     "C3v":  dict(kernel="k_run_population<5,2,11,256,1>", profile=None, seed=2, Np=5, Nc=2, constraints=(1, 1, 0), het=False, cells=1 << 20, what="limits 2C/4.1V, constraints [1 1 0] (no side-reaction constraint)"),
-    "C4":   dict(kernel="k_run_population<20,5,15,256,1>", profile="r01_c4_ncu_summary.csv", seed=3, Np=20, Nc=5, constraints=(1, 1, 1), het=False, cells=65536, what="extended horizon, 80 constraint rows, limits 2C/4.1V/80mV"),
+    "C4":   dict(kernel="k_run_population<20,5,15,256,1>", profile="r02_c4_ncu_summary.csv", seed=3, Np=20, Nc=5, constraints=(1, 1, 1), het=False, cells=65536, what="extended horizon, 80 constraint rows, limits 2C/4.1V/80mV"),
     "C5":   dict(kernel="k_run_population<5,2,15,256,1>", profile=None, seed=4, Np=5, Nc=2, constraints=(1, 1, 1), het=True, cells=1 << 20, what="heterogeneous per-cell limits and temperature 15..35 C"),
 }
 
@@ -257,7 +257,7 @@ def main_mek(a):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_per_cellstep * float(B) * a.nsim / (kern_avg_ms * 1e-3) / 1e9
         # DRAM bytes per cell-step and issue-slot / FP64-pipe utilisation measured by `ncu --set full` on this kernel
-        # (profiles/r01_defer_ncu_summary.csv); traffic is scaled to the units one launch of this run processes
+        # (profiles/r02_*_ncu_summary.csv); traffic is scaled to the units one launch of this run processes
         traffic, prof = None, {}
         try:
             for line in open(os.path.join(ROOT, "profiles", (cfg["profile"] or "none") if kdef > 0 else "r01_final_ncu_summary.csv")):

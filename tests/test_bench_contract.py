@@ -44,7 +44,7 @@ def test_bench_side_files_exist_and_parse():
             assert float(line.split("=")[1].split("B")[0].replace(" ", "")) > 0
             assert "smsp__issue_active.avg.pct_of_peak_sustained_active" in txt
     # the committed bench lines carry every key of the contract
-    for f in ("r01_bench_C3_1Mcells.json", "r01_bench_C3v_1Mcells.json", "r01_bench_C4_65536cells.json", "r01_bench_C5_1Mcells.json"):
+    for f in ("r02_bench_C3_1Mcells.json", "r02_bench_C3v_1Mcells.json", "r02_bench_C4_65536cells.json", "r02_bench_C5_1Mcells.json"):
         d = json.load(open(os.path.join(ROOT, "profiles", f)))
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                   "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):

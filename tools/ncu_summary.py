@@ -1,6 +1,10 @@
-"""Summarise an .ncu-rep: key metrics + instruction / stall-sample share by function.  usage: ncu_summary.py REPORT [top_lines]"""
+"""Summarise an .ncu-rep: key metrics + instruction / stall-sample share by function.
+usage: ncu_summary.py REPORT [top_lines [CELLSTEPS "title / command line"]]
+With CELLSTEPS (cell-steps the profiled launch processed) the header carries the DRAM traffic and the executed FP64 operations per cell-step."""
 import csv, sys, re, subprocess, collections, bisect, io
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+cellsteps = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
+title = sys.argv[4] if len(sys.argv) > 4 else ""
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -11,6 +15,29 @@ want = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.a
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__average_warp_latency_per_inst_issued.ratio']
+if cellsteps:
+    g = lambda name: float(vals[hdr.index(name)]) if name in hdr and vals[hdr.index(name)] not in ("", "n/a") else 0.0
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    rd = g("dram__bytes_read.sum") * scale.get(units[hdr.index("dram__bytes_read.sum")], 1.0)
+    wr = g("dram__bytes_write.sum") * scale.get(units[hdr.index("dram__bytes_write.sum")], 1.0)
+    for line in title.split("|"):
+        if line.strip():
+            print("# " + line.strip())
+    print("# DRAM traffic per cell-step: (%.2f + %.2f) GB / %.0f = %.0f B" % (rd / 1e9, wr / 1e9, cellsteps, (rd + wr) / cellsteps))
+    sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(io.StringIO(sass)))
+    sh = next((r for r in srows if "Thread Instructions Executed" in r), None)
+    if sh:
+        it, isrc = sh.index("Predicated-On Thread Instructions Executed"), sh.index("Source")
+        ops = collections.Counter()
+        for r in srows:
+            if len(r) == len(sh) and r is not sh:
+                m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[isrc])
+                if m and m.group(2) in ("DFMA", "DMUL", "DADD"):
+                    try: ops[m.group(2)] += int(r[it] or 0)
+                    except ValueError: pass
+        print("# executed FP64 per cell-step: DFMA %.0f, DMUL %.0f, DADD %.0f = %.0f flops" % (
+            ops["DFMA"] / cellsteps, ops["DMUL"] / cellsteps, ops["DADD"] / cellsteps, (2 * ops["DFMA"] + ops["DMUL"] + ops["DADD"]) / cellsteps))
 print("metric,unit,value")
 for i, h in enumerate(hdr):
     if h in want or ('issue_stalled' in h and 'per_issue_active' in h and 'not_issued' not in h and float(vals[i] or 0) > 0.05):
