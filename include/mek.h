@@ -93,6 +93,9 @@ typedef struct {
                                instead of the lean one that applies when the only all-zero row is the first z_max row;
                                2: the lean sweep never skips the tail of a row that is idle in every cell of the warp
                                (results are unchanged either way)                                                  */
+  int ekf_method;           /* initKF's `blend` argument (initKF.m:44-53): 0 = 'OutB' output blend (what runMPC.m:16 selects; the
+                               fused loop mek_run supports only this), 1 = 'MdlB' model blend: one blended model per cell,
+                               served by the function-level entry mek_pop_iter_ekf (iterEKF.m MB branches)               */
 } mek_config;
 
 /* ---- bank ---- */

@@ -48,6 +48,7 @@ struct Dims {
   double zinv;       // (nZ-1)/(Zpts[nZ-1]-Zpts[0]): bracket guess of two_nearest_z
   long long B, ld;   // cells in this shard, cells rounded up to whole 32-cell tiles
   int f_lambda, f_bigx, f_xhat, f_sig, nfields;
+  int mb, f_mbx, f_mbs;   // model-blend EKF (function-level entry only): ekfData.xhat (6) and ekfData.SigmaX (21, upper triangle) behind the model rows
 };
 
 struct BankSmem {

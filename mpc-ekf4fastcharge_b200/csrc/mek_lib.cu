@@ -212,6 +212,7 @@ extern "C" double mek_bank_capacity_Ah(const mek_bank* b) { return b ? b->params
 
 #include "mek_kernels.cuh"
 #include "mek_entry.h"
+#include "mek_ekf_mb.cuh"
 
 // ---- initialisation: initKF.m:37-133, initMPC.m:32-72, OB_step.m:63-71 and the first I = 0 call (runMPC.m:72-74) ----
 __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params P) {
@@ -245,6 +246,11 @@ __global__ void __launch_bounds__(128) k_pop_init(const __grid_constant__ Params
       int q = 0;
       for (int i = 0; i < N5; ++i)
         for (int j = i; j < N5; ++j, ++q) c.f(d.f_sig + m * NSYM + q) = sx[j * 6 + i];
+    }
+    if (d.mb) {                                                      // initKF.m:100-101: xhat = 0 (zero fill above), SigmaX = SigmaX0
+      int q = 0;
+      for (int i = 0; i < N6; ++i)
+        for (int j = i; j < N6; ++j, ++q) c.f(d.f_mbs + q) = sx[j * 6 + i];
     }
     for (int k = 0; k < 7; ++k) c.f(S_UMAX + k) = P.in_lim[id * 7 + k];
     c.f(S_MIN_PHISE) = INFINITY;
@@ -316,12 +322,6 @@ __device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, doub
   zk[d.nz + 1] = soc;       // the per-kind corrections (iterEKF.m:331-413) follow in k_iter_ekf
 }
 
-struct RowLists {            // output-row kinds for the full-zk corrections and the 3-sigma bounds
-  int n_negtss, n_postss, n_thetae, n_negphise, n_posphise, n_phie, n_posphis, r_phise0;
-  int negtss[64], postss[64], thetae[64], negphise[64], posphise[64], phie[64], posphis[64];   // nz <= 64 (mek_bank_create): no group can overflow
-  int r_ifdl0, r_ifdl3, r_if0, r_if3, r_tss0, r_tss3, r_the0, r_the3, r_phie_last;   // rows in the full output numbering
-  unsigned char kind[64];    // per output row: 0 plain, 1 posPhis, 2 negThetass, 3 posThetass, 4 negPhise, 5 posPhise, 6 Phie
-};
 
 // boundzk = 3*sqrt([diag(SigmaZ); SigmaV; SigmaSOC]) (iterEKF.m:185-205, getChatZ :523-602).  Function-level entry only:
 // the control path never reads the bounds.  zk is the corrected output vector of this call.
@@ -456,6 +456,25 @@ __global__ void __launch_bounds__(128) k_iter_ekf(const __grid_constant__ Params
       for (int k = 0; k < RL.n_posphis; ++k) z[RL.posphis[k]] = z[RL.posphis[k]] + e.vhat;
       if (bounds) ekf_bounds(P, bk, RL, c, Scratch{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x}, z, bounds + id * (d.nz + 2));
     }
+  }
+}
+
+// iterEKF with the model-blend method + EKFmatsHandler (function-level entry of a population created with ekf_method = 1)
+__global__ void __launch_bounds__(128) k_iter_ekf_mb(const __grid_constant__ Params P, const __grid_constant__ RowLists RL, const double* vk,
+                                                      const double* ik, double* zk, double* mats, double* bounds) {
+  extern __shared__ __align__(16) double sm[];
+  BankSmem bk;
+  stage_bank(sm, P, bk);
+  const Dims& d = P.d;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
+    Cell c = cell_ref(P.st, d, cell);
+    EkfOut e;
+    memset(&e, 0, sizeof(e));
+    const long long id = cell_id(P, cell);
+    ekf_step_mb(P, bk, RL, c, vk[id], ik[id], e, Scratch{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x},
+                zk ? zk + id * (d.nz + 2) : nullptr, bounds ? bounds + id * (d.nz + 2) : nullptr);
+    if (mats) pack_mats(e, mats + id * MEK_NMATS);
   }
 }
 
@@ -885,6 +904,9 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   d.ld = (B + 31) / 32 * 32;
   d.f_lambda = S_HDR; d.f_bigx = d.f_lambda + d.nC; d.f_xhat = d.f_bigx + 6 * d.M; d.f_sig = d.f_xhat + N5 * d.M;
   d.nfields = d.f_sig + NSYM * d.M;
+  d.mb = cfg->ekf_method == 1 ? 1 : 0;                               // initKF.m:44-53: 'OutB' (0) or 'MdlB' (1)
+  d.f_mbx = d.f_mbs = 0;
+  if (d.mb) { d.f_mbx = d.nfields; d.f_mbs = d.f_mbx + N6; d.nfields = d.f_mbs + NSYM6; }
   memcpy(p->P.cp, bank->params.data(), sizeof(double) * N_PARAMS);
   // row lists for the full-zk corrections
   RowLists& RL = p->RL;
@@ -897,7 +919,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   fill(bank->phie, RL.phie, RL.n_phie); fill(bank->posphis, RL.posphis, RL.n_posphis);
   RL.r_phise0 = bank->r_phise0;
   RL.r_ifdl0 = bank->r_ifdl0; RL.r_ifdl3 = bank->r_ifdl3; RL.r_if0 = bank->r_if0; RL.r_if3 = bank->r_if3;
-  RL.r_tss0 = bank->r_tss0; RL.r_tss3 = bank->r_tss3; RL.r_the0 = bank->r_the0; RL.r_the3 = bank->r_the3; RL.r_phie_last = bank->r_phie_last;
+  RL.r_tss0 = bank->r_tss0; RL.r_tss3 = bank->r_tss3; RL.r_the0 = bank->r_the0; RL.r_the3 = bank->r_the3; RL.r_phie_last = bank->r_phie_last; RL.r_phi = bank->r_phi;
   for (int r : bank->posphis) RL.kind[r] = 1;
   for (int r : bank->negtss) RL.kind[r] = 2;
   for (int r : bank->postss) RL.kind[r] = 3;
@@ -944,6 +966,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   rc |= prep_kernel(k_pop_init, p->smem_bytes);
   rc |= prep_kernel(k_ob_step, p->smem_bytes);
   rc |= prep_kernel(k_iter_ekf, p->smem_bytes);
+  rc |= prep_kernel(k_iter_ekf_mb, p->smem_bytes);
   p->minb = 1;
   p->cons = -1;
   p->run_threads = p->threads;
@@ -1219,6 +1242,7 @@ static int launch_run(mek_pop* p, int k0, int k1) {
 extern "C" int mek_run(mek_pop* p, int k0, int k1) {
   if (!p || k1 < k0 || k0 < 0) return fail(MEK_ERR_ARG, "bad argument to mek_run");
   if (!p->inited) return fail(MEK_ERR_STATE, "mek_run before mek_pop_init");
+  if (p->P.d.mb) return fail(MEK_ERR_UNSUPPORTED, "the fused loop runs the output-blend filter (runMPC.m:16 'OutB'); the model-blend filter is available through mek_pop_iter_ekf");
   CUDA_TRY(cudaSetDevice(p->device));
   return launch_run(p, k0, k1);
 }
@@ -1226,6 +1250,7 @@ extern "C" int mek_run(mek_pop* p, int k0, int k1) {
 extern "C" int mek_run_timed(mek_pop* p, int k0, int k1, float* ms) {
   if (!p || k1 < k0 || k0 < 0) return fail(MEK_ERR_ARG, "bad argument to mek_run_timed");
   if (!p->inited) return fail(MEK_ERR_STATE, "mek_run before mek_pop_init");
+  if (p->P.d.mb) return fail(MEK_ERR_UNSUPPORTED, "the fused loop runs the output-blend filter (runMPC.m:16 'OutB'); the model-blend filter is available through mek_pop_iter_ekf");
   CUDA_TRY(cudaSetDevice(p->device));
   CUDA_TRY(cudaEventRecord(p->ev0, p->stream));
   int rc = launch_run(p, k0, k1);
@@ -1397,7 +1422,8 @@ extern "C" int mek_pop_iter_ekf(mek_pop* p, const double* vk, const double* ik, 
   double* dm = db + B * nzk;
   CUDA_TRY(cudaMemcpyAsync(dv, vk, 8 * B, cudaMemcpyHostToDevice, p->stream));
   CUDA_TRY(cudaMemcpyAsync(di, ik, 8 * B, cudaMemcpyHostToDevice, p->stream));
-  k_iter_ekf<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, dv, di, zk ? dz : nullptr, dm, boundzk ? db : nullptr);
+  if (p->P.d.mb) k_iter_ekf_mb<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, dv, di, zk ? dz : nullptr, dm, boundzk ? db : nullptr);
+  else k_iter_ekf<<<grid_for(p, p->P.d.B, p->threads), p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, dv, di, zk ? dz : nullptr, dm, boundzk ? db : nullptr);
   CUDA_TRY(cudaGetLastError());
   p->launches++;
   if (zk) CUDA_TRY(cudaMemcpyAsync(zk, dz, 8 * B * nzk, cudaMemcpyDeviceToHost, p->stream));

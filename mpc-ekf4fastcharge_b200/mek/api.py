@@ -69,7 +69,7 @@ class CellBatch:
 
     def __init__(self, rom: RomBank, B, Np=5, Nc=2, constraints=(1, 1, 1), ref=95.0, SigmaV=1e-3, SigmaW=1e2, maxHild=100,
                  use_zmax=True, force_jacobi=False, device=0, threads_per_block=0, blocks_per_sm=0, generic_path=False, sync_steps=True, keep_cell_order=False,
-                 defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=0):
+                 defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=0, ekf_method="OutB"):
         L = _lib.lib()
         self.rom = rom
         self.B = int(B)
@@ -88,6 +88,8 @@ class CellBatch:
         cfg.defer_narrow_test = int(bool(defer_narrow_test))
         cfg.general_sweep_test = int(general_sweep_test)
         cfg.regroup_every = int(regroup_every)
+        blend = str(ekf_method).upper()                      # initKF.m:44-53: unknown strings fall back to output blending
+        cfg.ekf_method = 1 if blend in ("MDLB", "MB") else 0
         self.cfg = cfg
         self._log_cache, self._pinned_ptrs = {}, []
         self.h = C.c_void_p()

@@ -168,6 +168,14 @@ class COracle:
                             C.c_double(ik), _dp(zk), _dp(mats))
         return zk, mats
 
+    def iter_ekf_mb(self, c, vk, ik):
+        """iterEKF with the model-blend method ('MdlB') + EKFmatsHandler for cell c: zk, boundzk, mats."""
+        nzk = self.bank.nz + 2
+        zk = np.empty(nzk); bz = np.empty(nzk); mats = np.empty(31)
+        self.L.mko_iter_ekf_mb(C.byref(self.b), C.byref(self.cf), C.c_void_p(self.state[c].ctypes.data), C.c_double(vk),
+                               C.c_double(ik), _dp(zk), _dp(bz), _dp(mats))
+        return zk, bz, mats
+
     def hildreth(self, E, F, M, gamma, lambda0=None, maxIter=100):
         E = np.ascontiguousarray(E, float); F = np.ascontiguousarray(F, float)
         M = np.ascontiguousarray(M, float); gamma = np.ascontiguousarray(gamma, float)

@@ -238,8 +238,6 @@ def initKF(SOC0, T0, SigmaX0, SigmaV, SigmaW, blend, ROMs):
     if b in ("OUTB", "OB"): kf.method = "OB"                                             # :44-53
     elif b in ("MDLB", "MB"): kf.method = "MB"
     else: kf.method = "OB"
-    if kf.method != "OB":
-        raise NotImplementedError("model-blend EKF is out of scope (SURVEY.md section 2)")
     mdls = ROMs.ROMmdls
     nT, nZ = len(mdls), len(mdls[0])
     T = np.array([[m.T for m in row] for row in mdls]); Z = np.array([[m.SOC for m in row] for row in mdls])
@@ -273,7 +271,7 @@ def initKF(SOC0, T0, SigmaX0, SigmaV, SigmaW, blend, ROMs):
 
 
 # ------------------------------------------------------------------------------------------
-# iterEKF.m (OB branches)
+# iterEKF.m (both blend methods: 'OB' output blend -- what runMPC.m:16 selects -- and 'MB' model blend)
 # ------------------------------------------------------------------------------------------
 class EKFLost(Exception):
     """warnCount > 10 (iterEKF.m:55-59): the reference returns NaNs and EKFmatsHandler then fails."""
@@ -317,7 +315,7 @@ def _ekf_setupIndsLocs(ekfData):
 
 
 def iterEKF(vk, ik, Tk, ekfData):
-    """[zk,boundzk,ekfData,Xind] = iterEKF(vk,ik,Tk,ekfData)   (iterEKF.m:30-210, OB mode)"""
+    """[zk,boundzk,ekfData,Xind] = iterEKF(vk,ik,Tk,ekfData)   (iterEKF.m:30-210, ekfData.method 'OB' or 'MB')"""
     P = ekfData._persist
     if P is None:                                                                        # :32-53
         ind, loc, warned = _ekf_setupIndsLocs(ekfData)
@@ -343,6 +341,7 @@ def iterEKF(vk, ik, Tk, ekfData):
     else: Tk = Tk + 273.15
 
     M = ekfData.M
+    MB = ekfData.method == "MB"
     res_per_amp = ekfData.Ts / (3600 * ekfData.Q)
 
     # ---- helpers (nested functions of iterEKF.m) ----
@@ -371,8 +370,13 @@ def iterEKF(vk, ik, Tk, ekfData):
                   theZ=np.array([iZlower, iZupper, iZlower, iZupper]))
 
     def getVariables(ik, Xind, T):                                                       # :259-417
-        xk = [M[Xind.theT[m]][Xind.theZ[m]].xhat for m in range(4)]
-        x0 = ekfData.x0
+        if MB:                                                                           # :266-275
+            xhat = ekfData.xhat
+            xk = [xhat[:n]] * 4                                                          # :310-312: every model reads xhat(1:n)
+            x0 = xhat[-1]
+        else:
+            xk = [M[Xind.theT[m]][Xind.theZ[m]].xhat for m in range(4)]
+            x0 = ekfData.x0
         xSOC = ekfData.SOC0 - x0 * res_per_amp                                           # :277
         SOCnAvg = fn.neg.soc(xSOC, T); SOCpAvg = fn.pos.soc(xSOC, T)                     # :282-295
         if SOCnAvg < 0: shortWarn("SOCnAvg < 0"); SOCnAvg = 1e-6
@@ -425,10 +429,26 @@ def iterEKF(vk, ik, Tk, ekfData):
 
     def getChatV(Xind, Z, Tk):                                                           # :421-519
         Cs = [Xind.gamma[m] * M[Xind.theT[m]][Xind.theZ[m]].C for m in range(4)]         # :423-426
-        x0 = ekfData.x0
+        x0 = ekfData.xhat[-1] if MB else ekfData.x0                                      # :437 / :449
         xSOC = ekfData.SOC0 - x0 * res_per_amp
         SOCnAvg = fn.neg.soc(xSOC, Tk); SOCpAvg = fn.pos.soc(xSOC, Tk)
         Rfn = fn.neg.Rf(SOCnAvg, Tk); Rfp = fn.pos.Rf(SOCpAvg, Tk)
+        if MB:                                                                           # :448-460, 475-479, 489-491, 512-518
+            rsum = lambda key: np.sum(np.vstack([C[ind[key][0 if key != "Phie" else -1], :] for C in Cs]), axis=0)
+            Chat = Rfp * rsum("Ifdl3") - Rfn * rsum("Ifdl0")
+            k0n = fn.neg.k0(SOCnAvg, Tk); k0p = fn.pos.k0(SOCpAvg, Tk)
+            th0 = Z[ind["Thetass0"][0]]; th3 = Z[ind["Thetass3"][0]]
+            i0n = k0n * np.sqrt(Z[ind["Thetae"][0]] * (1 - th0) * th0)
+            i0p = k0p * np.sqrt(Z[ind["Thetae"][-1]] * (1 - th3) * th3)
+            Rctn = R * Tk / (F * i0n); Rctp = R * Tk / (F * i0p)
+            Chat = Chat + Rctp * rsum("If3") - Rctn * rsum("If0")
+            Chat = Chat + rsum("Phie")
+            dUocpn0 = fn.neg.dUocp(th0, Tk); dUocpp3 = fn.pos.dUocp(th3, Tk)
+            res0n = -dUocpn0 * ekfData.Ts * (fn.neg.soc(1, Tk) - fn.neg.soc(0, Tk)) / (3600 * ekfData.Q)
+            res0p = -dUocpp3 * ekfData.Ts * (fn.pos.soc(1, Tk) - fn.pos.soc(0, Tk)) / (3600 * ekfData.Q)
+            Chat0 = res0p - res0n
+            Chat = Chat + dUocpp3 * rsum("Thetass3") - dUocpn0 * rsum("Thetass0")
+            return np.concatenate([Chat, [Chat0]]), Chat0                                # :517 augmented with the integrator
         Chat = [Rfp * C[ind["Ifdl3"][0], :] - Rfn * C[ind["Ifdl0"][0], :] for C in Cs]   # :444-447
         k0n = fn.neg.k0(SOCnAvg, Tk); k0p = fn.pos.k0(SOCpAvg, Tk)                       # :463-468
         th0 = Z[ind["Thetass0"][0]]; th3 = Z[ind["Thetass3"][0]]
@@ -447,6 +467,26 @@ def iterEKF(vk, ik, Tk, ekfData):
 
     def getChatZ(Xind, Z, Tk):                                                           # :523-602
         Cs = [Xind.gamma[m] * M[Xind.theT[m]][Xind.theZ[m]].C for m in range(4)]
+        if MB:                                                                           # :538, 554-558, 572-575, 596-600
+            Chat = Cs[0] + Cs[1] + Cs[2] + Cs[3]
+            Chat0 = np.zeros(Cs[0].shape[0])
+            ChatV, _ = getChatV(Xind, Z, Tk)
+            for r in ind["posPhis"]:
+                Chat[r, :] = Chat[r, :] + ChatV[:-1]
+            Chat0[ind["posPhis"]] = ChatV[-1]
+            res0n = -ekfData.Ts * (fn.neg.soc(1, Tk) - fn.neg.soc(0, Tk)) / (3600 * ekfData.Q)
+            res0p = -ekfData.Ts * (fn.pos.soc(1, Tk) - fn.pos.soc(0, Tk)) / (3600 * ekfData.Q)
+            Chat0[ind["negThetass"]] = res0n; Chat0[ind["posThetass"]] = res0p
+            x0 = ekfData.xhat[-1]
+            xSOC = ekfData.SOC0 - x0 * res_per_amp
+            SOCnAvg = fn.neg.soc(xSOC, Tk); SOCpAvg = fn.pos.soc(xSOC, Tk)
+            dUocpn = fn.neg.dUocp(SOCnAvg, Tk); dUocpp = fn.pos.dUocp(SOCpAvg, Tk)
+            Chat0[ind["negPhise"]] = dUocpn * res0n
+            Chat0[ind["posPhise"]] = dUocpp * res0p
+            Chat0[ind["Phie"]] = -dUocpn * res0n
+            for r in ind["Phie"]:
+                Chat[r, :] = Chat[r, :] - Chat[ind["Phise0"][0], :]
+            return np.column_stack([Chat, Chat0]), ChatV, None, None
         Chat = [C.copy() for C in Cs]                                                    # :536
         Chat0 = np.zeros(Cs[0].shape[0])                                                 # :540
         ChatV, ChatV0 = getChatV(Xind, Z, Tk)                                            # :543
@@ -470,6 +510,44 @@ def iterEKF(vk, ik, Tk, ekfData):
                 C[r, :] = C[r, :] - C[ind["Phise0"][0], :]
         return Chat, ChatV, Chat0, ChatV0
 
+    if MB:
+        # ---- Steps 1a/1b, model blend: one blended model (:90-102) ----
+        SOC = ekfData.SOC0 - ekfData.xhat[-1] * res_per_amp                              # :92
+        Xind = getXind(Tk, SOC)
+        As = np.column_stack([M[Xind.theT[m]][Xind.theZ[m]].A for m in range(4)])
+        AMB = np.concatenate([As @ Xind.gamma, [1.0]])                                   # :98
+        ekfData.xhat = AMB * ekfData.xhat + ekfData.priorI                               # :99
+        ekfData.SigmaX = np.diag(AMB) @ ekfData.SigmaX @ np.diag(AMB) + ekfData.SigmaW   # :101
+        SOC = ekfData.SOC0 - ekfData.xhat[-1] * res_per_amp                              # :102
+        Xind = getXind(Tk, SOC)                                                          # :107-108
+        vhat, Z, _ = getVariables(ik, Xind, Tk)
+        ChatV, _ = getChatV(Xind, Z, Tk)                                                 # :125-128
+        SigmaVtilde = ChatV @ ekfData.SigmaX @ ChatV + ekfData.SigmaV
+        L = ekfData.SigmaX @ ChatV / SigmaVtilde
+        residual = vk - vhat                                                             # :133
+        ekfData.xhat = ekfData.xhat + L * residual                                       # :161
+        SigmaX = ekfData.SigmaX - np.outer(L * SigmaVtilde, L)                           # :163
+        _, SS, VVt = np.linalg.svd(SigmaX)                                               # :164-166
+        HH = VVt.T @ np.diag(SS) @ VVt
+        SigmaX = (SigmaX + SigmaX.T + HH + HH.T) / 4
+        nbump = 0
+        if residual ** 2 > 9 * SigmaVtilde:                                              # :169-172
+            SigmaX = SigmaX * 2; nbump = 1
+        ekfData.SigmaX = SigmaX
+        SOC = ekfData.SOC0 - ekfData.xhat[-1] * res_per_amp                              # :176
+        Xind = getXind(Tk, SOC)                                                          # :181-183
+        vhat, zk, Zsoc = getVariables(ik, Xind, Tk)
+        zk = np.concatenate([zk, [vhat, Zsoc]])
+        res = -ekfData.Ts / (3600 * ekfData.Q)
+        ChatZ, ChatVb, _, _ = getChatZ(Xind, zk, Tk)                                     # :199-203
+        SigmaZ = ChatZ @ ekfData.SigmaX @ ChatZ.T
+        SigmaVb = ChatVb @ ekfData.SigmaX @ ChatVb
+        SigmaSOC = res * ekfData.SigmaX[-1, -1] * res
+        with np.errstate(invalid="ignore"):
+            boundzk = 3 * np.sqrt(np.concatenate([np.diag(SigmaZ), [SigmaVb, SigmaSOC]]))    # :205
+        ekfData.priorI = ik                                                              # :210
+        ekfData.nbump_last = nbump
+        return zk, boundzk, ekfData, Xind
     # ---- Steps 1a/1b: time update of ALL models (:73-89) ----
     for theT in range(P.numT):
         for theZ in range(P.numZ):

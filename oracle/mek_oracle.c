@@ -13,6 +13,7 @@
  *   plant_step      MPC-EKF4FastCharge/OB_step.m:188-357 (simStep), :63-71 (init)
  *   ekf_step        UTILITY/iterEKF.m:55-210 OB branches, helpers :219-255 (getXind),
  *                   :259-417 (getVariables), :421-519 (getChatV); UTILITY/initKF.m:37-133
+ *   ekf_step_mb     the same file's MB (model-blend) branches, incl. getChatZ :523-602 for the 3-sigma bounds
  *   pick_linearise  MPC-EKF4FastCharge/EKFmatsHandler.m:26-114
  *   pred_row        MPC-EKF4FastCharge/predMat.m:15-50
  *   mpc_step        MPC-EKF4FastCharge/iterMPC.m:17-95, constraintsMPC.m:18-101, hildreth.m:16-46,
@@ -83,7 +84,12 @@ enum {
 static int st_off_bigx(void) { return S_LAMBDA + NCON_MAX; }
 static int st_off_xhat(int M) { return st_off_bigx() + 6 * M; }
 static int st_off_sig(int M) { return st_off_xhat(M) + N5 * M; }
-int mko_state_len(int M) { return st_off_sig(M) + NSYM * M; }
+/* model-blend EKF (initKF.m:100-101): ekfData.xhat (n+1) and ekfData.SigmaX ((n+1)x(n+1), upper triangle row-major) */
+#define N6 6
+#define NSYM6 21
+static int st_off_mbx(int M) { return st_off_sig(M) + NSYM * M; }
+static int st_off_mbs(int M) { return st_off_mbx(M) + N6; }
+int mko_state_len(int M) { return st_off_mbs(M) + NSYM6; }
 int mko_ncon_max(void) { return NCON_MAX; }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -349,13 +355,14 @@ static void get_xind(const mko_bank *bk, double Tk, double SOC, xind_t *X) { /* 
 }
 
 /* getVariables (iterEKF.m:259-417): Z holds all nz corrected outputs; returns Vcell */
+/* xmb: NULL for the output-blend filter; the model-blend filter's ekfData.xhat (n+1) otherwise (:266-275, :310-312) */
 static double get_variables(const mko_bank *bk, double *st, double ik, const xind_t *X, double T, double *Z,
-                            double *SOCn_out, double *SOCp_out) {
+                            double *SOCn_out, double *SOCp_out, const double *xmb) {
   const double *p = bk->params;
   const int M = bk->nT * bk->nZ, nz = bk->nz;
   const double *xhat = st + st_off_xhat(M);
   const double rpa = bk->Ts / (3600.0 * p[P_Q]);
-  const double xSOC = st[S_EKFSOC0] - st[S_X0] * rpa;              /* :277 */
+  const double xSOC = st[S_EKFSOC0] - (xmb ? xmb[5] : st[S_X0]) * rpa; /* :277 */
   double SOCn = soc_e(p, P_NEG, xSOC), SOCp = soc_e(p, P_POS, xSOC); /* :282-283 */
   if (SOCn < 0.0) { st[S_WARN] += 1.0; SOCn = 1e-6; }              /* :284-295 */
   if (SOCn > 1.0) { st[S_WARN] += 1.0; SOCn = 1.0 - 1e-6; }
@@ -365,7 +372,7 @@ static double get_variables(const mko_bank *bk, double *st, double ik, const xin
     double yc[4];
     for (int c = 0; c < 4; ++c) {
       const double *cr = bk->C + ((size_t)X->m[c] * nz + r) * 6;
-      const double *x = xhat + N5 * X->m[c];
+      const double *x = xmb ? xmb : xhat + N5 * X->m[c];
       double acc = cr[0] * x[0];
       for (int j = 1; j < N5; ++j) acc = fma(cr[j], x[j], acc);
       yc[c] = fma(bk->D[(size_t)X->m[c] * nz + r], ik, acc);
@@ -487,6 +494,53 @@ typedef struct {
   int lost;
 } ekf_out;
 
+/* EKFmatsHandler.m:26-114 on the corrected outputs Z of the last getVariables call; x_int = ekfData.xhat(end) (:33, Q3) */
+static void ekf_mats(const mko_bank *bk, double *st, const xind_t *Xp, const double *Z, double Zsoc, double x_int, ekf_out *o) {
+  const double *p = bk->params;
+  const int M = bk->nT * bk->nZ, nz = bk->nz;
+  const double *xhat = st + st_off_xhat(M);
+  const xind_t X = *Xp;
+  OPC_BLOCK(4);
+  int imax = 0;                                                    /* :26 first max, NaN ignored */
+  {
+    int have = 0;
+    double best = 0.0;
+    for (int c = 0; c < 4; ++c) {
+      double g = X.gamma[c];
+      if (g != g) continue;
+      if (!have || g > best) { best = g; imax = c; have = 1; }
+    }
+  }
+  const int mp = X.m[imax];
+  o->iT = X.iT[imax];
+  o->iZ = X.iZ[imax];
+  o->mpick = mp;
+  for (int j = 0; j < N5; ++j) { o->xhat[j] = xhat[N5 * mp + j]; o->a[j] = bk->A[6 * mp + j]; }
+  o->xhat[5] = x_int;                                              /* :33 (Q3) ekfData.xhat(end): 0 in OB mode */
+  {
+    const double TK = st[S_TC] + 273.15;                           /* :53 */
+    const double SOCavg = Zsoc;                                    /* :56 */
+    const double sn = soc_e(p, P_NEG, SOCavg), sp = soc_e(p, P_POS, SOCavg);
+    const double k0n = k0_e(p, P_NEG, sn, st[S_ARRK0N]), k0p = k0_e(p, P_POS, sp, st[S_ARRK0P]);
+    const double th0 = Z[bk->r_tss0], th3 = Z[bk->r_tss3];
+    const double i0n = k0n * sqrt((Z[bk->thetae[0]] * (1.0 - th0)) * th0);   /* :63-66 */
+    const double i0p = k0p * sqrt((Z[bk->thetae[bk->n_thetae - 1]] * (1.0 - th3)) * th3);
+    const double Rfn = rf_e(p, P_NEG, sn, st[S_ARRRFN]), Rfp = rf_e(p, P_POS, sp, st[S_ARRRFP]);
+    const double *Cm = bk->C + (size_t)mp * nz * 6, *Dm = bk->D + (size_t)mp * nz;
+    for (int j = 0; j < N5; ++j)                                   /* :75-76 */
+      o->Cv[j] = (Rfp * Cm[bk->r_ifdl3 * 6 + j] - Rfn * Cm[bk->r_ifdl0 * 6 + j]) + Cm[bk->r_phie_last * 6 + j];
+    o->Dv = (Rfp * Dm[bk->r_ifdl3] - Rfn * Dm[bk->r_ifdl0]) + Dm[bk->r_phie_last]; /* :79-80 */
+    const double Upos = uocp_p(p, th3), Uneg = uocp_n(p, th0);     /* :84-85 */
+    const double pref = ((2.0 * p[P_R]) * TK) / p[P_F];
+    const double negEta0 = pref * mko_asinh(Z[bk->r_if0] / (2.0 * i0n)); /* :88-89 */
+    const double posEta3 = pref * mko_asinh(Z[bk->r_if3] / (2.0 * i0p));
+    o->bv = ((Upos - Uneg) + (posEta3 - negEta0)) + 0.0;           /* :92 */
+    o->bphi = uocp_n(p, sn);                                       /* :96 */
+    for (int j = 0; j < N5; ++j) o->Cphi[j] = Cm[bk->r_phi * 6 + j]; /* :97 */
+    o->Dphi = Dm[bk->r_phi];                                       /* :98 */
+  }
+}
+
 /* one EKF iteration + EKFmatsHandler; Zfull (nz+2) optional */
 static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, double vk, double ik, ekf_out *o, double *zk_out) {
   const double *p = bk->params;
@@ -519,7 +573,7 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
   xind_t X;
   get_xind(bk, Tk, SOC, &X);                                       /* :107 */
   double SOCn, SOCp;
-  double vhat = get_variables(bk, st, ik, &X, Tk, Z, &SOCn, &SOCp); /* :108 */
+  double vhat = get_variables(bk, st, ik, &X, Tk, Z, &SOCn, &SOCp, NULL); /* :108 */
   /* ---- getChatV (:421-519); SOCn/SOCp re-derived there from the same x0 (unclamped, :438-440) ---- */
   double Chat[4][N5], C0;
   {
@@ -588,7 +642,7 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
   st[S_SIGX0] = st[S_SIGX0] - (L0 * svt0) * L0;                    /* :156 */
   SOC = st[S_EKFSOC0] - st[S_X0] * rpa;                            /* :159 */
   get_xind(bk, Tk, SOC, &X);                                       /* :181 */
-  vhat = get_variables(bk, st, ik, &X, Tk, Z, &SOCn, &SOCp);       /* :182 */
+  vhat = get_variables(bk, st, ik, &X, Tk, Z, &SOCn, &SOCp, NULL); /* :182 */
   const double Zsoc = st[S_EKFSOC0] - st[S_X0] * rpa;              /* :416 */
   st[S_PRIORI] = ik;                                               /* :210 */
   if (zk_out) {
@@ -603,46 +657,246 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
   }
   o->vhat = vhat;
   o->soc = Zsoc;
-  /* ---- EKFmatsHandler (EKFmatsHandler.m:26-114) ---- */
-  OPC_BLOCK(4);
-  int imax = 0;                                                    /* :26 first max, NaN ignored */
-  {
-    int have = 0;
-    double best = 0.0;
-    for (int c = 0; c < 4; ++c) {
-      double g = X.gamma[c];
-      if (g != g) continue;
-      if (!have || g > best) { best = g; imax = c; have = 1; }
+  ekf_mats(bk, st, &X, Z, Zsoc, 0.0, o);                           /* EKFmatsHandler.m:26-114 */
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* EKF: iterEKF.m, model-blend method ('MB': initKF.m:46-47,100-101; iterEKF.m:90-102,125-128,  */
+/* 160-176,199-203 and the MB branches of getVariables / getChatV / getChatZ)                   */
+/* ------------------------------------------------------------------------------------------ */
+static int sym6(int i, int j) { /* upper triangle of a 6x6, row-major */
+  static const int base[6] = {0, 6, 11, 15, 18, 20};
+  return (i <= j) ? base[i] + (j - i) : base[j] + (i - j);
+}
+
+/* PSD repair (iterEKF.m:164-166) of the 6x6 covariance: same two paths as psd_repair */
+static int psd_repair6(double *S, int force) {
+  if (!force) {
+    double L[6][6], d[6];
+    int pd = 1;
+    for (int j = 0; j < 6 && pd; ++j) {
+      double dj = S[sym6(j, j)];
+      for (int k = 0; k < j; ++k) dj = fma(-(L[j][k] * L[j][k]), d[k], dj);
+      if (!(dj > 0.0)) { pd = 0; break; }
+      d[j] = dj;
+      const double idj = 1.0 / dj;
+      for (int i = j + 1; i < 6; ++i) {
+        double v = S[sym6(i, j)];
+        for (int k = 0; k < j; ++k) v = fma(-(L[i][k] * L[j][k]), d[k], v);
+        L[i][j] = v * idj;
+      }
     }
+    if (pd) return 0;
   }
-  const int mp = X.m[imax];
-  o->iT = X.iT[imax];
-  o->iZ = X.iZ[imax];
-  o->mpick = mp;
-  for (int j = 0; j < N5; ++j) { o->xhat[j] = xhat[N5 * mp + j]; o->a[j] = bk->A[6 * mp + j]; }
-  o->xhat[5] = 0.0;                                                /* :33 (Q3) ekfData.xhat(end) == 0 in OB mode */
+  double A[6][6], V[6][6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) { A[i][j] = S[sym6(i, j)]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < 6; ++i) {
+      dg = dg + A[i][i] * A[i][i];
+      for (int j = i + 1; j < 6; ++j) off = off + A[i][j] * A[i][j];
+    }
+    if (!(off > 1e-34 * dg)) break;
+    for (int pI = 0; pI < 5; ++pI)
+      for (int q = pI + 1; q < 6; ++q) {
+        double apq = A[pI][q];
+        if (apq == 0.0) continue;
+        double theta = (A[q][q] - A[pI][pI]) / (2.0 * apq);
+        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 6; ++k) {
+          double akp = A[k][pI], akq = A[k][q];
+          A[k][pI] = c * akp - sn * akq;
+          A[k][q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 6; ++k) {
+          double apk = A[pI][k], aqk = A[q][k];
+          A[pI][k] = c * apk - sn * aqk;
+          A[q][k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 6; ++k) {
+          double vkp = V[k][pI], vkq = V[k][q];
+          V[k][pI] = c * vkp - sn * vkq;
+          V[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      double hh = 0.0;
+      for (int k = 0; k < 6; ++k) hh = hh + (V[i][k] * fabs(A[k][k])) * V[j][k];
+      double sv = S[sym6(i, j)];
+      S[sym6(i, j)] = (((sv + sv) + hh) + hh) / 4.0;               /* :166 */
+    }
+  return 1;
+}
+
+/* one iteration of the model-blend filter + EKFmatsHandler; zk_out (nz+2) and bound_out (nz+2) optional */
+static void ekf_step_mb(const mko_bank *bk, const mko_config *cf, double *st, double vk, double ik, ekf_out *o, double *zk_out,
+                        double *bound_out) {
+  const double *p = bk->params;
+  const int M = bk->nT * bk->nZ, nz = bk->nz;
+  double *x = st + st_off_mbx(M), *S = st + st_off_mbs(M);
+  double Z[64 + 2];
+  o->lost = 0;
+  if (st[S_WARN] > 10.0) {                                         /* iterEKF.m:55-59 (Q19) */
+    st[S_STATUS] = (double)((unsigned)st[S_STATUS] | ST_LOST);
+    o->lost = 1;
+    if (zk_out) for (int r = 0; r < nz + 2; ++r) zk_out[r] = NAN;
+    if (bound_out) for (int r = 0; r < nz + 2; ++r) bound_out[r] = NAN;
+    return;
+  }
+  const double Tk = st[S_TC] + 273.15;                             /* :65 */
+  const double prior = st[S_PRIORI], Sw = cf->SigmaW;
+  const double rpa = bk->Ts / (3600.0 * p[P_Q]);
+  double SOC = st[S_EKFSOC0] - x[5] * rpa;                         /* :92 */
+  xind_t X;
+  get_xind(bk, Tk, SOC, &X);                                       /* :93 */
+  double amb[N6];
+  for (int j = 0; j < N5; ++j) {                                   /* :94-98 [A1,A2,A3,A4]*gamma */
+    const double a0 = bk->A[6 * X.m[0] + j], a1 = bk->A[6 * X.m[1] + j], a2 = bk->A[6 * X.m[2] + j], a3 = bk->A[6 * X.m[3] + j];
+    amb[j] = fma(a3, X.gamma[3], fma(a2, X.gamma[2], fma(a1, X.gamma[1], a0 * X.gamma[0])));
+  }
+  amb[5] = 1.0;
+  for (int j = 0; j < N6; ++j) x[j] = fma(amb[j], x[j], prior);    /* :99 */
+  for (int i = 0; i < N6; ++i)
+    for (int j = i; j < N6; ++j) S[sym6(i, j)] = fma(amb[i] * S[sym6(i, j)], amb[j], Sw);   /* :101 */
+  SOC = st[S_EKFSOC0] - x[5] * rpa;                                /* :102 */
+  get_xind(bk, Tk, SOC, &X);                                       /* :107 */
+  double SOCn, SOCp;
+  double vhat = get_variables(bk, st, ik, &X, Tk, Z, &SOCn, &SOCp, x);   /* :108 */
+  /* gamma-weighted row sums sum([C1(r,:); C2(r,:); C3(r,:); C4(r,:)]) with Ck = gamma(k)*C (:423-426) */
+#define MB_RSUM(r, j)                                                                                                  \
+  (((X.gamma[0] * bk->C[((size_t)X.m[0] * nz + (r)) * 6 + (j)] + X.gamma[1] * bk->C[((size_t)X.m[1] * nz + (r)) * 6 + (j)]) + \
+    X.gamma[2] * bk->C[((size_t)X.m[2] * nz + (r)) * 6 + (j)]) +                                                       \
+   X.gamma[3] * bk->C[((size_t)X.m[3] * nz + (r)) * 6 + (j)])
+  /* ---- getChatV, MB branches (:448-460,475-479,489-491,512-518) ---- */
+  double Chat[N6];
   {
-    const double TK = st[S_TC] + 273.15;                           /* :53 */
-    const double SOCavg = Zsoc;                                    /* :56 */
-    const double sn = soc_e(p, P_NEG, SOCavg), sp = soc_e(p, P_POS, SOCavg);
+    const double xSOC = st[S_EKFSOC0] - x[5] * rpa;                /* :449-450 */
+    const double sn = soc_e(p, P_NEG, xSOC), sp = soc_e(p, P_POS, xSOC);
+    const double Rfn = rf_e(p, P_NEG, sn, st[S_ARRRFN]), Rfp = rf_e(p, P_POS, sp, st[S_ARRRFP]);
     const double k0n = k0_e(p, P_NEG, sn, st[S_ARRK0N]), k0p = k0_e(p, P_POS, sp, st[S_ARRK0P]);
     const double th0 = Z[bk->r_tss0], th3 = Z[bk->r_tss3];
-    const double i0n = k0n * sqrt((Z[bk->thetae[0]] * (1.0 - th0)) * th0);   /* :63-66 */
+    const double i0n = k0n * sqrt((Z[bk->thetae[0]] * (1.0 - th0)) * th0);
     const double i0p = k0p * sqrt((Z[bk->thetae[bk->n_thetae - 1]] * (1.0 - th3)) * th3);
-    const double Rfn = rf_e(p, P_NEG, sn, st[S_ARRRFN]), Rfp = rf_e(p, P_POS, sp, st[S_ARRRFP]);
-    const double *Cm = bk->C + (size_t)mp * nz * 6, *Dm = bk->D + (size_t)mp * nz;
-    for (int j = 0; j < N5; ++j)                                   /* :75-76 */
-      o->Cv[j] = (Rfp * Cm[bk->r_ifdl3 * 6 + j] - Rfn * Cm[bk->r_ifdl0 * 6 + j]) + Cm[bk->r_phie_last * 6 + j];
-    o->Dv = (Rfp * Dm[bk->r_ifdl3] - Rfn * Dm[bk->r_ifdl0]) + Dm[bk->r_phie_last]; /* :79-80 */
-    const double Upos = uocp_p(p, th3), Uneg = uocp_n(p, th0);     /* :84-85 */
-    const double pref = ((2.0 * p[P_R]) * TK) / p[P_F];
-    const double negEta0 = pref * mko_asinh(Z[bk->r_if0] / (2.0 * i0n)); /* :88-89 */
-    const double posEta3 = pref * mko_asinh(Z[bk->r_if3] / (2.0 * i0p));
-    o->bv = ((Upos - Uneg) + (posEta3 - negEta0)) + 0.0;           /* :92 */
-    o->bphi = uocp_n(p, sn);                                       /* :96 */
-    for (int j = 0; j < N5; ++j) o->Cphi[j] = Cm[bk->r_phi * 6 + j]; /* :97 */
-    o->Dphi = Dm[bk->r_phi];                                       /* :98 */
+    const double Rctn = (p[P_R] * Tk) / (p[P_F] * i0n), Rctp = (p[P_R] * Tk) / (p[P_F] * i0p);
+    const double dUn0 = duocp_n(p, th0), dUp3 = duocp_p(p, th3);
+    const double dsn = soc_e(p, P_NEG, 1.0) - soc_e(p, P_NEG, 0.0), dsp = soc_e(p, P_POS, 1.0) - soc_e(p, P_POS, 0.0);
+    const double res0n = (((-dUn0) * bk->Ts) * dsn) / (3600.0 * p[P_Q]);
+    const double res0p = (((-dUp3) * bk->Ts) * dsp) / (3600.0 * p[P_Q]);
+    for (int j = 0; j < N5; ++j) {
+      double v = Rfp * MB_RSUM(bk->r_ifdl3, j) - Rfn * MB_RSUM(bk->r_ifdl0, j);       /* :456-459 */
+      v = (v + Rctp * MB_RSUM(bk->r_if3, j)) - Rctn * MB_RSUM(bk->r_if0, j);           /* :476-479 */
+      v = v + MB_RSUM(bk->r_phie_last, j);                                             /* :490-491 */
+      v = (v + dUp3 * MB_RSUM(bk->r_tss3, j)) - dUn0 * MB_RSUM(bk->r_tss0, j);         /* :513-516 */
+      Chat[j] = v;
+    }
+    Chat[5] = res0p - res0n;                                       /* :501, :517 */
   }
+  /* ---- gain (:126-127) ---- */
+  double v6[N6], L[N6];
+  for (int i = 0; i < N6; ++i) {
+    double acc = S[sym6(i, 0)] * Chat[0];
+    for (int j = 1; j < N6; ++j) acc = fma(S[sym6(i, j)], Chat[j], acc);
+    v6[i] = acc;
+  }
+  double sq = Chat[0] * v6[0];
+  for (int i = 1; i < N6; ++i) sq = fma(Chat[i], v6[i], sq);
+  const double svt = sq + cf->SigmaV;
+  const double isv = 1.0 / svt;
+  for (int i = 0; i < N6; ++i) L[i] = v6[i] * isv;
+  const double resid = vk - vhat;                                  /* :133 */
+  for (int j = 0; j < N6; ++j) x[j] = fma(L[j], resid, x[j]);      /* :161 */
+  for (int i = 0; i < N6; ++i)
+    for (int j = i; j < N6; ++j) S[sym6(i, j)] = fma(-(L[i] * svt), L[j], S[sym6(i, j)]);   /* :163 */
+  if (psd_repair6(S, cf->force_jacobi)) st[S_NJAC] += 1.0;         /* :164-166 */
+  if (resid * resid > 9.0 * svt) {                                 /* :169-172 */
+    for (int k = 0; k < NSYM6; ++k) S[k] = S[k] * 2.0;
+    st[S_NBUMP] += 1.0;
+  }
+  SOC = st[S_EKFSOC0] - x[5] * rpa;                                /* :176 */
+  get_xind(bk, Tk, SOC, &X);                                       /* :181 */
+  vhat = get_variables(bk, st, ik, &X, Tk, Z, &SOCn, &SOCp, x);    /* :182 */
+  const double Zsoc = st[S_EKFSOC0] - x[5] * rpa;                  /* :416 */
+  st[S_PRIORI] = ik;                                               /* :210 */
+  double zk[64 + 2];
+  for (int r = 0; r < nz; ++r) zk[r] = Z[r];
+  {
+    const double Phise0 = Z[bk->r_phise0];
+    for (int k = 0; k < bk->n_phie; ++k) zk[bk->phie[k]] = Z[bk->phie[k]] - Phise0;
+    for (int k = 0; k < bk->n_posphis; ++k) zk[bk->posphis[k]] = Z[bk->posphis[k]] + vhat;
+    zk[nz] = vhat;
+    zk[nz + 1] = Zsoc;
+  }
+  if (zk_out) for (int r = 0; r < nz + 2; ++r) zk_out[r] = zk[r];
+  if (bound_out) {                                                 /* :199-205 with getChatZ's MB branches (:538,554-558,596-600) */
+    const double xSOC = st[S_EKFSOC0] - x[5] * rpa;
+    const double sn = soc_e(p, P_NEG, xSOC), sp = soc_e(p, P_POS, xSOC);
+    const double Rfn = rf_e(p, P_NEG, sn, st[S_ARRRFN]), Rfp = rf_e(p, P_POS, sp, st[S_ARRRFP]);
+    const double k0n = k0_e(p, P_NEG, sn, st[S_ARRK0N]), k0p = k0_e(p, P_POS, sp, st[S_ARRK0P]);
+    const double th0 = zk[bk->r_tss0], th3 = zk[bk->r_tss3];
+    const double i0n = k0n * sqrt((zk[bk->thetae[0]] * (1.0 - th0)) * th0);
+    const double i0p = k0p * sqrt((zk[bk->thetae[bk->n_thetae - 1]] * (1.0 - th3)) * th3);
+    const double Rctn = (p[P_R] * Tk) / (p[P_F] * i0n), Rctp = (p[P_R] * Tk) / (p[P_F] * i0p);
+    const double dUn0 = duocp_n(p, th0), dUp3 = duocp_p(p, th3);
+    const double dsn = soc_e(p, P_NEG, 1.0) - soc_e(p, P_NEG, 0.0), dsp = soc_e(p, P_POS, 1.0) - soc_e(p, P_POS, 0.0);
+    double CV[N6];
+    for (int j = 0; j < N5; ++j) {
+      double v = Rfp * MB_RSUM(bk->r_ifdl3, j) - Rfn * MB_RSUM(bk->r_ifdl0, j);
+      v = (v + Rctp * MB_RSUM(bk->r_if3, j)) - Rctn * MB_RSUM(bk->r_if0, j);
+      v = v + MB_RSUM(bk->r_phie_last, j);
+      v = (v + dUp3 * MB_RSUM(bk->r_tss3, j)) - dUn0 * MB_RSUM(bk->r_tss0, j);
+      CV[j] = v;
+    }
+    CV[5] = (((-dUp3) * bk->Ts) * dsp) / (3600.0 * p[P_Q]) - (((-dUn0) * bk->Ts) * dsn) / (3600.0 * p[P_Q]);
+    const double res0n = ((-bk->Ts) * dsn) / (3600.0 * p[P_Q]), res0p = ((-bk->Ts) * dsp) / (3600.0 * p[P_Q]);   /* :562-565 */
+    const double dUn = duocp_n(p, sn), dUp = duocp_p(p, sp);       /* :579-580 */
+    unsigned char kind[64];
+    memset(kind, 0, sizeof kind);
+    for (int k = 0; k < bk->n_posphis; ++k) kind[bk->posphis[k]] = 1;
+    for (int k = 0; k < bk->n_negtss; ++k) kind[bk->negtss[k]] = 2;
+    for (int k = 0; k < bk->n_postss; ++k) kind[bk->postss[k]] = 3;
+    for (int k = 0; k < bk->n_negphise; ++k) kind[bk->negphise[k]] = 4;
+    for (int k = 0; k < bk->n_posphise; ++k) kind[bk->posphise[k]] = 5;
+    for (int k = 0; k < bk->n_phie; ++k) kind[bk->phie[k]] = 6;
+    for (int r = 0; r <= nz; ++r) {
+      double row[N6];
+      if (r < nz) {
+        double c0 = 0.0;
+        if (kind[r] == 1) c0 = CV[5];
+        else if (kind[r] == 2) c0 = res0n;
+        else if (kind[r] == 3) c0 = res0p;
+        else if (kind[r] == 4) c0 = dUn * res0n;
+        else if (kind[r] == 5) c0 = dUp * res0p;
+        else if (kind[r] == 6) c0 = -dUn * res0n;
+        for (int j = 0; j < N5; ++j) {
+          double v = MB_RSUM(r, j);
+          if (kind[r] == 1) v = v + CV[j];                         /* :555-557 */
+          if (kind[r] == 6) v = v - MB_RSUM(bk->r_phise0, j);      /* :597-599 */
+          row[j] = v;
+        }
+        row[5] = c0;
+      } else {
+        for (int j = 0; j < N6; ++j) row[j] = CV[j];
+      }
+      double t = 0.0;
+      for (int i = 0; i < N6; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < N6; ++j) acc += S[sym6(i, j)] * row[j];
+        t += row[i] * acc;
+      }
+      bound_out[r] = 3.0 * sqrt(t);                                /* :205 */
+    }
+    const double res = -bk->Ts / (3600.0 * p[P_Q]);
+    bound_out[nz + 1] = 3.0 * sqrt((res * S[sym6(5, 5)]) * res);   /* :203 */
+  }
+#undef MB_RSUM
+  o->vhat = vhat;
+  o->soc = Zsoc;
+  ekf_mats(bk, st, &X, Z, Zsoc, x[5], o);                          /* EKFmatsHandler.m:26-114; M(iT,iZ).xhat stays 0 in MB mode */
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -965,6 +1219,12 @@ void mko_cell_init(const mko_bank *bk, const mko_config *cf, double *st, double 
     for (int i = 0; i < N5; ++i)
       for (int j = i; j < N5; ++j, ++q) Sig[NSYM * m + q] = SigmaX0[j * 6 + i];
   }
+  {                                                                /* initKF.m:100-101 (used by the MB method only) */
+    double *xm = st + st_off_mbx(M), *Sm = st + st_off_mbs(M);
+    for (int j = 0; j < N6; ++j) xm[j] = 0.0;
+    for (int i = 0; i < N6; ++i)
+      for (int j = i; j < N6; ++j) Sm[sym6(i, j)] = SigmaX0[j * 6 + i];
+  }
   st[S_UK] = 0.0;                                                  /* initMPC.m:51, runMPC.m:72 */
   for (int k = 0; k < 7; ++k) st[S_UMAX + k] = limits[k];
   plant_step(bk, st, 0.0);                                         /* runMPC.m:74 (Q20) */
@@ -1041,6 +1301,22 @@ void mko_iter_ekf(const mko_bank *bk, const mko_config *cf, double *st, double v
   for (int j = 0; j < 5; ++j) mats[q++] = e.Cphi[j];
   mats[q++] = e.Dphi; mats[q++] = e.bv; mats[q++] = e.bphi; mats[q++] = e.vhat; mats[q++] = e.soc;
   mats[q++] = 0.0; /* reserved */
+}
+
+/* the same call with the model-blend filter ('MdlB'); bounds (nz+2) optional */
+void mko_iter_ekf_mb(const mko_bank *bk, const mko_config *cf, double *st, double vk, double ik, double *zk, double *bounds, double *mats) {
+  ekf_out e;
+  memset(&e, 0, sizeof e);
+  ekf_step_mb(bk, cf, st, vk, ik, &e, zk, bounds);
+  int q = 0;
+  mats[q++] = e.lost; mats[q++] = e.iT + 1; mats[q++] = e.iZ + 1;
+  for (int j = 0; j < 6; ++j) mats[q++] = e.xhat[j];
+  for (int j = 0; j < 5; ++j) mats[q++] = e.a[j];
+  for (int j = 0; j < 5; ++j) mats[q++] = e.Cv[j];
+  mats[q++] = e.Dv;
+  for (int j = 0; j < 5; ++j) mats[q++] = e.Cphi[j];
+  mats[q++] = e.Dphi; mats[q++] = e.bv; mats[q++] = e.bphi; mats[q++] = e.vhat; mats[q++] = e.soc;
+  mats[q++] = 0.0;
 }
 
 /* predMat for a scalar output (returns h[0..Np], Phi*x part) */

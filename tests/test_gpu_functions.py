@@ -248,3 +248,34 @@ def test_kelvin_temperature_is_rejected(bank):
         cb.init(pop.SOC0, T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
     cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)        # the batch is still usable
     assert np.isfinite(cb.ob_step(np.zeros(8))).all()
+
+
+def test_model_blend_ekf_vs_c_oracle(bank, coracle_mod):
+    """mek_pop_iter_ekf of a population created with ekf_method = 'MdlB' (initKF's blend argument): zk, boundzk and mats
+    bit for bit like the C restatement of iterEKF.m's MB branches; the fused loop refuses this method."""
+    from mek import api, population as P
+    B = 24
+    pop = P.make_population(bank.params[2], B, seed=15, heterogeneous=True, ekf_soc_error=3.0)
+    cb = api.CellBatch(api.RomBank(bank), B, ekf_method="MdlB")
+    cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    co = coracle_mod.COracle(bank)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    rng = np.random.default_rng(6)
+    for k in range(40):
+        I = rng.uniform(-60, 5, B)
+        V = cb.ob_step(I)
+        zk, bz, mats = cb.iter_ekf(V, I, want_bounds=True)
+        for c in range(B):
+            assert V[c] == co.ob_step(c, I[c])
+            zkc, bzc, matsc = co.iter_ekf_mb(c, V[c], I[c])
+            assert np.array_equal(zk[c], zkc), (k, c)
+            assert np.array_equal(bz[c], bzc, equal_nan=True), (k, c)
+            assert np.array_equal(mats[c], matsc), (k, c)
+    assert np.all(mats[:, 8] != 0.0) and np.all(mats[:, 3:8] == 0.0)     # EKFmatsHandler.m:33 in MB mode
+    # the state block carries the blended filter behind the model rows; a round trip preserves it
+    st = cb.read_state()
+    assert st.shape[1] == cb.state_len and cb.state_len == 40 + cb.nC + 26 * bank.M + 27
+    with pytest.raises(api.MekError, match="output-blend"):
+        cb.run(0, 5)
+    # and the method names of initKF.m:44-53
+    assert api.CellBatch(api.RomBank(bank), 2, ekf_method="nonsense").cfg.ekf_method == 0

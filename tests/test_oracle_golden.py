@@ -99,3 +99,32 @@ def test_function_level_c_vs_literal(bank, coracle_mod):
         assert np.allclose(mats[14:19], MPC.Cv[:5], rtol=1e-10) and np.isclose(mats[19], MPC.Dv, rtol=1e-10)
         assert np.allclose(mats[20:25], MPC.Cphi[:5], rtol=1e-12) and mats[25] == MPC.Dphi
         assert np.isclose(mats[26], MPC.bv, rtol=1e-10) and np.isclose(mats[27], MPC.bphi, rtol=1e-12)
+
+
+def test_model_blend_ekf_c_vs_literal(bank, coracle_mod):
+    """iterEKF's other `blend` method ('MdlB', iterEKF.m:90-102,125-128,160-176,199-203 + the MB branches of getVariables /
+    getChatV / getChatZ): one blended 6-state model per cell.  C restatement vs the literal one on a driven cell: full zk,
+    the 3-sigma bounds and EKFmatsHandler's output (whose integrator entry ekfData.xhat(end) is non-zero in this mode, Q3)."""
+    from oracle import literal as L
+    ROM = L.build_rom(bank)
+    SigmaX0 = np.diag([1.0] * 5 + [2e6])
+    kf = L.initKF(22.0, 30.0, SigmaX0, 1e-3, 1e2, "MdlB", ROM)
+    assert kf.method == "MB"
+    V, obs, cs = L.OB_step(0.0, 30.0, None, ROM, dict(SOC0=20.0, warnOff=True))
+    co = coracle_mod.COracle(bank)
+    co.init([20.0], 30.0, SigmaX0, coracle_mod.default_limits(bank), [22.0])
+    rng = np.random.default_rng(0)
+    for k in range(250):
+        I = float(rng.uniform(-60, 5)) if k < 180 else -30.0
+        V, obs, cs = L.OB_step(I, 30.0, cs, ROM)
+        Vc = co.ob_step(0, I)
+        zk, zb, kf, X = L.iterEKF(V, I, 30.0, kf)
+        MPC, xhat = L.EKFmatsHandler(kf, X, zk, 30.0)
+        zkc, zbc, mats = co.iter_ekf_mb(0, Vc, I)
+        assert np.allclose(zk, zkc, rtol=1e-9, atol=1e-12), k
+        assert np.allclose(zb, zbc, rtol=1e-9, atol=1e-14), k
+        assert mats[1] == MPC.iT and mats[2] == MPC.iZ
+        assert np.allclose(mats[3:9], xhat, rtol=1e-9, atol=1e-9) and xhat[5] != 0.0 and np.all(xhat[:5] == 0.0)
+        assert np.allclose(mats[14:19], MPC.Cv[:5], rtol=1e-10) and np.isclose(mats[26], MPC.bv, rtol=1e-9)
+    th0, th100 = bank.params[5], bank.params[6]                   # neg.theta0 / theta100: electrode stoichiometry -> cell SOC
+    assert abs(zk[-1] - (cs.SOCnAvg - th0) / (th100 - th0)) < 0.03    # the filter (started 2 % off) tracks the driven plant
