@@ -93,6 +93,10 @@ typedef struct {
                                instead of the lean one that applies when the only all-zero row is the first z_max row;
                                2: the lean sweep never skips the tail of a row that is idle in every cell of the warp
                                (results are unchanged either way)                                                  */
+  int z_target_terminal;    /* mpcData.const.z_target_terminal (constraintsMPC.m:104-112; never set by runMPC): one more row,
+                               -G_soc(end,:)*DU <= -z_max + Phi_soc(end,:)*x_aug.  Generic kernel instances only           */
+  double z_tol;             /* mpcData.const.z_tol (runMPC.m:44, 0 there).  limits[6] carries z_max + z_tol; the terminal row
+                               uses limits[6] - z_tol for z_max                                                            */
   int ekf_method;           /* initKF's `blend` argument (initKF.m:44-53): 0 = 'OutB' output blend (what runMPC.m:16 selects; the
                                fused loop mek_run supports only this), 1 = 'MdlB' model blend: one blended model per cell,
                                served by the function-level entry mek_pop_iter_ekf (iterEKF.m MB branches)               */
@@ -185,6 +189,7 @@ int mek_pred_mat(int64_t B, const double *a, const double *c, const double *d, i
  * mek_pop_iter_ekf (diag A, Cv, Dv, Cphi, Dphi, bv, bphi are read); SOCk_1[B]; limits[7*B]; r = -Ts/(3600*Q)
  * (EKFmatsHandler.m:43); ref = mpcData.ref.  Outputs M[nC*Nc*B], gamma[nC*B]; optional E[Nc*Nc*B], F[Nc*B],
  * DU[Nc*B] (iterMPC.m:38-48). */
+/* use_zmax: bit 0 = the SOC upper-bound rows, bit 1 = the optional terminal row (with z_tol = 0) */
 int mek_constraints(int64_t B, int Np, int Nc, const int *constraints, int use_zmax, const double *x_aug, const double *mats,
                     const double *SOCk_1, const double *limits, double *M, double *gamma, double r, double ref, double *E,
                     double *F, double *DU, int device);

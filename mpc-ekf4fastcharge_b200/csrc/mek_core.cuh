@@ -41,6 +41,8 @@ struct Dims {
   int nC;            // constraint rows
   int Np, Nc, maxHild;
   int useCurrent, useVoltage, useEta, useZmax;
+  int useTerm;       // mpcData.const.z_target_terminal (constraintsMPC.m:104-112): one more row; generic instances only
+  double z_tol;      // mpcData.const.z_tol: the per-cell z_max limit carries z_max + z_tol, the terminal row wants z_max
   int force_jacobi;
   int no_lean_sweep;  // test hook: static-shape instances always take the general Hildreth sweep
   int no_row_skip;    // test hook: the lean sweep never skips the tail of an idle row
@@ -1051,7 +1053,7 @@ __device__ __forceinline__ int hildreth_core(int Nc, int nC, const double* LU, c
 // constraints M, gamma in the reference's row order.
 template <int NPM, int NCM>
 struct MpcProblem {
-  static constexpr int NCONM = 4 * NCM + 3 * NPM;
+  static constexpr int NCONM = 4 * NCM + 3 * NPM + 1;   // + the optional terminal row
   double F[NCM], E[NCM * NCM], LU[NCM * NCM], DU[NCM];
   double Mm[NCONM * NCM], gam[NCONM];
   int nC;
@@ -1163,6 +1165,12 @@ __device__ __forceinline__ void mpc_setup(const Dims& d, double r /* Csoc(end), 
       gam[nC] = lim.z_max - ((pxs[i - 1] + hs[i] * uk_1) + e.soc);
     }
   }
+  if (d.useTerm) {                                                   // constraintsMPC.m:104-112: -G_s(end,:)*DU <= -z_max + Phi_s(end,:)*x_aug
+#pragma unroll
+    for (int j = 0; j < NCM; ++j) Mm[nC * NCM + j] = (Np - 1 - j >= 0 && j < Nc) ? -hs[Np - 1 - j >= 0 ? Np - 1 - j : 0] : -0.0;
+    gam[nC] = -(lim.z_max - d.z_tol) + (pxs[Np - 1] + hs[Np] * uk_1);
+    ++nC;
+  }
   q.nC = nC;
 }
 
@@ -1190,7 +1198,7 @@ __device__ __forceinline__ double mpc_cost_J(int Np, int Nc, const MpcProblem<NP
 template <int NPM, int NCM>
 __device__ __forceinline__ void mpc_step(const Dims& d, const double* __restrict__ p, const Cell& c, const EkfOut& e, double uk_applied,
                                          MpcOut& o, double* cost = nullptr /* J_uncon, J_final, norm_DU, viol */) {
-  constexpr int NCONM = 4 * NCM + 3 * NPM;
+  constexpr int NCONM = MpcProblem<NPM, NCM>::NCONM;
   const int Nc = d.Nc;
   const double uk_1 = c.f(S_UK);                                     // iterMPC.m:19
   {                                                                  // runMPC.m:94-95 (Q24)

@@ -892,7 +892,9 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   d.Np = Np; d.Nc = Nc; d.maxHild = cfg->maxHild > 0 ? cfg->maxHild : 100;
   d.useCurrent = cfg->constraints[0] == 1; d.useVoltage = cfg->constraints[1] == 1; d.useEta = cfg->constraints[2] == 1;
   d.useZmax = cfg->use_zmax != 0;
-  d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax);
+  d.useTerm = cfg->z_target_terminal != 0;
+  d.z_tol = cfg->z_tol;
+  d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax) + d.useTerm;
   if (d.nC > 128) { return fail(MEK_ERR_UNSUPPORTED, "more than 128 constraint rows"); }
   d.force_jacobi = cfg->force_jacobi;
   d.no_lean_sweep = cfg->general_sweep_test == 1 ? 1 : 0;
@@ -973,14 +975,14 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   p->run_smem = p->smem_bytes;
   {
     const int mask = (d.useCurrent ? 1 : 0) | (d.useVoltage ? 2 : 0) | (d.useEta ? 4 : 0) | (d.useZmax ? 8 : 0);
-    if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path) {
+    if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path && !d.useTerm) {
       p->cons = mask;
       p->run_threads = (cfg->threads_per_block == 384) ? 384 : 256;   // 256 threads x 255 registers: fewest spills, least DRAM traffic
       const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
       p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
     }
-    if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path) {   // config C4: long-horizon static-shape instance
+    if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path && !d.useTerm) {   // config C4: long-horizon static-shape instance
       using WS = WideShape<20, 5, 15>;
       p->cons = mask;
       // 256 threads (default): lambda in shared memory, the read-mostly columns in L2; 64 threads: every column in shared memory
@@ -1563,8 +1565,9 @@ extern "C" int mek_constraints(int64_t B, int Np, int Nc, const int* constraints
   Dims d;
   memset(&d, 0, sizeof(d));
   d.Np = Np; d.Nc = Nc; d.Ts = 1.0; d.ref = ref;
-  d.useCurrent = constraints[0] == 1; d.useVoltage = constraints[1] == 1; d.useEta = constraints[2] == 1; d.useZmax = use_zmax != 0;
-  d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax);
+  d.useCurrent = constraints[0] == 1; d.useVoltage = constraints[1] == 1; d.useEta = constraints[2] == 1; d.useZmax = (use_zmax & 1) != 0;
+  d.useTerm = (use_zmax & 2) != 0;
+  d.nC = (d.useCurrent ? 4 * Nc : 0) + Np * (d.useVoltage + d.useEta + d.useZmax) + d.useTerm;
   if (d.nC < 1 || d.nC > 128) return fail(MEK_ERR_UNSUPPORTED, "constraint row count outside 1..128");
   d.sigmin = sigma_min_gtg(Np, Nc, r);
   const size_t b = (size_t)B, nC = (size_t)d.nC;

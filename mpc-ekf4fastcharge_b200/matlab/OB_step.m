@@ -5,7 +5,8 @@ function [Vcell, obs, cellState] = OB_step(Iapp, Tc, cellState, ROM, initCfg)
 if nargin < 3 || isempty(cellState)
   if nargin < 5 || ~isfield(initCfg, 'SOC0'), error('First call requires initCfg.SOC0 (in %).'); end   % OB_step.m:40-42
   kf = initCfg.ekfData; mp = initCfg.mpcData; c = mp.const; B = numel(initCfg.SOC0);
-  cfg = [mp.Np mp.Nc mp.maxHild double(c.constraints) 1 mp.ref kf.SigmaV kf.SigmaW double(strcmp(kf.method, 'MB'))];
+  term = isfield(c, 'z_target_terminal') && c.z_target_terminal;                                       % constraintsMPC.m:104
+  cfg = [mp.Np mp.Nc mp.maxHild double(c.constraints) 1 mp.ref kf.SigmaV kf.SigmaW double(strcmp(kf.method, 'MB')) double(term) c.z_tol];
   pop = mek_mex('pop_create', ROM.bank, cfg, B, 0);
   one = ones(1, B);
   lim = [c.u_max.*one; c.u_min.*one; c.du_max.*one; c.du_min.*one; c.v_max.*one; c.phise_min.*one; (c.z_max + c.z_tol).*one];

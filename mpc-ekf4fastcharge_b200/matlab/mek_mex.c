@@ -43,7 +43,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     mexLock();
     plhs[0] = put_handle(b);
   } else if (!strcmp(cmd, "pop_create")) {               /* h = mek_mex('pop_create', bank, cfgvec, B, device) */
-    const double *c = mxGetPr(prhs[2]);                  /* [Np Nc maxHild c1 c2 c3 use_zmax ref SigmaV SigmaW (ekf_method)] */
+    const double *c = mxGetPr(prhs[2]);                  /* [Np Nc maxHild c1 c2 c3 use_zmax ref SigmaV SigmaW (ekf_method (z_target_terminal z_tol))] */
     mek_config cfg;
     mek_pop *p = NULL;
     memset(&cfg, 0, sizeof cfg);
@@ -51,6 +51,9 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     cfg.constraints[0] = (int)c[3]; cfg.constraints[1] = (int)c[4]; cfg.constraints[2] = (int)c[5];
     cfg.use_zmax = (int)c[6]; cfg.ref = c[7]; cfg.SigmaV = c[8]; cfg.SigmaW = c[9];
     if (mxGetNumberOfElements(prhs[2]) > 10) cfg.ekf_method = (int)c[10];   /* initKF's blend: 0 'OutB', 1 'MdlB' */
+    if (mxGetNumberOfElements(prhs[2]) > 12) {                              /* mpcData.const.z_target_terminal, .z_tol (constraintsMPC.m:104-112) */
+      cfg.z_target_terminal = c[11] != 0.0; cfg.z_tol = c[12];
+    }
     chk(mek_pop_create((mek_bank *)get_handle(prhs[1]), &cfg, (int64_t)mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[4]), &p));
     plhs[0] = put_handle(p);
   } else if (!strcmp(cmd, "pop_init")) {                 /* mek_mex('pop_init', pop, SOC0, ekfSOC0, Tc, SigmaX0(6,6,B), limits(7,B)) */

@@ -28,7 +28,8 @@ class MekConfig(C.Structure):
     _fields_ = [("Np", C.c_int), ("Nc", C.c_int), ("maxHild", C.c_int), ("constraints", C.c_int * 3), ("use_zmax", C.c_int),
                 ("ref", C.c_double), ("SigmaV", C.c_double), ("SigmaW", C.c_double), ("force_jacobi", C.c_int),
                 ("threads_per_block", C.c_int), ("blocks_per_sm", C.c_int), ("generic_path", C.c_int), ("sync_steps", C.c_int), ("keep_cell_order", C.c_int),
-                ("defer_block", C.c_int), ("defer_stagger", C.c_int), ("regroup_every", C.c_int), ("defer_narrow_test", C.c_int), ("general_sweep_test", C.c_int), ("ekf_method", C.c_int)]
+                ("defer_block", C.c_int), ("defer_stagger", C.c_int), ("regroup_every", C.c_int), ("defer_narrow_test", C.c_int), ("general_sweep_test", C.c_int),
+                ("z_target_terminal", C.c_int), ("z_tol", C.c_double), ("ekf_method", C.c_int)]
 
 
 class MekBankDesc(C.Structure):

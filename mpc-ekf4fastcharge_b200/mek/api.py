@@ -69,7 +69,8 @@ class CellBatch:
 
     def __init__(self, rom: RomBank, B, Np=5, Nc=2, constraints=(1, 1, 1), ref=95.0, SigmaV=1e-3, SigmaW=1e2, maxHild=100,
                  use_zmax=True, force_jacobi=False, device=0, threads_per_block=0, blocks_per_sm=0, generic_path=False, sync_steps=True, keep_cell_order=False,
-                 defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=0, ekf_method="OutB"):
+                 defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=0, ekf_method="OutB",
+                 z_target_terminal=False, z_tol=0.0):
         L = _lib.lib()
         self.rom = rom
         self.B = int(B)
@@ -88,6 +89,7 @@ class CellBatch:
         cfg.defer_narrow_test = int(bool(defer_narrow_test))
         cfg.general_sweep_test = int(general_sweep_test)
         cfg.regroup_every = int(regroup_every)
+        cfg.z_target_terminal, cfg.z_tol = int(bool(z_target_terminal)), float(z_tol)
         blend = str(ekf_method).upper()                      # initKF.m:44-53: unknown strings fall back to output blending
         cfg.ekf_method = 1 if blend in ("MDLB", "MB") else 0
         self.cfg = cfg
@@ -272,15 +274,15 @@ def pred_mat_batch(a, c, d, Np, Nc, device=0):
     return Phi, G
 
 
-def constraints_batch(x_aug, mats, SOCk_1, limits, Np, Nc, constraints, r, ref=95.0, use_zmax=True, device=0):
+def constraints_batch(x_aug, mats, SOCk_1, limits, Np, Nc, constraints, r, ref=95.0, use_zmax=True, device=0, z_target_terminal=False):
     """constraintsMPC.m (+ iterMPC.m:38-48) over B problems -> M [B,nC,Nc], gamma [B,nC], E, F, DU."""
     x_aug = _f64(x_aug); mats = _f64(mats); SOCk_1 = _f64(SOCk_1); limits = _f64(limits)
     B = x_aug.shape[0]
     Np = max(1, int(round(Np))); Nc = max(1, min(int(round(Nc)), Np))
     cons = (C.c_int * 3)(*[int(c) for c in constraints])
-    nC = (4 * Nc if cons[0] == 1 else 0) + Np * (int(cons[1] == 1) + int(cons[2] == 1) + int(bool(use_zmax)))
+    nC = (4 * Nc if cons[0] == 1 else 0) + Np * (int(cons[1] == 1) + int(cons[2] == 1) + int(bool(use_zmax))) + int(bool(z_target_terminal))
     M = np.empty((B, nC, Nc)); g = np.empty((B, nC)); E = np.empty((B, Nc, Nc)); F = np.empty((B, Nc)); DU = np.empty((B, Nc))
-    check(_lib.lib().mek_constraints(B, Np, Nc, cons, int(bool(use_zmax)), _p(x_aug), _p(mats), _p(SOCk_1), _p(limits), _p(M), _p(g),
+    check(_lib.lib().mek_constraints(B, Np, Nc, cons, int(bool(use_zmax)) | (2 if z_target_terminal else 0), _p(x_aug), _p(mats), _p(SOCk_1), _p(limits), _p(M), _p(g),
                                      float(r), float(ref), _p(E), _p(F), _p(DU), int(device)))
     return M, g, E, F, DU
 

@@ -40,7 +40,7 @@
 #define NSYM 15
 #define NP_MAX 32
 #define NC_MAX 8
-#define NCON_MAX (4 * NC_MAX + 3 * NP_MAX)
+#define NCON_MAX (4 * NC_MAX + 3 * NP_MAX + 1)   /* + the optional terminal row (constraintsMPC.m:104-112) */
 #define MAXROWS 64   /* nz <= 64: no group of output rows can overflow */
 
 /* parameter vector layout (restated; equals mek/bank.py) */
@@ -72,6 +72,8 @@ typedef struct {
   int useCurrent, useVoltage, useEta, useZmax;
   double ref, SigmaV, SigmaW;
   int force_jacobi; /* 1: always run the eigen-decomposition PSD repair (validation of the PD fast path) */
+  int z_target_terminal; /* mpcData.const.z_target_terminal (constraintsMPC.m:104): one more row, SOC(Np) >= z_max */
+  double z_tol;          /* mpcData.const.z_tol (runMPC.m:44); the z_max limit of the state carries z_max + z_tol */
 } mko_config;
 
 /* per-cell state, flat doubles (also the host-side AoS layout of mek_read_state) */
@@ -1158,6 +1160,11 @@ static void mpc_step(const mko_bank *bk, const mko_config *cf, double sigmin, do
       for (int j = 0; j < Nc; ++j) Mm[nC * Nc + j] = (i - 1 - j >= 0) ? hs[i - 1 - j] : 0.0;
       gam[nC] = st[S_ZMAX] - ((pxs[i - 1] + hs[i] * uk_1) + e->soc);
     }
+  }
+  if (cf->z_target_terminal) {                                     /* :104-112: -G_s(end,:)*DU <= -z_max + Phi_s(end,:)*x_aug (no SOC_k baseline) */
+    for (int j = 0; j < Nc; ++j) Mm[nC * Nc + j] = (Np - 1 - j >= 0) ? -hs[Np - 1 - j] : -0.0;
+    gam[nC] = -(st[S_ZMAX] - cf->z_tol) + (pxs[Np - 1] + hs[Np] * uk_1);
+    ++nC;
   }
   OPC_BLOCK(5);
   int viol = 0;                                                    /* iterMPC.m:66 (Q8) */

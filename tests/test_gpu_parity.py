@@ -314,3 +314,23 @@ def test_cuda_matches_literal_golden(bank, path):
     for k in ("u", "V", "SOC", "phise"):
         assert rel_err(o[k], g[k], SCALE[k]) <= 1e-9, k
 
+
+
+def test_terminal_constraint_row(bank, coracle_mod):
+    """The optional terminal row of constraintsMPC.m:104-112 (generic kernel instance: 24 rows at Np 5 / Nc 2)."""
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 48, seed=61)
+    cb, g, co, c = None, None, None, None
+    from mek import api
+    rom = api.RomBank(bank)
+    cb = api.CellBatch(rom, len(pop), z_target_terminal=True)
+    assert cb.nC == 24
+    cb.set_logging(len(pop), 200)
+    cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    cb.run(0, 200)
+    g = cb.logs(0, 200)
+    co = coracle_mod.COracle(bank, z_target_terminal=True)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    c = co.run(0, 200, nthreads=8)
+    _assert_bit_exact(g, c)
+    assert ((g["active"][:, :, 0] >> 23) & 1).any()

@@ -128,3 +128,21 @@ def test_model_blend_ekf_c_vs_literal(bank, coracle_mod):
         assert np.allclose(mats[14:19], MPC.Cv[:5], rtol=1e-10) and np.isclose(mats[26], MPC.bv, rtol=1e-9)
     th0, th100 = bank.params[5], bank.params[6]                   # neg.theta0 / theta100: electrode stoichiometry -> cell SOC
     assert abs(zk[-1] - (cs.SOCnAvg - th0) / (th100 - th0)) < 0.03    # the filter (started 2 % off) tracks the driven plant
+
+
+def test_terminal_constraint_row_c_vs_literal(bank, coracle_mod):
+    """mpcData.const.z_target_terminal (constraintsMPC.m:104-112; runMPC never sets it): one more row demanding SOC(Np) >= z_max,
+    with Phi_s(end,:)*x_aug but WITHOUT the SOC_k baseline the z_max rows add (:90).  From 10 % SOC that QP is infeasible and
+    the loop answers with kA-sized commands -- the reference's behaviour, reproduced, not fixed."""
+    from oracle import literal as L
+    N = 120
+    o = L.run_mpc(bank, SOC0=10.0, N=N, limits=dict(z_target_terminal=True))
+    co = coracle_mod.COracle(bank, z_target_terminal=True)
+    assert co.nC == 24
+    co.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
+    c = co.run(0, N, nthreads=1)
+    assert np.array_equal(o["nexec"][:N], c["nexec"][:, 0]) and np.array_equal(o["active"][:N], c["active"][:, 0])
+    assert (c["active"][:, 0, 0] >> 23 & 1).any()                  # the terminal row (index 23) becomes active
+    for k in ("u", "V", "SOC", "phise"):
+        assert rel_err(c[k][:, 0], o[k][:N], SCALE[k]) <= TOL, k
+    assert np.nanmax(np.abs(c["u"])) > 1e3
