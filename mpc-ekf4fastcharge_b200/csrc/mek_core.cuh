@@ -429,6 +429,7 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   double tlo[9], tcur[9];
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
+    if (h ? (aT == 0.0) : (aT == 1.0)) continue;                     // that row's blend weight is exactly zero (see below)
     const int iT = h ? iTup : iTlo;
     const int ma = iT * d.nZ + iZlo, mb = iT * d.nZ + iZup;
     const double* ra = bk.mdl + ma * d.mstride + 6;
@@ -456,7 +457,8 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   if (ADVANCE) stream_models<true, false>(d, bk, c, Iapp, 0.0);         // :278 advance ALL models
   double yk[9];
 #pragma unroll
-  for (int r = 0; r < 9; ++r) yk[r] = (1.0 - aT) * tlo[r] + aT * tcur[r];   // :285
+  for (int r = 0; r < 9; ++r)                                        // :285; a zero weight leaves the other row as it is
+    yk[r] = (aT == 0.0) ? tlo[r] : ((aT == 1.0) ? tcur[r] : (1.0 - aT) * tlo[r] + aT * tcur[r]);
   double tss0 = yk[HR_TSS0] + c.f(S_SOC0N), tss3 = yk[HR_TSS3] + c.f(S_SOC0P);   // :304-305 (Q6)
   tss0 = fmin(fmax(tss0, 1e-6), 1.0 - 1e-6);                         // :309-310
   tss3 = fmin(fmax(tss3, 1e-6), 1.0 - 1e-6);
@@ -479,6 +481,52 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
 // ------------------------------------------------------------------------------------------
 // EKF pieces
 // ------------------------------------------------------------------------------------------
+// Blend of the four neighbours' outputs with the bilinear weights (iterEKF.m:302-313, "[...]*Xind.gamma").  A neighbour whose
+// weight is EXACTLY zero contributes nothing -- the rule of this build and of oracle/mek_oracle.c: the
+// reference adds its +-0 product, which changes nothing but the sign of an exact zero (or everything, if that neighbour's
+// output is non-finite).  A cell whose temperature sits on a set-point of the bank (runMPC's own 25 degC) has two such
+// neighbours at every instant.
+__device__ __forceinline__ double blend4(const double (&yc)[4], const double (&g)[4]) {
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc = (g[k] != 0.0) ? fma(yc[k], g[k], acc) : acc;
+  return acc;
+}
+
+// Rows of getVariables' blended output (iterEKF.m:302-313, hot rows only), left in sc[SC_Z + r].  Two bodies: all four
+// neighbours, and the two neighbours k0, k0+1 of ONE temperature row for a cell whose temperature sits on a set-point (the other
+// row's weights are exactly zero: blend4 leaves it out, so it is not even loaded).  k0 is a run-time value, one body serves both rows.
+template <int NK>
+__device__ __forceinline__ void gv_rows_n(const Dims& d, const BankSmem& bk, const Cell& c, double ik, Scratch sc, int k0) {
+  double xk[NK][N5], g[NK];
+  const double* mm[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int m = (int)sc[SC_M + k0 + k];
+    g[k] = sc[SC_GAMMA + k0 + k];
+    mm[k] = bk.mdl + m * d.mstride + 6;
+#pragma unroll
+    for (int j = 0; j < N5; ++j) xk[k][j] = ld_row(&c.xhat(m, j));   // :267-270
+  }
+#pragma unroll 1
+  for (int r = 0; r < d.R; ++r) {                                    // :302-313  Z = [C1*x1+D1*i, ...]*gamma
+    if (r == HR_PHI) continue;
+    double z = 0.0;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const double2* pr = reinterpret_cast<const double2*>(mm[k] + r * HRS);
+      const double2 c01 = pr[0], c23 = pr[1], c4d = pr[2];
+      const double cr[N5] = {c01.x, c01.y, c23.x, c23.y, c4d.x};
+      double acc = cr[0] * xk[k][0];
+#pragma unroll
+      for (int j = 1; j < N5; ++j) acc = fma(cr[j], xk[k][j], acc);
+      const double yc = fma(c4d.y, ik, acc);
+      z = (g[k] != 0.0) ? fma(yc, g[k], z) : z;                      // blend4, term by term
+    }
+    sc[SC_Z + r] = z;
+  }
+}
+
 // getVariables (iterEKF.m:259-417) restricted to the rows that feed Vcell, the warnings and
 // EKFmatsHandler.  Reads the neighbour set from the scratch column (get_xind), leaves the corrected
 // outputs in sc[SC_Z + HR_*] and returns Vcell.  Warnings go straight to the cell's counters.
@@ -487,16 +535,6 @@ static __device__ __noinline__ double get_variables(const Dims& d, const BankSme
 #ifdef __CUDA_ARCH__
   __builtin_assume(__isShared(sc.p));              // address-space hint: LDS/STS for the scratch column, not generic LD/ST
 #endif
-  double xk[4][N5], g[4];
-  const double* mm[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int m = (int)sc[SC_M + k];
-    g[k] = sc[SC_GAMMA + k];
-    mm[k] = bk.mdl + m * d.mstride + 6;
-#pragma unroll
-    for (int j = 0; j < N5; ++j) xk[k][j] = ld_row(&c.xhat(m, j));   // :267-270
-  }
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
   const double xSOC = c.f(S_EKFSOC0) - c.f(S_X0) * rpa;              // :277
   double SOCn = soc_e(p, P_NEG, xSOC), SOCp = soc_e(p, P_POS, xSOC); // :282-283
@@ -507,21 +545,11 @@ static __device__ __noinline__ double get_variables(const Dims& d, const BankSme
   if (SOCp < 0.0) { ++nwarn; SOCp = 1e-6; }
   if (SOCp > 0.998) { ++nwarn; SOCp = 0.998; }
   const bool soc_clamped = nwarn != 0;
-#pragma unroll 1
-  for (int r = 0; r < d.R; ++r) {                                    // :302-313  Z = [C1*x1+D1*i, ...]*gamma, hot rows only
-    if (r == HR_PHI) continue;
-    double yc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double2* pr = reinterpret_cast<const double2*>(mm[k] + r * HRS);
-      const double2 c01 = pr[0], c23 = pr[1], c4d = pr[2];
-      const double cr[N5] = {c01.x, c01.y, c23.x, c23.y, c4d.x};
-      double acc = cr[0] * xk[k][0];
-#pragma unroll
-      for (int j = 1; j < N5; ++j) acc = fma(cr[j], xk[k][j], acc);
-      yc[k] = fma(c4d.y, ik, acc);
-    }
-    sc[SC_Z + r] = fma(yc[3], g[3], fma(yc[2], g[2], fma(yc[1], g[1], yc[0] * g[0])));
+  {
+    // a temperature on a set-point of the bank zeroes the weights of one temperature row (both of its neighbours)
+    const bool lo0 = sc[SC_GAMMA + 0] == 0.0 && sc[SC_GAMMA + 1] == 0.0, hi0 = sc[SC_GAMMA + 2] == 0.0 && sc[SC_GAMMA + 3] == 0.0;
+    if (lo0 != hi0) gv_rows_n<2>(d, bk, c, ik, sc, lo0 ? 2 : 0);
+    else gv_rows_n<4>(d, bk, c, ik, sc, 0);
   }
   // negThetass rows (:331-343): Thetass0 plus the extra rows, which only matter for the warnings
   double tss0, tss3, the0, the3;
@@ -704,7 +732,8 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   get_xind(d, bk, Tk, SOC, sc, tt_cached);                           // :107
   if (df) {
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
+    for (int k = 0; k < 4; ++k)
+      defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
   }
   double vhat = get_variables(d, bk, p, c, ik, Tk, sc);              // :108
   // SigmaX of neighbour #1 *before* any update: every gain uses it (:117, Q1).  Loaded here so that the L2 round trip
@@ -740,6 +769,18 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   for (int k = 0; k < 4; ++k) {                                      // :116-121 gain, :136-154 update; sequential (Q2)
     const int mo = (int)sc[SC_M + k];
     const double g = sc[SC_GAMMA + k];
+    if (g == 0.0) {
+      // zero weight: Chat = 0, so the gain is 0, svt = SigmaV, xhat and SigmaX stay as they are (:138,:142 add +-0) and the
+      // repair (:143-145) of an unchanged covariance is the identity up to rounding -- skipped, here and in the oracle.
+      // What is left of the update is the Q-bump (:148-151).
+      if (resid * resid > 9.0 * (0.0 + d.SigmaV)) {
+        defer_ensure(d, bk, c, df, mo);
+#pragma unroll
+        for (int q2 = 0; q2 < NSYM; ++q2) st_row(&c.sig(mo, q2), ld_row(&c.sig(mo, q2)) * 2.0);
+        ++nbump;
+      }
+      continue;
+    }
     const double* mm = bk.mdl + mo * d.mstride + 6;
     double Chat[N5], v[N5], L[N5], S[NSYM], xs[N5];
     // this neighbour's state, requested before the gain is computed (the loads overlap it); after the previous
@@ -794,7 +835,8 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   get_xind(d, bk, Tk, SOC, sc, tt_cached);                           // :181
   if (df) {                                                          // the estimate may have moved to other set-points
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
+    for (int k = 0; k < 4; ++k)
+      defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
   }
   vhat = get_variables(d, bk, p, c, ik, Tk, sc);                     // :182
   const double Zsoc = c.f(S_EKFSOC0) - x0 * rpa;                     // :416

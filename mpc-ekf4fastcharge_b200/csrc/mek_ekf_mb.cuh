@@ -113,7 +113,7 @@ __device__ double mb_get_variables(const Params& P, const RowLists& RL, const Ce
       for (int j = 1; j < N5; ++j) acc = fma(cr[j], x[j], acc);
       yc[k] = fma(P.Dfull[(size_t)mk[k] * d.nz + r], ik, acc);
     }
-    Z[r] = fma(yc[3], g[3], fma(yc[2], g[2], fma(yc[1], g[1], yc[0] * g[0])));
+    Z[r] = blend4(yc, g);
   }
   const double If0 = Z[RL.r_if0], If3 = Z[RL.r_if3];                  // :324-325
   bool any;

@@ -316,7 +316,7 @@ __device__ void full_zk(const Params& P, const BankSmem& bk, const Cell& c, doub
       for (int j = 1; j < N5; ++j) acc = fma(cr[j], xk[k][j], acc);
       yc[k] = fma(P.Dfull[(size_t)mk[k] * d.nz + r], ik, acc);
     }
-    zk[r] = fma(yc[3], gam4[3], fma(yc[2], gam4[2], fma(yc[1], gam4[1], yc[0] * gam4[0])));
+    zk[r] = blend4(yc, gam4);
   }
   zk[d.nz] = vhat;
   zk[d.nz + 1] = soc;       // the per-kind corrections (iterEKF.m:331-413) follow in k_iter_ekf

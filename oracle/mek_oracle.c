@@ -249,6 +249,14 @@ static int sym_idx(int i, int j) { /* upper triangle, row-major, i <= j */
 /* ------------------------------------------------------------------------------------------ */
 /* plant: OB_step.m simStep                                                                   */
 /* ------------------------------------------------------------------------------------------ */
+/* Zero-weight rule, on by default -- it is what the CUDA kernels do: a neighbour model whose bilinear
+   weight is EXACTLY zero (a temperature on a set-point of the bank: two of the four neighbours, at every instant) is left
+   out of every blend, and its measurement update -- zero gain, x and SigmaX unchanged, the PSD repair of an unchanged
+   covariance -- is skipped; the Q-bump is kept.  mko_set_zero_weight_skip(0) restores the term-by-term restatement of the
+   reference (same trajectories; tests/test_oracle_units.py asserts it, and the op-count table is taken in that mode). */
+static int zw_skip = 1;
+void mko_set_zero_weight_skip(int on) { zw_skip = on != 0; }
+
 static double plant_step(const mko_bank *bk, double *st, double Iapp) {
   OPC_BLOCK(0);
   const double *p = bk->params;
@@ -297,8 +305,10 @@ static double plant_step(const mko_bank *bk, double *st, double Iapp) {
   if (Zup != Zlo) aZ = (cellSOC - Zlo) / (Zup - Zlo);
   if (Tup != Tlo) aT = (T - Tlo) / (Tup - Tlo);
   double yk[9];
-  for (int r = 0; r < 9; ++r)                                      /* :285 */
-    yk[r] = (1.0 - aT) * ((1.0 - aZ) * y[0][r] + aZ * y[1][r]) + aT * ((1.0 - aZ) * y[2][r] + aZ * y[3][r]);
+  for (int r = 0; r < 9; ++r) {                                    /* :285; a temperature row with weight exactly zero is left out */
+    const double lo = (1.0 - aZ) * y[0][r] + aZ * y[1][r], hi = (1.0 - aZ) * y[2][r] + aZ * y[3][r];
+    yk[r] = (zw_skip && aT == 0.0) ? lo : ((zw_skip && aT == 1.0) ? hi : (1.0 - aT) * lo + aT * hi);
+  }
   const double negIfdl0 = yk[0], posIfdl3 = yk[1], negIf0 = yk[2], posIf3 = yk[3];
   double tss0 = yk[4] + st[S_SOC0N], tss3 = yk[5] + st[S_SOC0P];   /* :304-305 (Q6) */
   tss0 = fmin(fmax(tss0, 1e-6), 1.0 - 1e-6);                       /* :309-310 */
@@ -379,7 +389,16 @@ static double get_variables(const mko_bank *bk, double *st, double ik, const xin
       for (int j = 1; j < N5; ++j) acc = fma(cr[j], x[j], acc);
       yc[c] = fma(bk->D[(size_t)X->m[c] * nz + r], ik, acc);
     }
-    Z[r] = fma(yc[3], X->gamma[3], fma(yc[2], X->gamma[2], fma(yc[1], X->gamma[1], yc[0] * X->gamma[0])));
+    /* "[...]*Xind.gamma" (:313).  Structure exploited: a neighbour whose weight is EXACTLY zero adds
+       nothing -- the reference adds its +-0 product, which changes nothing but the sign of an exact zero.  A cell whose
+       temperature sits on a set-point of the bank (runMPC's 25 degC) has two such neighbours at every instant. */
+    if (zw_skip) {
+      double acc = 0.0;
+      for (int c = 0; c < 4; ++c) if (X->gamma[c] != 0.0) acc = fma(yc[c], X->gamma[c], acc);
+      Z[r] = acc;
+    } else {
+      Z[r] = fma(yc[3], X->gamma[3], fma(yc[2], X->gamma[2], fma(yc[1], X->gamma[1], yc[0] * X->gamma[0])));
+    }
   }
   const double If0 = Z[bk->r_if0], If3 = Z[bk->r_if3];             /* :324-325 */
   int any;
@@ -627,6 +646,15 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
   const double resid = vk - vhat;                                  /* :133 */
   for (int c = 0; c < 4; ++c) {                                    /* :136-154 (Q2: sequential, duplicates re-processed) */
     double *x = xhat + N5 * X.m[c], *S = Sig + NSYM * X.m[c];
+    if (zw_skip && X.gamma[c] == 0.0) {
+      /* zero weight: Chat = 0, the gain is 0, svt = SigmaV, xhat and SigmaX stay as they are (:138,:142 add +-0) and the repair
+         (:143-145) of an unchanged covariance is the identity up to rounding: skipped.  The Q-bump (:148-151) is what is left. */
+      if (resid * resid > 9.0 * (0.0 + cf->SigmaV)) {
+        for (int k = 0; k < NSYM; ++k) S[k] = S[k] * 2.0;
+        st[S_NBUMP] += 1.0;
+      }
+      continue;
+    }
     for (int j = 0; j < N5; ++j) x[j] = fma(L[c][j], resid, x[j]);    /* :138 */
     int q = 0;
     for (int i = 0; i < N5; ++i)

@@ -53,6 +53,7 @@ def tally(bank, cfg, nsim=3001):
         pop = P.make_population(bank.params[2], cfg["cells"], cfg["seed"], heterogeneous=cfg["het"])
         co = coracle.COracle(bank, Np=cfg["Np"], Nc=cfg["Nc"], constraints=cfg["constraints"])
         co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        L.mko_set_zero_weight_skip(0)                       # the table counts the reference's algorithm term by term
         L.mko_opc_reset()
         lg = co.run(0, nsim, logs=True, nthreads=1)
         raw = np.zeros((len(BLOCKS), len(KINDS)), np.uint64)

@@ -85,7 +85,7 @@ def test_force_jacobi_path(bank, coracle_mod):
     pop = P.make_population(bank.params[2], 64, seed=5)
     cb, g, co, c = _run_both(bank, coracle_mod, pop, 400, force_jacobi=True)
     _assert_bit_exact(g, c)
-    assert cb.summary()["n_jacobi"] == 64 * 400 * 4
+    assert cb.summary()["n_jacobi"] == 64 * 400 * 2    # 25 degC sits on a set-point of the bank: two of the four neighbours carry a zero weight and are not repaired
 
 
 def test_resume_in_chunks_matches_single_launch(bank, coracle_mod):
@@ -334,3 +334,21 @@ def test_terminal_constraint_row(bank, coracle_mod):
     c = co.run(0, 200, nthreads=8)
     _assert_bit_exact(g, c)
     assert ((g["active"][:, :, 0] >> 23) & 1).any()
+
+
+def test_zero_weight_neighbours_mixed_temperatures(bank, coracle_mod):
+    """Cells at temperatures ON set-points of the bank (15 / 25 / 35 degC: one temperature row of neighbours carries weights that are
+    exactly zero and is left out -- gv_rows_n<2>, the plant's single row, the bump-only update) mixed, lane by lane, with cells
+    between set-points (all four neighbours); a large initial SOC error makes the first residuals trip the Q-bump, which the
+    zero-weight neighbours still receive; one cell starts exactly ON an SOC set-point (a zero weight on the SOC axis)."""
+    from mek import population as P
+    pop = P.make_population(bank.params[2], 160, seed=71, ekf_soc_error=15.0)
+    pop.T[:] = np.resize(np.array([25.0, 15.0, 20.0, 35.0, 25.0, 31.5, 25.0]), len(pop.T))
+    pop.SOC0[3] = 15.0; pop.ekf_SOC0[3] = 15.0
+    pop.SOC0[4] = 25.0; pop.ekf_SOC0[4] = 25.0
+    cb, g, co, c = _run_both(bank, coracle_mod, pop, 900, chunks=[(0, 7), (7, 900)])
+    _assert_bit_exact(g, c)
+    s = cb.summary()
+    assert s["n_bump"] > 100          # 175 in the oracle, most of them on zero-weight neighbours (svt = SigmaV there)
+    cb2, g2, co2, c2 = _run_both(bank, coracle_mod, pop, 300, generic_path=True, regroup_every=64)
+    _assert_bit_exact(g2, c2)

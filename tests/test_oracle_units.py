@@ -286,3 +286,26 @@ def test_portable_and_fma_builds_of_the_c_oracle_agree_bitwise(bank, coracle_mod
         outs.append(co.run(0, 900))
     for k in ("u", "V", "SOC", "phise", "nexec", "iT", "iZ", "active"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_zero_weight_rule_equals_the_term_by_term_restatement(bank, coracle_mod):
+    """The zero-weight rule of the C restatement and the CUDA kernels (a neighbour model with bilinear weight exactly 0 is left out
+    of the blends and of the measurement update) against the same oracle with the rule switched off, i.e.
+    the reference's term-by-term arithmetic: identical logs, bit for bit, on cells at 25 degC (on a set-point of the bank: two
+    zero-weight neighbours at every instant) and on cells at temperatures between set-points (no zero weight: same code path)."""
+    from mek import population as P
+    L = coracle_mod.lib()
+    for het, seed in ((False, 11), (True, 12)):
+        pop = P.make_population(bank.params[2], 24, seed=seed, heterogeneous=het)
+        runs = []
+        for on in (1, 0):
+            L.mko_set_zero_weight_skip(on)
+            try:
+                co = coracle_mod.COracle(bank)
+                co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+                runs.append(co.run(0, 3001, nthreads=8))
+            finally:
+                L.mko_set_zero_weight_skip(1)
+        a, b = runs
+        for k in ("u", "V", "SOC", "phise", "nexec", "iT", "iZ", "active"):
+            assert np.array_equal(a[k], b[k], equal_nan=True) if a[k].dtype.kind == "f" else np.array_equal(a[k], b[k]), (het, k)
