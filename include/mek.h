@@ -97,9 +97,10 @@ typedef struct {
                                -G_soc(end,:)*DU <= -z_max + Phi_soc(end,:)*x_aug.  Generic kernel instances only           */
   double z_tol;             /* mpcData.const.z_tol (runMPC.m:44, 0 there).  limits[6] carries z_max + z_tol; the terminal row
                                uses limits[6] - z_tol for z_max                                                            */
-  int ekf_method;           /* initKF's `blend` argument (initKF.m:44-53): 0 = 'OutB' output blend (what runMPC.m:16 selects; the
-                               fused loop mek_run supports only this), 1 = 'MdlB' model blend: one blended model per cell,
-                               served by the function-level entry mek_pop_iter_ekf (iterEKF.m MB branches)               */
+  int ekf_method;           /* initKF's `blend` argument (initKF.m:44-53): 0 = 'OutB' output blend (what runMPC.m:16 selects: the
+                               optimised fused kernels), 1 = 'MdlB' model blend: one blended model per cell (iterEKF.m MB
+                               branches).  mek_run then runs the plain loop kernel k_run_population_mb; mek_pop_iter_ekf serves
+                               the function-level call                                                                      */
 } mek_config;
 
 /* ---- bank ---- */

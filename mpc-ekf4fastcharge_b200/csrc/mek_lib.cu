@@ -478,6 +478,60 @@ __global__ void __launch_bounds__(128) k_iter_ekf_mb(const __grid_constant__ Par
   }
 }
 
+// The loop of runMPC.m:83-112 with the model-blend filter (a script whose initKF call says 'MdlB' instead of runMPC.m:16's
+// 'OutB').  Plain instant-by-instant form: OB_step advances all M local models (the filter keeps ONE blended model per
+// cell, so there is no per-model EKF stream and nothing to defer), then ekf_step_mb, then the runtime-shape MPC.
+template <int NPM, int NCM>
+__global__ void __launch_bounds__(128) k_run_population_mb(const __grid_constant__ Params P, const __grid_constant__ RowLists RL, int k0, int k1) {
+  extern __shared__ __align__(16) double sm[];
+  BankSmem bk;
+  stage_bank(sm, P, bk);
+  const Dims& d = P.d;
+  const Scratch sc{sm + P.blob_doubles + threadIdx.x, (int)blockDim.x};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < d.B; cell += stride) {
+    Cell c = cell_ref(P.st, d, cell);
+    const int tt = two_nearest(c.f(S_TC) + 273.15, bk.Tpts, d.nT);
+    const long long id = cell_id(P, cell);
+#pragma unroll 1
+    for (int k = k0; k < k1; ++k) {
+      StepLog lg;
+      lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
+      for (int w = 0; w < 4; ++w) lg.active[w] = 0u;
+      if (!((unsigned)c.f(S_STATUS) & ST_LOST)) {                    // Q19: a lost cell idles
+        const double uk = c.f(S_UK);
+        const double V = plant_step<true>(d, bk, P.cp, c, uk, tt);   // runMPC.m:85
+        EkfOut e;
+        memset(&e, 0, sizeof(e));
+        ekf_step_mb(P, bk, RL, c, V, uk, e, sc, nullptr, nullptr);   // runMPC.m:88,92
+        if (!e.lost) {
+          MpcOut o;
+          mpc_step<NPM, NCM>(d, P.cp, c, e, uk, o);                  // runMPC.m:94-103
+          lg.u = o.u; lg.V = V; lg.soc = e.soc; lg.phise = o.phise;  // runMPC.m:106-109
+          lg.iT = e.iT + 1; lg.iZ = e.iZ + 1; lg.nexec = o.nexec;
+          for (int w = 0; w < 4; ++w) lg.active[w] = o.active[w];
+        }
+      }
+      if (lg.nexec > 0) {
+        c.f(S_SUM_NEXEC) += (double)lg.nexec;
+        c.f(S_N_QP) += 1.0;
+        if (lg.nexec >= d.maxHild) c.f(S_N_CAP) += 1.0;
+      }
+      c.f(S_MIN_PHISE) = fmin(c.f(S_MIN_PHISE), lg.phise);
+      c.f(S_MAX_V) = fmax(c.f(S_MAX_V), lg.V);
+      if (c.f(S_T_REACH) < 0.0 && lg.soc >= c.f(S_ZMAX) - 1e-3) c.f(S_T_REACH) = (double)k;
+      c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
+      if (id < P.nlog && k < P.log_steps) {
+        const long long o = (long long)k * P.nlog + id;
+        P.log_u[o] = lg.u; P.log_V[o] = lg.V; P.log_soc[o] = lg.soc; P.log_phise[o] = lg.phise;
+        P.log_iT[o] = (unsigned char)lg.iT; P.log_iZ[o] = (unsigned char)lg.iZ; P.log_nexec[o] = (unsigned short)lg.nexec;
+        for (int w = 0; w < P.log_words; ++w) P.log_active[o * P.log_words + w] = lg.active[w];
+      }
+    }
+    c.f(S_STEPS) += (double)(k1 - k0);
+  }
+}
+
 template <int NPM, int NCM>
 __global__ void __launch_bounds__(128) k_iter_mpc(const __grid_constant__ Params P, const double* mats, const double* uk_applied, double* uk,
                                                    double* phise, int* nexec, unsigned* active, double* cost) {
@@ -969,6 +1023,9 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   rc |= prep_kernel(k_ob_step, p->smem_bytes);
   rc |= prep_kernel(k_iter_ekf, p->smem_bytes);
   rc |= prep_kernel(k_iter_ekf_mb, p->smem_bytes);
+  rc |= prep_kernel(k_run_population_mb<5, 2>, p->smem_bytes);
+  rc |= prep_kernel(k_run_population_mb<20, 5>, p->smem_bytes);
+  rc |= prep_kernel(k_run_population_mb<32, 8>, p->smem_bytes);
   p->minb = 1;
   p->cons = -1;
   p->run_threads = p->threads;
@@ -1168,7 +1225,7 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
       p->heterogeneous = het;
       int every = p->cfg.regroup_every;
       if (every == 0) every = het ? MEK_REGROUP_DEFAULT : -1;
-      p->regroup_every = every > 0 ? every : 0;
+      p->regroup_every = (every > 0 && !p->P.d.mb) ? every : 0;   // the model-blend loop is one plain kernel: nothing to regroup for
       if (p->regroup_every > 0) {
         if (!p->d_slot2cell0) CUDA_TRY(cudaMalloc(&p->d_slot2cell0, sizeof(int) * B));
         CUDA_TRY(cudaMemcpyAsync(p->d_slot2cell0, p->d_slot2cell, sizeof(int) * B, cudaMemcpyDeviceToDevice, p->stream));
@@ -1182,6 +1239,15 @@ extern "C" int mek_pop_init(mek_pop* p, const double* SOC0pct, const double* ekf
 }
 
 static int launch_segment(mek_pop* p, int k0, int k1) {
+  if (p->P.d.mb) {                                                   // model-blend filter: its own (runtime-shape) loop kernel
+    const int g = grid_for(p, p->P.d.B, p->threads);
+    if (p->inst == 0) k_run_population_mb<5, 2><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, k0, k1);
+    else if (p->inst == 1) k_run_population_mb<20, 5><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, k0, k1);
+    else k_run_population_mb<32, 8><<<g, p->threads, p->smem_bytes, p->stream>>>(p->P, p->RL, k0, k1);
+    CUDA_TRY(cudaGetLastError());
+    p->launches++;
+    return MEK_OK;
+  }
   const int g = grid_for(p, p->P.d.B, p->run_threads);
   void* args[] = {&p->P, &k0, &k1};
   const int rc = launch_kernel(p->fn_run, g, p->run_threads, p->run_smem, p->stream, args);
@@ -1244,7 +1310,6 @@ static int launch_run(mek_pop* p, int k0, int k1) {
 extern "C" int mek_run(mek_pop* p, int k0, int k1) {
   if (!p || k1 < k0 || k0 < 0) return fail(MEK_ERR_ARG, "bad argument to mek_run");
   if (!p->inited) return fail(MEK_ERR_STATE, "mek_run before mek_pop_init");
-  if (p->P.d.mb) return fail(MEK_ERR_UNSUPPORTED, "the fused loop runs the output-blend filter (runMPC.m:16 'OutB'); the model-blend filter is available through mek_pop_iter_ekf");
   CUDA_TRY(cudaSetDevice(p->device));
   return launch_run(p, k0, k1);
 }
@@ -1252,7 +1317,6 @@ extern "C" int mek_run(mek_pop* p, int k0, int k1) {
 extern "C" int mek_run_timed(mek_pop* p, int k0, int k1, float* ms) {
   if (!p || k1 < k0 || k0 < 0) return fail(MEK_ERR_ARG, "bad argument to mek_run_timed");
   if (!p->inited) return fail(MEK_ERR_STATE, "mek_run before mek_pop_init");
-  if (p->P.d.mb) return fail(MEK_ERR_UNSUPPORTED, "the fused loop runs the output-blend filter (runMPC.m:16 'OutB'); the model-blend filter is available through mek_pop_iter_ekf");
   CUDA_TRY(cudaSetDevice(p->device));
   CUDA_TRY(cudaEventRecord(p->ev0, p->stream));
   int rc = launch_run(p, k0, k1);

@@ -51,7 +51,7 @@ class MkoBank(C.Structure):
 class MkoConfig(C.Structure):
     _fields_ = [("Np", C.c_int), ("Nc", C.c_int), ("maxHild", C.c_int), ("useCurrent", C.c_int), ("useVoltage", C.c_int),
                 ("useEta", C.c_int), ("useZmax", C.c_int), ("ref", C.c_double), ("SigmaV", C.c_double),
-                ("SigmaW", C.c_double), ("force_jacobi", C.c_int), ("z_target_terminal", C.c_int), ("z_tol", C.c_double)]
+                ("SigmaW", C.c_double), ("force_jacobi", C.c_int), ("z_target_terminal", C.c_int), ("z_tol", C.c_double), ("ekf_method", C.c_int)]
 
 
 def build(force=False):
@@ -91,7 +91,7 @@ class COracle:
     """Population runner over the C restatement."""
 
     def __init__(self, bank, Np=5, Nc=2, constraints=(1, 1, 1), ref=95.0, SigmaV=1e-3, SigmaW=1e2, maxHild=100,
-                 force_jacobi=False, z_target_terminal=False, z_tol=0.0):
+                 force_jacobi=False, z_target_terminal=False, z_tol=0.0, ekf_method="OutB"):
         self.bank = bank
         self.L = lib()
         self._keep = dict(
@@ -124,6 +124,7 @@ class COracle:
         cf.ref, cf.SigmaV, cf.SigmaW = ref, SigmaV, SigmaW
         cf.force_jacobi = int(force_jacobi)
         cf.z_target_terminal, cf.z_tol = int(bool(z_target_terminal)), float(z_tol)
+        cf.ekf_method = 1 if str(ekf_method).upper() in ("MDLB", "MB") else 0          # initKF.m:44-53
         self.cf = cf
         self.Np, self.Nc = Np, Nc
         self.nC = (4 * Nc if cf.useCurrent else 0) + Np * (cf.useVoltage + cf.useEta + 1) + cf.z_target_terminal

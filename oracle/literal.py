@@ -831,13 +831,13 @@ DEFAULT_LIMITS = dict(u_max=2.0, du_min=-50.0, du_max=50.0, v_min=3.4, v_max=4.1
 
 def run_mpc(bank, SOC0=10.0, TC=25.0, N=3001, Np=5, Nc=2, targetSOC=95.0, constraints=(1, 1, 1),
             Crate=2.0, limits=None, SigmaX0=None, SigmaV=1e-3, SigmaW=1e2, ekf_SOC0=None,
-            diagnostics=False, keep_zk=False):
+            diagnostics=False, keep_zk=False, blend="OutB"):
     """runMPC.m:4-112 with its literals exposed as arguments.  Returns a dict of per-step stores."""
     ROM = build_rom(bank)
     Ts = 1                                                                               # :9
     if SigmaX0 is None:
         SigmaX0 = np.diag([1.0] * 5 + [2e6])                                             # :17
-    ekfData = initKF(1 * (SOC0 if ekf_SOC0 is None else ekf_SOC0), TC, SigmaX0, SigmaV, SigmaW, "OutB", ROM)   # :20
+    ekfData = initKF(1 * (SOC0 if ekf_SOC0 is None else ekf_SOC0), TC, SigmaX0, SigmaV, SigmaW, blend, ROM)    # :20 (runMPC.m:16 says 'OutB')
     lim = dict(DEFAULT_LIMITS)
     lim["z_max"] = targetSOC / 100; lim["z_tol"] = 0 * 5 / 100                           # :43-44
     if limits: lim.update(limits)

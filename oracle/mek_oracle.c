@@ -74,6 +74,7 @@ typedef struct {
   int force_jacobi; /* 1: always run the eigen-decomposition PSD repair (validation of the PD fast path) */
   int z_target_terminal; /* mpcData.const.z_target_terminal (constraintsMPC.m:104): one more row, SOC(Np) >= z_max */
   double z_tol;          /* mpcData.const.z_tol (runMPC.m:44); the z_max limit of the state carries z_max + z_tol */
+  int ekf_method;        /* initKF's blend (initKF.m:44-53): 0 'OutB' (runMPC.m:16), 1 'MdlB': mko_cell_step then runs ekf_step_mb */
 } mko_config;
 
 /* per-cell state, flat doubles (also the host-side AoS layout of mek_read_state) */
@@ -1276,7 +1277,8 @@ void mko_cell_step(const mko_bank *bk, const mko_config *cf, double sigmin, doub
   }
   const double V = plant_step(bk, st, uk);                         /* :85 */
   ekf_out e;
-  ekf_step(bk, cf, st, V, uk, &e, NULL);                           /* :88,92 */
+  if (cf->ekf_method == 1) ekf_step_mb(bk, cf, st, V, uk, &e, NULL, NULL);
+  else ekf_step(bk, cf, st, V, uk, &e, NULL);                      /* :88,92 */
   if (e.lost) {
     *log_u = NAN; *log_V = NAN; *log_soc = NAN; *log_phise = NAN; *log_iT = 0; *log_iZ = 0; *log_nexec = 0;
     for (int w = 0; w < 4; ++w) log_active[w] = 0;

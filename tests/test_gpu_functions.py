@@ -275,7 +275,6 @@ def test_model_blend_ekf_vs_c_oracle(bank, coracle_mod):
     # the state block carries the blended filter behind the model rows; a round trip preserves it
     st = cb.read_state()
     assert st.shape[1] == cb.state_len and cb.state_len == 40 + cb.nC + 26 * bank.M + 27
-    with pytest.raises(api.MekError, match="output-blend"):
-        cb.run(0, 5)
+    cb.run(0, 5)                                          # the loop runs in this mode too (tests/test_gpu_parity.py::test_model_blend_fused_loop)
     # and the method names of initKF.m:44-53
     assert api.CellBatch(api.RomBank(bank), 2, ekf_method="nonsense").cfg.ekf_method == 0

@@ -352,3 +352,23 @@ def test_zero_weight_neighbours_mixed_temperatures(bank, coracle_mod):
     assert s["n_bump"] > 100          # 175 in the oracle, most of them on zero-weight neighbours (svt = SigmaV there)
     cb2, g2, co2, c2 = _run_both(bank, coracle_mod, pop, 300, generic_path=True, regroup_every=64)
     _assert_bit_exact(g2, c2)
+
+
+def test_model_blend_fused_loop(bank, coracle_mod):
+    """mek_run with the model-blend filter (mek_config.ekf_method = 1: a script that says initKF(...,'MdlB',...)): kernel
+    k_run_population_mb against the C restatement's loop in the same mode, bit for bit; resumed in chunks."""
+    from mek import population as P
+    for het, seed in ((False, 81), (True, 82)):
+        pop = P.make_population(bank.params[2], 96, seed=seed, heterogeneous=het, ekf_soc_error=2.0)
+        from mek import api
+        cb = api.CellBatch(api.RomBank(bank), len(pop), ekf_method="MdlB")
+        N = 700
+        cb.set_logging(len(pop), N)
+        cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        cb.run(0, 5); cb.run(5, N)
+        g = cb.logs(0, N)
+        co = coracle_mod.COracle(bank, ekf_method="MdlB")
+        co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        c = co.run(0, N, nthreads=8)
+        _assert_bit_exact(g, c)
+        assert cb.summary()["n_qp"] > 0

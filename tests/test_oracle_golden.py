@@ -146,3 +146,21 @@ def test_terminal_constraint_row_c_vs_literal(bank, coracle_mod):
     for k in ("u", "V", "SOC", "phise"):
         assert rel_err(c[k][:, 0], o[k][:N], SCALE[k]) <= TOL, k
     assert np.nanmax(np.abs(c["u"])) > 1e3
+
+
+def test_model_blend_loop_c_vs_literal(bank, coracle_mod):
+    """The whole loop of runMPC.m:83-112 with initKF's other blend ('MdlB' instead of runMPC.m:16's 'OutB'): C restatement
+    (mko_config.ekf_method = 1) vs the literal one.  In this mode EKFmatsHandler hands the MPC xhat = [0 0 0 0 0, integrator]
+    (M(iT,iZ).xhat is never written by the MB filter, Q3) -- reproduced, not fixed."""
+    from oracle import literal as L
+    N = 1500
+    o = L.run_mpc(bank, SOC0=10.0, N=N, blend="MdlB")
+    assert o["status"] == 0
+    co = coracle_mod.COracle(bank, ekf_method="MdlB")
+    co.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
+    c = co.run(0, N, nthreads=1)
+    assert np.array_equal(o["nexec"][:N], c["nexec"][:, 0]) and np.array_equal(o["active"][:N], c["active"][:, 0])
+    assert np.array_equal(o["iT"][:N], c["iT"][:, 0]) and np.array_equal(o["iZ"][:N], c["iZ"][:, 0])
+    for k in ("u", "V", "SOC", "phise"):
+        assert rel_err(c[k][:, 0], o[k][:N], SCALE[k]) <= TOL, k
+    assert c["SOC"][-1, 0] > 0.5                                    # the charge proceeds
