@@ -105,10 +105,20 @@ typedef struct {
 
 /* ---- bank ---- */
 int mek_bank_create(const mek_bank_desc *desc, mek_bank **out);
-int mek_bank_load(const char *path, mek_bank **out);           /* MEKBANK1 file (mek/bank.py)  */
+int mek_bank_load(const char *path, mek_bank **out);           /* MEKBANK1 file (mek/bank.py; version 2 may carry tables) */
 void mek_bank_destroy(mek_bank *bank);
 int mek_bank_dims(const mek_bank *bank, int *n, int *nz, int *nT, int *nZ);
 double mek_bank_capacity_Ah(const mek_bank *bank);               /* cellData.function.const.Q()  */
+/* Tabulated cell functions (optional).  ROM.cellData.function.{neg,pos}.{Uocp,dUocp,k0,Rf} are MATLAB function handles inside
+ * the ROM file (call sites: OB_step.m:231-232,329-330,337-340; iterEKF.m:362-363,392-393,404-407,441-442,463-464,495-496;
+ * EKFmatsHandler.m:60-61,68-69,84-85,96).  Without tables the library evaluates the closed forms of the parameter vector;
+ * with them -- eight tables of n points on a uniform stoichiometry grid [theta_lo, theta_hi], order Uocp_neg, dUocp_neg,
+ * Uocp_pos, dUocp_pos, k0_neg, k0_pos, Rf_neg, Rf_pos (k0, Rf at the reference temperature: the Arrhenius factors of the
+ * parameter vector still apply), sampled from the handles by matlab/mek_sample_celldata.m -- it interpolates linearly
+ * (interp1 'linear', argument clamped to the grid).  Call before mek_pop_create; populations on a tabulated bank run the
+ * runtime-shape kernel instances.  n = 0 removes the tables. */
+int mek_bank_set_lut(mek_bank *bank, int n, double theta_lo, double theta_hi, const double *tables /* [8][n] */);
+int mek_bank_lut_points(const mek_bank *bank);
 
 /* ---- population (one shard on one device) ---- */
 int mek_pop_create(const mek_bank *bank, const mek_config *cfg, int64_t B, int device, mek_pop **out);

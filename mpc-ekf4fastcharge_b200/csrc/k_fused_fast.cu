@@ -1,4 +1,5 @@
 // static-shape short-horizon instances of the fused kernel (runMPC's own configuration and the [1 1 0] variant)
+#define MEK_LUT_OFF   // tabulated cell functions are served by the runtime-shape instances (mek_cellfn.cuh)
 #include "mek_kernels.cuh"
 #include "mek_entry.h"
 const void* mek_fused_fast_kernel(int cons, int threads) {

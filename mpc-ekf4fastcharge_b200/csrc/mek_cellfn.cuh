@@ -13,18 +13,48 @@ enum : int { P_F = 0, P_R, P_Q, P_RC, P_TREF, P_NEG = 5, P_POS = 16, P_UN = 27, 
 enum : int { E_THETA0 = 0, E_THETA100, E_K0REF, E_K0SLOPE, E_EA_K0, E_RFREF, E_RFSLOPE, E_EA_RF, E_WDL, E_CDL, E_NDL };
 constexpr int UP_MAXCOEF = 8;
 
+// ---- tabulated cell functions (optional) ----
+// The reference's cellData.function.* are MATLAB function handles inside ROM_NMC30_HRA.mat; a user who owns that file samples
+// them on a uniform stoichiometry grid (matlab/mek_sample_celldata.m) and hands the tables to mek_bank_set_lut.  Eight tables
+// of n points over [lo, hi]: Uocp, dUocp (both electrodes), k0 and Rf at the reference temperature (the Arrhenius factor
+// of the parameter vector still applies).  Evaluation = MATLAB's interp1(...,'linear') with the argument clamped to the grid.
+// The library appends four entries to the parameter vector it hands to the kernels: n (0 = closed forms), lo, 1/step and the
+// table base address (bit pattern of a pointer).  Compiled out of the static-shape fused instances (MEK_LUT_OFF): a
+// population on a tabulated bank runs the runtime-shape instances.
+enum : int { P_LUT_N = N_PARAMS, P_LUT_LO, P_LUT_INVH, P_LUT_PTR, N_PARAMS_X };
+enum : int { LUT_UN = 0, LUT_DUN, LUT_UP, LUT_DUP, LUT_K0N, LUT_K0P, LUT_RFN, LUT_RFP, LUT_NTAB };
+#ifndef MEK_LUT_OFF
+MEK_HDN double lut_eval(const double* p, int tab, double th) {
+  if (th != th) return th;
+  const int n = (int)p[P_LUT_N];
+  const double* y = reinterpret_cast<const double*>((uintptr_t)double_to_bits(p[P_LUT_PTR])) + (size_t)tab * (size_t)n;
+  double t = (th - p[P_LUT_LO]) * p[P_LUT_INVH];
+  if (!(t > 0.0)) t = 0.0;                              // clamped to the grid
+  if (t > (double)(n - 1)) t = (double)(n - 1);
+  int i = (int)t;
+  if (i > n - 2) i = n - 2;
+  const double f = t - (double)i;
+  return fma(f, y[i + 1] - y[i], y[i]);
+}
+#define MEK_IF_LUT(p, expr) if ((p)[P_LUT_N] != 0.0) return (expr)
+#else
+#define MEK_IF_LUT(p, expr)
+#endif
+
 // function.{neg,pos}.soc(z,T)
 MEK_HD double soc_e(const double* p, int base, double z) {
   return p[base + E_THETA0] + z * (p[base + E_THETA100] - p[base + E_THETA0]);
 }
 // function.neg.Uocp / dUocp
 MEK_HDN double uocp_n(const double* p, double th) {
+  MEK_IF_LUT(p, lut_eval(p, LUT_UN, th));
   const double* c = p + P_UN;
   const double x = (th - c[4]) / c[5];
   const double t = th + c[2];
   return (c[0] + c[1] / (t * t)) + c[3] * (1.0 - x / sqrt(1.0 + x * x));
 }
 MEK_HDN double duocp_n(const double* p, double th) {
+  MEK_IF_LUT(p, lut_eval(p, LUT_DUN, th));
   const double* c = p + P_UN;
   const double x = (th - c[4]) / c[5];
   const double q = 1.0 + x * x;
@@ -33,6 +63,7 @@ MEK_HDN double duocp_n(const double* p, double th) {
 }
 // function.pos.Uocp / dUocp: Horner polynomial in x = (th - centre)/width
 MEK_HDN double uocp_p(const double* p, double th) {
+  MEK_IF_LUT(p, lut_eval(p, LUT_UP, th));
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
   double acc = p[P_UP_COEF + nc - 1];
@@ -40,6 +71,7 @@ MEK_HDN double uocp_p(const double* p, double th) {
   return acc;
 }
 MEK_HDN double duocp_p(const double* p, double th) {
+  MEK_IF_LUT(p, lut_eval(p, LUT_DUP, th));
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
   double acc = (double)(nc - 1) * p[P_UP_COEF + nc - 1];
@@ -48,9 +80,11 @@ MEK_HDN double duocp_p(const double* p, double th) {
 }
 // function.{neg,pos}.k0(theta,T), .Rf(theta,T): Arrhenius factor hoisted (T is constant per cell)
 MEK_HD double k0_e(const double* p, int base, double th, double arr) {
+  MEK_IF_LUT(p, lut_eval(p, base == P_NEG ? LUT_K0N : LUT_K0P, th) * arr);
   return (p[base + E_K0REF] * (1.0 + p[base + E_K0SLOPE] * (th - 0.5))) * arr;
 }
 MEK_HD double rf_e(const double* p, int base, double th, double arr) {
+  MEK_IF_LUT(p, lut_eval(p, base == P_NEG ? LUT_RFN : LUT_RFP, th) * arr);
   return (p[base + E_RFREF] * (1.0 + p[base + E_RFSLOPE] * th)) * arr;
 }
 MEK_HD double arrhenius(const double* p, double T, double Ea) {

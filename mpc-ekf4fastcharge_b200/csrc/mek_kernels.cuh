@@ -16,7 +16,7 @@ using namespace mek;
 // ------------------------------------------------------------------------------------------
 struct Params {
   Dims d;
-  double cp[N_PARAMS];        // cellData closed-form parameters
+  double cp[N_PARAMS_X];      // cellData closed-form parameters + the descriptor of the optional tables (mek_cellfn.cuh)
   double* st;                 // SoA state block [nfields][ld]
   const double* bank_blob;    // hot bank in global memory (source of the TMA bulk copy)
   int blob_doubles, off_mdl;
@@ -125,7 +125,14 @@ __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
 }
 
 // ---- k_run_population: the fused persistent kernel ----
-template <int NPM, int NCM, int CONS, int THREADS, int MINB>   // THREADS/MINB: launch bounds (register cap)
+// KTAG only makes the instances of different translation units different symbols: a unit compiled with MEK_LUT_OFF (closed-form
+// cell functions only, tag 0) and one compiled with the tabulated cell functions (tag 1) both instantiate <5,2,15,256,1,...>
+#ifdef MEK_LUT_OFF
+#define MEK_KTAG 0
+#else
+#define MEK_KTAG 1
+#endif
+template <int NPM, int NCM, int CONS, int THREADS, int MINB, int KTAG = MEK_KTAG>   // THREADS/MINB: launch bounds (register cap)
 __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_constant__ Params P, int k0, int k1) {
   extern __shared__ __align__(16) double sm[];
   BankSmem bk;

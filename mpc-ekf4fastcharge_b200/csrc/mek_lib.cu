@@ -56,6 +56,10 @@ struct mek_bank {
   // hot bank blob: [Tpts nT][Zpts nZ][pad][M][mstride]
   int R, nx_negtss, nx_postss, nx_thetae, mstride, off_mdl;
   std::vector<double> blob;
+  // optional tabulated cell functions (mek_bank_set_lut): LUT_NTAB tables of lut_n points over [lut_lo, lut_hi]
+  int lut_n = 0;
+  double lut_lo = 0.0, lut_hi = 1.0;
+  std::vector<double> lut;
 };
 
 static std::vector<int> find_rows(const mek_bank& b, const char* nm, double loc = -1.0, bool use_loc = false) {
@@ -176,7 +180,7 @@ extern "C" int mek_bank_load(const char* path, mek_bank** out) {
   int hdr[6];
   memcpy(hdr, &buf[off], 24); off += 24;
   const int n = hdr[1], nz = hdr[2], nT = hdr[3], nZ = hdr[4], npar = hdr[5];
-  if (hdr[0] != 1) return fail(MEK_ERR_BANK, "unsupported bank version");
+  if (hdr[0] != 1 && hdr[0] != 2) return fail(MEK_ERR_BANK, "unsupported bank version");
   const size_t M = (size_t)nT * nZ;
   const size_t need = off + 8 + 8 * ((size_t)nT + nZ) + (size_t)nz * 24 + 8 * (2 * M + M * (n + 1) + M * nz * (n + 1) + M * nz + npar);
   if (n < 1 || nz < 1 || nT < 1 || nZ < 1 || buf.size() < need) return fail(MEK_ERR_BANK, "truncated bank file");
@@ -199,8 +203,35 @@ extern "C" int mek_bank_load(const char* path, mek_bank** out) {
   take(M); take(M);   // ROMmdls.T / .SOC per model (the grid vectors above are what the loop uses)
   std::vector<double> A = take(M * (n + 1)), C = take(M * nz * (n + 1)), D = take(M * nz), par = take(npar);
   mek_bank_desc d = {n, nz, nT, nZ, Tsamp, Tp.data(), Zp.data(), cnames.data(), xloc.data(), A.data(), C.data(), D.data(), par.data(), npar};
-  return mek_bank_create(&d, out);
+  int rc = mek_bank_create(&d, out);
+  if (rc != MEK_OK || hdr[0] < 2) return rc;
+  // version 2: [int32 lut_n][f64 lo][f64 hi][f64 tables[LUT_NTAB][lut_n]] behind the parameter vector (lut_n = 0: none)
+  if (buf.size() < off + 20) { mek_bank_destroy(*out); *out = nullptr; return fail(MEK_ERR_BANK, "truncated bank file"); }
+  int ln;
+  double lo, hi;
+  memcpy(&ln, &buf[off], 4); off += 4;
+  memcpy(&lo, &buf[off], 8); off += 8;
+  memcpy(&hi, &buf[off], 8); off += 8;
+  if (ln > 0) {
+    if (ln > (1 << 20) || buf.size() < off + 8 * (size_t)LUT_NTAB * (size_t)ln) { mek_bank_destroy(*out); *out = nullptr; return fail(MEK_ERR_BANK, "truncated bank file"); }
+    std::vector<double> tb = take((size_t)LUT_NTAB * (size_t)ln);
+    rc = mek_bank_set_lut(*out, ln, lo, hi, tb.data());
+    if (rc != MEK_OK) { mek_bank_destroy(*out); *out = nullptr; }
+  }
+  return rc;
 }
+
+extern "C" int mek_bank_set_lut(mek_bank* b, int n, double theta_lo, double theta_hi, const double* tables) {
+  if (!b) return fail(MEK_ERR_ARG, "null bank");
+  if (n == 0) { b->lut_n = 0; b->lut.clear(); return MEK_OK; }     // back to the closed forms
+  if (!tables || n < 2 || n > (1 << 20) || !(theta_hi > theta_lo)) return fail(MEK_ERR_ARG, "bad table description");
+  for (size_t i = 0; i < (size_t)LUT_NTAB * (size_t)n; ++i)
+    if (!(std::fabs(tables[i]) <= kDblMax)) return fail(MEK_ERR_BANK, "non-finite entry in a cell-function table");
+  b->lut_n = n; b->lut_lo = theta_lo; b->lut_hi = theta_hi;
+  b->lut.assign(tables, tables + (size_t)LUT_NTAB * (size_t)n);
+  return MEK_OK;
+}
+extern "C" int mek_bank_lut_points(const mek_bank* b) { return b ? b->lut_n : 0; }
 
 extern "C" void mek_bank_destroy(mek_bank* b) { delete b; }
 extern "C" int mek_bank_dims(const mek_bank* b, int* n, int* nz, int* nT, int* nZ) {
@@ -829,6 +860,7 @@ struct mek_pop {
   Params P;
   RowLists RL;
   double *d_blob, *d_Cfull, *d_Dfull, *d_st, *d_in, *d_totals, *d_scratch;
+  double* d_lut;               // tabulated cell functions of the bank (null: closed forms)
   int* d_slot2cell;           // cell order inside the state block (sorted by initial SOC at mek_pop_init)
   size_t scratch_bytes;
   void* d_logs;
@@ -933,6 +965,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   p->d_keys = nullptr; p->d_keys2 = nullptr; p->d_cubtmp = nullptr; p->cubtmp_bytes = 0; p->regroups = 0;
   p->d_scratch = nullptr;
   p->scratch_bytes = 0;
+  p->d_lut = nullptr;
   int Np = cfg->Np < 1 ? 1 : cfg->Np;                               // initMPC.m:32-33 (Q23)
   int Nc = cfg->Nc < 1 ? 1 : (cfg->Nc > Np ? Np : cfg->Nc);
   if (Np == 5 && Nc == 2) p->inst = 0;
@@ -992,6 +1025,15 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&p->ev0));
   CUDA_TRY(cudaEventCreate(&p->ev1));
+  if (bank->lut_n > 0) {                                             // tabulated cell functions: tables in global memory, descriptor behind the parameters
+    const size_t lb = sizeof(double) * bank->lut.size();
+    CUDA_TRY(cudaMalloc(&p->d_lut, lb));
+    CUDA_TRY(cudaMemcpy(p->d_lut, bank->lut.data(), lb, cudaMemcpyHostToDevice));
+    p->P.cp[P_LUT_N] = (double)bank->lut_n;
+    p->P.cp[P_LUT_LO] = bank->lut_lo;
+    p->P.cp[P_LUT_INVH] = (double)(bank->lut_n - 1) / (bank->lut_hi - bank->lut_lo);
+    p->P.cp[P_LUT_PTR] = bits_to_double((unsigned long long)(uintptr_t)p->d_lut);
+  }
   CUDA_TRY(cudaMalloc(&p->d_blob, p->blob_bytes));
   CUDA_TRY(cudaMemcpy(p->d_blob, bank->blob.data(), p->blob_bytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&p->d_Cfull, bank->C.size() * sizeof(double)));
@@ -1034,12 +1076,12 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
     const int mask = (d.useCurrent ? 1 : 0) | (d.useVoltage ? 2 : 0) | (d.useEta ? 4 : 0) | (d.useZmax ? 8 : 0);
     if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path && !d.useTerm) {
       p->cons = mask;
-      p->run_threads = (cfg->threads_per_block == 384) ? 384 : 256;   // 256 threads x 255 registers: fewest spills, least DRAM traffic
+      p->run_threads = (cfg->threads_per_block == 384 && bank->lut_n == 0) ? 384 : 256;   // 256 threads x 255 registers: fewest spills, least DRAM traffic
       const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
       p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
     }
-    if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path && !d.useTerm) {   // config C4: long-horizon static-shape instance
+    if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path && !d.useTerm && bank->lut_n == 0) {   // config C4: long-horizon static-shape instance
       using WS = WideShape<20, 5, 15>;
       p->cons = mask;
       // 256 threads (default): lambda in shared memory, the read-mostly columns in L2; 64 threads: every column in shared memory
@@ -1063,7 +1105,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
     if (kb > 0) p->run_smem += sizeof(double) * (size_t)(kb + 1) * (size_t)p->run_threads;
   }
   if (p->inst == 1 && p->cons == 15) p->fn_run = mek_fused_wide_kernel(p->run_threads);
-  else if (p->cons >= 0) p->fn_run = mek_fused_fast_kernel(p->cons, p->run_threads);
+  else if (p->cons >= 0) p->fn_run = bank->lut_n > 0 ? mek_fused_fast_lut_kernel(p->cons, p->run_threads) : mek_fused_fast_kernel(p->cons, p->run_threads);
   else p->fn_run = mek_fused_generic_kernel(p->inst);
   rc |= prep_fn(p->fn_run, p->run_threads, p->run_smem, &occ);
   if (rc != MEK_OK) { return rc; }
@@ -1113,6 +1155,7 @@ extern "C" void mek_pop_destroy(mek_pop* p) {
   if (p->d_keys) cudaFree(p->d_keys);
   if (p->d_keys2) cudaFree(p->d_keys2);
   if (p->d_cubtmp) cudaFree(p->d_cubtmp);
+  if (p->d_lut) cudaFree(p->d_lut);
   cudaFree(p->d_blob); cudaFree(p->d_Cfull); cudaFree(p->d_Dfull); cudaFree(p->d_st); cudaFree(p->d_in); cudaFree(p->d_totals);
   if (p->d_logs) cudaFree(p->d_logs);
   if (p->d_scratch) cudaFree(p->d_scratch);

@@ -42,6 +42,16 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     mxFree(path);
     mexLock();
     plhs[0] = put_handle(b);
+  } else if (!strcmp(cmd, "bank_set_lut")) {             /* mek_mex('bank_set_lut', bank, theta_lo, theta_hi, tables(8,n))  <- mek_sample_celldata.m */
+    const mwSize n = mxGetN(prhs[4]);                    /* column-major 8 x n -> row-major [8][n] */
+    double *t = (double *)mxMalloc(sizeof(double) * 8 * (n > 0 ? n : 1));
+    const double *src = mxGetPr(prhs[4]);
+    mwSize i, k;
+    if (mxGetM(prhs[4]) != 8) mexErrMsgIdAndTxt("mek:usage", "tables must be 8 x n");
+    for (k = 0; k < 8; ++k)
+      for (i = 0; i < n; ++i) t[k * n + i] = src[i * 8 + k];
+    chk(mek_bank_set_lut((mek_bank *)get_handle(prhs[1]), (int)n, mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), t));
+    mxFree(t);
   } else if (!strcmp(cmd, "pop_create")) {               /* h = mek_mex('pop_create', bank, cfgvec, B, device) */
     const double *c = mxGetPr(prhs[2]);                  /* [Np Nc maxHild c1 c2 c3 use_zmax ref SigmaV SigmaW (ekf_method (z_target_terminal z_tol))] */
     mek_config cfg;

@@ -21,6 +21,7 @@ mxArray *mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray *mxCreateDoubleScalar(double);
 mxArray *mxCreateNumericMatrix(mwSize, mwSize, mxClassID, mxComplexity);
 char *mxArrayToString(const mxArray *);
+void *mxMalloc(size_t);
 void mxFree(void *);
 void mexErrMsgIdAndTxt(const char *, const char *, ...);
 void mexLock(void);

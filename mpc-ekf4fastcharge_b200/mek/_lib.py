@@ -13,7 +13,7 @@ STAT_NAMES = ["cells", "cellsteps", "sum_nexec", "n_qp", "n_cap", "n_reached", "
               "n_lost", "n_nonfinite", "sum_soc", "n_jacobi", "n_bump", "n_warn", "n_q18"]
 
 # every symbol include/mek.h declares (tests check that the library exports all of them)
-SYMBOLS = ["mek_bank_create", "mek_bank_load", "mek_bank_destroy", "mek_bank_dims", "mek_bank_capacity_Ah",
+SYMBOLS = ["mek_bank_create", "mek_bank_load", "mek_bank_destroy", "mek_bank_dims", "mek_bank_capacity_Ah", "mek_bank_set_lut", "mek_bank_lut_points",
            "mek_pop_create", "mek_pop_destroy", "mek_pop_set_logging", "mek_pop_init", "mek_pop_reset", "mek_run",
            "mek_run_timed", "mek_sync", "mek_pop_stream", "mek_pop_launches", "mek_pop_ncon", "mek_pop_defer_block", "mek_pop_regroups", "mek_pop_state_len",
            "mek_read_logs", "mek_read_state", "mek_write_state", "mek_summary", "mek_pop_ob_step", "mek_pop_iter_ekf",
@@ -61,6 +61,8 @@ def lib():
         L.mek_pop_regroups.restype = C.c_int64
         L.mek_pop_regroups.argtypes = [C.c_void_p]
         L.mek_pop_state_len.argtypes = [C.c_void_p]
+        L.mek_bank_set_lut.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double)]
+        L.mek_bank_lut_points.argtypes = [C.c_void_p]
         L.mek_bank_destroy.argtypes = [C.c_void_p]
         L.mek_bank_destroy.restype = None
         L.mek_pop_destroy.argtypes = [C.c_void_p]

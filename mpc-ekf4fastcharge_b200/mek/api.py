@@ -50,6 +50,10 @@ class RomBank:
             d = _lib.MekBankDesc(b.n, b.nz, b.nT, b.nZ, float(b.Tsamp), dp(keep["T"]), dp(keep["Z"]), names, dp(keep["x"]),
                                  dp(keep["A"]), dp(keep["Cm"]), dp(keep["D"]), dp(keep["p"]), len(b.params))
             check(L.mek_bank_create(C.byref(d), C.byref(self.h)))
+        if self.bank.lut is not None and L.mek_bank_lut_points(self.h) == 0:    # tabulated cellData.function.* (mek_bank_set_lut)
+            t = _f64(self.bank.lut.reshape(-1))
+            check(L.mek_bank_set_lut(self.h, int(self.bank.lut.shape[1]), float(self.bank.lut_range[0]), float(self.bank.lut_range[1]),
+                                     t.ctypes.data_as(C.POINTER(C.c_double))))
         self.Q = L.mek_bank_capacity_Ah(self.h)
 
     def close(self):

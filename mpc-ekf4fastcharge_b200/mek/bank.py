@@ -22,7 +22,9 @@ from dataclasses import dataclass, field
 import numpy as np
 
 MAGIC = b"MEKBANK1"
-VERSION = 1
+VERSION = 1                      # written when the bank has no tables (files of earlier builds stay valid)
+VERSION_LUT = 2                  # + [int32 n][f64 lo][f64 hi][f64 tables[8][n]] behind the parameter vector
+LUT_NAMES = ("Uocp_neg", "dUocp_neg", "Uocp_pos", "dUocp_pos", "k0_neg", "k0_pos", "Rf_neg", "Rf_pos")   # table order (include/mek.h)
 
 # ---- parameter-vector layout (mirrored by csrc/mek_params.h and oracle/mek_oracle.c) ----
 P_F, P_R, P_Q, P_RC, P_TREF = 0, 1, 2, 3, 4
@@ -64,6 +66,8 @@ class Bank:
     params: np.ndarray          # [N_PARAMS]
     T_K: np.ndarray = field(default=None)   # [nT,nZ] ROMmdls.T (K)
     Z: np.ndarray = field(default=None)     # [nT,nZ] ROMmdls.SOC (0..1)
+    lut: np.ndarray = field(default=None)   # optional [8,n] tables of cellData.function.* on a uniform stoichiometry grid (LUT_NAMES)
+    lut_range: tuple = (0.0, 1.0)           # the grid's end points
 
     def __post_init__(self):
         self.Tpts_C = np.asarray(self.Tpts_C, dtype=np.float64)
@@ -100,14 +104,29 @@ class Bank:
         if len(self.params) != N_PARAMS:
             raise BankError("parameter vector has wrong length")
         resolve_indices(self.names, self.xloc)                   # OB_step.m:140-158, iterEKF.m:692-734
+        if self.lut is not None:
+            self.lut = np.ascontiguousarray(self.lut, dtype=np.float64)
+            if self.lut.ndim != 2 or self.lut.shape[0] != len(LUT_NAMES) or self.lut.shape[1] < 2 or not np.all(np.isfinite(self.lut)):
+                raise BankError("cell-function tables must be a finite [8, n >= 2] array")
+            if not (self.lut_range[1] > self.lut_range[0]):
+                raise BankError("cell-function tables need an ascending stoichiometry range")
         return self
+
+    def with_tables(self, n=2001, lo=0.0, hi=1.0):
+        """A copy of this bank whose cellData.function.{Uocp,dUocp,k0,Rf} are TABLES sampled from its own closed forms on a
+        uniform grid (what matlab/mek_sample_celldata.m does to the reference's function handles)."""
+        import copy
+        b = copy.copy(self)
+        b.lut = sample_closed_forms(self.params, np.linspace(lo, hi, int(n)))
+        b.lut_range = (float(lo), float(hi))
+        return b
 
     # -- binary file ----------------------------------------------------------------------------
     def save(self, path):
         nT, nZ = self.nT, self.nZ
         with open(path, "wb") as f:
             f.write(MAGIC)
-            f.write(struct.pack("<6i", VERSION, self.n, self.nz, nT, nZ, len(self.params)))
+            f.write(struct.pack("<6i", VERSION if self.lut is None else VERSION_LUT, self.n, self.nz, nT, nZ, len(self.params)))
             f.write(struct.pack("<d", self.Tsamp))
             f.write(np.ascontiguousarray(self.Tpts_C, "<f8").tobytes())
             f.write(np.ascontiguousarray(self.Zpts_pct, "<f8").tobytes())
@@ -116,6 +135,9 @@ class Bank:
                 f.write(struct.pack("<d", float(xl)))
             for a in (self.T_K, self.Z, self.A, self.C, self.D, self.params):
                 f.write(np.ascontiguousarray(a, "<f8").tobytes())
+            if self.lut is not None:
+                f.write(struct.pack("<idd", self.lut.shape[1], float(self.lut_range[0]), float(self.lut_range[1])))
+                f.write(np.ascontiguousarray(self.lut, "<f8").tobytes())
 
     @staticmethod
     def load(path):
@@ -125,7 +147,7 @@ class Bank:
             raise BankError("not a MEKBANK1 file")
         off = 8
         ver, n, nz, nT, nZ, npar = struct.unpack_from("<6i", buf, off); off += 24
-        if ver != VERSION:
+        if ver not in (VERSION, VERSION_LUT):
             raise BankError("unsupported bank version %d" % ver)
         (Tsamp,) = struct.unpack_from("<d", buf, off); off += 8
 
@@ -142,7 +164,12 @@ class Bank:
         T_K = take((nT, nZ)); Z = take((nT, nZ))
         A = take((nT, nZ, n + 1)); C = take((nT, nZ, nz, n + 1)); D = take((nT, nZ, nz))
         params = take((npar,))
-        return Bank(n, nz, Tpts, Zpts, Tsamp, names, np.array(xloc), A, C, D, params, T_K, Z)
+        lut, rng = None, (0.0, 1.0)
+        if ver >= VERSION_LUT:
+            ln, lo, hi = struct.unpack_from("<idd", buf, off); off += 20
+            if ln > 0:
+                lut, rng = take((len(LUT_NAMES), ln)), (lo, hi)
+        return Bank(n, nz, Tpts, Zpts, Tsamp, names, np.array(xloc), A, C, D, params, T_K, Z, lut, rng)
 
 
 def resolve_indices(names, xloc):
@@ -197,6 +224,23 @@ def resolve_indices(names, xloc):
     if len(ind["negPhise"]) < 2:                           # EKFmatsHandler.m:97 indexes negPhise(2)
         raise BankError("EKFmatsHandler needs a second negPhise output (ind.negPhise(2))")
     return ind
+
+
+def sample_closed_forms(params, theta):
+    """The eight tabulated functions (LUT_NAMES order) of the closed-form parameter vector at stoichiometries `theta`; k0 and Rf
+    at the reference temperature (Arrhenius factor 1)."""
+    p = np.asarray(params, dtype=np.float64); th = np.asarray(theta, dtype=np.float64)
+    c = p[P_UN:P_UN + 6]
+    x = (th - c[4]) / c[5]
+    un = c[0] + c[1] / ((th + c[2]) ** 2) + c[3] * (1.0 - x / np.sqrt(1.0 + x * x))
+    dun = -2.0 * c[1] / ((th + c[2]) ** 3) - (c[3] / c[5]) / ((1.0 + x * x) ** 1.5)
+    nc = int(p[P_UP + 2]); coef = p[P_UP_COEF:P_UP_COEF + nc]
+    xp = (th - p[P_UP]) / p[P_UP + 1]
+    up = np.polynomial.polynomial.polyval(xp, coef)
+    dup = np.polynomial.polynomial.polyval(xp, np.polynomial.polynomial.polyder(coef)) / p[P_UP + 1]
+    k0 = [p[b + E_K0REF] * (1.0 + p[b + E_K0SLOPE] * (th - 0.5)) for b in (P_NEG, P_POS)]
+    rf = [p[b + E_RFREF] * (1.0 + p[b + E_RFSLOPE] * th) for b in (P_NEG, P_POS)]
+    return np.stack([un, dun, up, dup, k0[0], k0[1], rf[0], rf[1]])
 
 
 def default_params():
@@ -300,7 +344,7 @@ def default_bank_path():
 # ------------------------------------------------------------------------------------------------
 # MATLAB .mat import / export of the numeric part of the reference's ROM file
 # ------------------------------------------------------------------------------------------------
-def from_mat(path, params=None, var="ROM"):
+def from_mat(path, params=None, var="ROM", lut_mat=None):
     """Build a Bank from the reference's ``ROM_NMC30_HRA.mat`` (loaded at runMPC.m:4-5) or any file with the same
     structure (MATLAB v5..v7; v7.3/HDF5 is not readable without h5py).
 
@@ -312,7 +356,10 @@ def from_mat(path, params=None, var="ROM"):
     NOT read: ``cellData.function.*`` -- MATLAB function handles, which a .mat file stores as opaque objects.  The closed
     forms are supplied as the parameter vector ``params`` (layout P_*/E_* above; ``default_params()`` when None, with F and
     R taken from the file).  Fitting that vector to a real cell's handles is the user's step: sample the handles in
-    MATLAB, fit, pass the result here.
+    MATLAB, fit, pass the result here -- or, without fitting, sample them with matlab/mek_sample_celldata.m,
+    ``save('celldata_lut.mat','-struct','lut')`` and pass that file as ``lut_mat``: Uocp, dUocp, k0 and Rf of both electrodes
+    are then tables (``Bank.lut``, linear interpolation), and only the scalars of ``params`` (F, R, Q, Rc, Tref, the
+    stoichiometry windows, activation energies and double-layer constants) remain to be supplied.
     """
     import scipy.io
     try:
@@ -369,7 +416,18 @@ def from_mat(path, params=None, var="ROM"):
         cst = one(getattr(cd, "const", None)) if cd is not None else None
         if cst is not None and hasattr(cst, "F") and hasattr(cst, "R"):
             params[P_F] = float(np.asarray(cst.F).reshape(-1)[0]); params[P_R] = float(np.asarray(cst.R).reshape(-1)[0])
-    return Bank(n, nz, Tpts, Zpts, Tsamp, names, xloc, A, C, D, np.asarray(params, float), T_K, Z).validate()
+    lut, rng = None, (0.0, 1.0)
+    if lut_mat is not None:                                       # matlab/mek_sample_celldata.m: theta [1,n] uniform, tables [8,n]
+        lm = scipy.io.loadmat(lut_mat)
+        if "theta" not in lm or "tables" not in lm:
+            raise BankError("%s: expected the variables 'theta' and 'tables' (mek_sample_celldata.m)" % lut_mat)
+        th = np.asarray(lm["theta"], float).reshape(-1); lut = np.asarray(lm["tables"], float)
+        if lut.shape != (len(LUT_NAMES), len(th)) or len(th) < 2:
+            raise BankError("tables must be %d x numel(theta)" % len(LUT_NAMES))
+        if np.max(np.abs(np.diff(th) - (th[-1] - th[0]) / (len(th) - 1))) > 1e-12 * max(1.0, abs(th[-1] - th[0])):
+            raise BankError("theta must be a uniform grid")
+        rng = (float(th[0]), float(th[-1]))
+    return Bank(n, nz, Tpts, Zpts, Tsamp, names, xloc, A, C, D, np.asarray(params, float), T_K, Z, lut, rng).validate()
 
 
 def to_mat(bank, path, var="ROM"):

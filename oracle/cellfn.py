@@ -37,7 +37,23 @@ def _electrode(p, base, uocp, duocp):
     return e
 
 
-def make_cell_data(params):
+def _interp1(grid_lo, grid_hi, y):
+    """MATLAB's interp1(theta, y, x, 'linear') on a uniform grid with x clamped to the grid (the tabulated form of a handle)."""
+    n = len(y)
+    def f(th, T=None):
+        th = float(th)
+        if th != th:
+            return th
+        t = (th - grid_lo) * ((n - 1) / (grid_hi - grid_lo))
+        t = min(max(t, 0.0), float(n - 1))
+        i = min(int(t), n - 2)
+        return y[i] + (t - i) * (y[i + 1] - y[i])
+    return f
+
+
+def make_cell_data(params, lut=None, lut_range=(0.0, 1.0)):
+    """lut: optional [8,n] tables (order: Uocp_neg, dUocp_neg, Uocp_pos, dUocp_pos, k0_neg, k0_pos, Rf_neg, Rf_pos) replacing the
+    closed forms of those handles; k0 / Rf tables are at the reference temperature and keep the Arrhenius factor."""
     p = np.asarray(params, dtype=np.float64)
     c = p[P_UN:P_UN + 6]
 
@@ -59,6 +75,9 @@ def make_cell_data(params):
     def dup(th):
         x = (th - pc) / pw
         return np.polynomial.polynomial.polyval(x, np.polynomial.polynomial.polyder(coef)) / pw
+    if lut is not None:
+        T = [_interp1(lut_range[0], lut_range[1], np.asarray(row, dtype=np.float64)) for row in lut]
+        un, dun, up, dup = T[0], T[1], T[2], T[3]
     cd = SimpleNamespace()
     cd.const = SimpleNamespace(F=p[P_F], R=p[P_R])
     cd.function = SimpleNamespace(
@@ -66,4 +85,8 @@ def make_cell_data(params):
         neg=_electrode(p, P_NEG, un, dun),
         pos=_electrode(p, P_POS, up, dup),
     )
+    if lut is not None:
+        for e, base, k0t, rft in ((cd.function.neg, P_NEG, T[4], T[6]), (cd.function.pos, P_POS, T[5], T[7])):
+            e.k0 = (lambda k0t, base: lambda th, Tk: k0t(th) * _arr(p, Tk, p[base + E_EA_K0]))(k0t, base)
+            e.Rf = (lambda rft, base: lambda th, Tk: rft(th) * _arr(p, Tk, -p[base + E_EA_RF]))(rft, base)
     return cd

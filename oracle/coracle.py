@@ -97,7 +97,7 @@ class COracle:
         self._keep = dict(
             Tpts=np.ascontiguousarray(bank.Tpts_C + 273.15), Zpts=np.ascontiguousarray(bank.Zpts_pct / 100.0),
             A=np.ascontiguousarray(bank.A.reshape(-1)), Cm=np.ascontiguousarray(bank.C.reshape(-1)),
-            D=np.ascontiguousarray(bank.D.reshape(-1)), params=np.ascontiguousarray(bank.params))
+            D=np.ascontiguousarray(bank.D.reshape(-1)), params=self._params_x(bank))
         # row indices from the literal restatement's own set-up code (iterEKF.m:610-735)
         ind, loc, _ = literal._ekf_setupIndsLocs(NS(tfData=NS(names=list(bank.names), xLoc=bank.xloc)))
         b = MkoBank()
@@ -129,6 +129,20 @@ class COracle:
         self.Np, self.Nc = Np, Nc
         self.nC = (4 * Nc if cf.useCurrent else 0) + Np * (cf.useVoltage + cf.useEta + 1) + cf.z_target_terminal
         self.SL = self.L.mko_state_len(bank.M)
+
+    def _params_x(self, bank):
+        """the parameter vector + the descriptor of the optional cell-function tables (mek_oracle.c: P_LUT_*)"""
+        import struct
+        px = np.zeros(len(bank.params) + 4)
+        px[:len(bank.params)] = bank.params
+        lut = getattr(bank, "lut", None)
+        if lut is not None:
+            self._lut = np.ascontiguousarray(lut, dtype=np.float64)
+            n = self._lut.shape[1]
+            lo, hi = bank.lut_range
+            px[-4], px[-3], px[-2] = float(n), float(lo), float(n - 1) / (float(hi) - float(lo))
+            px[-1] = struct.unpack("<d", struct.pack("<Q", self._lut.ctypes.data))[0]
+        return px
 
     def init(self, SOC0pct, Tc, SigmaX0, limits, ekf_SOC0pct=None):
         """SigmaX0: [B,6,6]; limits: [B,7] = u_max,u_min,du_max,du_min,v_max,phise_min,z_max(+z_tol)."""

@@ -41,7 +41,7 @@ def build_rom(bank):
     return NS(ROMmdls=mdls,
               tfData=NS(names=list(bank.names), xLoc=np.asarray(bank.xloc, float).copy()),
               xraData=NS(T=bank.Tpts_C.copy(), SOC=bank.Zpts_pct.copy(), Tsamp=float(bank.Tsamp)),
-              cellData=cellfn.make_cell_data(bank.params))
+              cellData=cellfn.make_cell_data(bank.params, getattr(bank, "lut", None), getattr(bank, "lut_range", (0.0, 1.0))))
 
 
 def _find(names, nm):

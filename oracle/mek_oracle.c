@@ -46,6 +46,10 @@
 /* parameter vector layout (restated; equals mek/bank.py) */
 enum { P_F = 0, P_R, P_Q, P_RC, P_TREF, P_NEG = 5, P_POS = 16, P_UN = 27, P_UP = 33, P_UP_COEF = 36, N_PARAMS = 44 };
 enum { E_THETA0 = 0, E_THETA100, E_K0REF, E_K0SLOPE, E_EA_K0, E_RFREF, E_RFSLOPE, E_EA_RF, E_WDL, E_CDL, E_NDL };
+/* optional tables of cellData.function.{Uocp,dUocp,k0,Rf} (include/mek.h: mek_bank_set_lut): the caller appends n (0 = closed
+   forms), lo, 1/step and the table base address (bit pattern of a pointer) to the parameter vector */
+enum { P_LUT_N = N_PARAMS, P_LUT_LO, P_LUT_INVH, P_LUT_PTR, N_PARAMS_X };
+enum { LUT_UN = 0, LUT_DUN, LUT_UP, LUT_DUP, LUT_K0N, LUT_K0P, LUT_RFN, LUT_RFP, LUT_NTAB };
 
 /* status bits */
 #define ST_LOST 1u        /* warnCount > 10 (iterEKF.m:55-59)              */
@@ -187,13 +191,31 @@ double mko_test_asinh(double x) { return mko_asinh(x); }
 static double soc_e(const double *p, int base, double z) {
   return p[base + E_THETA0] + z * (p[base + E_THETA100] - p[base + E_THETA0]);
 }
+/* interp1(grid, table, th, 'linear') on a uniform grid, th clamped to the grid */
+static double lut_eval(const double *p, int tab, double th) {
+  if (th != th) return th;
+  const int n = (int)p[P_LUT_N];
+  uint64_t bits;
+  memcpy(&bits, &p[P_LUT_PTR], 8);
+  const double *y = (const double *)(uintptr_t)bits + (size_t)tab * (size_t)n;
+  double t = (th - p[P_LUT_LO]) * p[P_LUT_INVH];
+  if (!(t > 0.0)) t = 0.0;
+  if (t > (double)(n - 1)) t = (double)(n - 1);
+  int i = (int)t;
+  if (i > n - 2) i = n - 2;
+  const double f = t - (double)i;
+  return fma(f, y[i + 1] - y[i], y[i]);
+}
+#define IF_LUT(p, expr) if ((p)[P_LUT_N] != 0.0) return (expr)
 static double uocp_n(const double *p, double th) {
+  IF_LUT(p, lut_eval(p, LUT_UN, th));
   const double *c = p + P_UN;
   double x = (th - c[4]) / c[5];
   double t = th + c[2];
   return (c[0] + c[1] / (t * t)) + c[3] * (1.0 - x / sqrt(1.0 + x * x));
 }
 static double duocp_n(const double *p, double th) {
+  IF_LUT(p, lut_eval(p, LUT_DUN, th));
   const double *c = p + P_UN;
   double x = (th - c[4]) / c[5];
   double q = 1.0 + x * x;
@@ -201,6 +223,7 @@ static double duocp_n(const double *p, double th) {
   return (-2.0 * c[1]) / ((t * t) * t) - (c[3] / c[5]) / (q * sqrt(q));
 }
 static double uocp_p(const double *p, double th) {
+  IF_LUT(p, lut_eval(p, LUT_UP, th));
   double x = (th - p[P_UP]) / p[P_UP + 1];
   int nc = (int)p[P_UP + 2];
   double acc = p[P_UP_COEF + nc - 1];
@@ -208,6 +231,7 @@ static double uocp_p(const double *p, double th) {
   return acc;
 }
 static double duocp_p(const double *p, double th) {
+  IF_LUT(p, lut_eval(p, LUT_DUP, th));
   double x = (th - p[P_UP]) / p[P_UP + 1];
   int nc = (int)p[P_UP + 2];
   double acc = (double)(nc - 1) * p[P_UP_COEF + nc - 1];
@@ -215,9 +239,11 @@ static double duocp_p(const double *p, double th) {
   return acc / p[P_UP + 1];
 }
 static double k0_e(const double *p, int base, double th, double arr) {
+  IF_LUT(p, lut_eval(p, base == P_NEG ? LUT_K0N : LUT_K0P, th) * arr);
   return (p[base + E_K0REF] * (1.0 + p[base + E_K0SLOPE] * (th - 0.5))) * arr;
 }
 static double rf_e(const double *p, int base, double th, double arr) {
+  IF_LUT(p, lut_eval(p, base == P_NEG ? LUT_RFN : LUT_RFP, th) * arr);
   return (p[base + E_RFREF] * (1.0 + p[base + E_RFSLOPE] * th)) * arr;
 }
 static double arrhenius(const double *p, double T, double Ea) {

@@ -372,3 +372,29 @@ def test_model_blend_fused_loop(bank, coracle_mod):
         c = co.run(0, N, nthreads=8)
         _assert_bit_exact(g, c)
         assert cb.summary()["n_qp"] > 0
+
+
+def test_tabulated_cell_functions(bank, coracle_mod, tmp_path):
+    """A bank whose cellData.function.{Uocp,dUocp,k0,Rf} are tables (mek_bank_set_lut / bank file version 2): the fused kernels
+    (k_fused_fast_lut.cu and the runtime-shape instances) against the C restatement, bit for bit; through the descriptor +
+    set_lut and through a file."""
+    from mek import population as P, api
+    bt = bank.with_tables(n=1001)
+    pop = P.make_population(bank.params[2], 96, seed=91, heterogeneous=True, ekf_soc_error=2.0)
+    N = 900
+    co = coracle_mod.COracle(bt)
+    co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    c = co.run(0, N, nthreads=8)
+    f = str(tmp_path / "tab.bin")
+    bt.save(f)
+    for src, generic in ((bt, False), (f, False), (bt, True)):      # static-shape instances with the look-up compiled in; runtime-shape ones
+        rom = api.RomBank(src)
+        cb = api.CellBatch(rom, len(pop), generic_path=generic)
+        cb.set_logging(len(pop), N)
+        cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        cb.run(0, N)
+        _assert_bit_exact(cb.logs(0, N), c)
+        cb.close()
+    # the closed forms of the same bank give another trajectory: the tables are what ran
+    cb0, g0, co0, c0 = _run_both(bank, coracle_mod, pop, N)
+    assert np.nanmax(np.abs(g0["V"] - c["V"])) > 0

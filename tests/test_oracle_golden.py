@@ -164,3 +164,28 @@ def test_model_blend_loop_c_vs_literal(bank, coracle_mod):
     for k in ("u", "V", "SOC", "phise"):
         assert rel_err(c[k][:, 0], o[k][:N], SCALE[k]) <= TOL, k
     assert c["SOC"][-1, 0] > 0.5                                    # the charge proceeds
+
+
+def test_tabulated_cell_functions_c_vs_literal(bank, coracle_mod):
+    """cellData.function.{Uocp,dUocp,k0,Rf} as TABLES (what a user of the real ROM file supplies: the handles sampled on a
+    stoichiometry grid, mek_bank_set_lut) instead of the closed forms: C restatement vs literal restatement of the whole loop,
+    and -- sanity of the interpolation -- a finely tabulated bank stays close to its closed forms."""
+    from oracle import literal as L
+    N = 1200
+    bt = bank.with_tables(n=257)                                    # coarse on purpose: the interpolation error is visible
+    o = L.run_mpc(bt, SOC0=10.0, N=N)
+    co = coracle_mod.COracle(bt)
+    co.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bt))
+    c = co.run(0, N, nthreads=1)
+    assert np.array_equal(o["nexec"][:N], c["nexec"][:, 0]) and np.array_equal(o["active"][:N], c["active"][:, 0])
+    assert np.array_equal(o["iT"][:N], c["iT"][:, 0]) and np.array_equal(o["iZ"][:N], c["iZ"][:, 0])
+    for k in ("u", "V", "SOC", "phise"):
+        assert rel_err(c[k][:, 0], o[k][:N], SCALE[k]) <= TOL, k
+    co0 = coracle_mod.COracle(bank)
+    co0.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
+    c0 = co0.run(0, N, nthreads=1)
+    assert 0 < np.abs(c["V"] - c0["V"]).max() < 5e-3                # tables are in use, and they are a fair copy
+    cf = coracle_mod.COracle(bank.with_tables(n=20001))
+    cf.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
+    c1 = cf.run(0, N, nthreads=1)
+    assert np.abs(c1["V"] - c0["V"]).max() < 1e-5 and np.abs(c1["SOC"] - c0["SOC"]).max() < 1e-6
