@@ -101,7 +101,16 @@ typedef struct {
                                optimised fused kernels), 1 = 'MdlB' model blend: one blended model per cell (iterEKF.m MB
                                branches).  mek_run then runs the plain loop kernel k_run_population_mb; mek_pop_iter_ekf serves
                                the function-level call                                                                      */
+  /* Scenario beyond the reference's loop (runMPC.m:88 feeds iterEKF the noiseless plant voltage): measurement noise.  The filter
+     sees V + meas_sigma * g(noise_seed, first_cell + cell, k) with g the counter-based sequence below; logs keep the plant's V. */
+  double meas_sigma;        /* standard deviation [V]; 0 (default) = the reference's loop                                    */
+  uint64_t noise_seed;      /* key of the sequence                                                                           */
+  int64_t first_cell;       /* global index of this population's cell 0, so that any shard reproduces any cell's sequence    */
 } mek_config;
+
+/* g(seed, cell, k): x = seed ^ cell*0x9E3779B97F4A7C15 ^ (k+1)*0xD1B54A32D192ED03; twelve splitmix64 steps of x, each output's top
+ * 53 bits as a uniform on [0,1), summed in order, minus 6 (mean 0, variance 1).  Exported for callers who want the sequence. */
+double mek_noise(uint64_t seed, uint64_t cell, uint64_t k);
 
 /* ---- bank ---- */
 int mek_bank_create(const mek_bank_desc *desc, mek_bank **out);

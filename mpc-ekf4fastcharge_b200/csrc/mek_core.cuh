@@ -50,6 +50,9 @@ struct Dims {
   double zinv;       // (nZ-1)/(Zpts[nZ-1]-Zpts[0]): bracket guess of two_nearest_z
   long long B, ld;   // cells in this shard, cells rounded up to whole 32-cell tiles
   int f_lambda, f_bigx, f_xhat, f_sig, nfields;
+  double meas_sigma;            // noisy-sensor scenario (mek_config.meas_sigma): 0 = runMPC.m:88 as written
+  unsigned long long noise_seed;
+  long long first_cell;
   int mb, f_mbx, f_mbs;   // model-blend EKF (function-level entry only): ekfData.xhat (6) and ekfData.SigmaX (21, upper triangle) behind the model rows
 };
 

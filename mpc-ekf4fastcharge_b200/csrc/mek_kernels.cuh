@@ -87,7 +87,7 @@ struct StepLog {
 
 template <int NPM, int NCM, int CONS, int BATCH>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
 __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms, int tt,
-                                          Defer* df) {
+                                          Defer* df, long long id, int k) {
   const Dims& d = P.d;
   lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
 #pragma unroll
@@ -101,7 +101,11 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   if (df) defer_stream(d, bk, c, *df, uk, c.f(S_PRIORI));
   else stream_models<true, true, BATCH>(d, bk, c, uk, c.f(S_PRIORI));
   EkfOut e;
-  ekf_step<false>(d, bk, P.cp, c, V, uk, e, Scratch{smt, sms}, tt, df);  // runMPC.m:88,92
+  double vk = V;                                                     // runMPC.m:88 feeds the filter the plant voltage itself
+#ifndef MEK_LUT_OFF                                                  // scenarios live in the full-featured instances only
+  if (d.meas_sigma != 0.0) vk = V + d.meas_sigma * noise_gauss(d.noise_seed, (unsigned long long)(d.first_cell + id), (unsigned long long)k);
+#endif
+  ekf_step<false>(d, bk, P.cp, c, vk, uk, e, Scratch{smt, sms}, tt, df);  // runMPC.m:88,92
   if (e.lost) return;
   MpcOut o;
   if constexpr (CONS >= 0 && NPM == 5 && NCM == 2) mpc_step_fast<NPM, NCM, CONS>(d, P.cp, c, e, uk, o, smt, sms);   // runMPC.m:94-103
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
       }
       if (!active) continue;
       StepLog lg;
-      cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt, KB > 0 ? &df : nullptr);
+      cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt, KB > 0 ? &df : nullptr, id, k);
       // per-cell summary, kept in the state header (not in registers: they are the scarce resource of this kernel)
       if (lg.nexec > 0) {
         c.f(S_SUM_NEXEC) += (double)lg.nexec;

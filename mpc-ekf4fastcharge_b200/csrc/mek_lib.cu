@@ -221,6 +221,8 @@ extern "C" int mek_bank_load(const char* path, mek_bank** out) {
   return rc;
 }
 
+extern "C" double mek_noise(uint64_t seed, uint64_t cell, uint64_t k) { return noise_gauss(seed, cell, k); }
+
 extern "C" int mek_bank_set_lut(mek_bank* b, int n, double theta_lo, double theta_hi, const double* tables) {
   if (!b) return fail(MEK_ERR_ARG, "null bank");
   if (n == 0) { b->lut_n = 0; b->lut.clear(); return MEK_OK; }     // back to the closed forms
@@ -534,7 +536,9 @@ __global__ void __launch_bounds__(128) k_run_population_mb(const __grid_constant
         const double V = plant_step<true>(d, bk, P.cp, c, uk, tt);   // runMPC.m:85
         EkfOut e;
         memset(&e, 0, sizeof(e));
-        ekf_step_mb(P, bk, RL, c, V, uk, e, sc, nullptr, nullptr);   // runMPC.m:88,92
+        double vk = V;
+        if (d.meas_sigma != 0.0) vk = V + d.meas_sigma * noise_gauss(d.noise_seed, (unsigned long long)(d.first_cell + id), (unsigned long long)k);
+        ekf_step_mb(P, bk, RL, c, vk, uk, e, sc, nullptr, nullptr);   // runMPC.m:88,92
         if (!e.lost) {
           MpcOut o;
           mpc_step<NPM, NCM>(d, P.cp, c, e, uk, o);                  // runMPC.m:94-103
@@ -993,6 +997,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   d.ld = (B + 31) / 32 * 32;
   d.f_lambda = S_HDR; d.f_bigx = d.f_lambda + d.nC; d.f_xhat = d.f_bigx + 6 * d.M; d.f_sig = d.f_xhat + N5 * d.M;
   d.nfields = d.f_sig + NSYM * d.M;
+  d.meas_sigma = cfg->meas_sigma; d.noise_seed = cfg->noise_seed; d.first_cell = cfg->first_cell;
   d.mb = cfg->ekf_method == 1 ? 1 : 0;                               // initKF.m:44-53: 'OutB' (0) or 'MdlB' (1)
   d.f_mbx = d.f_mbs = 0;
   if (d.mb) { d.f_mbx = d.nfields; d.f_mbs = d.f_mbx + N6; d.nfields = d.f_mbs + NSYM6; }
@@ -1072,16 +1077,19 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   p->cons = -1;
   p->run_threads = p->threads;
   p->run_smem = p->smem_bytes;
+  // tabulated cell functions and the noisy-sensor scenario are compiled into the full-featured instances only (k_fused_fast_lut.cu,
+  // k_fused_generic.cu); the lean ones (MEK_LUT_OFF) serve everything else
+  const bool full = bank->lut_n > 0 || cfg->meas_sigma != 0.0;
   {
     const int mask = (d.useCurrent ? 1 : 0) | (d.useVoltage ? 2 : 0) | (d.useEta ? 4 : 0) | (d.useZmax ? 8 : 0);
     if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path && !d.useTerm) {
       p->cons = mask;
-      p->run_threads = (cfg->threads_per_block == 384 && bank->lut_n == 0) ? 384 : 256;   // 256 threads x 255 registers: fewest spills, least DRAM traffic
+      p->run_threads = (cfg->threads_per_block == 384 && !full) ? 384 : 256;   // 256 threads x 255 registers: fewest spills, least DRAM traffic
       const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
       p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
     }
-    if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path && !d.useTerm && bank->lut_n == 0) {   // config C4: long-horizon static-shape instance
+    if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path && !d.useTerm && !full) {   // config C4: long-horizon static-shape instance
       using WS = WideShape<20, 5, 15>;
       p->cons = mask;
       // 256 threads (default): lambda in shared memory, the read-mostly columns in L2; 64 threads: every column in shared memory
@@ -1105,7 +1113,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
     if (kb > 0) p->run_smem += sizeof(double) * (size_t)(kb + 1) * (size_t)p->run_threads;
   }
   if (p->inst == 1 && p->cons == 15) p->fn_run = mek_fused_wide_kernel(p->run_threads);
-  else if (p->cons >= 0) p->fn_run = bank->lut_n > 0 ? mek_fused_fast_lut_kernel(p->cons, p->run_threads) : mek_fused_fast_kernel(p->cons, p->run_threads);
+  else if (p->cons >= 0) p->fn_run = full ? mek_fused_fast_lut_kernel(p->cons, p->run_threads) : mek_fused_fast_kernel(p->cons, p->run_threads);
   else p->fn_run = mek_fused_generic_kernel(p->inst);
   rc |= prep_fn(p->fn_run, p->run_threads, p->run_smem, &occ);
   if (rc != MEK_OK) { return rc; }

@@ -17,7 +17,7 @@ SYMBOLS = ["mek_bank_create", "mek_bank_load", "mek_bank_destroy", "mek_bank_dim
            "mek_pop_create", "mek_pop_destroy", "mek_pop_set_logging", "mek_pop_init", "mek_pop_reset", "mek_run",
            "mek_run_timed", "mek_sync", "mek_pop_stream", "mek_pop_launches", "mek_pop_ncon", "mek_pop_defer_block", "mek_pop_regroups", "mek_pop_state_len",
            "mek_read_logs", "mek_read_state", "mek_write_state", "mek_summary", "mek_pop_ob_step", "mek_pop_iter_ekf",
-           "mek_pop_iter_mpc", "mek_pop_iter_mpc_cost", "mek_read_cell_summaries", "mek_host_alloc", "mek_host_free", "mek_hildreth", "mek_pred_mat", "mek_constraints", "mek_fp64_peak", "mek_last_error", "mek_version"]
+           "mek_pop_iter_mpc", "mek_pop_iter_mpc_cost", "mek_read_cell_summaries", "mek_host_alloc", "mek_host_free", "mek_hildreth", "mek_pred_mat", "mek_constraints", "mek_fp64_peak", "mek_noise", "mek_last_error", "mek_version"]
 
 
 class MekError(RuntimeError):
@@ -29,7 +29,8 @@ class MekConfig(C.Structure):
                 ("ref", C.c_double), ("SigmaV", C.c_double), ("SigmaW", C.c_double), ("force_jacobi", C.c_int),
                 ("threads_per_block", C.c_int), ("blocks_per_sm", C.c_int), ("generic_path", C.c_int), ("sync_steps", C.c_int), ("keep_cell_order", C.c_int),
                 ("defer_block", C.c_int), ("defer_stagger", C.c_int), ("regroup_every", C.c_int), ("defer_narrow_test", C.c_int), ("general_sweep_test", C.c_int),
-                ("z_target_terminal", C.c_int), ("z_tol", C.c_double), ("ekf_method", C.c_int)]
+                ("z_target_terminal", C.c_int), ("z_tol", C.c_double), ("ekf_method", C.c_int),
+                ("meas_sigma", C.c_double), ("noise_seed", C.c_uint64), ("first_cell", C.c_int64)]
 
 
 class MekBankDesc(C.Structure):
@@ -61,6 +62,8 @@ def lib():
         L.mek_pop_regroups.restype = C.c_int64
         L.mek_pop_regroups.argtypes = [C.c_void_p]
         L.mek_pop_state_len.argtypes = [C.c_void_p]
+        L.mek_noise.restype = C.c_double
+        L.mek_noise.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.mek_bank_set_lut.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double)]
         L.mek_bank_lut_points.argtypes = [C.c_void_p]
         L.mek_bank_destroy.argtypes = [C.c_void_p]

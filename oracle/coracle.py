@@ -51,7 +51,8 @@ class MkoBank(C.Structure):
 class MkoConfig(C.Structure):
     _fields_ = [("Np", C.c_int), ("Nc", C.c_int), ("maxHild", C.c_int), ("useCurrent", C.c_int), ("useVoltage", C.c_int),
                 ("useEta", C.c_int), ("useZmax", C.c_int), ("ref", C.c_double), ("SigmaV", C.c_double),
-                ("SigmaW", C.c_double), ("force_jacobi", C.c_int), ("z_target_terminal", C.c_int), ("z_tol", C.c_double), ("ekf_method", C.c_int)]
+                ("SigmaW", C.c_double), ("force_jacobi", C.c_int), ("z_target_terminal", C.c_int), ("z_tol", C.c_double), ("ekf_method", C.c_int),
+                ("meas_sigma", C.c_double), ("noise_seed", C.c_uint64), ("first_cell", C.c_int64)]
 
 
 def build(force=False):
@@ -74,6 +75,8 @@ def lib():
         L.mko_ncon_max.restype = C.c_int
         L.mko_sigma_min_gtg.restype = C.c_double
         L.mko_sigma_min_gtg.argtypes = [C.c_int, C.c_int, C.c_double]
+        L.mko_noise.restype = C.c_double
+        L.mko_noise.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.mko_ob_step.restype = C.c_double
         L.mko_ob_step.argtypes = [C.POINTER(MkoBank), C.c_void_p, C.c_double]
         for f in ("mko_test_log", "mko_test_exp", "mko_test_asinh"):
@@ -91,7 +94,7 @@ class COracle:
     """Population runner over the C restatement."""
 
     def __init__(self, bank, Np=5, Nc=2, constraints=(1, 1, 1), ref=95.0, SigmaV=1e-3, SigmaW=1e2, maxHild=100,
-                 force_jacobi=False, z_target_terminal=False, z_tol=0.0, ekf_method="OutB"):
+                 force_jacobi=False, z_target_terminal=False, z_tol=0.0, ekf_method="OutB", meas_sigma=0.0, noise_seed=0, first_cell=0):
         self.bank = bank
         self.L = lib()
         self._keep = dict(
@@ -125,6 +128,7 @@ class COracle:
         cf.force_jacobi = int(force_jacobi)
         cf.z_target_terminal, cf.z_tol = int(bool(z_target_terminal)), float(z_tol)
         cf.ekf_method = 1 if str(ekf_method).upper() in ("MDLB", "MB") else 0          # initKF.m:44-53
+        cf.meas_sigma, cf.noise_seed, cf.first_cell = float(meas_sigma), int(noise_seed), int(first_cell)
         self.cf = cf
         self.Np, self.Nc = Np, Nc
         self.nC = (4 * Nc if cf.useCurrent else 0) + Np * (cf.useVoltage + cf.useEta + 1) + cf.z_target_terminal

@@ -829,9 +829,25 @@ def iterMPC(xk, cellState, mpcData, diagnostics=True):
 DEFAULT_LIMITS = dict(u_max=2.0, du_min=-50.0, du_max=50.0, v_min=3.4, v_max=4.1, phise_min=0.08)
 
 
+def noise(seed, cell, k):
+    """Measurement-noise sample for (seed, cell, 0-based instant): Irwin-Hall sum of twelve splitmix64 uniforms minus 6 (the
+    same integer recipe as include/mek.h documents; Python integers, IEEE additions in the same order)."""
+    M64 = (1 << 64) - 1
+    x = (seed ^ (cell * 0x9E3779B97F4A7C15) ^ ((k + 1) * 0xD1B54A32D192ED03)) & M64
+    s = 0.0
+    for _ in range(12):
+        x = (x + 0x9E3779B97F4A7C15) & M64
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+        z = z ^ (z >> 31)
+        s = s + float(z >> 11) * 2.0 ** -53
+    return s - 6.0
+
+
 def run_mpc(bank, SOC0=10.0, TC=25.0, N=3001, Np=5, Nc=2, targetSOC=95.0, constraints=(1, 1, 1),
             Crate=2.0, limits=None, SigmaX0=None, SigmaV=1e-3, SigmaW=1e2, ekf_SOC0=None,
-            diagnostics=False, keep_zk=False, blend="OutB"):
+            diagnostics=False, keep_zk=False, blend="OutB", meas_sigma=0.0, noise_seed=0, cell_id=0):
     """runMPC.m:4-112 with its literals exposed as arguments.  Returns a dict of per-step stores."""
     ROM = build_rom(bank)
     Ts = 1                                                                               # :9
@@ -855,7 +871,8 @@ def run_mpc(bank, SOC0=10.0, TC=25.0, N=3001, Np=5, Nc=2, targetSOC=95.0, constr
     voltage, obs, cellState = OB_step(uk, TC, None, ROM, dict(SOC0=SOC0, warnOff=True))  # :74 (Q20)
     for k in range(1, N + 1):                                                            # :83-112
         voltage, obs, cellState = OB_step(uk, TC, cellState, ROM)                        # :85
-        zk, zbk, ekfData, Xind = iterEKF(voltage, uk, TC, ekfData)                       # :88
+        vk = voltage if meas_sigma == 0.0 else voltage + meas_sigma * noise(noise_seed, cell_id, k - 1)   # scenario: a noisy sensor
+        zk, zbk, ekfData, Xind = iterEKF(vk, uk, TC, ekfData)                            # :88
         try:
             MPC, xhat = EKFmatsHandler(ekfData, Xind, zk, TC)                            # :92
         except EKFLost:

@@ -79,6 +79,10 @@ typedef struct {
   int z_target_terminal; /* mpcData.const.z_target_terminal (constraintsMPC.m:104): one more row, SOC(Np) >= z_max */
   double z_tol;          /* mpcData.const.z_tol (runMPC.m:44); the z_max limit of the state carries z_max + z_tol */
   int ekf_method;        /* initKF's blend (initKF.m:44-53): 0 'OutB' (runMPC.m:16), 1 'MdlB': mko_cell_step then runs ekf_step_mb */
+  double meas_sigma;     /* scenario beyond runMPC.m:88 (which feeds the filter the noiseless plant voltage): standard deviation [V] of
+                            measurement noise added to vk; 0 = the reference's loop */
+  uint64_t noise_seed;   /* key of the counter-based noise sequence (seed, cell, instant) */
+  int64_t first_cell;    /* global index of cell 0 of this run: any shard reproduces any cell's sequence */
 } mko_config;
 
 /* per-cell state, flat doubles (also the host-side AoS layout of mek_read_state) */
@@ -1248,6 +1252,23 @@ static void mpc_step(const mko_bank *bk, const mko_config *cf, double sigmin, do
   if (!(fabs(uk) <= 1.79769313486231570815e308)) st[S_STATUS] = (double)((unsigned)st[S_STATUS] | ST_NONFINITE);
 }
 
+/* Measurement-noise sample for (seed, cell, instant): twelve splitmix64 outputs as uniforms on [0,1) with 53 bits, summed in
+   order, minus 6 (Irwin-Hall: mean 0, variance 1).  Integer arithmetic and IEEE additions only, so every implementation gives
+   the same bits. */
+double mko_noise(uint64_t seed, uint64_t cell, uint64_t k) {
+  uint64_t x = seed ^ (cell * 0x9E3779B97F4A7C15ull) ^ ((k + 1ull) * 0xD1B54A32D192ED03ull);
+  double s = 0.0;
+  for (int i = 0; i < 12; ++i) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    s = s + (double)(z >> 11) * 0x1.0p-53;
+  }
+  return s - 6.0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* cell init: initKF.m:37-133 + initMPC.m:32-72 + OB_step.m:63-71 and the first I=0 call       */
 /* (runMPC.m:72-74, Q20)                                                                      */
@@ -1294,7 +1315,7 @@ void mko_cell_init(const mko_bank *bk, const mko_config *cf, double *st, double 
 
 /* one pass of the loop body runMPC.m:83-112 */
 void mko_cell_step(const mko_bank *bk, const mko_config *cf, double sigmin, double *st, double *log_u, double *log_V, double *log_soc,
-                   double *log_phise, int *log_iT, int *log_iZ, int *log_nexec, uint32_t *log_active) {
+                   double *log_phise, int *log_iT, int *log_iZ, int *log_nexec, uint32_t *log_active, int64_t cell, int k) {
   const double uk = st[S_UK];
   if ((unsigned)st[S_STATUS] & ST_LOST) {                          /* Q19: a lost cell idles, outputs NaN */
     *log_u = NAN; *log_V = NAN; *log_soc = NAN; *log_phise = NAN; *log_iT = 0; *log_iZ = 0; *log_nexec = 0;
@@ -1303,8 +1324,10 @@ void mko_cell_step(const mko_bank *bk, const mko_config *cf, double sigmin, doub
   }
   const double V = plant_step(bk, st, uk);                         /* :85 */
   ekf_out e;
-  if (cf->ekf_method == 1) ekf_step_mb(bk, cf, st, V, uk, &e, NULL, NULL);
-  else ekf_step(bk, cf, st, V, uk, &e, NULL);                      /* :88,92 */
+  double vk = V;                                                   /* :88 feeds the plant voltage itself */
+  if (cf->meas_sigma != 0.0) vk = V + cf->meas_sigma * mko_noise(cf->noise_seed, (uint64_t)(cf->first_cell + cell), (uint64_t)k);
+  if (cf->ekf_method == 1) ekf_step_mb(bk, cf, st, vk, uk, &e, NULL, NULL);
+  else ekf_step(bk, cf, st, vk, uk, &e, NULL);                     /* :88,92 */
   if (e.lost) {
     *log_u = NAN; *log_V = NAN; *log_soc = NAN; *log_phise = NAN; *log_iT = 0; *log_iZ = 0; *log_nexec = 0;
     for (int w = 0; w < 4; ++w) log_active[w] = 0;
@@ -1333,7 +1356,7 @@ int mko_run(const mko_bank *bk, const mko_config *cf, int B, double *state, int 
       double lu, lV, ls, lp;
       int liT, liZ, ln;
       uint32_t la[4];
-      mko_cell_step(bk, cf, sigmin, st, &lu, &lV, &ls, &lp, &liT, &liZ, &ln, la);
+      mko_cell_step(bk, cf, sigmin, st, &lu, &lV, &ls, &lp, &liT, &liZ, &ln, la, (int64_t)c, k);
       if (u) {
         size_t o = (size_t)(k - k0) * B + c;
         u[o] = lu; V[o] = lV; soc[o] = ls; phise[o] = lp; iT[o] = liT; iZ[o] = liZ; nexec[o] = ln;

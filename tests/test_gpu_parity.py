@@ -398,3 +398,42 @@ def test_tabulated_cell_functions(bank, coracle_mod, tmp_path):
     # the closed forms of the same bank give another trajectory: the tables are what ran
     cb0, g0, co0, c0 = _run_both(bank, coracle_mod, pop, N)
     assert np.nanmax(np.abs(g0["V"] - c["V"])) > 0
+
+
+def test_noisy_sensor_scenario(bank, coracle_mod):
+    """mek_config.meas_sigma: the filter sees V + sigma*g(seed, first_cell + cell, k).  CUDA (full-featured static-shape instances,
+    runtime-shape ones and the model-blend loop) against the C restatement, bit for bit; a shard that starts at cell 40 of the
+    population reproduces those cells' trajectories exactly."""
+    from mek import population as P, api
+    lib = api._lib.lib()
+    assert lib.mek_noise(3, 4, 5) == coracle_mod.lib().mko_noise(3, 4, 5)
+    pop = P.make_population(bank.params[2], 96, seed=95, ekf_soc_error=2.0)
+    kw = dict(meas_sigma=1.5e-3, noise_seed=424242)
+    N = 800
+    cb, g, co, c = _run_both_kw(bank, coracle_mod, pop, N, {}, kw)
+    _assert_bit_exact(g, c)
+    cb2, g2, _, _ = _run_both_kw(bank, coracle_mod, pop, N, dict(generic_path=True), kw, oracle=False)
+    _assert_bit_exact(g2, c)
+    cb3, g3, co3, c3 = _run_both_kw(bank, coracle_mod, pop, 300, dict(ekf_method="MdlB"), dict(kw, ekf_method="MdlB"))
+    _assert_bit_exact(g3, c3)
+    sub = pop.slice(40, 96)
+    cb4, g4, _, _ = _run_both_kw(bank, coracle_mod, sub, N, {}, dict(kw, first_cell=40), oracle=False)
+    for k in ("u", "V", "SOC", "phise", "nexec"):
+        assert np.array_equal(g4[k], g[k][:, 40:], equal_nan=(g[k].dtype.kind == "f")), k
+    cb0, g0, _, _ = _run_both_kw(bank, coracle_mod, pop, N, {}, {}, oracle=False)
+    assert np.nanmax(np.abs(g0["SOC"] - g["SOC"])) > 1e-6
+
+
+def _run_both_kw(bank, coracle_mod, pop, N, cuda_only, both, oracle=True):
+    from mek import api
+    cb = api.CellBatch(api.RomBank(bank), len(pop), **dict(both, **cuda_only))
+    cb.set_logging(len(pop), N)
+    cb.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    cb.run(0, N)
+    g = cb.logs(0, N)
+    co = c = None
+    if oracle:
+        co = coracle_mod.COracle(bank, **both)
+        co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+        c = co.run(0, N, nthreads=8)
+    return cb, g, co, c

@@ -189,3 +189,29 @@ def test_tabulated_cell_functions_c_vs_literal(bank, coracle_mod):
     cf.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
     c1 = cf.run(0, N, nthreads=1)
     assert np.abs(c1["V"] - c0["V"]).max() < 1e-5 and np.abs(c1["SOC"] - c0["SOC"]).max() < 1e-6
+
+
+def test_noisy_sensor_scenario_c_vs_literal(bank, coracle_mod):
+    """Measurement noise on the voltage the filter sees (a scenario beyond runMPC.m:88, which feeds the noiseless plant voltage):
+    the counter-based sequence agrees bit for bit between the C and the Python code, and the loop with it agrees within TOL."""
+    from oracle import literal as L
+    lib = coracle_mod.lib()
+    rng = np.random.default_rng(5)
+    for _ in range(500):
+        s, c, k = (int(x) for x in rng.integers(0, 2 ** 62, 3))
+        assert lib.mko_noise(s, c, k) == L.noise(s, c, k)
+    g = np.array([lib.mko_noise(11, c, k) for c in range(100) for k in range(300)])
+    assert abs(g.mean()) < 0.02 and abs(g.std() - 1.0) < 0.02 and np.abs(g).max() <= 6.0
+    N = 900
+    o = L.run_mpc(bank, SOC0=10.0, N=N, meas_sigma=2e-3, noise_seed=77, cell_id=1005)
+    co = coracle_mod.COracle(bank, meas_sigma=2e-3, noise_seed=77, first_cell=1005)
+    co.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
+    c = co.run(0, N, nthreads=1)
+    assert np.array_equal(o["nexec"][:N], c["nexec"][:, 0]) and np.array_equal(o["active"][:N], c["active"][:, 0])
+    for k in ("u", "V", "SOC", "phise"):
+        assert rel_err(c[k][:, 0], o[k][:N], SCALE[k]) <= TOL, k
+    c0 = coracle_mod.COracle(bank)
+    c0.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
+    q = c0.run(0, N, nthreads=1)
+    assert np.abs(q["SOC"] - c["SOC"]).max() > 1e-6                 # the estimate is perturbed ...
+    assert np.abs(q["SOC"] - c["SOC"]).max() < 5e-3                 # ... and the filter keeps tracking
