@@ -12,7 +12,8 @@ _MAX_KEYS = ("max_V",)
 
 
 def shard_range(B, rank, world):
-    """Contiguous cell range [lo, hi) of `rank`; sizes differ by at most one cell."""
+    """Contiguous cell range [lo, hi) of `rank`; sizes differ by at most one cell.  (A noisy-sensor population passes `lo` as
+    CellBatch(first_cell=lo): the noise sequence is keyed by the global cell index.)"""
     base, rem = divmod(int(B), int(world))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
