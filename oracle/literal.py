@@ -59,21 +59,21 @@ def _msort(v):
 def OB_step(Iapp, Tc, cellState, ROM, initCfg=None):
     """[Vcell, obs, cellState] = OB_step(Iapp, Tc, cellState, ROM, initCfg)   (OB_step.m:1-80)"""
     if cellState is None or not getattr(cellState, "initialized", False):      # :39
-        if initCfg is None or "SOC0" not in initCfg:
+        if initCfg is None or "SOC0" not in initCfg:                           # :40
             raise ValueError("First call requires initCfg.SOC0 (in %).")       # :41
-        cellState = NS()
-        cellState.initialized = True
+        cellState = NS()                                                       # :43
+        cellState.initialized = True                                           # :44
         cellState.warnOff = bool(initCfg.get("warnOff", False))                # :45
         cellState.ROMmdls = copy.deepcopy(ROM.ROMmdls)                         # :48 (value copy)
-        cellState.cellData = ROM.cellData
+        cellState.cellData = ROM.cellData                                      # :49
         cellState.Ts = ROM.xraData.Tsamp                                       # :50
-        cellState.ROM = ROM
+        cellState.ROM = ROM                                                    # :53
         _ob_setupIndsLocs(cellState)                                           # :54
         _ob_setupBlend(cellState, ROM)                                         # :55-60
         Tk1 = Tc + 273.15                                                      # :63
         fn = cellState.cellData.function
-        SOC0n = fn.neg.soc(initCfg["SOC0"] / 100, Tk1)
-        SOC0p = fn.pos.soc(initCfg["SOC0"] / 100, Tk1)
+        SOC0n = fn.neg.soc(initCfg["SOC0"] / 100, Tk1)                         # :64
+        SOC0p = fn.pos.soc(initCfg["SOC0"] / 100, Tk1)                         # :65
         cellState.SOCnAvg = SOC0n; cellState.SOCpAvg = SOC0p                   # :66-67
         cellState.SOC0n = SOC0n; cellState.SOC0p = SOC0p                       # :70-71
         cellState.warnings = 0
@@ -86,17 +86,17 @@ def OB_step(Iapp, Tc, cellState, ROM, initCfg=None):
 
 def _ob_setupIndsLocs(cs):
     """OB_step.m:86-163"""
-    names = cs.ROM.tfData.names; locs = np.asarray(cs.ROM.tfData.xLoc, float)
-    cs.tfLocs = locs
+    names = cs.ROM.tfData.names; locs = np.asarray(cs.ROM.tfData.xLoc, float)            # :87-89
+    cs.tfLocs = locs                                                                     # :90
     ind = {}; loc = {}
     for nm in ("negIfdl", "negIf", "negIdl", "negPhis", "negPhise", "negThetass", "posIfdl", "posIf",
                "posIdl", "posPhis", "posPhise", "posThetass", "negPhie", "sepPhie", "posPhie",
                "negThetae", "sepThetae", "posThetae"):
-        ind[nm] = _find(names, nm)
-    loc["Phie"] = [locs[i] for i in ind["negPhie"] + ind["sepPhie"] + ind["posPhie"]]
+        ind[nm] = _find(names, nm)                                                       # :93-98,101-106,109-111,120-122
+    loc["Phie"] = [locs[i] for i in ind["negPhie"] + ind["sepPhie"] + ind["posPhie"]]    # :112-114,117
     ind["Phie"] = ind["negPhie"] + ind["sepPhie"] + ind["posPhie"]                       # :116
     ind["Thetae"] = ind["negThetae"] + ind["sepThetae"] + ind["posThetae"]               # :127
-    loc["Thetae"] = [locs[i] for i in ind["Thetae"]]
+    loc["Thetae"] = [locs[i] for i in ind["Thetae"]]                                     # :123-125,128
 
     def at(nm, x):
         return [i for i in _find(names, nm) if locs[i] == x]
@@ -116,43 +116,46 @@ def _ob_setupIndsLocs(cs):
     if not ind["negPhise0"]: raise ValueError("Requires phise at negative collector")
     if loc["Phie"][0] == 0:                                                              # :151-155
         ind["Phie"] = ind["Phie"][1:]; loc["Phie"] = loc["Phie"][1:]
-    if loc["Phie"][-1] > 3 + EPS or loc["Phie"][-1] < 3 - EPS:
+    if loc["Phie"][-1] > 3 + EPS or loc["Phie"][-1] < 3 - EPS:                           # :156-158
         raise ValueError("Requires phie at positive collector")
-    cs.ind = ind; cs.loc = loc
+    cs.ind = ind; cs.loc = loc                                                           # :161-162
 
 
 def _ob_setupBlend(cs, ROM):
     """OB_step.m:165-186"""
     cs.Tspts = np.sort(np.asarray(ROM.xraData.T, float)) + 273.15                        # :166
     cs.Zspts = np.sort(np.asarray(ROM.xraData.SOC, float) / 100)                         # :167
-    TT, ZZ = len(cs.ROMmdls), len(cs.ROMmdls[0])
+    TT, ZZ = len(cs.ROMmdls), len(cs.ROMmdls[0])                                         # :168
     nA = cs.ROMmdls[0][0].A.shape[0]
-    bigA = np.zeros((nA, TT * ZZ))
-    for tt in range(TT):
+    bigA = np.zeros((nA, TT * ZZ))                                                       # :171
+    for tt in range(TT):                                                                 # :172-173
         for zz in range(ZZ):
             col = tt * ZZ + zz                                                           # :174
-            R = cs.ROMmdls[tt][zz]
+            R = cs.ROMmdls[tt][zz]                                                       # :175,182 (a reference here: stored back in place)
             bigA[:, col] = np.real(np.diag(R.A))                                         # :176
             R.C[cs.ind["negPhise"], -1] = 0                                              # :178
             if cs.ind["posPhise"]:
                 R.C[cs.ind["posPhise"], -1] = 0                                          # :179-181
-    cs.bigA = bigA; cs.bigX = np.zeros_like(bigA); cs.ZZ = ZZ
+    cs.bigA = bigA; cs.bigX = np.zeros_like(bigA); cs.ZZ = ZZ                            # :185 (and OB_step.m:56-60)
 
 
 def _ob_warn(cs, msg):
-    cs.warnings += 1          # console-only in the reference (suppressed by warnOff, runMPC.m:73)
+    """OB_step.m:359-370 (shortWarn of the plant)"""
+    # not restated :360-368 (warnOff early-out -- runMPC.m:73 sets it --, the 'on'/'off' switch and the console print: only a count is kept here)
+    cs.warnings += 1
 
 
 def _ob_simStep(Iapp, T, cs):
     """OB_step.m:188-357"""
-    ind = cs.ind; Ts = cs.Ts; ROMmdls = cs.ROMmdls; bigX = cs.bigX
-    Tspts, Zspts, ZZ = cs.Tspts, cs.Zspts, cs.ZZ
-    cd = cs.cellData; fn = cd.function
-    SOC0n, SOC0p = cs.SOC0n, cs.SOC0p
+    # not restated :289-290,294-295,299-300 (the vector entries negIfdl/posIfdl, negIf/posIf, negIdl/posIdl of obs: runMPC reads nothing of obs)
+    ind = cs.ind; Ts = cs.Ts; ROMmdls = cs.ROMmdls; bigX = cs.bigX                       # :190-195 (loc :191 is not used by simStep)
+    Tspts, Zspts, ZZ = cs.Tspts, cs.Zspts, cs.ZZ                                         # :196-198
+    cd = cs.cellData; fn = cd.function                                                   # :199
+    SOC0n, SOC0p = cs.SOC0n, cs.SOC0p                                                    # :200-201
     F, R = cd.const.F, cd.const.R                                                        # :203-204
-    Q = fn.const.Q(); Rc = fn.const.Rc()
-    theta0n, theta0p = fn.neg.theta0(), fn.pos.theta0()
-    theta100n, theta100p = fn.neg.theta100(), fn.pos.theta100()
+    Q = fn.const.Q(); Rc = fn.const.Rc()                                                 # :205-206
+    theta0n, theta0p = fn.neg.theta0(), fn.pos.theta0()                                  # :207-208
+    theta100n, theta100p = fn.neg.theta100(), fn.pos.theta100()                          # :209-210
     wDLn = fn.neg.wDL(SOC0n, T); wDLp = fn.pos.wDL(SOC0p, T)                             # :212-219
     Cdln = fn.neg.Cdl(SOC0n, T); Cdlp = fn.pos.Cdl(SOC0p, T)
     nDLn = fn.neg.nDL(); nDLp = fn.pos.nDL()
@@ -188,8 +191,8 @@ def _ob_simStep(Iapp, T, cs):
     def corner(it, iz):                                                                  # :272-275
         m = ROMmdls[it][iz]
         return m.C @ bigX[:, it * ZZ + iz] + m.D[:, 0] * Iapp
-    yk1 = corner(iTlower, iZlower); yk2 = corner(iTlower, iZupper)
-    yk3 = corner(iTupper, iZlower); yk4 = corner(iTupper, iZupper)
+    yk1 = corner(iTlower, iZlower); yk2 = corner(iTlower, iZupper)                       # :272-273
+    yk3 = corner(iTupper, iZlower); yk4 = corner(iTupper, iZupper)                       # :274-275
     bigX = cs.bigA * bigX + Iapp                                                         # :278
     alphaZ = 0.0; alphaT = 0.0                                                           # :281-285
     if Zupper != Zlower: alphaZ = (obs.cellSOC - Zlower) / (Zupper - Zlower)
@@ -222,8 +225,8 @@ def _ob_simStep(Iapp, T, cs):
     Vcell = posEta3 - negEta0 + yk[ind["Phie"][-1]] + Uocpp3 - Uocpn0 + (Rfp * obs.posIfdl3 - Rfn * obs.negIfdl0)
     Vcell = Vcell - Rc * Iapp
     obs.negPhis = yk[ind["negPhis"]]; obs.posPhis = yk[ind["posPhis"]] + Vcell           # :347-348
-    obs.Vcell = Vcell
-    return float(Vcell), NS(bigX=bigX, SOCnAvg=SOCnAvg, SOCpAvg=SOCpAvg), obs
+    obs.Vcell = Vcell                                                                    # :356
+    return float(Vcell), NS(bigX=bigX, SOCnAvg=SOCnAvg, SOCpAvg=SOCpAvg), obs            # :351-353
 
 
 # ------------------------------------------------------------------------------------------
@@ -231,6 +234,9 @@ def _ob_simStep(Iapp, T, cs):
 # ------------------------------------------------------------------------------------------
 def initKF(SOC0, T0, SigmaX0, SigmaV, SigmaW, blend, ROMs):
     """kfData = initKF(SOC0,T0,SigmaX0,SigmaV,SigmaW,blend,ROMs)   (initKF.m:30-136)"""
+    # not restated :32 (clear iterSPKF: another filter's persistent variables)
+    # not restated :42 (kfData.T = T0 + 273.15 is overwritten by the set-point grid at :124 before anything reads it)
+    # not restated :108-118 (sigma-point weights of the SPKF variant; the EKF never reads alpham / alphac / h)
     kf = NS()
     kf.SOC = SOC0 / 100                                                                  # :37
     if T0 > 100: T0 = T0 - 273.15                                                        # :38-41
@@ -240,20 +246,20 @@ def initKF(SOC0, T0, SigmaX0, SigmaV, SigmaW, blend, ROMs):
     else: kf.method = "OB"
     mdls = ROMs.ROMmdls
     nT, nZ = len(mdls), len(mdls[0])
-    T = np.array([[m.T for m in row] for row in mdls]); Z = np.array([[m.SOC for m in row] for row in mdls])
+    T = np.array([[m.T for m in row] for row in mdls]); Z = np.array([[m.SOC for m in row] for row in mdls])   # :57-59
     n = mdls[0][0].A.shape[0] - 1                                                        # :60
-    nz = mdls[0][0].C.shape[0]
+    nz = mdls[0][0].C.shape[0]                                                           # :61
     SigmaX0 = np.asarray(SigmaX0, float)
     if SigmaX0.shape != (n + 1, n + 1):                                                  # :66-69
         raise ValueError("Input argument SigmaX0 has wrong dimension. Should be %d by %d" % (n + 1, n + 1))
     SigmaX = SigmaX0[:-1, :-1]                                                           # :70
     kf.M = [[None] * nZ for _ in range(nT)]
-    for theT in range(nT):
+    for theT in range(nT):                                                               # :71-72
         for theZ in range(nZ):
-            A = mdls[theT][theZ].A
+            A = mdls[theT][theZ].A                                                       # :73
             if A[-1, -1] != 1: raise ValueError("A does not have integrator state")      # :74-77
             if not np.array_equal(np.diag(np.diag(A)), A): raise ValueError("A is not diagonal")   # :78-81
-            B = mdls[theT][theZ].B
+            B = mdls[theT][theZ].B                                                       # :84
             if np.prod(B) != 1: raise ValueError("B is not all units values")            # :85-88
             kf.M[theT][theZ] = NS(A=np.diag(A[:n, :n]).copy(),                            # :82
                                   C=mdls[theT][theZ].C[:, :-1].copy(),                    # :91
@@ -265,8 +271,8 @@ def initKF(SOC0, T0, SigmaX0, SigmaV, SigmaW, blend, ROMs):
     kf.priorI = 0.0                                                                      # :121
     kf.T = T; kf.Z = Z; kf.n = n; kf.nz = nz                                             # :124-127
     kf.tfData = ROMs.tfData; kf.Ts = ROMs.xraData.Tsamp; kf.SOC0 = SOC0 / 100            # :130-133
-    kf.cellData = ROMs.cellData
-    kf._persist = None                    # per-instance stand-in for iterEKF's persistent vars (:31)
+    kf.cellData = ROMs.cellData                                                          # :135
+    kf._persist = None                    # per-instance stand-in for iterEKF's persistent variables, which :31 clears   # :31
     return kf
 
 
@@ -279,11 +285,12 @@ class EKFLost(Exception):
 
 def _ekf_setupIndsLocs(ekfData):
     """iterEKF.m:610-735"""
-    names = ekfData.tfData.names; locs = np.asarray(ekfData.tfData.xLoc, float)
+    # not restated :689-690 (ind.Thetae0 / ind.Thetae3: nothing reads them)
+    names = ekfData.tfData.names; locs = np.asarray(ekfData.tfData.xLoc, float)          # :612-613
     ind = {}; loc = {}
     for nm in ("negIfdl", "negIf", "negPhis", "negPhise", "negThetass", "posIfdl", "posIf", "posPhis",
                "posPhise", "posThetass", "negPhie", "sepPhie", "posPhie", "negThetae", "sepThetae", "posThetae"):
-        ind[nm] = _find(names, nm); loc[nm] = [locs[i] for i in ind[nm]]
+        ind[nm] = _find(names, nm); loc[nm] = [locs[i] for i in ind[nm]]                 # :616-625,628-637,640-645,648-653
     for key, parts in (("Ifdl", ("negIfdl", "posIfdl")), ("If", ("negIf", "posIf")), ("Phis", ("negPhis", "posPhis")),
                        ("Phise", ("negPhise", "posPhise")), ("Thetass", ("negThetass", "posThetass")),
                        ("Phie", ("negPhie", "sepPhie", "posPhie")), ("Thetae", ("negThetae", "sepThetae", "posThetae"))):
@@ -291,7 +298,7 @@ def _ekf_setupIndsLocs(ekfData):
 
     def at(key, x):
         return [i for i in ind[key] if locs[i] == x]
-    ind["Ifdl0"], ind["Ifdl3"] = at("Ifdl", 0), at("Ifdl", 3)                            # :682-690
+    ind["Ifdl0"], ind["Ifdl3"] = at("Ifdl", 0), at("Ifdl", 3)                            # :682-688
     ind["If0"], ind["If3"] = at("If", 0), at("If", 3)
     ind["Thetass0"], ind["Thetass3"] = at("Thetass", 0), at("Thetass", 3)
     ind["Phise0"] = at("Phise", 0)
@@ -316,8 +323,9 @@ def _ekf_setupIndsLocs(ekfData):
 
 def iterEKF(vk, ik, Tk, ekfData):
     """[zk,boundzk,ekfData,Xind] = iterEKF(vk,ik,Tk,ekfData)   (iterEKF.m:30-210, ekfData.method 'OB' or 'MB')"""
-    P = ekfData._persist
-    if P is None:                                                                        # :32-53
+    # not restated :47-52 (SOC0 guessed from the voltage when ekfData.SOC0 is empty: initKF.m:133 always sets it)
+    P = ekfData._persist                                                                 # :31
+    if P is None:                                                                        # :32-45
         ind, loc, warned = _ekf_setupIndsLocs(ekfData)
         P = NS(ind=ind, loc=loc, Tpts=np.unique(ekfData.T), Zpts=np.unique(ekfData.Z), n=ekfData.n,
                warnCount=0, q18=0, cellData=ekfData.cellData, F=ekfData.cellData.const.F, R=ekfData.cellData.const.R)
@@ -330,8 +338,9 @@ def iterEKF(vk, ik, Tk, ekfData):
     fn = cellData.function
     Tpts, Zpts = P.Tpts, P.Zpts
 
+    # not restated :742-748 (the 'on'/'off' switch of shortWarn, never used, and the console print)
     def shortWarn(msg):                                                                  # :741-751
-        P.warnCount += 1
+        P.warnCount += 1                                                                 # :749
 
     if P.warnCount > 10:                                                                 # :55-59
         zk = np.full(ekfData.nz + 2, np.nan)
@@ -346,31 +355,32 @@ def iterEKF(vk, ik, Tk, ekfData):
 
     # ---- helpers (nested functions of iterEKF.m) ----
     def getXind(Tk, SOC):                                                                # :219-255
-        dZ = np.abs(SOC - Zpts); iZ = _msort(dZ)
-        Zupper = Zlower = Zpts[0]; iZupper = iZlower = iZ[0]
-        if len(iZ) > 1:
+        dZ = np.abs(SOC - Zpts); iZ = _msort(dZ)                                         # :221
+        Zupper = Zlower = Zpts[0]; iZupper = iZlower = iZ[0]                             # :222-223
+        if len(iZ) > 1:                                                                  # :224-231
             Zupper = Zpts[iZ[0]]; iZupper = iZ[0]
             Zlower = Zpts[iZ[1]]; iZlower = iZ[1]
             if Zupper < Zlower:
                 Zupper = Zpts[iZ[1]]; iZupper = iZ[1]
                 Zlower = Zpts[iZ[0]]; iZlower = iZ[0]
-        dT = np.abs(Tk - Tpts); iT = _msort(dT)
-        Tupper = Tlower = Tpts[0]; iTupper = iTlower = iT[0]
-        if len(iT) > 1:
+        dT = np.abs(Tk - Tpts); iT = _msort(dT)                                          # :234
+        Tupper = Tlower = Tpts[0]; iTupper = iTlower = iT[0]                             # :235-236
+        if len(iT) > 1:                                                                  # :237-244
             Tupper = Tpts[iT[0]]; iTupper = iT[0]
             Tlower = Tpts[iT[1]]; iTlower = iT[1]
             if Tupper < Tlower:
                 Tupper = Tpts[iT[1]]; iTupper = iT[1]
                 Tlower = Tpts[iT[0]]; iTlower = iT[0]
-        alphaZ = 0.0; alphaT = 0.0
-        if len(iZ) > 1: alphaZ = (SOC - Zlower) / (Zupper - Zlower)
-        if len(iT) > 1: alphaT = (Tk - Tlower) / (Tupper - Tlower)
+        alphaZ = 0.0; alphaT = 0.0                                                       # :246
+        if len(iZ) > 1: alphaZ = (SOC - Zlower) / (Zupper - Zlower)                      # :247 (Q14)
+        if len(iT) > 1: alphaT = (Tk - Tlower) / (Tupper - Tlower)                       # :248
+        # :249-254
         gamma = np.array([(1 - alphaT) * (1 - alphaZ), (1 - alphaT) * alphaZ, alphaT * (1 - alphaZ), alphaT * alphaZ])
         return NS(gamma=gamma, theT=np.array([iTlower, iTlower, iTupper, iTupper]),
                   theZ=np.array([iZlower, iZupper, iZlower, iZupper]))
 
     def getVariables(ik, Xind, T):                                                       # :259-417
-        if MB:                                                                           # :266-275
+        if MB:                                                                           # :265-275
             xhat = ekfData.xhat
             xk = [xhat[:n]] * 4                                                          # :310-312: every model reads xhat(1:n)
             x0 = xhat[-1]
@@ -383,8 +393,8 @@ def iterEKF(vk, ik, Tk, ekfData):
         if SOCnAvg > 1: shortWarn("SOCnAvg > 1"); SOCnAvg = 1 - 1e-6
         if SOCpAvg < 0: shortWarn("SOCpAvg < 0"); SOCpAvg = 1e-6
         if SOCpAvg > 0.998: shortWarn("SOCpAvg > 1"); SOCpAvg = 0.998
-        cols = []
-        for m in range(4):                                                               # :302-313
+        cols = []                                                                        # :301 (Z preallocated)
+        for m in range(4):                                                               # :302-317 (both methods: xk holds xhat(1:n) four times for 'MB', :314-316)
             mdl = M[Xind.theT[m]][Xind.theZ[m]]
             cols.append(mdl.C @ xk[m] + mdl.D[:, 0] * ik)
         Z = np.column_stack(cols) @ Xind.gamma
@@ -429,11 +439,11 @@ def iterEKF(vk, ik, Tk, ekfData):
 
     def getChatV(Xind, Z, Tk):                                                           # :421-519
         Cs = [Xind.gamma[m] * M[Xind.theT[m]][Xind.theZ[m]].C for m in range(4)]         # :423-426
-        x0 = ekfData.xhat[-1] if MB else ekfData.x0                                      # :437 / :449
-        xSOC = ekfData.SOC0 - x0 * res_per_amp
-        SOCnAvg = fn.neg.soc(xSOC, Tk); SOCpAvg = fn.pos.soc(xSOC, Tk)
-        Rfn = fn.neg.Rf(SOCnAvg, Tk); Rfp = fn.pos.Rf(SOCpAvg, Tk)
-        if MB:                                                                           # :448-460, 475-479, 489-491, 512-518
+        x0 = ekfData.xhat[-1] if MB else ekfData.x0                                      # :435-437 / :449
+        xSOC = ekfData.SOC0 - x0 * res_per_amp                                           # :438 / :450
+        SOCnAvg = fn.neg.soc(xSOC, Tk); SOCpAvg = fn.pos.soc(xSOC, Tk)                   # :439-440 / :451-452
+        Rfn = fn.neg.Rf(SOCnAvg, Tk); Rfp = fn.pos.Rf(SOCpAvg, Tk)                       # :441-442 / :453-454
+        if MB:                                                                           # :448-460,475-479,489-491,512-518; the switches at :469-470,483-484,502-503
             rsum = lambda key: np.sum(np.vstack([C[ind[key][0 if key != "Phie" else -1], :] for C in Cs]), axis=0)
             Chat = Rfp * rsum("Ifdl3") - Rfn * rsum("Ifdl0")
             k0n = fn.neg.k0(SOCnAvg, Tk); k0p = fn.pos.k0(SOCpAvg, Tk)
@@ -466,8 +476,8 @@ def iterEKF(vk, ik, Tk, ekfData):
         return Chat, Chat0
 
     def getChatZ(Xind, Z, Tk):                                                           # :523-602
-        Cs = [Xind.gamma[m] * M[Xind.theT[m]][Xind.theZ[m]].C for m in range(4)]
-        if MB:                                                                           # :538, 554-558, 572-575, 596-600
+        Cs = [Xind.gamma[m] * M[Xind.theT[m]][Xind.theZ[m]].C for m in range(4)]         # :525-528
+        if MB:                                                                           # :534-535,537-538,544-545,554-558,570-575,587-588,596-600 (the method switches)
             Chat = Cs[0] + Cs[1] + Cs[2] + Cs[3]
             Chat0 = np.zeros(Cs[0].shape[0])
             ChatV, _ = getChatV(Xind, Z, Tk)
@@ -513,8 +523,8 @@ def iterEKF(vk, ik, Tk, ekfData):
     if MB:
         # ---- Steps 1a/1b, model blend: one blended model (:90-102) ----
         SOC = ekfData.SOC0 - ekfData.xhat[-1] * res_per_amp                              # :92
-        Xind = getXind(Tk, SOC)
-        As = np.column_stack([M[Xind.theT[m]][Xind.theZ[m]].A for m in range(4)])
+        Xind = getXind(Tk, SOC)                                                          # :93
+        As = np.column_stack([M[Xind.theT[m]][Xind.theZ[m]].A for m in range(4)])       # :94-97
         AMB = np.concatenate([As @ Xind.gamma, [1.0]])                                   # :98
         ekfData.xhat = AMB * ekfData.xhat + ekfData.priorI                               # :99
         ekfData.SigmaX = np.diag(AMB) @ ekfData.SigmaX @ np.diag(AMB) + ekfData.SigmaW   # :101
@@ -525,15 +535,15 @@ def iterEKF(vk, ik, Tk, ekfData):
         SigmaVtilde = ChatV @ ekfData.SigmaX @ ChatV + ekfData.SigmaV
         L = ekfData.SigmaX @ ChatV / SigmaVtilde
         residual = vk - vhat                                                             # :133
-        ekfData.xhat = ekfData.xhat + L * residual                                       # :161
-        SigmaX = ekfData.SigmaX - np.outer(L * SigmaVtilde, L)                           # :163
+        ekfData.xhat = ekfData.xhat + L * residual                                       # :160-161
+        SigmaX = ekfData.SigmaX - np.outer(L * SigmaVtilde, L)                           # :162-163
         _, SS, VVt = np.linalg.svd(SigmaX)                                               # :164-166
         HH = VVt.T @ np.diag(SS) @ VVt
         SigmaX = (SigmaX + SigmaX.T + HH + HH.T) / 4
         nbump = 0
         if residual ** 2 > 9 * SigmaVtilde:                                              # :169-172
             SigmaX = SigmaX * 2; nbump = 1
-        ekfData.SigmaX = SigmaX
+        ekfData.SigmaX = SigmaX                                                          # :173
         SOC = ekfData.SOC0 - ekfData.xhat[-1] * res_per_amp                              # :176
         Xind = getXind(Tk, SOC)                                                          # :181-183
         vhat, zk, Zsoc = getVariables(ik, Xind, Tk)
@@ -548,7 +558,7 @@ def iterEKF(vk, ik, Tk, ekfData):
         ekfData.priorI = ik                                                              # :210
         ekfData.nbump_last = nbump
         return zk, boundzk, ekfData, Xind
-    # ---- Steps 1a/1b: time update of ALL models (:73-89) ----
+    # ---- Steps 1a/1b: time update of ALL models (:70-89; the switch at :70-71 / :90 is the `if MB` above) ----
     for theT in range(P.numT):
         for theZ in range(P.numZ):
             mdl = M[theT][theZ]
@@ -561,7 +571,7 @@ def iterEKF(vk, ik, Tk, ekfData):
     # ---- Step 1c (:107-108) ----
     Xind = getXind(Tk, SOC)
     vhat, Z, _ = getVariables(ik, Xind, Tk)
-    # ---- Step 2a (:114-124) ----
+    # ---- Step 2a (:112-124) ----
     ChatV, C0 = getChatV(Xind, Z, Tk)
     SigmaVtilde = [None] * 4; L = [None] * 4
     for m in range(4):
@@ -616,17 +626,17 @@ def EKFmatsHandler(ekfData, Xind, zk, Tk):
     g = np.asarray(Xind.gamma, float).ravel()
     if np.all(np.isnan(g)):
         raise EKFLost("Xind is NaN (iterEKF.m:55-59); MATLAB would fail indexing M(NaN,NaN)")
-    imax = int(np.nanargmax(g))                      # first maximum, NaN ignored (:26)
-    iT = int(Xind.theT[imax]); iZ = int(Xind.theZ[imax])
-    mdl = ekfData.M[iT][iZ]
+    imax = int(np.nanargmax(g))                      # first maximum, NaN ignored   # :26
+    iT = int(Xind.theT[imax]); iZ = int(Xind.theZ[imax])                                 # :27-28
+    mdl = ekfData.M[iT][iZ]                                                              # :30
     xhat = np.concatenate([mdl.xhat, [ekfData.xhat[-1]]])                                # :33 (Q3)
     Ad = np.concatenate([mdl.A, [1.0]])                                                  # :35
-    nx = len(Ad)
-    A = np.diag(Ad); B = np.ones((nx, 1)); C = mdl.C; D = mdl.D
+    nx = len(Ad)                                                                         # :36
+    A = np.diag(Ad); B = np.ones((nx, 1)); C = mdl.C; D = mdl.D                          # :37-40
     r = -ekfData.Ts / (3600 * ekfData.Q)                                                 # :43-45
     Csoc = np.concatenate([np.zeros(nx - 1), [r]]); Dsoc = 0.0
-    ind = ekfData.ind; cellData = ekfData.cellData; fn = cellData.function
-    F = cellData.const.F; R = cellData.const.R
+    ind = ekfData.ind; cellData = ekfData.cellData; fn = cellData.function               # :49-50
+    F = cellData.const.F; R = cellData.const.R                                           # :51-52
     TK = Tk + 273.15                                                                     # :53
     SOCavg = zk[-1]                                                                      # :56-58
     SOCnAvg = fn.neg.soc(SOCavg, TK); SOCpAvg = fn.pos.soc(SOCavg, TK)
@@ -638,14 +648,14 @@ def EKFmatsHandler(ekfData, Xind, zk, Tk):
     Cv = Rfp * C[ind["Ifdl3"][0], :] - Rfn * C[ind["Ifdl0"][0], :] + C[ind["Phie"][-1], :]      # :75-76
     Dv = Rfp * D[ind["Ifdl3"][0], 0] - Rfn * D[ind["Ifdl0"][0], 0] + D[ind["Phie"][-1], 0]      # :79-80
     Upos = fn.pos.Uocp(th3, TK); Uneg = fn.neg.Uocp(th0, TK)                             # :84-85
-    If0 = zk[ind["If0"][0]]; If3 = zk[ind["If3"][0]]
+    If0 = zk[ind["If0"][0]]; If3 = zk[ind["If3"][0]]                                     # :87
     negEta0 = 2 * R * TK / F * np.arcsinh(If0 / (2 * i0n))                               # :88-89
     posEta3 = 2 * R * TK / F * np.arcsinh(If3 / (2 * i0p))
-    b_phi = 0.01 * 0
+    b_phi = 0.01 * 0                                                                     # :91
     bv = (Upos - Uneg) + (posEta3 - negEta0) + b_phi                                     # :92
     Uocpn = fn.neg.Uocp(SOCnAvg)                                                         # :96 (Q21)
     Cphi = C[ind["negPhise"][1], :]; Dphi = D[ind["negPhise"][1], 0]                     # :97-98
-    MPC = NS(A=A, B=B, Csoc=Csoc, Dsoc=Dsoc, Cv=np.concatenate([Cv, [0.0]]), Dv=Dv,
+    MPC = NS(A=A, B=B, Csoc=Csoc, Dsoc=Dsoc, Cv=np.concatenate([Cv, [0.0]]), Dv=Dv,       # :101-114
              Cphi=np.concatenate([Cphi, [0.0]]), Dphi=Dphi, bv=bv, bphi=Uocpn,
              iT=iT + 1, iZ=iZ + 1, pickWeight=g[imax])
     return MPC, xhat
@@ -658,13 +668,13 @@ def predMat(A, B, C, D, Np, Nc):
     """[Phi, G, aug] = predMat(A, B, C, D, Np, Nc)   (predMat.m:1-54)"""
     A = np.atleast_2d(np.asarray(A, float)); B = np.asarray(B, float).reshape(A.shape[0], -1)
     C = np.atleast_2d(np.asarray(C, float)); D = np.asarray(D, float).reshape(C.shape[0], -1)
-    nx = A.shape[0]; m = B.shape[1]; q = C.shape[0]
+    nx = A.shape[0]; m = B.shape[1]; q = C.shape[0]                                      # :12-14
     Np = max(1, int(round(Np))); Nc = max(1, min(int(round(Nc)), Np))                    # :15-16
     Abar = np.block([[A, B], [np.zeros((m, nx)), np.eye(m)]])                            # :20-22
     Bbar = np.vstack([np.zeros((nx, m)), np.eye(m)])
     Cbar = np.hstack([C, D])
-    nx_aug = nx + m
-    Phi = np.zeros((q * Np, nx_aug)); G = np.zeros((q * Np, m * Nc))
+    nx_aug = nx + m                                                                      # :24
+    Phi = np.zeros((q * Np, nx_aug)); G = np.zeros((q * Np, m * Nc))                     # :27-28
     H = []; X = Bbar                                                                     # :31-36
     for _ in range(Np):
         H.append(Cbar @ X); X = Abar @ X
@@ -675,17 +685,17 @@ def predMat(A, B, C, D, Np, Nc):
         Phi[r, :] = Cbar @ Ap
         for j in range(1, min(i, Nc) + 1):
             G[r, (j - 1) * m:j * m] = H[i - j]
-    return Phi, G, NS(A=Abar, B=Bbar, C=Cbar, nx_aug=nx_aug, m=m, q=q)
+    return Phi, G, NS(A=Abar, B=Bbar, C=Cbar, nx_aug=nx_aug, m=m, q=q)                   # :53
 
 
 def constraintsMPC(x_aug_k, cellState, mpcData):
     """[M, gamma] = constraintsMPC(x_aug_k, cellState, mpcData)   (constraintsMPC.m:1-113)"""
-    Nc, Np = mpcData.Nc, mpcData.Np
+    Nc, Np = mpcData.Nc, mpcData.Np                                                      # :15
     cons = np.asarray(mpcData.const.constraints).ravel()
     useCurrent = len(cons) >= 1 and cons[0] == 1                                         # :18-20
     useVoltage = len(cons) >= 2 and cons[1] == 1
     useEta = len(cons) >= 3 and cons[2] == 1
-    Ms = []; gs = []
+    Ms = []; gs = []                                                                     # :16
     c = mpcData.const
     mpc = cellState.MPC
     if useCurrent:                                                                       # :23-42
@@ -729,7 +739,7 @@ def hildreth(E, F, M, gamma, lambda0=None, maxIter=100):
     """[DU, lambda, nexec] = hildreth(E, F, M, gamma, lambda0, maxIter)   (hildreth.m:1-47)"""
     E = np.atleast_2d(np.asarray(E, float)); F = np.asarray(F, float).ravel()
     M = np.atleast_2d(np.asarray(M, float)); gamma = np.asarray(gamma, float).ravel()
-    nConstr = M.shape[0]
+    nConstr = M.shape[0]                                                                 # :17,23-25 (maxIter's default: the signature's)
     if lambda0 is None or np.size(lambda0) == 0:                                         # :18-22
         lam = np.zeros(nConstr)
     else:
@@ -745,27 +755,28 @@ def hildreth(E, F, M, gamma, lambda0=None, maxIter=100):
                 lam[i] = np.fmax(0.0, w)                                                 # :36  max(0,NaN)=0
             if np.max(np.abs(lam - lam_old)) < 1e-6:                                     # :39  NaN-propagating
                 break
-        nexec = k
+        nexec = k                                                                        # :43
         DU = -np.linalg.solve(E, F + M.T @ lam)                                          # :46
     return DU, lam, nexec
 
 
 def initMPC(SOC0, Np, Nc, targetSOC, opts=None):
-    """mpcData = initMPC(SOC0, Np, Nc, targetSOC, opts)   (initMPC.m:1-74)"""
-    opts = opts or {}
+    """mpcData = initMPC(SOC0, Np, Nc, targetSOC, opts)   (initMPC.m:1-84)"""
+    # :76-79 getfield_with_default is dict.get below; :81-84 copyfields is the setattr loop at the end
+    opts = opts or {}                                                                    # :29
     Np = max(1, int(round(Np))); Nc = max(1, min(int(round(Nc)), Np))                    # :32-33
     d = NS()
-    d.Np, d.Nc = Np, Nc
-    d.Ts = opts.get("Ts", 1)
+    d.Np, d.Nc = Np, Nc                                                                  # :36-37
+    d.Ts = opts.get("Ts", 1)                                                              # :38
     d.ref = targetSOC                                                                    # :39 (Q9)
-    d.Sigma = np.tril(np.ones((Nc, Nc)))
-    d.Nsim = opts.get("Nsim", np.nan)
+    d.Sigma = np.tril(np.ones((Nc, Nc)))                                                 # :40
+    d.Nsim = opts.get("Nsim", np.nan)                                                    # :41
     d.maxHild = 100                                                                      # :47
     d.lambda_ = None                                                                     # :48  []
-    d.DUk_1 = np.zeros(Nc); d.xk_1 = None; d.uk_1 = 0.0; d.SOCk_1 = 0.0; d.SOC0 = SOC0
+    d.DUk_1 = np.zeros(Nc); d.xk_1 = None; d.uk_1 = 0.0; d.SOCk_1 = 0.0; d.SOC0 = SOC0   # :49-53
     cons = np.asarray(opts.get("constraints", [1, 1, 1])).ravel() != 0                   # :56-59
     d.const = NS(constraints=cons.astype(int))
-    L = dict(opts.get("limits", {}))
+    L = dict(opts.get("limits", {}))                                                     # :62-63
     Imax = -opts["ROM"].cellData.function.const.Q(0.5) * opts["Crate"]                   # :66-67
     L["u_min"] = Imax
     for k, v in L.items():                                                               # :72
@@ -775,18 +786,18 @@ def initMPC(SOC0, Np, Nc, targetSOC, opts=None):
 
 def iterMPC(xk, cellState, mpcData, diagnostics=True):
     """[uk, mpcData] = iterMPC(xk,cellState,mpcData)   (iterMPC.m:1-96)"""
-    Np, Nc = mpcData.Np, mpcData.Nc
-    uk_1 = mpcData.uk_1
+    Np, Nc = mpcData.Np, mpcData.Nc                                                      # :17-18
+    uk_1 = mpcData.uk_1                                                                  # :19
     Ref = mpcData.ref * np.ones(Np)                                                      # :20
-    mpc = cellState.MPC
+    mpc = cellState.MPC                                                                  # :23-26
     dx = np.concatenate([np.asarray(xk, float).ravel(), [uk_1]])                         # :29
     Phi_soc, G_soc, Aug = predMat(mpc.A, mpc.B, mpc.Csoc, mpc.Dsoc, Np, Nc)              # :33
-    mpcData.Phi_soc = Phi_soc; mpcData.G_soc = G_soc
+    mpcData.Phi_soc = Phi_soc; mpcData.G_soc = G_soc                                     # :34
     F = -2 * G_soc.T @ (Ref - Phi_soc @ dx)                                              # :38
     S = np.linalg.svd(G_soc.T @ G_soc, compute_uv=False)                                 # :41
-    Ru = (np.linalg.norm(F, 2) / (2 * mpcData.const.du_max * np.sqrt(Nc))) - S[-1]       # :43
-    Ru = Ru * np.eye(Nc)
-    mpcData.Ru = Ru
+    Ru = (np.linalg.norm(F, 2) / (2 * mpcData.const.du_max * np.sqrt(Nc))) - S[-1]       # :42-43
+    Ru = Ru * np.eye(Nc)                                                                 # :44
+    mpcData.Ru = Ru                                                                      # :45
     E = 2 * (G_soc.T @ G_soc + Ru)                                                       # :47
     with np.errstate(all="ignore"):
         DU = -np.linalg.solve(E, F)                                                      # :48
@@ -800,20 +811,20 @@ def iterMPC(xk, cellState, mpcData, diagnostics=True):
     M, gamma = constraintsMPC(dx, cellState, mpcData)                                    # :63
     mpcData.M_last, mpcData.gamma_last = M, gamma
     if np.sum(M @ DU - gamma > 0) > 0:                                                   # :66 (Q8)
-        DU, lam, nexec = hildreth(E, F, M, gamma, mpcData.lambda_, mpcData.maxHild)
+        DU, lam, nexec = hildreth(E, F, M, gamma, mpcData.lambda_, mpcData.maxHild)      # :67
         mpcData.lambda_ = lam                                                            # :68 (Q11)
-        mpcData.nexec = nexec
+        mpcData.nexec = nexec                                                            # :69
         mpcData.active = lam > 0
     else:
-        mpcData.nexec = 0
+        mpcData.nexec = 0                                                                # :72
         mpcData.active = np.zeros(M.shape[0], bool)
     du = DU[0]
     uk = du + mpcData.uk_1                                                               # :75-76
     mpcData.uk_1 = uk; mpcData.xk_1 = xk; mpcData.DUk_1 = DU                             # :78-80
-    vres = M @ DU - gamma
+    vres = M @ DU - gamma                                                                # :82
     nviol = int(np.sum(vres > 1e-9))                                                     # :83
     e = Ref - Phi_soc @ dx - G_soc @ DU
-    J_fin = e @ e + DU @ Ru @ DU
+    J_fin = e @ e + DU @ Ru @ DU                                                         # :85-86
     if hasattr(mpcData, "cost"):                                                         # :88-95
         k = mpcData.k - 1
         cst = mpcData.cost
@@ -848,27 +859,32 @@ def noise(seed, cell, k):
 def run_mpc(bank, SOC0=10.0, TC=25.0, N=3001, Np=5, Nc=2, targetSOC=95.0, constraints=(1, 1, 1),
             Crate=2.0, limits=None, SigmaX0=None, SigmaV=1e-3, SigmaW=1e2, ekf_SOC0=None,
             diagnostics=False, keep_zk=False, blend="OutB", meas_sigma=0.0, noise_seed=0, cell_id=0):
-    """runMPC.m:4-112 with its literals exposed as arguments.  Returns a dict of per-step stores."""
-    ROM = build_rom(bank)
+    """runMPC.m:3-115 with its literals exposed as arguments.  Returns a dict of per-step stores."""
+    # not restated :3 (clear; clc; close all)
+    # not restated :115 (plot4Figures: MATLAB graphics)
+    # :8,10-13,16,18-19,28-30,33,36 are this function's arguments, with the script's values as defaults
+    # not restated :21-22 (ekfData.maxWarn / .trueSOC0: fields nothing reads)
+    # not restated :76-78 (seed entries of the stores; the loop overwrites them at k = 1)
+    ROM = build_rom(bank)                                                                # :4-5
     Ts = 1                                                                               # :9
     if SigmaX0 is None:
         SigmaX0 = np.diag([1.0] * 5 + [2e6])                                             # :17
     ekfData = initKF(1 * (SOC0 if ekf_SOC0 is None else ekf_SOC0), TC, SigmaX0, SigmaV, SigmaW, blend, ROM)    # :20 (runMPC.m:16 says 'OutB')
-    lim = dict(DEFAULT_LIMITS)
+    lim = dict(DEFAULT_LIMITS)                                                           # :37-42
     lim["z_max"] = targetSOC / 100; lim["z_tol"] = 0 * 5 / 100                           # :43-44
     if limits: lim.update(limits)
-    opts = dict(Ts=Ts, constraints=list(constraints), limits=lim, ROM=ROM, Crate=Crate, Nsim=N - 1)
+    opts = dict(Ts=Ts, constraints=list(constraints), limits=lim, ROM=ROM, Crate=Crate, Nsim=N - 1)   # :45-50
     mpcData = initMPC(SOC0, Np, Nc, targetSOC, opts)                                     # :52
-    out = dict(u=np.full(N, np.nan), V=np.full(N, np.nan), SOC=np.full(N, np.nan), phise=np.full(N, np.nan),
+    out = dict(u=np.full(N, np.nan), V=np.full(N, np.nan), SOC=np.full(N, np.nan), phise=np.full(N, np.nan),   # :55-60
                x=np.full((6, N), np.nan), iT=np.zeros(N, np.int32), iZ=np.zeros(N, np.int32),
                nexec=np.zeros(N, np.int32), active=np.zeros((N, 4), np.uint32), nbump=np.zeros(N, np.int32),
                u_applied=np.full(N, np.nan), status=0, lost_at=-1)
-    if keep_zk:
+    if keep_zk:                                                                          # :24-25
         out["zk"] = np.full((ekfData.nz + 2, N), np.nan); out["zb"] = np.full((ekfData.nz + 2, N), np.nan)
     mpcData.cost = dict(t=np.arange(N, dtype=float), J_uncon=np.full(N, np.nan), J_final=np.full(N, np.nan),
-                        norm_DU=np.full(N, np.nan), viol=np.full(N, np.nan), nexec=np.full(N, np.nan))
+                        norm_DU=np.full(N, np.nan), viol=np.full(N, np.nan), nexec=np.full(N, np.nan))   # :63-69
     uk = 0.0                                                                             # :72
-    voltage, obs, cellState = OB_step(uk, TC, None, ROM, dict(SOC0=SOC0, warnOff=True))  # :74 (Q20)
+    voltage, obs, cellState = OB_step(uk, TC, None, ROM, dict(SOC0=SOC0, warnOff=True))  # :73-74 (Q20)
     for k in range(1, N + 1):                                                            # :83-112
         voltage, obs, cellState = OB_step(uk, TC, cellState, ROM)                        # :85
         vk = voltage if meas_sigma == 0.0 else voltage + meas_sigma * noise(noise_seed, cell_id, k - 1)   # scenario: a noisy sensor
@@ -878,7 +894,7 @@ def run_mpc(bank, SOC0=10.0, TC=25.0, N=3001, Np=5, Nc=2, targetSOC=95.0, constr
         except EKFLost:
             out["status"] |= 1; out["lost_at"] = k
             break
-        cellState.MPC = MPC
+        cellState.MPC = MPC                                                              # :93
         out["u_applied"][k - 1] = uk
         out["phise"][k - 1] = MPC.Cphi @ xhat + uk * MPC.Dphi + MPC.bphi                 # :94-95 (Q24)
         mpcData.SOCk_1 = zk[-1]; mpcData.k = k                                           # :99,102
