@@ -1532,7 +1532,7 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
       for (int j = 1; j < NC; ++j) { hd = fma(Mi[j], P[j], hd); k = fma(Mi[j], x[j], k); }
       double gam;
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(gam) : "r"(kra + (unsigned)i * krs) : "memory");
-      sts_pair(kra + (unsigned)i * krs, k + gam, rcp_d(hd));         // K(i), 1/H(i,i)
+      sts_pair(kra + (unsigned)i * krs, -(k + gam), rcp_d(hd));      // -K(i), 1/H(i,i): the idle test below compares against -K
       if (hd == 0.0) {
         zmask |= 1u << i;
       } else {
@@ -1560,8 +1560,8 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     bool lean = (zmask == ZEXP) && (pmask == 0u) && !d.no_lean_sweep;
     if (FS::UZ) {
       double kz, hz;
-      lds_pair(kra + (unsigned)FS::O_Z * krs, kz, hz);
-      lean = lean && !(kz < 0.0);
+      lds_pair(kra + (unsigned)FS::O_Z * krs, kz, hz);                 // kz = -K of that row
+      lean = lean && !(kz > 0.0);
     }
     if (lean) {
       const bool skip_ok = pfin && hpos && !d.no_row_skip;
@@ -1575,18 +1575,21 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
           if constexpr (!(FS::UZ && i == FS::O_Z)) {
             double Mi[NC];
             mrow(ic, Mi);
-            double Ki, rHi;
-            lds_pair(kra + (unsigned)i * krs, Ki, rHi);
+            double nKi, rHi;
+            lds_pair(kra + (unsigned)i * krs, nKi, rHi);
             const double li = lam[i];
             double hl = Mi[0] * v[0];
 #pragma unroll
             for (int j = 1; j < NC; ++j) hl = fma(Mi[j], v[j], hl);
-            const double t = Ki + hl;
-            // An inactive row that stays inactive: lambda_i = 0 and K_i + H(i,:)*lambda >= 0 give w = -t/H_ii <= 0 (H_ii > 0),
+            // An inactive row that stays inactive: lambda_i = 0 and t = K_i + H(i,:)*lambda >= 0 give w = -t/H_ii <= 0 (H_ii > 0),
             // max(0,w) = 0, lambda_i and v exactly as they were (v + P*0 = v for finite P; v is never -0).  Most rows of most
-            // sweeps are like that; when they are for every cell of the warp the rest of the row is skipped.
-            const bool idle = skip_ok && (li == 0.0) && (t >= 0.0);
+            // sweeps are like that; when they are for every cell of the warp the rest of the row is skipped.  The test reads
+            // H(i,:)*lambda >= -K_i -- the sign of the rounded sum t is the sign of the exact one -- which takes the addition off
+            // the dependent chain of an idle row (if K_i and H(i,:)*lambda are infinities of opposite sign, t is NaN where this
+            // test says idle: the update of such a row with lambda_i = 0 is max(0, NaN) = 0, a no-op as well).
+            const bool idle = skip_ok && (li == 0.0) && (hl >= nKi);
             if (!__all_sync(__activemask(), idle)) {
+              const double t = hl - nKi;                             // = K_i + H(i,:)*lambda, bit for bit
               const double w = fma(-t, rHi, li);
               const double nl = pos_or_zero(w);                      // max(0,w); max(0,NaN) = 0
               const double dl = nl - li;
@@ -1616,9 +1619,9 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
         double hl = Mi[0] * v[0];
 #pragma unroll
         for (int j = 1; j < NC; ++j) hl = fma(Mi[j], v[j], hl);
-        double Kg, rHg;
-        lds_pair(kra + (unsigned)i * krs, Kg, rHg);
-        double w = fma(-(Kg + hl), rHg, li);
+        double nKg, rHg;
+        lds_pair(kra + (unsigned)i * krs, nKg, rHg);
+        double w = fma(-(hl - nKg), rHg, li);                        // hl - (-K) = K + hl, bit for bit
         w = (pmask != 0u) ? NAN : w;
         const double nl = (w > 0.0) ? w : 0.0;                       // max(0,w); max(0,NaN) = 0
         const double dl = nl - li;
