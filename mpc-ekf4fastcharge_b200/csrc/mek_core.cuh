@@ -1897,7 +1897,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
 #pragma unroll
       for (int j = 1; j < NC; ++j) { hd = fma(M[j], P[j], hd); k = fma(M[j], x[j], k); }
       const double li = lc[i * ls];
-      wc[(WS::W_K + i) * wst] = k + wc[(WS::W_K + i) * wst];     // K(i) = M(i,:)*(E\F) + gamma(i)
+      wc[(WS::W_K + i) * wst] = -(k + wc[(WS::W_K + i) * wst]);  // -K(i), K(i) = M(i,:)*(E\F) + gamma(i): the block test compares against -K
       wc[(WS::W_H + i) * wst] = rcp_d(hd);                         // 1/H(i,i)
       if (hd == 0.0) {
         const unsigned bit = 1u << (i & 31);
@@ -1974,7 +1974,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
           double hl = win[NC - 1 + r] * v[0];
 #pragma unroll
           for (int j = 1; j < NC; ++j) hl = fma(win[NC - 1 + r - j], v[j], hl);
-          idle = idle && (li[r] == 0.0) && (Kc[r] + hl >= 0.0);
+          idle = idle && (li[r] == 0.0) && (hl >= Kc[r]);             // Kc = -K: K + H(i,:)lambda >= 0 without the addition on the chain
         }
         if (__all_sync(__activemask(), idle)) continue;
         double rH[BL];
@@ -1990,7 +1990,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
             double hl = win[NC - 1 + r] * v[0];
 #pragma unroll
             for (int j = 1; j < NC; ++j) hl = fma(win[NC - 1 + r - j], v[j], hl);
-            w = fma(-(Kc[r] + hl), rH[r], li[r]);
+            w = fma(-(hl - Kc[r]), rH[r], li[r]);                    // hl - (-K) = K + hl, bit for bit
           }
           const double nl = (w > 0.0) ? w : 0.0;                     // max(0,w); max(0,NaN) = 0
           const double dl = nl - li[r];
