@@ -338,8 +338,24 @@ static __device__ __noinline__ unsigned long long defer_hot_set(const Dims& d, c
   int zh = (b & 0xffff) > (b >> 16) ? (b & 0xffff) : (b >> 16);
   if (zl > zh) { const int t = zl; zl = zh; zh = t; }
   const int t1 = tt & 0xffff, t2 = tt >> 16;
+  // A cell on a temperature set-point gives one of its two temperature rows a weight of exactly zero (alphaT = 0 or 1, get_xind):
+  // the plant and the filter never read that row's states, except the covariance of neighbour #1 = (Tlower, Zlower), which
+  // every gain uses (iterEKF.m:117, Q1).  So of the zero-weight row only the models that can be neighbour #1 during the block
+  // stay hot -- all of it is cold when neighbour #1 lies in the other row -- and anything else it turns out to need is
+  // replayed on demand (defer_ensure).
+  int zrow = -1, zrow_hi = zh;
+  if (!narrow && d.nT > 1 && t1 != t2) {
+    const double Tk = c.f(S_TC) + 273.15;
+    const int iup = bk.Tpts[t1] < bk.Tpts[t2] ? t2 : t1, ilo = (iup == t1) ? t2 : t1;
+    const double aT = (Tk - bk.Tpts[ilo]) / (bk.Tpts[iup] - bk.Tpts[ilo]);
+    if (aT == 1.0) { zrow = ilo; zrow_hi = zh > zl ? zh - 1 : zl; }     // neighbour #1 is in the zero-weight row: its Zlower candidates stay
+    else if (aT == 0.0) { zrow = iup; zrow_hi = zl - 1; }              // neighbour #1 is in the other row: nothing of this one is read
+  }
   unsigned long long mask = 0ull;
-  for (int z = zl; z <= zh; ++z) mask |= (1ull << (t1 * d.nZ + z)) | (1ull << (t2 * d.nZ + z));
+  for (int z = zl; z <= zh; ++z) {
+    if (t1 != zrow || z <= zrow_hi) mask |= 1ull << (t1 * d.nZ + z);
+    if (t2 != zrow || z <= zrow_hi) mask |= 1ull << (t2 * d.nZ + z);
+  }
   return mask;
 }
 
@@ -733,10 +749,10 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   const double rpa = d.Ts / (3600.0 * p[P_Q]);
   double SOC = c.f(S_EKFSOC0) - x0 * rpa;                            // :89
   get_xind(d, bk, Tk, SOC, sc, tt_cached);                           // :107
-  if (df) {
+  if (df) {                                                          // what this instant reads: the weighted neighbours, and neighbour #1's SigmaX (Q1)
 #pragma unroll 1
     for (int k = 0; k < 4; ++k)
-      defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
+      if (k == 0 || sc[SC_GAMMA + k] != 0.0) defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
   }
   double vhat = get_variables(d, bk, p, c, ik, Tk, sc);              // :108
   // SigmaX of neighbour #1 *before* any update: every gain uses it (:117, Q1).  Loaded here so that the L2 round trip
@@ -839,7 +855,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   if (df) {                                                          // the estimate may have moved to other set-points
 #pragma unroll 1
     for (int k = 0; k < 4; ++k)
-      defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
+      if (sc[SC_GAMMA + k] != 0.0) defer_ensure(d, bk, c, df, (int)sc[SC_M + k]);
   }
   vhat = get_variables(d, bk, p, c, ik, Tk, sc);                     // :182
   const double Zsoc = c.f(S_EKFSOC0) - x0 * rpa;                     // :416
