@@ -30,6 +30,8 @@ constexpr int HR_MAX = 24;
 // One hot row of a local model in the shared-memory bank: 8 doubles, 16-byte aligned, [C(1..5) | D | C(6) | pad], so that the
 // EKF's row (five transient states + feed-through) is three 16-byte loads and the plant's (all six states) four.
 constexpr int HRS = 8, HR_D = 5, HR_C6 = 6;
+// A model of the hot bank: diag A (6), the products a_i*a_j of the covariance time update (upper triangle, 15 + 1 pad), then the rows.
+constexpr int HB_AA = 6, HB_ROWS = HB_AA + 16;
 
 struct Dims {
   int M, nT, nZ, nz;
@@ -209,8 +211,11 @@ __device__ __forceinline__ void model_load(const Cell& c, int m, ModelRegs<PLANT
     for (int k = 0; k < NSYM; ++k) r.s[k] = ld_state<KEEP>(w + k * TILE);
   }
 }
+// aa[q] = a_i*a_j (q = upper-triangle index): SigmaX(i,j) <- (a_i*a_j)*SigmaX(i,j) + SigmaW, the entries of
+// diag(A)*SigmaX*diag(A) + SigmaW (iterEKF.m:81, Q12) with the two factors of each entry multiplied first -- one FMA per
+// entry instead of a multiplication and an FMA (numerics contract; oracle/mek_oracle.c does the same)
 template <bool PLANT, bool EKF>
-__device__ __forceinline__ void model_update(const double* a, double Iapp, double prior, double Sw, ModelRegs<PLANT, EKF>& r) {
+__device__ __forceinline__ void model_update(const double* a, const double* aa, double Iapp, double prior, double Sw, ModelRegs<PLANT, EKF>& r) {
   if (PLANT) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) r.bx[j] = fma(a[j], r.bx[j], Iapp);               // OB_step.m:278
@@ -218,11 +223,8 @@ __device__ __forceinline__ void model_update(const double* a, double Iapp, doubl
   if (EKF) {
 #pragma unroll
     for (int j = 0; j < N5; ++j) r.x[j] = fma(a[j], r.x[j], prior);              // iterEKF.m:77
-    int q = 0;
 #pragma unroll
-    for (int i = 0; i < N5; ++i)
-#pragma unroll
-      for (int j = i; j < N5; ++j, ++q) r.s[q] = fma(a[i] * r.s[q], a[j], Sw);   // iterEKF.m:81 (Q12)
+    for (int q = 0; q < NSYM; ++q) r.s[q] = fma(aa[q], r.s[q], Sw);             // iterEKF.m:81 (Q12)
   }
 }
 template <bool PLANT, bool EKF, bool KEEP = false>
@@ -265,7 +267,7 @@ __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk,
 #pragma unroll
     for (int b = 0; b < BATCH; ++b) model_load<PLANT, EKF>(c, m + b, r[b]);
 #pragma unroll
-    for (int b = 0; b < BATCH; ++b) model_update<PLANT, EKF>(bk.mdl + (m + b) * d.mstride, Iapp, prior, Sw, r[b]);
+    for (int b = 0; b < BATCH; ++b) model_update<PLANT, EKF>(bk.mdl + (m + b) * d.mstride, bk.mdl + (m + b) * d.mstride + HB_AA, Iapp, prior, Sw, r[b]);
 #pragma unroll
     for (int b = 0; b < BATCH; ++b) model_store<PLANT, EKF>(c, m + b, r[b]);
   }
@@ -273,7 +275,7 @@ __device__ __forceinline__ void stream_models(const Dims& d, const BankSmem& bk,
   for (; m < d.M; ++m) {
     ModelRegs<PLANT, EKF> r0;
     model_load<PLANT, EKF>(c, m, r0);
-    model_update<PLANT, EKF>(bk.mdl + m * d.mstride, Iapp, prior, Sw, r0);
+    model_update<PLANT, EKF>(bk.mdl + m * d.mstride, bk.mdl + m * d.mstride + HB_AA, Iapp, prior, Sw, r0);
     model_store<PLANT, EKF>(c, m, r0);
   }
 }
@@ -304,13 +306,15 @@ struct Defer {
 static __device__ __noinline__ void defer_catch_up(const Dims& d, const BankSmem& bk, const Cell& c, int m, int n, const double* h, int hs) {
   ModelRegs<true, true> r;
   model_load<true, true>(c, m, r);
-  double a[6];
+  double a[6], aa[NSYM];
   const double* am = bk.mdl + m * d.mstride;
 #pragma unroll
   for (int j = 0; j < 6; ++j) a[j] = am[j];
+#pragma unroll
+  for (int q = 0; q < NSYM; ++q) aa[q] = am[HB_AA + q];
   const double Sw = d.SigmaW;
 #pragma unroll 1
-  for (int j = 0; j < n; ++j) model_update<true, true>(a, h[(j + 1) * hs], h[j * hs], Sw, r);
+  for (int j = 0; j < n; ++j) model_update<true, true>(a, aa, h[(j + 1) * hs], h[j * hs], Sw, r);
   model_store<true, true>(c, m, r);
 }
 
@@ -374,14 +378,14 @@ __device__ __forceinline__ void defer_stream(const Dims& d, const BankSmem& bk, 
       ModelRegs<true, true> r0, r1;
       model_load<true, true, true>(c, m0, r0);
       model_load<true, true, true>(c, m1, r1);
-      model_update<true, true>(bk.mdl + m0 * d.mstride, Iapp, prior, Sw, r0);
-      model_update<true, true>(bk.mdl + m1 * d.mstride, Iapp, prior, Sw, r1);
+      model_update<true, true>(bk.mdl + m0 * d.mstride, bk.mdl + m0 * d.mstride + HB_AA, Iapp, prior, Sw, r0);
+      model_update<true, true>(bk.mdl + m1 * d.mstride, bk.mdl + m1 * d.mstride + HB_AA, Iapp, prior, Sw, r1);
       model_store<true, true, true>(c, m0, r0);
       model_store<true, true, true>(c, m1, r1);
     } else {
       ModelRegs<true, true> r0;
       model_load<true, true, true>(c, m0, r0);
-      model_update<true, true>(bk.mdl + m0 * d.mstride, Iapp, prior, Sw, r0);
+      model_update<true, true>(bk.mdl + m0 * d.mstride, bk.mdl + m0 * d.mstride + HB_AA, Iapp, prior, Sw, r0);
       model_store<true, true, true>(c, m0, r0);
     }
   }
@@ -392,7 +396,7 @@ __device__ __forceinline__ void defer_stream(const Dims& d, const BankSmem& bk, 
     x &= x - 1;
     ModelRegs<true, true> r0;
     model_load<true, true, true>(c, m0, r0);
-    model_update<true, true>(bk.mdl + m0 * d.mstride, Iapp, prior, Sw, r0);
+    model_update<true, true>(bk.mdl + m0 * d.mstride, bk.mdl + m0 * d.mstride + HB_AA, Iapp, prior, Sw, r0);
     model_store<true, true, true>(c, m0, r0);
   }
   df.n += 1;
@@ -451,8 +455,8 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
     if (h ? (aT == 0.0) : (aT == 1.0)) continue;                     // that row's blend weight is exactly zero (see below)
     const int iT = h ? iTup : iTlo;
     const int ma = iT * d.nZ + iZlo, mb = iT * d.nZ + iZup;
-    const double* ra = bk.mdl + ma * d.mstride + 6;
-    const double* rb = bk.mdl + mb * d.mstride + 6;
+    const double* ra = bk.mdl + ma * d.mstride + HB_ROWS;
+    const double* rb = bk.mdl + mb * d.mstride + HB_ROWS;
     defer_ensure(d, bk, c, df, ma);
     defer_ensure(d, bk, c, df, mb);
     double xa[6], xb[6];
@@ -523,7 +527,7 @@ __device__ __forceinline__ void gv_rows_n(const Dims& d, const BankSmem& bk, con
   for (int k = 0; k < NK; ++k) {
     const int m = (int)sc[SC_M + k0 + k];
     g[k] = sc[SC_GAMMA + k0 + k];
-    mm[k] = bk.mdl + m * d.mstride + 6;
+    mm[k] = bk.mdl + m * d.mstride + HB_ROWS;
 #pragma unroll
     for (int j = 0; j < N5; ++j) xk[k][j] = ld_row(&c.xhat(m, j));   // :267-270
   }
@@ -800,7 +804,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
       }
       continue;
     }
-    const double* mm = bk.mdl + mo * d.mstride + 6;
+    const double* mm = bk.mdl + mo * d.mstride + HB_ROWS;
     double Chat[N5], v[N5], L[N5], S[NSYM], xs[N5];
     // this neighbour's state, requested before the gain is computed (the loads overlap it); after the previous
     // neighbour's stores in program order, so a duplicate neighbour sees its own update (Q2)
@@ -888,7 +892,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     const double TK = c.f(S_TC) + 273.15;                            // :53
     const double sn = soc_e(p, P_NEG, Zsoc), sp = soc_e(p, P_POS, Zsoc);   // :56-58
     const double Rfn2 = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)), Rfp2 = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
-    const double* mm = am + 6;
+    const double* mm = am + HB_ROWS;
 #pragma unroll
     for (int j = 0; j < N5; ++j)                                     // :75-76
       o.Cv[j] = (Rfp2 * mm[HR_IFDL3 * HRS + j] - Rfn2 * mm[HR_IFDL0 * HRS + j]) + mm[HR_PHIE * HRS + j];

@@ -120,7 +120,7 @@ static int bank_finalize(mek_bank* b) {
   for (int r : b->thetae) if (r != b->r_the0 && r != b->r_the3) { hot.push_back(r); b->nx_thetae++; }
   b->R = (int)hot.size();
   if (b->R > HR_MAX) return fail(MEK_ERR_UNSUPPORTED, "too many Thetass/Thetae rows for the shared-memory hot bank");
-  b->mstride = 6 + b->R * HRS;
+  b->mstride = HB_ROWS + b->R * HRS;
   int head = b->nT + b->nZ;
   if (head & 1) head++;                                      // keep the model block 16-byte aligned
   b->off_mdl = head;
@@ -132,9 +132,14 @@ static int bank_finalize(mek_bank* b) {
   for (int m = 0; m < b->M; ++m) {
     double* dst = &b->blob[(size_t)b->off_mdl + (size_t)m * b->mstride];
     for (int j = 0; j < 6; ++j) dst[j] = b->A[(size_t)m * 6 + j];
+    {                                                        // a_i*a_j, upper triangle row-major (sym_idx order): the covariance time update's factors
+      int q = 0;
+      for (int i = 0; i < N5; ++i)
+        for (int j = i; j < N5; ++j, ++q) dst[HB_AA + q] = b->A[(size_t)m * 6 + i] * b->A[(size_t)m * 6 + j];
+    }
     for (int r = 0; r < b->R; ++r) {
       const double* Cr = &b->C[((size_t)m * b->nz + hot[r]) * 6];
-      double* row = dst + 6 + r * HRS;                         // [C(1..5) | D | C(6) | pad]  (mek_core.cuh HRS)
+      double* row = dst + HB_ROWS + r * HRS;                         // [C(1..5) | D | C(6) | pad]  (mek_core.cuh HRS)
       for (int j = 0; j < 5; ++j) row[j] = Cr[j];
       row[HR_D] = b->D[(size_t)m * b->nz + hot[r]];
       row[HR_C6] = Cr[5];

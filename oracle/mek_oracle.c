@@ -613,9 +613,9 @@ static void ekf_step(const mko_bank *bk, const mko_config *cf, double *st, doubl
     const double *a = bk->A + 6 * m;
     double *x = xhat + N5 * m, *S = Sig + NSYM * m;
     for (int j = 0; j < N5; ++j) x[j] = fma(a[j], x[j], prior);    /* :77 */
-    int q = 0;
-    for (int i = 0; i < N5; ++i)
-      for (int j = i; j < N5; ++j, ++q) S[q] = fma(a[i] * S[q], a[j], Sw); /* :81 (Q12) */
+    int q = 0;                                                     /* :81 (Q12): entry (i,j) of diag(A)*SigmaX*diag(A) + SigmaW with the two factors */
+    for (int i = 0; i < N5; ++i)                                   /* multiplied first, (a_i*a_j)*SigmaX(i,j) (numerics contract) */
+      for (int j = i; j < N5; ++j, ++q) S[q] = fma(a[i] * a[j], S[q], Sw);
   }
   OPC_BLOCK(2);
   st[S_X0] = st[S_X0] + prior;                                     /* :85 */
