@@ -106,6 +106,10 @@ typedef struct {
   double meas_sigma;        /* standard deviation [V]; 0 (default) = the reference's loop                                    */
   uint64_t noise_seed;      /* key of the sequence                                                                           */
   int64_t first_cell;       /* global index of this population's cell 0, so that any shard reproduces any cell's sequence    */
+  /* Plant-model mismatch scenario (in the reference: OB_step called with another ROM struct than initKF / initMPC).  The PLANT's
+     capacity is Q * plant_q_scale * (1 + plant_q_spread * (2u - 1)), u a per-cell uniform keyed by (noise_seed, first_cell + cell),
+     and its collector resistance Rc * plant_rc_scale; the filter and the MPC keep the bank's values.  0 means 1 for the scales.  */
+  double plant_q_scale, plant_q_spread, plant_rc_scale;
 } mek_config;
 
 /* g(seed, cell, k): x = seed ^ cell*0x9E3779B97F4A7C15 ^ (k+1)*0xD1B54A32D192ED03; twelve splitmix64 steps of x, each output's top

@@ -53,6 +53,7 @@ struct Dims {
   long long B, ld;   // cells in this shard, cells rounded up to whole 32-cell tiles
   int f_lambda, f_bigx, f_xhat, f_sig, nfields;
   double meas_sigma;            // noisy-sensor scenario (mek_config.meas_sigma): 0 = runMPC.m:88 as written
+  double plant_q_scale, plant_q_spread, plant_rc_scale;   // plant-model mismatch scenario (1, 0, 1 = the reference)
   unsigned long long noise_seed;
   long long first_cell;
   int mb, f_mbx, f_mbs;   // model-blend EKF (function-level entry only): ekfData.xhat (6) and ekfData.SigmaX (21, upper triangle) behind the model rows
@@ -419,11 +420,13 @@ __device__ __forceinline__ void defer_flush(const Dims& d, const BankSmem& bk, c
 // ------------------------------------------------------------------------------------------
 template <bool ADVANCE>   // ADVANCE=false: the caller runs stream_models<true,...> right after (fused pass)
 __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c,
-                                             double Iapp, int tt_cached, Defer* df = nullptr) {
+                                             double Iapp, int tt_cached, Defer* df = nullptr, double qs = 1.0, double rcs = 1.0) {
+  // qs, rcs: plant-model mismatch scenario (mek_config.plant_q_scale / plant_rc_scale): the PLANT's capacity and collector
+  // resistance are the bank's times these factors; 1.0 (the default, a compile-time constant in the lean instances) is the reference
   const double T = c.f(S_TC) + 273.15;                               // OB_step.m:75
   const double th0n = p[P_NEG + E_THETA0], th100n = p[P_NEG + E_THETA100];
   const double th0p = p[P_POS + E_THETA0], th100p = p[P_POS + E_THETA100];
-  const double Q = p[P_Q];
+  const double Q = p[P_Q] * qs;
   double SOCn = c.f(S_SOCN), SOCp = c.f(S_SOCP);
   const double negSOC = SOCn, posSOC = SOCp;                         // :226-227 (Q16)
   const double cellSOC = (SOCn - th0n) / (th100n - th0n);            // :228
@@ -495,7 +498,7 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   const double Un0 = uocp_n(p, tss0), Up3 = uocp_p(p, tss3);         // :337-340
   const double Rfn = rf_e(p, P_NEG, negSOC, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, posSOC, c.f(S_ARRRFP));
   double V = ((((posEta3 - negEta0) + yk[HR_PHIE]) + Up3) - Un0) + (Rfp * yk[HR_IFDL3] - Rfn * yk[HR_IFDL0]);   // :341-342
-  V = V - p[P_RC] * Iapp;                                            // :344
+  V = V - (p[P_RC] * rcs) * Iapp;                                    // :344
   c.f(S_SOCN) = SOCn;
   c.f(S_SOCP) = SOCp;
   return V;

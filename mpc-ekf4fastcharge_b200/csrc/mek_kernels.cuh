@@ -87,7 +87,7 @@ struct StepLog {
 
 template <int NPM, int NCM, int CONS, int BATCH>   // CONS >= 0: static-shape fast MPC path (constraint switches compile-time), -1: generic
 __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, const Cell& c, StepLog& lg, double* smt, const int sms, int tt,
-                                          Defer* df, long long id, int k) {
+                                          Defer* df, long long id, int k, double qs, double rcs) {
   const Dims& d = P.d;
   lg.u = NAN; lg.V = NAN; lg.soc = NAN; lg.phise = NAN; lg.iT = 0; lg.iZ = 0; lg.nexec = 0;
 #pragma unroll
@@ -95,7 +95,7 @@ __device__ __forceinline__ void cell_step(const Params& P, const BankSmem& bk, c
   if ((unsigned)c.f(S_STATUS) & ST_LOST) return;                     // Q19: a lost cell idles
   const double uk = c.f(S_UK);
   if (!df) prefetch_models(d, c, 0, 6, true, true);                  // first rows of this instant's HBM stream -> L2 while the plant outputs are computed
-  const double V = plant_step<false>(d, bk, P.cp, c, uk, tt, df);    // runMPC.m:85 (outputs; the state advance is fused below)
+  const double V = plant_step<false>(d, bk, P.cp, c, uk, tt, df, qs, rcs);   // runMPC.m:85 (outputs; the state advance is fused below)
   // OB_step.m:278 with u_k and iterEKF.m:73-84 with priorI = u_{k-1}: one HBM pass over all M local models, or (deferral
   // on) over the cell's hot models only -- the rest catch up at the end of the block
   if (df) defer_stream(d, bk, c, *df, uk, c.f(S_PRIORI));
@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
     // the cell temperature is constant over a run: its two nearest set-points are looked up once (same rule as every step)
     const int tt = active ? two_nearest(c.f(S_TC) + 273.15, bk.Tpts, d.nT) : 0;
     const long long id = active ? cell_id(P, cell) : 0;   // the caller's index of this cell (logs are addressed by it)
+#ifndef MEK_LUT_OFF                                        // scenarios live in the full-featured instances only
+    const double qs = plant_q_factor(d.plant_q_scale, d.plant_q_spread, d.noise_seed, (unsigned long long)(d.first_cell + id)), rcs = d.plant_rc_scale;
+#else
+    constexpr double qs = 1.0, rcs = 1.0;
+#endif
 #pragma unroll 1
     for (int k = k0; k < k1; ++k) {
       if (P.sync_steps) __syncthreads();             // keeps the CTA's warps on the same stretch of code (instruction-cache sharing)
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
       }
       if (!active) continue;
       StepLog lg;
-      cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt, KB > 0 ? &df : nullptr, id, k);
+      cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt, KB > 0 ? &df : nullptr, id, k, qs, rcs);
       // per-cell summary, kept in the state header (not in registers: they are the scarce resource of this kernel)
       if (lg.nexec > 0) {
         c.f(S_SUM_NEXEC) += (double)lg.nexec;

@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(128) k_ob_step(const __grid_constant__ Params 
   for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < P.d.B; cell += stride) {
     Cell c = cell_ref(P.st, P.d, cell);
     const long long id = cell_id(P, cell);
-    V[id] = plant_step<true>(P.d, bk, P.cp, c, Iapp[id], -1);
+    V[id] = plant_step<true>(P.d, bk, P.cp, c, Iapp[id], -1, nullptr,
+                             plant_q_factor(P.d.plant_q_scale, P.d.plant_q_spread, P.d.noise_seed, (unsigned long long)(P.d.first_cell + id)), P.d.plant_rc_scale);
   }
 }
 
@@ -531,6 +532,7 @@ __global__ void __launch_bounds__(128) k_run_population_mb(const __grid_constant
     Cell c = cell_ref(P.st, d, cell);
     const int tt = two_nearest(c.f(S_TC) + 273.15, bk.Tpts, d.nT);
     const long long id = cell_id(P, cell);
+    const double qs = plant_q_factor(d.plant_q_scale, d.plant_q_spread, d.noise_seed, (unsigned long long)(d.first_cell + id));
 #pragma unroll 1
     for (int k = k0; k < k1; ++k) {
       StepLog lg;
@@ -538,7 +540,7 @@ __global__ void __launch_bounds__(128) k_run_population_mb(const __grid_constant
       for (int w = 0; w < 4; ++w) lg.active[w] = 0u;
       if (!((unsigned)c.f(S_STATUS) & ST_LOST)) {                    // Q19: a lost cell idles
         const double uk = c.f(S_UK);
-        const double V = plant_step<true>(d, bk, P.cp, c, uk, tt);   // runMPC.m:85
+        const double V = plant_step<true>(d, bk, P.cp, c, uk, tt, nullptr, qs, d.plant_rc_scale);   // runMPC.m:85
         EkfOut e;
         memset(&e, 0, sizeof(e));
         double vk = V;
@@ -1003,6 +1005,8 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   d.f_lambda = S_HDR; d.f_bigx = d.f_lambda + d.nC; d.f_xhat = d.f_bigx + 6 * d.M; d.f_sig = d.f_xhat + N5 * d.M;
   d.nfields = d.f_sig + NSYM * d.M;
   d.meas_sigma = cfg->meas_sigma; d.noise_seed = cfg->noise_seed; d.first_cell = cfg->first_cell;
+  d.plant_q_scale = cfg->plant_q_scale > 0.0 ? cfg->plant_q_scale : 1.0; d.plant_q_spread = cfg->plant_q_spread;
+  d.plant_rc_scale = cfg->plant_rc_scale > 0.0 ? cfg->plant_rc_scale : 1.0;
   d.mb = cfg->ekf_method == 1 ? 1 : 0;                               // initKF.m:44-53: 'OutB' (0) or 'MdlB' (1)
   d.f_mbx = d.f_mbs = 0;
   if (d.mb) { d.f_mbx = d.nfields; d.f_mbs = d.f_mbx + N6; d.nfields = d.f_mbs + NSYM6; }
@@ -1084,7 +1088,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
   p->run_smem = p->smem_bytes;
   // tabulated cell functions and the noisy-sensor scenario are compiled into the full-featured instances only (k_fused_fast_lut.cu,
   // k_fused_generic.cu); the lean ones (MEK_LUT_OFF) serve everything else
-  const bool full = bank->lut_n > 0 || cfg->meas_sigma != 0.0;
+  const bool full = bank->lut_n > 0 || cfg->meas_sigma != 0.0 || d.plant_q_scale != 1.0 || d.plant_q_spread != 0.0 || d.plant_rc_scale != 1.0;
   {
     const int mask = (d.useCurrent ? 1 : 0) | (d.useVoltage ? 2 : 0) | (d.useEta ? 4 : 0) | (d.useZmax ? 8 : 0);
     if (p->inst == 0 && (mask == 15 || mask == 11) && !cfg->generic_path && !d.useTerm) {

@@ -53,7 +53,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     chk(mek_bank_set_lut((mek_bank *)get_handle(prhs[1]), (int)n, mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), t));
     mxFree(t);
   } else if (!strcmp(cmd, "pop_create")) {               /* h = mek_mex('pop_create', bank, cfgvec, B, device) */
-    const double *c = mxGetPr(prhs[2]);                  /* [Np Nc maxHild c1 c2 c3 use_zmax ref SigmaV SigmaW (ekf_method (z_target_terminal z_tol (meas_sigma noise_seed)))] */
+    const double *c = mxGetPr(prhs[2]);                  /* [Np Nc maxHild c1 c2 c3 use_zmax ref SigmaV SigmaW (ekf_method (z_target_terminal z_tol (meas_sigma noise_seed (plant_q_scale plant_q_spread plant_rc_scale))))] */
     mek_config cfg;
     mek_pop *p = NULL;
     memset(&cfg, 0, sizeof cfg);
@@ -66,6 +66,9 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     }
     if (mxGetNumberOfElements(prhs[2]) > 14) {                              /* noisy-sensor scenario (include/mek.h): sigma [V], seed */
       cfg.meas_sigma = c[13]; cfg.noise_seed = (uint64_t)c[14];
+    }
+    if (mxGetNumberOfElements(prhs[2]) > 17) {                              /* plant-model mismatch scenario: q scale, q spread, Rc scale */
+      cfg.plant_q_scale = c[15]; cfg.plant_q_spread = c[16]; cfg.plant_rc_scale = c[17];
     }
     chk(mek_pop_create((mek_bank *)get_handle(prhs[1]), &cfg, (int64_t)mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[4]), &p));
     plhs[0] = put_handle(p);

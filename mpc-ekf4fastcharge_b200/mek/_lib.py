@@ -30,7 +30,8 @@ class MekConfig(C.Structure):
                 ("threads_per_block", C.c_int), ("blocks_per_sm", C.c_int), ("generic_path", C.c_int), ("sync_steps", C.c_int), ("keep_cell_order", C.c_int),
                 ("defer_block", C.c_int), ("defer_stagger", C.c_int), ("regroup_every", C.c_int), ("defer_narrow_test", C.c_int), ("general_sweep_test", C.c_int),
                 ("z_target_terminal", C.c_int), ("z_tol", C.c_double), ("ekf_method", C.c_int),
-                ("meas_sigma", C.c_double), ("noise_seed", C.c_uint64), ("first_cell", C.c_int64)]
+                ("meas_sigma", C.c_double), ("noise_seed", C.c_uint64), ("first_cell", C.c_int64),
+                ("plant_q_scale", C.c_double), ("plant_q_spread", C.c_double), ("plant_rc_scale", C.c_double)]
 
 
 class MekBankDesc(C.Structure):

@@ -74,7 +74,8 @@ class CellBatch:
     def __init__(self, rom: RomBank, B, Np=5, Nc=2, constraints=(1, 1, 1), ref=95.0, SigmaV=1e-3, SigmaW=1e2, maxHild=100,
                  use_zmax=True, force_jacobi=False, device=0, threads_per_block=0, blocks_per_sm=0, generic_path=False, sync_steps=True, keep_cell_order=False,
                  defer_block=0, defer_stagger=False, defer_narrow_test=False, regroup_every=0, general_sweep_test=0, ekf_method="OutB",
-                 z_target_terminal=False, z_tol=0.0, meas_sigma=0.0, noise_seed=0, first_cell=0):
+                 z_target_terminal=False, z_tol=0.0, meas_sigma=0.0, noise_seed=0, first_cell=0,
+                 plant_q_scale=1.0, plant_q_spread=0.0, plant_rc_scale=1.0):
         L = _lib.lib()
         self.rom = rom
         self.B = int(B)
@@ -95,6 +96,7 @@ class CellBatch:
         cfg.regroup_every = int(regroup_every)
         cfg.z_target_terminal, cfg.z_tol = int(bool(z_target_terminal)), float(z_tol)
         cfg.meas_sigma, cfg.noise_seed, cfg.first_cell = float(meas_sigma), int(noise_seed), int(first_cell)   # noisy-sensor scenario (include/mek.h)
+        cfg.plant_q_scale, cfg.plant_q_spread, cfg.plant_rc_scale = float(plant_q_scale), float(plant_q_spread), float(plant_rc_scale)   # plant-model mismatch
         blend = str(ekf_method).upper()                      # initKF.m:44-53: unknown strings fall back to output blending
         cfg.ekf_method = 1 if blend in ("MDLB", "MB") else 0
         self.cfg = cfg

@@ -52,7 +52,8 @@ class MkoConfig(C.Structure):
     _fields_ = [("Np", C.c_int), ("Nc", C.c_int), ("maxHild", C.c_int), ("useCurrent", C.c_int), ("useVoltage", C.c_int),
                 ("useEta", C.c_int), ("useZmax", C.c_int), ("ref", C.c_double), ("SigmaV", C.c_double),
                 ("SigmaW", C.c_double), ("force_jacobi", C.c_int), ("z_target_terminal", C.c_int), ("z_tol", C.c_double), ("ekf_method", C.c_int),
-                ("meas_sigma", C.c_double), ("noise_seed", C.c_uint64), ("first_cell", C.c_int64)]
+                ("meas_sigma", C.c_double), ("noise_seed", C.c_uint64), ("first_cell", C.c_int64),
+                ("plant_q_scale", C.c_double), ("plant_q_spread", C.c_double), ("plant_rc_scale", C.c_double)]
 
 
 def build(force=False):
@@ -75,8 +76,11 @@ def lib():
         L.mko_ncon_max.restype = C.c_int
         L.mko_sigma_min_gtg.restype = C.c_double
         L.mko_sigma_min_gtg.argtypes = [C.c_int, C.c_int, C.c_double]
+        L.mko_cell_uniform.restype = C.c_double
+        L.mko_cell_uniform.argtypes = [C.c_uint64, C.c_uint64]
         L.mko_noise.restype = C.c_double
         L.mko_noise.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        L.mko_ob_step_s.restype = C.c_double
         L.mko_ob_step.restype = C.c_double
         L.mko_ob_step.argtypes = [C.POINTER(MkoBank), C.c_void_p, C.c_double]
         for f in ("mko_test_log", "mko_test_exp", "mko_test_asinh"):
@@ -94,7 +98,8 @@ class COracle:
     """Population runner over the C restatement."""
 
     def __init__(self, bank, Np=5, Nc=2, constraints=(1, 1, 1), ref=95.0, SigmaV=1e-3, SigmaW=1e2, maxHild=100,
-                 force_jacobi=False, z_target_terminal=False, z_tol=0.0, ekf_method="OutB", meas_sigma=0.0, noise_seed=0, first_cell=0):
+                 force_jacobi=False, z_target_terminal=False, z_tol=0.0, ekf_method="OutB", meas_sigma=0.0, noise_seed=0, first_cell=0,
+                 plant_q_scale=1.0, plant_q_spread=0.0, plant_rc_scale=1.0):
         self.bank = bank
         self.L = lib()
         self._keep = dict(
@@ -129,6 +134,7 @@ class COracle:
         cf.z_target_terminal, cf.z_tol = int(bool(z_target_terminal)), float(z_tol)
         cf.ekf_method = 1 if str(ekf_method).upper() in ("MDLB", "MB") else 0          # initKF.m:44-53
         cf.meas_sigma, cf.noise_seed, cf.first_cell = float(meas_sigma), int(noise_seed), int(first_cell)
+        cf.plant_q_scale, cf.plant_q_spread, cf.plant_rc_scale = float(plant_q_scale), float(plant_q_spread), float(plant_rc_scale)
         self.cf = cf
         self.Np, self.Nc = Np, Nc
         self.nC = (4 * Nc if cf.useCurrent else 0) + Np * (cf.useVoltage + cf.useEta + 1) + cf.z_target_terminal
@@ -180,7 +186,7 @@ class COracle:
         return out
 
     def ob_step(self, c, Iapp):
-        return self.L.mko_ob_step(C.byref(self.b), C.c_void_p(self.state[c].ctypes.data), C.c_double(Iapp))
+        return self.L.mko_ob_step_s(C.byref(self.b), C.byref(self.cf), C.c_void_p(self.state[c].ctypes.data), C.c_double(Iapp), C.c_int64(c))
 
     def iter_ekf(self, c, vk, ik):
         zk = np.empty(self.bank.nz + 2); mats = np.empty(31)

@@ -856,9 +856,20 @@ def noise(seed, cell, k):
     return s - 6.0
 
 
+def cell_uniform(seed, cell):
+    """per-cell uniform on [0,1) of the plant-model mismatch scenario (include/mek.h): one splitmix64 step of a key of (seed, cell)"""
+    M64 = (1 << 64) - 1
+    z = ((seed ^ (cell * 0x9E3779B97F4A7C15) ^ 0xA5A5A5A5A5A5A5A5) + 0x9E3779B97F4A7C15) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    z = z ^ (z >> 31)
+    return float(z >> 11) * 2.0 ** -53
+
+
 def run_mpc(bank, SOC0=10.0, TC=25.0, N=3001, Np=5, Nc=2, targetSOC=95.0, constraints=(1, 1, 1),
             Crate=2.0, limits=None, SigmaX0=None, SigmaV=1e-3, SigmaW=1e2, ekf_SOC0=None,
-            diagnostics=False, keep_zk=False, blend="OutB", meas_sigma=0.0, noise_seed=0, cell_id=0):
+            diagnostics=False, keep_zk=False, blend="OutB", meas_sigma=0.0, noise_seed=0, cell_id=0,
+            plant_q_scale=1.0, plant_q_spread=0.0, plant_rc_scale=1.0):
     """runMPC.m:3-115 with its literals exposed as arguments.  Returns a dict of per-step stores."""
     # not restated :3 (clear; clc; close all)
     # not restated :115 (plot4Figures: MATLAB graphics)
@@ -884,9 +895,15 @@ def run_mpc(bank, SOC0=10.0, TC=25.0, N=3001, Np=5, Nc=2, targetSOC=95.0, constr
     mpcData.cost = dict(t=np.arange(N, dtype=float), J_uncon=np.full(N, np.nan), J_final=np.full(N, np.nan),
                         norm_DU=np.full(N, np.nan), viol=np.full(N, np.nan), nexec=np.full(N, np.nan))   # :63-69
     uk = 0.0                                                                             # :72
-    voltage, obs, cellState = OB_step(uk, TC, None, ROM, dict(SOC0=SOC0, warnOff=True))  # :73-74 (Q20)
+    ROMp = ROM                                               # the plant's ROM struct: the same one in the reference's script
+    if plant_q_scale != 1.0 or plant_q_spread != 0.0 or plant_rc_scale != 1.0:          # scenario: an aged cell under a nominal filter
+        qs = plant_q_scale if plant_q_spread == 0.0 else plant_q_scale * (1.0 + plant_q_spread * (2.0 * cell_uniform(noise_seed, cell_id) - 1.0))
+        ROMp = copy.copy(ROM); ROMp.cellData = copy.copy(ROM.cellData); ROMp.cellData.function = copy.copy(ROM.cellData.function)
+        Qn, Rcn = ROM.cellData.function.const.Q(), ROM.cellData.function.const.Rc()
+        ROMp.cellData.function.const = NS(Q=lambda *_: Qn * qs, Rc=lambda *_: Rcn * plant_rc_scale)
+    voltage, obs, cellState = OB_step(uk, TC, None, ROMp, dict(SOC0=SOC0, warnOff=True))  # :73-74 (Q20)
     for k in range(1, N + 1):                                                            # :83-112
-        voltage, obs, cellState = OB_step(uk, TC, cellState, ROM)                        # :85
+        voltage, obs, cellState = OB_step(uk, TC, cellState, ROMp)                       # :85
         vk = voltage if meas_sigma == 0.0 else voltage + meas_sigma * noise(noise_seed, cell_id, k - 1)   # scenario: a noisy sensor
         zk, zbk, ekfData, Xind = iterEKF(vk, uk, TC, ekfData)                            # :88
         try:

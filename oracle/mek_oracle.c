@@ -83,6 +83,9 @@ typedef struct {
                             measurement noise added to vk; 0 = the reference's loop */
   uint64_t noise_seed;   /* key of the counter-based noise sequence (seed, cell, instant) */
   int64_t first_cell;    /* global index of cell 0 of this run: any shard reproduces any cell's sequence */
+  /* plant-model mismatch scenario (the reference: OB_step given another ROM struct than the filter): the PLANT's capacity is
+     Q*q_scale*(1 + q_spread*(2u-1)), u per cell, and its collector resistance Rc*rc_scale; 0 means 1 for the scales */
+  double plant_q_scale, plant_q_spread, plant_rc_scale;
 } mko_config;
 
 /* per-cell state, flat doubles (also the host-side AoS layout of mek_read_state) */
@@ -288,7 +291,7 @@ static int sym_idx(int i, int j) { /* upper triangle, row-major, i <= j */
 static int zw_skip = 1;
 void mko_set_zero_weight_skip(int on) { zw_skip = on != 0; }
 
-static double plant_step(const mko_bank *bk, double *st, double Iapp) {
+static double plant_step(const mko_bank *bk, double *st, double Iapp, double qs, double rcs) {
   OPC_BLOCK(0);
   const double *p = bk->params;
   const int M = bk->nT * bk->nZ, nz = bk->nz;
@@ -296,7 +299,7 @@ static double plant_step(const mko_bank *bk, double *st, double Iapp) {
   const double T = st[S_TC] + 273.15;                              /* OB_step.m:75 */
   const double th0n = p[P_NEG + E_THETA0], th100n = p[P_NEG + E_THETA100];
   const double th0p = p[P_POS + E_THETA0], th100p = p[P_POS + E_THETA100];
-  const double Q = p[P_Q];
+  const double Q = p[P_Q] * qs;                                    /* qs, rcs: plant-model mismatch factors (1 = the reference) */
   double SOCn = st[S_SOCN], SOCp = st[S_SOCP];
   const double negSOC = SOCn, posSOC = SOCp;                       /* :226-227 (Q16: pre-update) */
   const double cellSOC = (SOCn - th0n) / (th100n - th0n);          /* :228 */
@@ -354,7 +357,7 @@ static double plant_step(const mko_bank *bk, double *st, double Iapp) {
   const double Uocpn0 = uocp_n(p, tss0), Uocpp3 = uocp_p(p, tss3); /* :337-340 */
   const double Rfn = rf_e(p, P_NEG, negSOC, st[S_ARRRFN]), Rfp = rf_e(p, P_POS, posSOC, st[S_ARRRFP]);
   double V = ((((posEta3 - negEta0) + yk[8]) + Uocpp3) - Uocpn0) + (Rfp * posIfdl3 - Rfn * negIfdl0); /* :341-342 */
-  V = V - p[P_RC] * Iapp;                                          /* :344 */
+  V = V - (p[P_RC] * rcs) * Iapp;                                  /* :344 */
   st[S_SOCN] = SOCn;
   st[S_SOCP] = SOCp;
   return V;
@@ -1269,6 +1272,20 @@ double mko_noise(uint64_t seed, uint64_t cell, uint64_t k) {
   return s - 6.0;
 }
 
+/* per-cell uniform on [0,1) (one splitmix64 step of a key of (seed, cell)) and the plant's capacity factor of a cell */
+double mko_cell_uniform(uint64_t seed, uint64_t cell) {
+  uint64_t z = (seed ^ (cell * 0x9E3779B97F4A7C15ull) ^ 0xA5A5A5A5A5A5A5A5ull) + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * 0x1.0p-53;
+}
+static double mko_plant_q_factor(const mko_config *cf, int64_t cell) {
+  const double scale = cf->plant_q_scale > 0.0 ? cf->plant_q_scale : 1.0;
+  if (cf->plant_q_spread == 0.0) return scale;
+  return scale * (1.0 + cf->plant_q_spread * (2.0 * mko_cell_uniform(cf->noise_seed, (uint64_t)(cf->first_cell + cell)) - 1.0));
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* cell init: initKF.m:37-133 + initMPC.m:32-72 + OB_step.m:63-71 and the first I=0 call       */
 /* (runMPC.m:72-74, Q20)                                                                      */
@@ -1310,7 +1327,7 @@ void mko_cell_init(const mko_bank *bk, const mko_config *cf, double *st, double 
   }
   st[S_UK] = 0.0;                                                  /* initMPC.m:51, runMPC.m:72 */
   for (int k = 0; k < 7; ++k) st[S_UMAX + k] = limits[k];
-  plant_step(bk, st, 0.0);                                         /* runMPC.m:74 (Q20) */
+  plant_step(bk, st, 0.0, 1.0, 1.0);                               /* runMPC.m:74 (Q20); I = 0: the mismatch factors do not enter */
 }
 
 /* one pass of the loop body runMPC.m:83-112 */
@@ -1322,7 +1339,7 @@ void mko_cell_step(const mko_bank *bk, const mko_config *cf, double sigmin, doub
     for (int w = 0; w < 4; ++w) log_active[w] = 0;
     return;
   }
-  const double V = plant_step(bk, st, uk);                         /* :85 */
+  const double V = plant_step(bk, st, uk, mko_plant_q_factor(cf, cell), cf->plant_rc_scale > 0.0 ? cf->plant_rc_scale : 1.0);   /* :85 */
   ekf_out e;
   double vk = V;                                                   /* :88 feeds the plant voltage itself */
   if (cf->meas_sigma != 0.0) vk = V + cf->meas_sigma * mko_noise(cf->noise_seed, (uint64_t)(cf->first_cell + cell), (uint64_t)k);
@@ -1371,7 +1388,11 @@ int mko_run(const mko_bank *bk, const mko_config *cf, int B, double *state, int 
 int mko_test_psd(double *S15, int force) { return psd_repair(S15, force); }
 void mko_test_two_nearest(double v, const double *pts, int n, int *i1, int *i2) { two_nearest(v, pts, n, i1, i2); }
 
-double mko_ob_step(const mko_bank *bk, double *st, double Iapp) { return plant_step(bk, st, Iapp); }
+double mko_ob_step(const mko_bank *bk, double *st, double Iapp) { return plant_step(bk, st, Iapp, 1.0, 1.0); }
+/* the same for cell `cell` of a run with the plant-model mismatch scenario of cf */
+double mko_ob_step_s(const mko_bank *bk, const mko_config *cf, double *st, double Iapp, int64_t cell) {
+  return plant_step(bk, st, Iapp, mko_plant_q_factor(cf, cell), cf->plant_rc_scale > 0.0 ? cf->plant_rc_scale : 1.0);
+}
 
 /* iterEKF + EKFmatsHandler; mats = [lost,iT,iZ, xhat(6), a(5), Cv(5), Dv, Cphi(5), Dphi, bv, bphi, vhat, soc] (31) */
 void mko_iter_ekf(const mko_bank *bk, const mko_config *cf, double *st, double vk, double ik, double *zk, double *mats) {

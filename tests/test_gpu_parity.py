@@ -437,3 +437,30 @@ def _run_both_kw(bank, coracle_mod, pop, N, cuda_only, both, oracle=True):
         co.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
         c = co.run(0, N, nthreads=8)
     return cb, g, co, c
+
+
+def test_plant_model_mismatch_scenario(bank, coracle_mod):
+    """mek_config.plant_q_scale / plant_q_spread / plant_rc_scale (an aged population under a nominal filter): CUDA -- the
+    full-featured static-shape instances, the runtime-shape ones, the step-at-a-time entry -- against the C restatement,
+    bit for bit; a shard reproduces its cells."""
+    from mek import population as P, api
+    pop = P.make_population(bank.params[2], 96, seed=97, heterogeneous=True)
+    kw = dict(plant_q_scale=0.92, plant_q_spread=0.06, plant_rc_scale=1.4, noise_seed=5150)
+    N = 800
+    cb, g, co, c = _run_both_kw(bank, coracle_mod, pop, N, {}, kw)
+    _assert_bit_exact(g, c)
+    cb2, g2, _, _ = _run_both_kw(bank, coracle_mod, pop, N, dict(generic_path=True), kw, oracle=False)
+    _assert_bit_exact(g2, c)
+    sub = pop.slice(32, 96)
+    cb3, g3, _, _ = _run_both_kw(bank, coracle_mod, sub, N, {}, dict(kw, first_cell=32), oracle=False)
+    for k in ("u", "V", "SOC", "phise", "nexec"):
+        assert np.array_equal(g3[k], g[k][:, 32:], equal_nan=(g[k].dtype.kind == "f")), k
+    cb0, g0, _, _ = _run_both_kw(bank, coracle_mod, pop, N, {}, {}, oracle=False)
+    assert np.nanmax(np.abs(g0["V"] - g["V"])) > 1e-3
+    # step-at-a-time entry: the plant of mek_pop_ob_step is the mismatched one too
+    cb4 = api.CellBatch(api.RomBank(bank), len(pop), **kw)
+    cb4.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    V = cb4.ob_step(np.full(len(pop), -20.0))
+    co4 = coracle_mod.COracle(bank, **kw)
+    co4.init(pop.SOC0, pop.T, pop.SigmaX0, pop.limits, pop.ekf_SOC0)
+    assert all(V[i] == co4.ob_step(i, -20.0) for i in range(len(pop)))

@@ -215,3 +215,33 @@ def test_noisy_sensor_scenario_c_vs_literal(bank, coracle_mod):
     q = c0.run(0, N, nthreads=1)
     assert np.abs(q["SOC"] - c["SOC"]).max() > 1e-6                 # the estimate is perturbed ...
     assert np.abs(q["SOC"] - c["SOC"]).max() < 5e-3                 # ... and the filter keeps tracking
+
+
+def test_plant_model_mismatch_scenario_c_vs_literal(bank, coracle_mod):
+    """An aged cell under a nominal filter (the reference: OB_step given another ROM struct than initKF / initMPC): the plant's
+    capacity is Q*0.9*(1 +- 5 %) per cell and its collector resistance 1.5*Rc; the filter and the MPC keep the bank's values.
+    C restatement vs literal restatement; and the scenario does what it says (the plant's SOC runs ahead of the estimate)."""
+    from oracle import literal as L
+    lib = coracle_mod.lib()
+    rng = np.random.default_rng(6)
+    for _ in range(300):
+        s, c = (int(x) for x in rng.integers(0, 2 ** 62, 2))
+        assert lib.mko_cell_uniform(s, c) == L.cell_uniform(s, c)
+    u = np.array([lib.mko_cell_uniform(9, c) for c in range(20000)])
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+    N = 1500
+    kw = dict(plant_q_scale=0.9, plant_q_spread=0.05, plant_rc_scale=1.5, noise_seed=31)
+    o = L.run_mpc(bank, SOC0=10.0, N=N, cell_id=7, **kw)
+    co = coracle_mod.COracle(bank, first_cell=7, **kw)
+    co.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
+    c = co.run(0, N, nthreads=1)
+    assert np.array_equal(o["nexec"][:N], c["nexec"][:, 0]) and np.array_equal(o["active"][:N], c["active"][:, 0])
+    for k in ("u", "V", "SOC", "phise"):
+        assert rel_err(c[k][:, 0], o[k][:N], SCALE[k]) <= TOL, k
+    c0 = coracle_mod.COracle(bank)
+    c0.init([10.0], 25.0, np.diag([1.0] * 5 + [2e6]), coracle_mod.default_limits(bank))
+    q = c0.run(0, N, nthreads=1)
+    assert np.abs(q["V"] - c["V"]).max() > 1e-3                     # another plant
+    th0, th100 = bank.params[5], bank.params[6]
+    soc_plant = (co.state[0, 0] - th0) / (th100 - th0)              # S_SOCN -> the plant's true cell SOC
+    assert soc_plant > c["SOC"][-1, 0] + 0.02                       # a smaller cell fills faster than the nominal model believes
