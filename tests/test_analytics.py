@@ -111,3 +111,27 @@ def test_cell_summaries_match_logs(bank):
     assert act["u_min"][50:300].mean() > 0.9                    # constant-current phase: the lower current bound is active
     env = A.trajectory_envelopes(lg)
     assert np.all(env["SOC"][2, 1:] >= env["SOC"][2, :-1] - 1e-6)  # median SOC never decreases during a charge
+
+
+def test_plot4figures_svg(tmp_path):
+    """mek/plots.py: the four panels of plot4Figures.m (current, voltage, SOC, overpotential with their limit lines) as an SVG
+    file, for one cell and for a population (median + 5-95 % band), from logs shaped like CellBatch.logs()."""
+    import xml.etree.ElementTree as ET
+    from mek import plots
+    rng = np.random.default_rng(3)
+    N, B = 400, 24
+    t = np.arange(N)[:, None]
+    logs = dict(u=-60.0 + 40.0 * (t / N) + rng.normal(0, 1, (N, B)), V=3.5 + 0.6 * (t / N) + rng.normal(0, 0.005, (N, B)),
+                SOC=0.1 + 0.85 * (t / N) * np.ones((1, B)), phise=0.2 - 0.12 * (t / N) + rng.normal(0, 0.002, (N, B)))
+    logs["V"][300:, 5] = np.nan                                      # a lost cell (Q19) must not break the figure
+    lim = dict(u_max=2.0, u_min=-59.7, v_max=4.1, v_min=3.4, phise_min=0.08)
+    for cell, f in ((None, "pop.svg"), (3, "cell.svg")):
+        p = str(tmp_path / f)
+        svg = plots.plot4figures_svg(logs, p, limits=lim, ref=95.0, cell=cell)
+        root = ET.fromstring(open(p).read())
+        assert root.tag.endswith("svg") and svg.startswith("<svg")
+        ns = "{http://www.w3.org/2000/svg}"
+        panels = [g.get("id") for g in root.iter(ns + "g")]
+        assert panels == ["panel-u", "panel-V", "panel-SOC", "panel-phise"]
+        assert len([l for l in root.iter(ns + "line") if l.get("class") == "limit"]) == 2 + 2 + 1 + 2   # u, V limits, target, phi_min + zero line
+        assert (len(list(root.iter(ns + "polygon"))) == 4) == (cell is None)
