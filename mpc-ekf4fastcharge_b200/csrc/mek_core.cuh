@@ -451,11 +451,15 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   if (Zup != Zlo) aZ = (cellSOC - Zlo) / (Zup - Zlo);
   if (Tup != Tlo) aT = (T - Tlo) / (Tup - Tlo);
   // four corner outputs (:272-275) blended as (1-aT)*((1-aZ)*y1 + aZ*y2) + aT*((1-aZ)*y3 + aZ*y4) (:285):
-  // one rolled pass per temperature set-point computes the inner SOC blend of its two corners
-  double tlo[9], tcur[9];
+  // one rolled pass per temperature set-point computes the inner SOC blend of its two corners and adds its share to yk:
+  // first (1-aT)*lower, then + aT*upper (the two roundings of the reference's expression); a row whose weight is exactly
+  // zero is left out and the other one taken as it is
+  double yk[9];
+  const bool whole = (aT == 0.0) || (aT == 1.0);
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
-    if (h ? (aT == 0.0) : (aT == 1.0)) continue;                     // that row's blend weight is exactly zero (see below)
+    if (h ? (aT == 0.0) : (aT == 1.0)) continue;                     // that row's blend weight is exactly zero
+    const double wgt = h ? aT : (1.0 - aT);
     const int iT = h ? iTup : iTlo;
     const int ma = iT * d.nZ + iZlo, mb = iT * d.nZ + iZup;
     const double* ra = bk.mdl + ma * d.mstride + HB_ROWS;
@@ -477,14 +481,11 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
       for (int j = 1; j < 6; ++j) { ya = fma(ca[j], xa[j], ya); yb = fma(cb[j], xb[j], yb); }
       ya = fma(ca[6], Iapp, ya);
       yb = fma(cb[6], Iapp, yb);
-      if (h == 0) tlo[r] = (1.0 - aZ) * ya + aZ * yb; else tcur[r] = (1.0 - aZ) * ya + aZ * yb;
+      const double inner = (1.0 - aZ) * ya + aZ * yb;
+      yk[r] = whole ? inner : (h == 0 ? wgt * inner : yk[r] + wgt * inner);   // :285
     }
   }
   if (ADVANCE) stream_models<true, false>(d, bk, c, Iapp, 0.0);         // :278 advance ALL models
-  double yk[9];
-#pragma unroll
-  for (int r = 0; r < 9; ++r)                                        // :285; a zero weight leaves the other row as it is
-    yk[r] = (aT == 0.0) ? tlo[r] : ((aT == 1.0) ? tcur[r] : (1.0 - aT) * tlo[r] + aT * tcur[r]);
   double tss0 = yk[HR_TSS0] + c.f(S_SOC0N), tss3 = yk[HR_TSS3] + c.f(S_SOC0P);   // :304-305 (Q6)
   tss0 = fmin(fmax(tss0, 1e-6), 1.0 - 1e-6);                         // :309-310
   tss3 = fmin(fmax(tss3, 1e-6), 1.0 - 1e-6);

@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
         const long long o = (long long)k * P.nlog + id;
         P.log_u[o] = lg.u; P.log_V[o] = lg.V; P.log_soc[o] = lg.soc; P.log_phise[o] = lg.phise;
         P.log_iT[o] = (unsigned char)lg.iT; P.log_iZ[o] = (unsigned char)lg.iZ; P.log_nexec[o] = (unsigned short)lg.nexec;
-        for (int w = 0; w < P.log_words; ++w) P.log_active[o * P.log_words + w] = lg.active[w];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)                                  // static indices: lg stays in registers
+          if (w < P.log_words) P.log_active[o * P.log_words + w] = lg.active[w];
       }
     }
     if (KB > 0 && active && k1 > k0) defer_flush(d, bk, c, df);      // the state block leaves the kernel fully advanced
