@@ -92,7 +92,8 @@ struct Scratch {
 };
 // SC_X: what getVariables leaves for EKFmatsHandler (negEta0, posEta3, Uocp_neg(thetass0), Uocp_pos(thetass3), SOC-clamp flag)
 // SC_Z comes last so that a launch only has to provide SC_Z + R slots (sc_slots) for the bank at hand
-enum : int { SC_GAMMA = 0, SC_M = 4, SC_IT = 8, SC_IZ = 12, SC_X = 16, SC_Z = SC_X + 5, SC_TOTAL = SC_Z + HR_MAX };
+// SC_S1: SigmaX of neighbour #1 before the measurement update (every gain uses it, Q1), parked here instead of in 30 registers
+enum : int { SC_GAMMA = 0, SC_M = 4, SC_S1 = 8, SC_X = SC_S1 + NSYM, SC_Z = SC_X + 5, SC_TOTAL = SC_Z + HR_MAX };
 __host__ __device__ constexpr int sc_slots(int R) { return SC_Z + R; }
 
 __device__ __forceinline__ int sym_idx(int i, int j) {
@@ -139,7 +140,7 @@ __device__ __forceinline__ int two_nearest_z(const Dims& d, double v, const doub
 }
 
 // getXind (iterEKF.m:219-255): ordering by value with swap, alphas not clamped (Q14).
-// Writes gamma[4], model column m[4] = iT*nZ+iZ, iT[4], iZ[4] into the scratch column.
+// Writes gamma[4] and the model column m[4] = iT*nZ+iZ of the four neighbours into the scratch column.
 static __device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc, int tt_cached) {
   const int zz = two_nearest_z(d, SOC, bk.Zpts), z1 = zz & 0xffff, z2 = zz >> 16;
   int iZup = z1, iZlo = z1;
@@ -162,8 +163,6 @@ static __device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, 
   sc[SC_GAMMA + 1] = (1.0 - aT) * aZ;
   sc[SC_GAMMA + 2] = aT * (1.0 - aZ);
   sc[SC_GAMMA + 3] = aT * aZ;
-  sc[SC_IT + 0] = (double)iTlo; sc[SC_IT + 1] = (double)iTlo; sc[SC_IT + 2] = (double)iTup; sc[SC_IT + 3] = (double)iTup;
-  sc[SC_IZ + 0] = (double)iZlo; sc[SC_IZ + 1] = (double)iZup; sc[SC_IZ + 2] = (double)iZlo; sc[SC_IZ + 3] = (double)iZup;
   sc[SC_M + 0] = (double)(iTlo * d.nZ + iZlo); sc[SC_M + 1] = (double)(iTlo * d.nZ + iZup);
   sc[SC_M + 2] = (double)(iTup * d.nZ + iZlo); sc[SC_M + 3] = (double)(iTup * d.nZ + iZup);
 }
@@ -765,11 +764,13 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
   double vhat = get_variables(d, bk, p, c, ik, Tk, sc);              // :108
   // SigmaX of neighbour #1 *before* any update: every gain uses it (:117, Q1).  Loaded here so that the L2 round trip
   // overlaps the scalar block below.
-  double S1[NSYM];
   {
     const int m0 = (int)sc[SC_M + 0];
+    double S1[NSYM];
 #pragma unroll
     for (int q = 0; q < NSYM; ++q) S1[q] = ld_row(&c.sig(m0, q));
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) sc[SC_S1 + q] = S1[q];
   }
   // ---- getChatV scalars (:421-519) ----
   const double tss0 = sc[SC_Z + HR_TSS0], tss3 = sc[SC_Z + HR_TSS3];
@@ -824,6 +825,9 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
       t = t + (dUp3 * (g * mm[HR_TSS3 * HRS + j]) - dUn0 * (g * mm[HR_TSS0 * HRS + j]));      // :504
       Chat[j] = t;
     }
+    double S1[NSYM];
+#pragma unroll
+    for (int q = 0; q < NSYM; ++q) S1[q] = sc[SC_S1 + q];
 #pragma unroll
     for (int i = 0; i < N5; ++i) {
       double acc = S1[sym_idx(i, 0)] * Chat[0];
@@ -885,8 +889,8 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     }
   }
   const int mp = (int)sc[SC_M + imax];
-  o.iT = (int)sc[SC_IT + imax];
-  o.iZ = (int)sc[SC_IZ + imax];
+  o.iT = mp / d.nZ;                                                  // the model column is iT*nZ + iZ (get_xind)
+  o.iZ = mp - o.iT * d.nZ;
   const double* am = bk.mdl + mp * d.mstride;
 #pragma unroll
   for (int j = 0; j < N5; ++j) { o.xhat[j] = ld_row(&c.xhat(mp, j)); o.a[j] = am[j]; }   // :33-35

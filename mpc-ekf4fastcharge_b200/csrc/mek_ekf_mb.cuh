@@ -324,8 +324,8 @@ __device__ void ekf_step_mb(const Params& P, const BankSmem& bk, const RowLists&
     }
   }
   const int mp = mk[imax];
-  o.iT = (int)sc[SC_IT + imax];
-  o.iZ = (int)sc[SC_IZ + imax];
+  o.iT = mp / d.nZ;
+  o.iZ = mp - o.iT * d.nZ;
   for (int j = 0; j < N5; ++j) { o.xhat[j] = c.xhat(mp, j); o.a[j] = bk.mdl[mp * d.mstride + j]; }   // :33-35
   o.xhat[5] = x[5];                                                   // :33 (Q3) ekfData.xhat(end): the MB integrator state
   {

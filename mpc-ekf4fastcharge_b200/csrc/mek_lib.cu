@@ -1095,7 +1095,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
       p->cons = mask;
       p->run_threads = (cfg->threads_per_block == 384 && !full) ? 384 : 256;   // 256 threads x 255 registers: fewest spills, least DRAM traffic
       const int slots = (mask == 15) ? FastShape<5, 2, 15>::SLOTS : FastShape<5, 2, 11>::SLOTS;
-      p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
+      p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > sc_slots(bank->R) ? slots : sc_slots(bank->R)) * (size_t)p->run_threads;
       if (p->run_smem > 227 * 1024) p->cons = -1, p->run_threads = p->threads, p->run_smem = p->smem_bytes;
     }
     if (p->inst == 1 && Np == 20 && Nc == 5 && mask == 15 && !cfg->generic_path && !d.useTerm && !full) {   // config C4: long-horizon static-shape instance
@@ -1104,7 +1104,7 @@ static int pop_build(mek_pop* p, const mek_bank* bank, const mek_config* cfg, in
       // 256 threads (default): lambda in shared memory, the read-mostly columns in L2; 64 threads: every column in shared memory
       p->run_threads = cfg->threads_per_block == 64 ? 64 : 256;
       const int slots = p->run_threads == 64 ? WS::SLOTS : WS::LSLOTS;
-      p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > SC_TOTAL ? slots : SC_TOTAL) * (size_t)p->run_threads;
+      p->run_smem = p->blob_bytes + sizeof(double) * (size_t)(slots > sc_slots(bank->R) ? slots : sc_slots(bank->R)) * (size_t)p->run_threads;
       p->wide_ws_slots = p->run_threads == 64 ? 0 : WS::WSLOTS;
     }
   }
