@@ -70,16 +70,17 @@ struct BankSmem {
 constexpr int TILE = 32;
 struct Cell {
   double* base;          // &st[tile][0][lane]
-  double *bx, *xh, *sg, *lm;   // first bigX / xhat / SigmaX / lambda field of this cell
+  const Dims* dd;        // where the arrays of a cell start (field offsets: kernel parameters, i.e. constant-bank operands)
   __device__ __forceinline__ double& f(int field) const { return base[field * TILE]; }
-  __device__ __forceinline__ double& bigx(int m, int j) const { return bx[(m * 6 + j) * TILE]; }
-  __device__ __forceinline__ double& xhat(int m, int j) const { return xh[(m * N5 + j) * TILE]; }
-  __device__ __forceinline__ double& sig(int m, int q) const { return sg[(m * NSYM + q) * TILE]; }
-  __device__ __forceinline__ double& lam(int i) const { return lm[i * TILE]; }
+  // one pointer per cell instead of five: the others were spilled and re-read from the stack all over the instant
+  __device__ __forceinline__ double& bigx(int m, int j) const { return base[(dd->f_bigx + m * 6 + j) * TILE]; }
+  __device__ __forceinline__ double& xhat(int m, int j) const { return base[(dd->f_xhat + m * N5 + j) * TILE]; }
+  __device__ __forceinline__ double& sig(int m, int q) const { return base[(dd->f_sig + m * NSYM + q) * TILE]; }
+  __device__ __forceinline__ double& lam(int i) const { return base[(dd->f_lambda + i) * TILE]; }
 };
 __device__ __forceinline__ Cell cell_ref(double* st, const Dims& d, long long cell) {
   double* b = st + (cell >> 5) * ((long long)d.nfields * TILE) + (cell & 31);
-  return Cell{b, b + d.f_bigx * TILE, b + d.f_xhat * TILE, b + d.f_sig * TILE, b + d.f_lambda * TILE};
+  return Cell{b, &d};
 }
 
 // Per-thread scratch column in shared memory ([slot][thread]: conflict-free).  Small arrays that are
