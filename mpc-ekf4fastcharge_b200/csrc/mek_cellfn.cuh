@@ -66,6 +66,12 @@ MEK_HDN double uocp_p(const double* p, double th) {
   MEK_IF_LUT(p, lut_eval(p, LUT_UP, th));
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
+  if (nc == 7) {                                        // the canonical bank's degree: the same Horner steps with static coefficient
+    double acc = p[P_UP_COEF + 6];                      // indices (constant-bank operands, no indexed loads, no loop)
+#pragma unroll
+    for (int i = 5; i >= 0; --i) acc = fma(acc, x, p[P_UP_COEF + i]);
+    return acc;
+  }
   double acc = p[P_UP_COEF + nc - 1];
   for (int i = nc - 2; i >= 0; --i) acc = fma(acc, x, p[P_UP_COEF + i]);
   return acc;
@@ -74,6 +80,12 @@ MEK_HDN double duocp_p(const double* p, double th) {
   MEK_IF_LUT(p, lut_eval(p, LUT_DUP, th));
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
+  if (nc == 7) {                                        // as in uocp_p
+    double acc = 6.0 * p[P_UP_COEF + 6];
+#pragma unroll
+    for (int i = 5; i >= 1; --i) acc = fma(acc, x, (double)i * p[P_UP_COEF + i]);
+    return acc / p[P_UP + 1];
+  }
   double acc = (double)(nc - 1) * p[P_UP_COEF + nc - 1];
   for (int i = nc - 2; i >= 1; --i) acc = fma(acc, x, (double)i * p[P_UP_COEF + i]);
   return acc / p[P_UP + 1];
