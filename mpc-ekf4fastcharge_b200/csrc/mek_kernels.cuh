@@ -179,15 +179,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k_run_population(const __grid_c
       StepLog lg;
       cell_step<NPM, NCM, CONS, MEK_STREAM_BATCH>(P, bk, c, lg, smt, sms, tt, KB > 0 ? &df : nullptr, id, k, qs, rcs);
       // per-cell summary, kept in the state header (not in registers: they are the scarce resource of this kernel)
-      if (lg.nexec > 0) {
-        c.f(S_SUM_NEXEC) += (double)lg.nexec;
-        c.f(S_N_QP) += 1.0;
-        if (lg.nexec >= d.maxHild) c.f(S_N_CAP) += 1.0;
+      // L2-only accesses: ten header rows per warp that nothing else reads stay out of L1 (which holds the hot header fields)
+      {
+        double* h = c.base;
+        if (lg.nexec > 0) {
+          __stcg(h + S_SUM_NEXEC * TILE, __ldcg(h + S_SUM_NEXEC * TILE) + (double)lg.nexec);
+          __stcg(h + S_N_QP * TILE, __ldcg(h + S_N_QP * TILE) + 1.0);
+          if (lg.nexec >= d.maxHild) __stcg(h + S_N_CAP * TILE, __ldcg(h + S_N_CAP * TILE) + 1.0);
+        }
+        __stcg(h + S_MIN_PHISE * TILE, fmin(__ldcg(h + S_MIN_PHISE * TILE), lg.phise));
+        __stcg(h + S_MAX_V * TILE, fmax(__ldcg(h + S_MAX_V * TILE), lg.V));
+        if (__ldcg(h + S_T_REACH * TILE) < 0.0 && lg.soc >= c.f(S_ZMAX) - 1e-3) __stcg(h + S_T_REACH * TILE, (double)k);
+        __stcg(h + S_LAST_SOC * TILE, lg.soc); __stcg(h + S_LAST_V * TILE, lg.V); __stcg(h + S_LAST_PHISE * TILE, lg.phise);
       }
-      c.f(S_MIN_PHISE) = fmin(c.f(S_MIN_PHISE), lg.phise);
-      c.f(S_MAX_V) = fmax(c.f(S_MAX_V), lg.V);
-      if (c.f(S_T_REACH) < 0.0 && lg.soc >= c.f(S_ZMAX) - 1e-3) c.f(S_T_REACH) = (double)k;
-      c.f(S_LAST_SOC) = lg.soc; c.f(S_LAST_V) = lg.V; c.f(S_LAST_PHISE) = lg.phise;
       if (id < P.nlog && k < P.log_steps) {
         const long long o = (long long)k * P.nlog + id;
         P.log_u[o] = lg.u; P.log_V[o] = lg.V; P.log_soc[o] = lg.soc; P.log_phise[o] = lg.phise;
