@@ -62,7 +62,8 @@ MEK_HDN double duocp_n(const double* p, double th) {
   return (-2.0 * c[1]) / ((t * t) * t) - (c[3] / c[5]) / (q * sqrt(q));
 }
 // function.pos.Uocp / dUocp: Horner polynomial in x = (th - centre)/width
-MEK_HDN double uocp_p(const double* p, double th) {
+// (inlined: with the static-degree Horner form the body is shorter than a call)
+MEK_HD double uocp_p(const double* p, double th) {
   MEK_IF_LUT(p, lut_eval(p, LUT_UP, th));
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
@@ -76,7 +77,7 @@ MEK_HDN double uocp_p(const double* p, double th) {
   for (int i = nc - 2; i >= 0; --i) acc = fma(acc, x, p[P_UP_COEF + i]);
   return acc;
 }
-MEK_HDN double duocp_p(const double* p, double th) {
+MEK_HD double duocp_p(const double* p, double th) {
   MEK_IF_LUT(p, lut_eval(p, LUT_DUP, th));
   const double x = (th - p[P_UP]) / p[P_UP + 1];
   const int nc = (int)p[P_UP + 2];
