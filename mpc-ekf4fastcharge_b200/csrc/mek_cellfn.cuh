@@ -46,14 +46,15 @@ MEK_HD double soc_e(const double* p, int base, double z) {
   return p[base + E_THETA0] + z * (p[base + E_THETA100] - p[base + E_THETA0]);
 }
 // function.neg.Uocp / dUocp
-MEK_HDN double uocp_n(const double* p, double th) {
+// (inlined, like the positive-electrode pair below: the call sequence -- registers saved around it -- cost more than the body)
+MEK_HD double uocp_n(const double* p, double th) {
   MEK_IF_LUT(p, lut_eval(p, LUT_UN, th));
   const double* c = p + P_UN;
   const double x = (th - c[4]) / c[5];
   const double t = th + c[2];
   return (c[0] + c[1] / (t * t)) + c[3] * (1.0 - x / sqrt(1.0 + x * x));
 }
-MEK_HDN double duocp_n(const double* p, double th) {
+MEK_HD double duocp_n(const double* p, double th) {
   MEK_IF_LUT(p, lut_eval(p, LUT_DUN, th));
   const double* c = p + P_UN;
   const double x = (th - c[4]) / c[5];

@@ -142,7 +142,15 @@ __device__ __forceinline__ int two_nearest_z(const Dims& d, double v, const doub
 
 // getXind (iterEKF.m:219-255): ordering by value with swap, alphas not clamped (Q14).
 // Writes gamma[4] and the model column m[4] = iT*nZ+iZ of the four neighbours into the scratch column.
-static __device__ __noinline__ void get_xind(const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc, int tt_cached) {
+#ifndef MEK_XIND_INLINE
+#define MEK_XIND_INLINE 1   // inlined: the call sequences (registers saved around them) cost more than the code they saved
+#endif
+#if MEK_XIND_INLINE
+static __device__ __forceinline__ void get_xind(
+#else
+static __device__ __noinline__ void get_xind(
+#endif
+    const Dims& d, const BankSmem& bk, double Tk, double SOC, Scratch sc, int tt_cached) {
   const int zz = two_nearest_z(d, SOC, bk.Zpts), z1 = zz & 0xffff, z2 = zz >> 16;
   int iZup = z1, iZlo = z1;
   double Zup = bk.Zpts[z1], Zlo = bk.Zpts[z1];
@@ -557,7 +565,15 @@ __device__ __forceinline__ void gv_rows_n(const Dims& d, const BankSmem& bk, con
 // getVariables (iterEKF.m:259-417) restricted to the rows that feed Vcell, the warnings and
 // EKFmatsHandler.  Reads the neighbour set from the scratch column (get_xind), leaves the corrected
 // outputs in sc[SC_Z + HR_*] and returns Vcell.  Warnings go straight to the cell's counters.
-static __device__ __noinline__ double get_variables(const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double ik,
+#ifndef MEK_GV_INLINE
+#define MEK_GV_INLINE 1
+#endif
+#if MEK_GV_INLINE
+static __device__ __forceinline__ double get_variables(
+#else
+static __device__ __noinline__ double get_variables(
+#endif
+    const Dims& d, const BankSmem& bk, const double* __restrict__ p, const Cell& c, double ik,
                                              double T, Scratch sc) {
 #ifdef __CUDA_ARCH__
   __builtin_assume(__isShared(sc.p));              // address-space hint: LDS/STS for the scratch column, not generic LD/ST
