@@ -1628,12 +1628,13 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
             for (int j = 1; j < NC; ++j) hl = fma(Mi[j], v[j], hl);
             // An inactive row that stays inactive: lambda_i = 0 and t = K_i + H(i,:)*lambda >= 0 give w = -t/H_ii <= 0 (H_ii > 0),
             // max(0,w) = 0, lambda_i and v exactly as they were (v + P*0 = v for finite P; v is never -0).  Most rows of most
-            // sweeps are like that; when they are for every cell of the warp the rest of the row is skipped.  The test reads
+            // sweeps are like that; the cell skips the rest of the row (a plain per-cell branch: a warp vote on the predicate cost
+            // three more instructions per row than the divergence it avoided).  The test reads
             // H(i,:)*lambda >= -K_i -- the sign of the rounded sum t is the sign of the exact one -- which takes the addition off
             // the dependent chain of an idle row (if K_i and H(i,:)*lambda are infinities of opposite sign, t is NaN where this
             // test says idle: the update of such a row with lambda_i = 0 is max(0, NaN) = 0, a no-op as well).
             const bool idle = skip_ok && (li == 0.0) && (hl >= nKi);
-            if (!__all_sync(__activemask(), idle)) {
+            if (!idle) {
               const double t = hl - nKi;                             // = K_i + H(i,:)*lambda, bit for bit
               const double w = fma(-t, rHi, li);
               const double nl = pos_or_zero(w);                      // max(0,w); max(0,NaN) = 0
@@ -1964,7 +1965,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
     // The 80 rows are walked in blocks of Nc rows; every block is a Toeplitz window [h(q) ... h(q-Nc+1)] over one table
     // (the current rows too: prefix rows are the table [s s s ...], identity rows [s 0 0 ...]).  A block is first tested
     // as a whole from the present v -- Nc independent short chains, their loads issued together one block ahead --
-    // and left alone when every row of it is idle in every cell of the warp: lambda_i = 0 and K_i + H(i,:)lambda >= 0
+    // and left alone by a cell in which every row of it is idle (a per-cell branch, no warp vote): lambda_i = 0 and K_i + H(i,:)lambda >= 0
     // give w <= 0 (or NaN on the all-zero row: 0*Inf), max(0,w) = 0, lambda and v exactly as they were, so the
     // sequential pass of hildreth.m:34-37 would have seen that same v in every row of the block and changed nothing.
     // Otherwise the block is walked row by row exactly as written there.
@@ -2021,7 +2022,7 @@ __device__ __forceinline__ void mpc_step_wide(const Dims& d, const double* __res
           for (int j = 1; j < NC; ++j) hl = fma(win[NC - 1 + r - j], v[j], hl);
           idle = idle && (li[r] == 0.0) && (hl >= Kc[r]);             // Kc = -K: K + H(i,:)lambda >= 0 without the addition on the chain
         }
-        if (__all_sync(__activemask(), idle)) continue;
+        if (idle) continue;                                          // per cell: see the lean sweep of mpc_step_fast
         double rH[BL];
 #pragma unroll
         for (int r = 0; r < BL; ++r) rH[r] = wc[(WS::W_H + i0 + r) * wst];
