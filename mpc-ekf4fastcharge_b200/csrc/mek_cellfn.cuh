@@ -92,6 +92,58 @@ MEK_HD double duocp_p(const double* p, double th) {
   for (int i = nc - 2; i >= 1; --i) acc = fma(acc, x, (double)i * p[P_UP_COEF + i]);
   return acc / p[P_UP + 1];
 }
+// ---- the two electrodes' OCP (and dOCP) side by side ----
+// Same operations in the same order as uocp_n / uocp_p (duocp_n / duocp_p); on the device the quotients and the root are the
+// speculative fast sequences of mek_math.cuh, so that the negative electrode's two chains and the positive electrode's Horner
+// chain share one basic block, and anything they do not accept (or a tabulated bank, or a non-canonical polynomial degree)
+// takes the standard evaluation.
+static __device__ __noinline__ double2 ocp2_std(const double* p, double thn, double thp) { return make_double2(uocp_n(p, thn), uocp_p(p, thp)); }
+static __device__ __noinline__ double2 docp2_std(const double* p, double thn, double thp) { return make_double2(duocp_n(p, thn), duocp_p(p, thp)); }
+#ifdef MEK_SPEC_ON
+__device__ __forceinline__ bool ocp_spec_ok(const double* p) {
+#ifndef MEK_LUT_OFF
+  if (p[P_LUT_N] != 0.0) return false;
+#endif
+  return (int)p[P_UP + 2] == 7;
+}
+__device__ __forceinline__ double2 ocp2(const double* p, double thn, double thp) {
+  if (!ocp_spec_ok(p)) return ocp2_std(p, thn, thp);
+  bool ok = true;
+  const double* c = p + P_UN;
+  const double x = div_spec(thn - c[4], c[5], ok);
+  const double t = thn + c[2];
+  const double a = div_spec(c[1], t * t, ok);
+  const double b = div_spec(x, sqrt_spec(1.0 + x * x, ok), ok);
+  const double un = (c[0] + a) + c[3] * (1.0 - b);
+  const double xp = div_spec(thp - p[P_UP], p[P_UP + 1], ok);
+  double acc = p[P_UP_COEF + 6];
+#pragma unroll
+  for (int i = 5; i >= 0; --i) acc = fma(acc, xp, p[P_UP_COEF + i]);
+  if (!ok) return ocp2_std(p, thn, thp);
+  return make_double2(un, acc);
+}
+__device__ __forceinline__ double2 docp2(const double* p, double thn, double thp) {
+  if (!ocp_spec_ok(p)) return docp2_std(p, thn, thp);
+  bool ok = true;
+  const double* c = p + P_UN;
+  const double x = div_spec(thn - c[4], c[5], ok);
+  const double q = 1.0 + x * x;
+  const double t = thn + c[2];
+  const double a = div_spec(-2.0 * c[1], (t * t) * t, ok);
+  const double b = div_spec(div_spec(c[3], c[5], ok), q * sqrt_spec(q, ok), ok);
+  const double xp = div_spec(thp - p[P_UP], p[P_UP + 1], ok);
+  double acc = 6.0 * p[P_UP_COEF + 6];
+#pragma unroll
+  for (int i = 5; i >= 1; --i) acc = fma(acc, xp, (double)i * p[P_UP_COEF + i]);
+  const double dp = div_spec(acc, p[P_UP + 1], ok);
+  if (!ok) return docp2_std(p, thn, thp);
+  return make_double2(a - b, dp);
+}
+#else
+MEK_HD double2 ocp2(const double* p, double thn, double thp) { return make_double2(uocp_n(p, thn), uocp_p(p, thp)); }
+MEK_HD double2 docp2(const double* p, double thn, double thp) { return make_double2(duocp_n(p, thn), duocp_p(p, thp)); }
+#endif
+
 // function.{neg,pos}.k0(theta,T), .Rf(theta,T): Arrhenius factor hoisted (T is constant per cell)
 MEK_HD double k0_e(const double* p, int base, double th, double arr) {
   MEK_IF_LUT(p, lut_eval(p, base == P_NEG ? LUT_K0N : LUT_K0P, th) * arr);

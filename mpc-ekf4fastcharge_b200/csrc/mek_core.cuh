@@ -438,7 +438,8 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   double SOCn = c.f(S_SOCN), SOCp = c.f(S_SOCP);
   const double negSOC = SOCn, posSOC = SOCp;                         // :226-227 (Q16)
   const double cellSOC = (SOCn - th0n) / (th100n - th0n);            // :228
-  const double dUn = duocp_n(p, SOCn), dUp = duocp_p(p, SOCp);       // :231-232
+  const double2 dU = docp2(p, SOCn, SOCp);                           // :231-232
+  const double dUn = dU.x, dUp = dU.y;
   const double dQn = fabs(th100n - th0n), dQp = fabs(th100p - th0p);
   const double res0n = -dQn / (3600.0 * Q - (c.f(S_CDLN) * dQn) * dUn);  // :235
   const double res0p = dQp / (3600.0 * Q - (c.f(S_CDLP) * dQp) * dUp);   // :236
@@ -502,9 +503,11 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   const double i0n = k0n * sqrt((the0 * (1.0 - tss0)) * tss0);       // :331-332
   const double i0p = k0p * sqrt((the3 * (1.0 - tss3)) * tss3);
   const double pref = ((2.0 * p[P_R]) * T) / p[P_F];
-  const double negEta0 = pref * asinh_d(yk[HR_IF0] / (2.0 * i0n));   // :333-334
-  const double posEta3 = pref * asinh_d(yk[HR_IF3] / (2.0 * i0p));
-  const double Un0 = uocp_n(p, tss0), Up3 = uocp_p(p, tss3);         // :337-340
+  const double2 ash = asinh2_q(yk[HR_IF0], 2.0 * i0n, yk[HR_IF3], 2.0 * i0p);
+  const double negEta0 = pref * ash.x;                               // :333-334
+  const double posEta3 = pref * ash.y;
+  const double2 U03 = ocp2(p, tss0, tss3);                           // :337-340
+  const double Un0 = U03.x, Up3 = U03.y;
   const double Rfn = rf_e(p, P_NEG, negSOC, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, posSOC, c.f(S_ARRRFP));
   double V = ((((posEta3 - negEta0) + yk[HR_PHIE]) + Up3) - Un0) + (Rfp * yk[HR_IFDL3] - Rfn * yk[HR_IFDL0]);   // :341-342
   V = V - (p[P_RC] * rcs) * Iapp;                                    // :344
@@ -647,9 +650,11 @@ static __device__ __noinline__ double get_variables(
   const double i0n = k0n * sqrt((the0 * (1.0 - tss0)) * tss0);       // :395-398
   const double i0p = k0p * sqrt((the3 * (1.0 - tss3)) * tss3);
   const double pref = ((2.0 * p[P_R]) * T) / p[P_F];
-  const double negEta0 = pref * asinh_d(If0 / (2.0 * i0n));          // :400-401
-  const double posEta3 = pref * asinh_d(If3 / (2.0 * i0p));
-  const double Un0 = uocp_n(p, tss0), Up3 = uocp_p(p, tss3);         // :404-407
+  const double2 ash = asinh2_q(If0, 2.0 * i0n, If3, 2.0 * i0p);
+  const double negEta0 = pref * ash.x;                               // :400-401
+  const double posEta3 = pref * ash.y;
+  const double2 U03 = ocp2(p, tss0, tss3);                           // :404-407
+  const double Un0 = U03.x, Up3 = U03.y;
   const double Rfn = rf_e(p, P_NEG, SOCn, c.f(S_ARRRFN)), Rfp = rf_e(p, P_POS, SOCp, c.f(S_ARRRFP));
   if (nwarn) c.f(S_WARN) += (double)nwarn;                           // shortWarn -> warnCount (:749)
   if (status) c.f(S_STATUS) = (double)((unsigned)c.f(S_STATUS) | status);
@@ -800,7 +805,7 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     const double i0n = k0n * sqrt((sc[SC_Z + HR_THE0] * (1.0 - tss0)) * tss0);
     const double i0p = k0p * sqrt((sc[SC_Z + HR_THE3] * (1.0 - tss3)) * tss3);
     Rctn = (p[P_R] * Tk) / (p[P_F] * i0n); Rctp = (p[P_R] * Tk) / (p[P_F] * i0p);   // :467-468
-    dUn0 = duocp_n(p, tss0); dUp3 = duocp_p(p, tss3);                // :495-496
+    { const double2 dU = docp2(p, tss0, tss3); dUn0 = dU.x; dUp3 = dU.y; }   // :495-496
     const double dsn = soc_e(p, P_NEG, 1.0) - soc_e(p, P_NEG, 0.0), dsp = soc_e(p, P_POS, 1.0) - soc_e(p, P_POS, 0.0);
     const double res0n = (((-dUn0) * d.Ts) * dsn) / (3600.0 * p[P_Q]);   // :497-500
     const double res0p = (((-dUp3) * d.Ts) * dsp) / (3600.0 * p[P_Q]);
@@ -931,10 +936,11 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
       const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
       const double i0n = k0n * sqrt((sc[SC_Z + HR_THE0] * (1.0 - ztss0)) * ztss0);   // :63-66
       const double i0p = k0p * sqrt((sc[SC_Z + HR_THE3] * (1.0 - ztss3)) * ztss3);
-      Upos = uocp_p(p, ztss3); Uneg = uocp_n(p, ztss0);              // :84-85
+      { const double2 U = ocp2(p, ztss0, ztss3); Uneg = U.x; Upos = U.y; }   // :84-85
       const double pref = ((2.0 * p[P_R]) * TK) / p[P_F];
-      negEta0 = pref * asinh_d(sc[SC_Z + HR_IF0] / (2.0 * i0n));     // :88-89
-      posEta3 = pref * asinh_d(sc[SC_Z + HR_IF3] / (2.0 * i0p));
+      const double2 ash = asinh2_q(sc[SC_Z + HR_IF0], 2.0 * i0n, sc[SC_Z + HR_IF3], 2.0 * i0p);
+      negEta0 = pref * ash.x;                                        // :88-89
+      posEta3 = pref * ash.y;
     }
     o.bv = ((Upos - Uneg) + (posEta3 - negEta0)) + 0.0;              // :92
     o.bphi = uocp_n(p, sn);                                          // :96 (Q21)
@@ -1560,6 +1566,9 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
     unsigned zmask = 0u;
     double pchk = 0.0;                                               // stays (+-)0 while every entry of E\M' is finite: Inf*0 = NaN sticks
     bool hpos = true;                                                // H_ii > 0 on every row that is not all-zero
+#ifdef MEK_SPEC_ON
+    bool rcp_ok = true;
+#endif
     static_for<0, nC>([&](auto ic) {
       constexpr int i = decltype(ic)::value;
       double Mi[NC], P[NC];
@@ -1577,7 +1586,15 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
       for (int j = 1; j < NC; ++j) { hd = fma(Mi[j], P[j], hd); k = fma(Mi[j], x[j], k); }
       double gam;
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(gam) : "r"(kra + (unsigned)i * krs) : "memory");
+#ifdef MEK_SPEC_ON
+      // 1/H(i,i) by the speculative quotient (mek_math.cuh): the 23 reciprocals are independent and share one basic block
+      // instead of one slow-path branch each; the structurally all-zero row keeps the standard operator (1/0 = +Inf)
+      double rh;
+      if constexpr (FS::UZ && i == FS::O_Z) rh = rcp_d(hd); else rh = div_spec(1.0, hd, rcp_ok);
+      sts_pair(kra + (unsigned)i * krs, -(k + gam), rh);             // -K(i), 1/H(i,i): the idle test below compares against -K
+#else
       sts_pair(kra + (unsigned)i * krs, -(k + gam), rcp_d(hd));      // -K(i), 1/H(i,i): the idle test below compares against -K
+#endif
       if (hd == 0.0) {
         zmask |= 1u << i;
       } else {
@@ -1586,6 +1603,24 @@ __device__ __forceinline__ void mpc_step_fast(const Dims& d, const double* __res
         for (int j = 0; j < NC; ++j) v[j] = fma(P[j], lam[i], v[j]);
       }
     });
+#ifdef MEK_SPEC_ON
+    if (!rcp_ok) {                                                   // some H(i,i) outside the fast sequence's range: the standard reciprocals
+      static_for<0, nC>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        double Mi[NC];
+        mrow(ic, Mi);
+        double hd = 0.0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          double acc = Ei[j][0] * Mi[0];
+#pragma unroll
+          for (int l = 1; l < NC; ++l) acc = fma(Ei[j][l], Mi[l], acc);
+          hd = (j == 0) ? Mi[0] * acc : fma(Mi[j], acc, hd);
+        }
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(kra + (unsigned)i * krs + 8u), "d"(rcp_d(hd)) : "memory");
+      });
+    }
+#endif
     // rows whose lambda is non-finite (only all-zero rows can get there): while any is set every row product is NaN
     unsigned pmask = 0u;
     constexpr unsigned ZEXP = FS::UZ ? (1u << FS::O_Z) : 0u;         // the one structurally all-zero row: first z_max row (Q7)
