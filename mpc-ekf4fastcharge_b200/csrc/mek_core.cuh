@@ -441,8 +441,8 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   const double2 dU = docp2(p, SOCn, SOCp);                           // :231-232
   const double dUn = dU.x, dUp = dU.y;
   const double dQn = fabs(th100n - th0n), dQp = fabs(th100p - th0p);
-  const double res0n = -dQn / (3600.0 * Q - (c.f(S_CDLN) * dQn) * dUn);  // :235
-  const double res0p = dQp / (3600.0 * Q - (c.f(S_CDLP) * dQp) * dUp);   // :236
+  const double2 res0 = div2(-dQn, 3600.0 * Q - (c.f(S_CDLN) * dQn) * dUn, dQp, 3600.0 * Q - (c.f(S_CDLP) * dQp) * dUp);   // :235-236
+  const double res0n = res0.x, res0p = res0.y;
   SOCn = SOCn + (res0n * Iapp) * d.Ts;                               // :239-240
   SOCp = SOCp + (res0p * Iapp) * d.Ts;
   int nw = 0;
@@ -500,8 +500,8 @@ __device__ __forceinline__ double plant_step(const Dims& d, const BankSmem& bk, 
   tss3 = fmin(fmax(tss3, 1e-6), 1.0 - 1e-6);
   const double the0 = fmax(yk[HR_THE0] + 1.0, 1e-6), the3 = fmax(yk[HR_THE3] + 1.0, 1e-6);   // :325-326
   const double k0n = k0_e(p, P_NEG, negSOC, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, posSOC, c.f(S_ARRK0P));
-  const double i0n = k0n * sqrt((the0 * (1.0 - tss0)) * tss0);       // :331-332
-  const double i0p = k0p * sqrt((the3 * (1.0 - tss3)) * tss3);
+  const double2 ri0 = sqrt2((the0 * (1.0 - tss0)) * tss0, (the3 * (1.0 - tss3)) * tss3);       // :331-332
+  const double i0n = k0n * ri0.x, i0p = k0p * ri0.y;
   const double pref = ((2.0 * p[P_R]) * T) / p[P_F];
   const double2 ash = asinh2_q(yk[HR_IF0], 2.0 * i0n, yk[HR_IF3], 2.0 * i0p);
   const double negEta0 = pref * ash.x;                               // :333-334
@@ -647,8 +647,8 @@ static __device__ __noinline__ double get_variables(
   sc[SC_Z + HR_TSS0] = tss0; sc[SC_Z + HR_TSS3] = tss3; sc[SC_Z + HR_THE0] = the0; sc[SC_Z + HR_THE3] = the3;
   const double If0 = sc[SC_Z + HR_IF0], If3 = sc[SC_Z + HR_IF3];     // :324-325
   const double k0n = k0_e(p, P_NEG, SOCn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, SOCp, c.f(S_ARRK0P));   // :392-393
-  const double i0n = k0n * sqrt((the0 * (1.0 - tss0)) * tss0);       // :395-398
-  const double i0p = k0p * sqrt((the3 * (1.0 - tss3)) * tss3);
+  const double2 ri0 = sqrt2((the0 * (1.0 - tss0)) * tss0, (the3 * (1.0 - tss3)) * tss3);       // :395-398
+  const double i0n = k0n * ri0.x, i0p = k0p * ri0.y;
   const double pref = ((2.0 * p[P_R]) * T) / p[P_F];
   const double2 ash = asinh2_q(If0, 2.0 * i0n, If3, 2.0 * i0p);
   const double negEta0 = pref * ash.x;                               // :400-401
@@ -802,13 +802,13 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
     const double sn = soc_e(p, P_NEG, xSOC), sp = soc_e(p, P_POS, xSOC);
     Rfn = rf_e(p, P_NEG, sn, c.f(S_ARRRFN)); Rfp = rf_e(p, P_POS, sp, c.f(S_ARRRFP));
     const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
-    const double i0n = k0n * sqrt((sc[SC_Z + HR_THE0] * (1.0 - tss0)) * tss0);
-    const double i0p = k0p * sqrt((sc[SC_Z + HR_THE3] * (1.0 - tss3)) * tss3);
-    Rctn = (p[P_R] * Tk) / (p[P_F] * i0n); Rctp = (p[P_R] * Tk) / (p[P_F] * i0p);   // :467-468
+    const double2 ri0 = sqrt2((sc[SC_Z + HR_THE0] * (1.0 - tss0)) * tss0, (sc[SC_Z + HR_THE3] * (1.0 - tss3)) * tss3);
+    const double i0n = k0n * ri0.x, i0p = k0p * ri0.y;
+    { const double2 rct = div2(p[P_R] * Tk, p[P_F] * i0n, p[P_R] * Tk, p[P_F] * i0p); Rctn = rct.x; Rctp = rct.y; }   // :467-468
     { const double2 dU = docp2(p, tss0, tss3); dUn0 = dU.x; dUp3 = dU.y; }   // :495-496
     const double dsn = soc_e(p, P_NEG, 1.0) - soc_e(p, P_NEG, 0.0), dsp = soc_e(p, P_POS, 1.0) - soc_e(p, P_POS, 0.0);
-    const double res0n = (((-dUn0) * d.Ts) * dsn) / (3600.0 * p[P_Q]);   // :497-500
-    const double res0p = (((-dUp3) * d.Ts) * dsp) / (3600.0 * p[P_Q]);
+    const double2 res0 = div2(((-dUn0) * d.Ts) * dsn, 3600.0 * p[P_Q], ((-dUp3) * d.Ts) * dsp, 3600.0 * p[P_Q]);   // :497-500
+    const double res0n = res0.x, res0p = res0.y;
     C0 = res0p - res0n;                                              // :501
   }
   const double svt0 = (C0 * sx0) * C0 + d.SigmaV;                    // :123
@@ -934,8 +934,8 @@ __device__ __forceinline__ void ekf_step(const Dims& d, const BankSmem& bk, cons
       negEta0 = sc[SC_X + 0]; posEta3 = sc[SC_X + 1]; Uneg = sc[SC_X + 2]; Upos = sc[SC_X + 3];
     } else {
       const double k0n = k0_e(p, P_NEG, sn, c.f(S_ARRK0N)), k0p = k0_e(p, P_POS, sp, c.f(S_ARRK0P));
-      const double i0n = k0n * sqrt((sc[SC_Z + HR_THE0] * (1.0 - ztss0)) * ztss0);   // :63-66
-      const double i0p = k0p * sqrt((sc[SC_Z + HR_THE3] * (1.0 - ztss3)) * ztss3);
+      const double2 ri0 = sqrt2((sc[SC_Z + HR_THE0] * (1.0 - ztss0)) * ztss0, (sc[SC_Z + HR_THE3] * (1.0 - ztss3)) * ztss3);   // :63-66
+      const double i0n = k0n * ri0.x, i0p = k0p * ri0.y;
       { const double2 U = ocp2(p, ztss0, ztss3); Uneg = U.x; Upos = U.y; }   // :84-85
       const double pref = ((2.0 * p[P_R]) * TK) / p[P_F];
       const double2 ash = asinh2_q(sc[SC_Z + HR_IF0], 2.0 * i0n, sc[SC_Z + HR_IF3], 2.0 * i0p);
