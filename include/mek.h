@@ -221,6 +221,14 @@ int mek_constraints(int64_t B, int Np, int Nc, const int *constraints, int use_z
 /* measured FP64 FMA throughput of the device (2 flops per DFMA), the FP64-pipe roofline denominator */
 int mek_fp64_peak(int device, double *tflops);
 
+/* Self-test of the speculative quotient / root sequences the kernels use beside the standard operators (csrc/mek_math.cuh,
+ * DESIGN.md section 8): for n host operand pairs, q_spec[i] / s_spec[i] = what a kernel computes for x[i] / y[i] and
+ * sqrt(x[i]) (fast sequence, or the standard operator when the sequence rejects the operands), q_std / s_std = the standard
+ * operators alone, fast[i] = bit 0: the quotient took the fast sequence, bit 1: the root did.  The two must agree bit for
+ * bit on every operand (tests/test_gpu_functions.py). */
+int mek_selftest_spec(int device, int64_t n, const double *x, const double *y, double *q_spec, double *q_std, double *s_spec,
+                      double *s_std, int *fast);
+
 const char *mek_last_error(void);
 int mek_version(void);
 

@@ -1768,5 +1768,45 @@ extern "C" int mek_fp64_peak(int device, double* tflops) {
   return MEK_OK;
 }
 
+// ---- self-test of the speculative quotient / root (mek_math.cuh) against the standard operators ----
+__global__ void k_selftest_spec(long long n, const double* x, const double* y, double* qs, double* qd, double* ss, double* sd, int* fast) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = x[i], b = y[i];
+    bool okq = false, oks = false;
+    double q = a / b, s = sqrt(a);
+#ifdef MEK_SPEC_ON                                                     // device pass of a build with the speculative sequences
+    okq = true; oks = true;
+    q = mek::div_spec(a, b, okq); s = mek::sqrt_spec(a, oks);
+    if (!okq) q = a / b;
+    if (!oks) s = sqrt(a);
+#endif
+    qs[i] = q; ss[i] = s;
+    qd[i] = a / b; sd[i] = sqrt(a);
+    fast[i] = (okq ? 1 : 0) | (oks ? 2 : 0);
+  }
+}
+extern "C" int mek_selftest_spec(int device, int64_t n, const double* x, const double* y, double* q_spec, double* q_std, double* s_spec,
+                                 double* s_std, int* fast) {
+  if (n <= 0 || !x || !y || !q_spec || !q_std || !s_spec || !s_std || !fast) return fail(MEK_ERR_ARG, "bad argument to mek_selftest_spec");
+  int rc = use_device(device);
+  if (rc != MEK_OK) return rc;
+  DevBuf buf;
+  const size_t b = (size_t)n;
+  CUDA_TRY(cudaMalloc(&buf.p, 8 * 6 * b + 4 * b));
+  double* dx = reinterpret_cast<double*>(buf.p);
+  double *dy = dx + b, *dqs = dy + b, *dqd = dqs + b, *dss = dqd + b, *dsd = dss + b;
+  int* df = reinterpret_cast<int*>(dsd + b);
+  CUDA_TRY(cudaMemcpy(dx, x, 8 * b, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dy, y, 8 * b, cudaMemcpyHostToDevice));
+  k_selftest_spec<<<148 * 4, 256>>>((long long)n, dx, dy, dqs, dqd, dss, dsd, df);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(q_spec, dqs, 8 * b, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(q_std, dqd, 8 * b, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(s_spec, dss, 8 * b, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(s_std, dsd, 8 * b, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(fast, df, 4 * b, cudaMemcpyDeviceToHost));
+  return MEK_OK;
+}
+
 extern "C" const char* mek_last_error(void) { return g_err.c_str(); }
 extern "C" int mek_version(void) { return 100; }

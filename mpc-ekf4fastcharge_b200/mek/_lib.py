@@ -17,7 +17,7 @@ SYMBOLS = ["mek_bank_create", "mek_bank_load", "mek_bank_destroy", "mek_bank_dim
            "mek_pop_create", "mek_pop_destroy", "mek_pop_set_logging", "mek_pop_init", "mek_pop_reset", "mek_run",
            "mek_run_timed", "mek_sync", "mek_pop_stream", "mek_pop_launches", "mek_pop_ncon", "mek_pop_defer_block", "mek_pop_regroups", "mek_pop_state_len",
            "mek_read_logs", "mek_read_state", "mek_write_state", "mek_summary", "mek_pop_ob_step", "mek_pop_iter_ekf",
-           "mek_pop_iter_mpc", "mek_pop_iter_mpc_cost", "mek_read_cell_summaries", "mek_host_alloc", "mek_host_free", "mek_hildreth", "mek_pred_mat", "mek_constraints", "mek_fp64_peak", "mek_noise", "mek_last_error", "mek_version"]
+           "mek_pop_iter_mpc", "mek_pop_iter_mpc_cost", "mek_read_cell_summaries", "mek_host_alloc", "mek_host_free", "mek_hildreth", "mek_pred_mat", "mek_constraints", "mek_fp64_peak", "mek_selftest_spec", "mek_noise", "mek_last_error", "mek_version"]
 
 
 class MekError(RuntimeError):
@@ -96,6 +96,7 @@ def lib():
         L.mek_pred_mat.argtypes = [C.c_int64] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 2 + [C.c_int]
         L.mek_constraints.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int] + [C.c_void_p] * 6 + [C.c_double, C.c_double] + [C.c_void_p] * 3 + [C.c_int]
         L.mek_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.mek_selftest_spec.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 7
         _lib = L
     return _lib
 

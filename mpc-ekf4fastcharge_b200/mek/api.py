@@ -294,6 +294,17 @@ def constraints_batch(x_aug, mats, SOCk_1, limits, Np, Nc, constraints, r, ref=9
     return M, g, E, F, DU
 
 
+def selftest_spec(x, y, device=0):
+    """The kernels' speculative quotient / root (csrc/mek_math.cuh) beside the standard operators on the same operands:
+    returns (q_spec, q_std, s_spec, s_std, fast) for x / y and sqrt(x)."""
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+    n = x.size
+    out = [np.empty(n) for _ in range(4)]
+    fast = np.empty(n, dtype=np.int32)
+    check(_lib.lib().mek_selftest_spec(int(device), n, _p(x), _p(y), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), fast.ctypes.data_as(C.c_void_p)))
+    return out[0], out[1], out[2], out[3], fast
+
+
 def fp64_peak_tflops(device=0):
     """Measured DFMA throughput (TFLOP/s, 2 flops per FMA) -- denominator of the FP64-pipe roofline."""
     t = C.c_double(0.0)

@@ -278,3 +278,31 @@ def test_model_blend_ekf_vs_c_oracle(bank, coracle_mod):
     cb.run(0, 5)                                          # the loop runs in this mode too (tests/test_gpu_parity.py::test_model_blend_fused_loop)
     # and the method names of initKF.m:44-53
     assert api.CellBatch(api.RomBank(bank), 2, ekf_method="nonsense").cfg.ekf_method == 0
+
+
+def test_speculative_quotient_and_root_are_the_standard_operators():
+    """csrc/mek_math.cuh div_spec / sqrt_spec (the fast sequences the kernels run side by side, with a replay by the standard
+    operators when their exponent tests reject the operands) against `/` and `sqrt` on the device: bit for bit on operands over
+    the whole exponent range, and on zeros, infinities, NaNs, subnormals and negative radicands."""
+    from mek import api
+    rng = np.random.default_rng(20261019)
+    n = 1 << 20
+    def wide(m):
+        return np.ldexp(rng.uniform(1.0, 2.0, m), rng.integers(-1070, 1023, m)) * rng.choice([-1.0, 1.0], m)
+    x = np.concatenate([wide(n), rng.uniform(-5, 5, n), rng.uniform(0, 1, n)])
+    y = np.concatenate([wide(n), rng.uniform(-5, 5, n), rng.uniform(0.5, 4.2, n)])
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+                   1e-310, 3.0, 1.0 / 3.0, 2.0 ** -1022, 2.0 ** 1023, 2.0 ** -537, 2.0 ** 600])
+    xs, ys = np.meshgrid(sp, sp)
+    x = np.concatenate([x, xs.ravel()]); y = np.concatenate([y, ys.ravel()])
+    q_spec, q_std, s_spec, s_std, fast = api.selftest_spec(x, y)
+    for a, b, what in ((q_spec, q_std, "x / y"), (s_spec, s_std, "sqrt(x)")):
+        nan = np.isnan(b)
+        assert np.array_equal(np.isnan(a), nan), what
+        bad = np.flatnonzero((a.view(np.uint64) != b.view(np.uint64)) & ~nan)
+        assert bad.size == 0, (what, bad[:5], x[bad[:5]], y[bad[:5]], a[bad[:5]], b[bad[:5]])
+    with np.errstate(all="ignore"):                     # and the device's standard operators are IEEE: numpy's on the host agree
+        assert np.array_equal(q_std, x / y, equal_nan=True) and np.array_equal(s_std, np.sqrt(x), equal_nan=True)
+    mid = slice(n, 3 * n)                               # ordinary operands: the fast sequences carry (almost) all of them
+    assert np.mean((fast[mid] & 1) != 0) > 0.99 and np.mean((fast[2 * n:3 * n] & 2) != 0) > 0.99
+    assert not np.any(fast[3 * n:][np.isnan(x[3 * n:]) | np.isnan(y[3 * n:])] & 1)      # a NaN operand is never accepted
